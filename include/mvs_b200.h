@@ -1,0 +1,134 @@
+/*
+ * mvs_b200.h — C ABI of libmvs_b200.so, the B200 (sm_100a) plane-sweep MVS depth engine.
+ *
+ * Drop-in boundary for ONE hot path of ewrfcas/MVSFormer: the per-reference-view cascade
+ * (homography warp -> group-wise correlation cost volume -> 3D-CNN regularisation ->
+ * temperature-softmax depth regression -> hypothesis re-scheduling).  The reference is pure
+ * Python/PyTorch, so "the reference's FFI for this path" is its Python call surface; every
+ * entry point below names the reference function (file:line in /root/reference) it replaces.
+ * The Python mirror in mvsformer_b200/{warping,module,mvsformer_model}.py binds these with
+ * ctypes and keeps the reference's names and signatures.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  All tensor pointers are DEVICE
+ *     pointers to fp32 unless marked [host].  The caller owns every buffer (inputs, outputs,
+ *     workspaces); the library allocates nothing persistent.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no
+ *     device synchronisation inside).
+ *   - Return value: 0 on success, negative on error; mvs_last_error_string() gives the
+ *     message of the last failing call on the calling thread.
+ *   - "channels-last volume" = [B, D, H, W, C] with C innermost (the engine's internal layout
+ *     for the cost volume and the 3D-CNN activations); "NCDHW" = PyTorch's default.
+ */
+#ifndef MVS_B200_H_
+#define MVS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_OK 0
+#define MVS_ERR_INVALID_ARGUMENT (-1)
+#define MVS_ERR_UNSUPPORTED (-2)
+#define MVS_ERR_CUDA (-3)
+
+#define MVS_MAX_SRC_VIEWS 16
+
+/* ---- library ------------------------------------------------------------------------------ */
+int mvs_version(void);
+const char* mvs_last_error_string(void);
+/* Fills SM count and compute capability of the current device. */
+int mvs_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- A1. cameras: models/mvsformer_model.py:69-72 + models/warping.py:80-82 ----------------
+ * proj_matrices [B,V,2,4,4] (extrinsic, intrinsic) -> relproj [B,V-1,12]: rows of the 3x4 matrix
+ * [R|t] of  M = P_src * inverse(P_ref),  P = [K*E[:3,:4]; 0 0 0 1].  Evaluated in fp64 on the
+ * device (one thread per source view), rounded once to fp32. */
+int mvs_relative_projections(const float* proj_matrices, int B, int V, float* relproj, void* stream);
+/* Same for already-composed 4x4 matrices (the homo_warping_* signature): src_proj, ref_proj [B,4,4]. */
+int mvs_relative_projection_pair(const float* src_proj, const float* ref_proj, int B, float* relproj, void* stream);
+
+/* ---- A2. homo_warping_3D / homo_warping_3D_with_mask: models/warping.py:69-109,155-189 ------
+ * src_fea [B,C,H,W]; relproj [B,12]; depth [B,D] (depth_is_map=0) or [B,D,H,W] (1);
+ * warped [B,C,D,H,W]; mask [B,D,H,W] uint8 (1 = out of bounds or z<=0) or NULL. */
+int mvs_homo_warp(const float* src_fea, const float* relproj, const float* depth, int depth_is_map,
+                  float* warped, uint8_t* mask, int B, int C, int D, int H, int W, void* stream);
+
+/* ---- A3/A4/A6. cost-volume build: models/mvsformer_model.py:61-105,151-156 ------------------
+ * Two sampling passes; the N x C x D x H x W warped tensor is never materialised.
+ *   features: pointer to view 0 of batch 0 of a [B,V,C,H,W] tensor whose [C,H,W] blocks are
+ *             contiguous; batch_stride / view_stride in elements.  View 0 is the reference view.
+ *   depth    [B,D,H,W].
+ * pass A: entropy [B,N,H,W] of softmax_d(sum_g corr) per source view (:88-90); optionally the
+ *         eval-only cosine-similarity volume summed over views, sim_sum [B,D,H,W] (:81-85), NULL to skip.
+ * pass B: volume [B,D,H,W,G] channels-last = sum_v w_v corr_v / (sum_v w_v + 1e-6) (:101-105);
+ *         vis_weight [B,N,H,W]. */
+int mvs_cost_volume_entropy(const float* features, int64_t batch_stride, int64_t view_stride,
+                            const float* relproj, const float* depth, float* entropy, float* sim_sum,
+                            int B, int V, int C, int G, int D, int H, int W, void* stream);
+int mvs_cost_volume_aggregate(const float* features, int64_t batch_stride, int64_t view_stride,
+                              const float* relproj, const float* depth, const float* vis_weight,
+                              float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream);
+/* sim_depth = depth[argmax_d sim_sum] (:151-156).  out [B,H,W]. */
+int mvs_argmax_gather(const float* score, const float* depth, float* out, int B, int D, int H, int W, void* stream);
+
+/* ---- A4. visibility net (StageNet.vis): models/mvsformer_model.py:37,91 ----------------------
+ * entropy [M,H,W] -> weight [M,H,W]; three 3x3 conv (BN folded, ReLU) 1->16->16->8, 1x1 conv
+ * 8->1 + bias, sigmoid.  params [host]: folded weights and shifts, packed as
+ *   w1[16][9] b1[16] w2[16][16][9] b2[16] w3[8][16][9] b3[8] w4[8] b4[1]   (3641 floats). */
+#define MVS_VIS_PARAM_FLOATS (16 * 9 + 16 + 16 * 16 * 9 + 16 + 8 * 16 * 9 + 8 + 8 + 1)
+int mvs_vis_weight(const float* entropy, const float* params_host, float* weight, int M, int H, int W, void* stream);
+
+/* ---- A7. 3D-CNN layers: models/module.py:83-159 (Conv3d / Deconv3d blocks), :469-594 --------
+ * Channels-last activations.  y = act(conv(x) + shift) (+ skip);  BN (eval) is folded by the
+ * caller: scale into the packed weights, shift passed per output channel.
+ *   conv:   x [B,D,H,W,Cin] -> y [B,Do,Ho,Wo,Cout], kernel (kd,3,3) with kd in {1,3}, pad k/2, stride (sd,sh,sw) in {1,2};
+ *           w packed [kd][3][3][Cin][Cout].
+ *   deconv: ConvTranspose3d kernel (kd,3,3), pad k/2, output_padding = stride-1; x [B,D,H,W,Cin] -> y [B,D*sd,H*2,W*2,Cout];
+ *           w packed [kd][3][3][Cin][Cout] (from torch's [Cin,Cout,kd,kh,kw]).
+ *   skip (same shape as y) is added AFTER the activation (x = conv4 + conv7(x), module.py:500-502); NULL for none.
+ *   shift NULL = zeros. */
+int mvs_conv3d_cl(const float* x, const float* w_packed, const float* shift, const float* skip, float* y,
+                  int B, int D, int H, int W, int Cin, int Cout, int kd, int sd, int sh, int sw, int relu, void* stream);
+int mvs_deconv3d_cl(const float* x, const float* w_packed, const float* shift, const float* skip, float* y,
+                    int B, int D, int H, int W, int Cin, int Cout, int kd, int sd, int relu, void* stream);
+/* Layout transforms at the module boundary (CostRegNet*.forward takes/returns NCDHW). */
+int mvs_ncdhw_to_cl(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);
+int mvs_cl_to_ncdhw(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);
+
+/* ---- A7/A8. prob conv + head: models/module.py:493,582; models/mvsformer_model.py:110-125 ----
+ * x channels-last [B,D,H,W,Cin] -> pre [B,D,H,W] with the 8->1 `prob` conv (ksize 1: 1x1x1 + bias;
+ * ksize 3: 3x3x3, pad 1, no bias).  w [host]: [ksize^3][Cin], bias [host] 1 float or NULL. */
+int mvs_prob_conv_cl(const float* x, const float* w_host, const float* bias_host, float* pre,
+                     int B, int D, int H, int W, int Cin, int ksize, void* stream);
+/* pre [B,D,H,W], depth_values [B,D,H,W] -> prob_volume = softmax_d(pre) [B,D,H,W] (NULL to skip),
+ * photometric_confidence = max_d prob [B,H,W], depth [B,H,W]:
+ *   mode 0 (eval):  sum_d softmax_d(pre * tmp) * depth_values   (module.py:597-603)
+ *   mode 1 (train): depth_values[argmax_d prob]                 (mvsformer_model.py:117-120) */
+int mvs_regression_head(const float* pre, const float* depth_values, float tmp, int mode,
+                        float* prob_volume, float* depth, float* confidence, int B, int D, int H, int W, void* stream);
+/* depth_regression(p, depth_values): module.py:597-603.  depth_is_map as in mvs_homo_warp. */
+int mvs_depth_regression(const float* p, const float* depth_values, int depth_is_map, float* out,
+                         int B, int D, int H, int W, void* stream);
+/* conf_regression(p, n): module.py:606-619. */
+int mvs_conf_regression(const float* p, int n, float* out, int B, int D, int H, int W, void* stream);
+
+/* ---- A9. hypothesis schedules: models/module.py:622-699 -------------------------------------
+ * cur_depth [B,ND] (the [B,192] range); out [B,D,H,W]. */
+int mvs_init_inverse_range(const float* cur_depth, int ND, float* out, int B, int D, int H, int W, void* stream);
+int mvs_init_range(const float* cur_depth, int ND, float* out, int B, int D, int H, int W, void* stream);
+/* depth [B,H/2,W/2], depth_hypo [B,Dprev,H/2,W/2] -> out [B,D,H,W] (module.py:642-653). */
+int mvs_schedule_inverse_range(const float* depth, const float* depth_hypo, int Dprev, float split_itv,
+                               float* out, int B, int D, int H, int W, void* stream);
+/* depth [B,H/2,W/2], interval [B] (device) -> out [B,D,H,W] (module.py:687-699). */
+int mvs_schedule_range(const float* depth, const float* interval, float* out, int B, int D, int H, int W, void* stream);
+/* Nearest-neighbour upsample + accumulate of the per-stage confidence (mvsformer_model.py:438-442):
+ * acc[B,H,W] += scale * conf[B,h,w] (nearest, F.interpolate semantics). */
+int mvs_confidence_accumulate(const float* conf, int h, int w, float* acc, int B, int H, int W, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVS_B200_H_ */

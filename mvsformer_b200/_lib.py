@@ -1,0 +1,98 @@
+"""ctypes binding of libmvs_b200.so (C ABI declared in include/mvs_b200.h).
+
+The library is the product: if it is missing, or a tensor is not a CUDA fp32 tensor, the
+wrappers raise — there is no CPU or PyTorch fallback anywhere in this package.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmvs_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mvs_b200.h")
+
+_lib = None
+
+c_f = ctypes.c_void_p      # device / host float pointers travel as void*
+c_i = ctypes.c_int
+c_l = ctypes.c_int64
+c_fl = ctypes.c_float
+
+_SIGNATURES = {
+    "mvs_version": (c_i, []),
+    "mvs_last_error_string": (ctypes.c_char_p, []),
+    "mvs_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
+    "mvs_relative_projections": (c_i, [c_f, c_i, c_i, c_f, c_f]),
+    "mvs_relative_projection_pair": (c_i, [c_f, c_f, c_i, c_f, c_f]),
+    "mvs_homo_warp": (c_i, [c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "mvs_cost_volume_entropy": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
+    "mvs_cost_volume_aggregate": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
+    "mvs_argmax_gather": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "mvs_vis_weight": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "mvs_conv3d_cl": (c_i, [c_f] * 5 + [c_i] * 11 + [c_f]),
+    "mvs_deconv3d_cl": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
+    "mvs_ncdhw_to_cl": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
+    "mvs_cl_to_ncdhw": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
+    "mvs_prob_conv_cl": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
+    "mvs_regression_head": (c_i, [c_f, c_f, c_fl, c_i, c_f, c_f, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_depth_regression": (c_i, [c_f, c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_conf_regression": (c_i, [c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_init_inverse_range": (c_i, [c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_init_range": (c_i, [c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_schedule_inverse_range": (c_i, [c_f, c_f, c_i, c_fl, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_schedule_range": (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f]),
+    "mvs_confidence_accumulate": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_fl, c_f]),
+}
+
+
+def declared_symbols():
+    """Every function name declared in include/mvs_b200.h (used by the ABI test)."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvs_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libmvs_b200.so is not built (%s). Run `python -m mvsformer_b200.build` "
+            "(or __graft_entry__.build()). There is no fallback path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mvs_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (%d): %s" % (what or "libmvs_b200", rc, msg))
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mvsformer_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path"
+                               % t.device.type)
+        if t.dtype != torch.float32:
+            raise RuntimeError("expected a float32 tensor, got %s" % t.dtype)
+        if not t.is_contiguous():
+            raise RuntimeError("expected a contiguous tensor (shape %s, strides %s)" % (tuple(t.shape), t.stride()))
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,242 @@
+"""Thin tensor-level wrappers over the C ABI (include/mvs_b200.h).
+
+Each function allocates its outputs with torch's caching allocator on the current device,
+enqueues the kernel(s) on torch's current CUDA stream and returns immediately.  PyTorch is only
+the owner of device memory and streams here; all arithmetic is in libmvs_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def relative_projections(proj_matrices):
+    """[B,V,2,4,4] -> relproj [B,V-1,12]  (mvsformer_model.py:69-72 + warping.py:80-82)."""
+    proj_matrices = _f32(proj_matrices).contiguous()
+    require_cuda(proj_matrices)
+    if proj_matrices.dim() != 5 or tuple(proj_matrices.shape[2:]) != (2, 4, 4):
+        raise RuntimeError("proj_matrices must be [B,V,2,4,4], got %s" % (tuple(proj_matrices.shape),))
+    b, v = proj_matrices.shape[:2]
+    out = torch.empty(b, v - 1, 12, device=proj_matrices.device, dtype=torch.float32)
+    check(_lib.load().mvs_relative_projections(ptr(proj_matrices), b, v, ptr(out), stream()), "mvs_relative_projections")
+    return out
+
+
+def relative_projection_pair(src_proj, ref_proj):
+    src_proj, ref_proj = _f32(src_proj).contiguous(), _f32(ref_proj).contiguous()
+    require_cuda(src_proj, ref_proj)
+    b = src_proj.shape[0]
+    out = torch.empty(b, 12, device=src_proj.device, dtype=torch.float32)
+    check(_lib.load().mvs_relative_projection_pair(ptr(src_proj), ptr(ref_proj), b, ptr(out), stream()),
+          "mvs_relative_projection_pair")
+    return out
+
+
+def homo_warp(src_fea, relproj, depth_values, want_mask):
+    src_fea, depth_values = _f32(src_fea).contiguous(), _f32(depth_values).contiguous()
+    require_cuda(src_fea, relproj, depth_values)
+    b, c, h, w = src_fea.shape
+    d = depth_values.shape[1]
+    is_map = 1 if depth_values.dim() == 4 else 0
+    if is_map and tuple(depth_values.shape) != (b, d, h, w):
+        raise RuntimeError("depth_values must be [B,D] or [B,D,H,W] matching the feature map")
+    warped = torch.empty(b, c, d, h, w, device=src_fea.device, dtype=torch.float32)
+    mask = torch.empty(b, d, h, w, device=src_fea.device, dtype=torch.uint8) if want_mask else None
+    check(_lib.load().mvs_homo_warp(ptr(src_fea), ptr(relproj), ptr(depth_values), is_map, ptr(warped), ptr(mask),
+                                    b, c, d, h, w, stream()), "mvs_homo_warp")
+    return warped, (mask.bool() if want_mask else None)
+
+
+def _feature_strides(features):
+    """features [B,V,C,H,W]: each [C,H,W] block must be dense NCHW; batch/view strides are free."""
+    b, v, c, h, w = features.shape
+    if features.stride(4) != 1 or features.stride(3) != w or features.stride(2) != h * w:
+        features = features.contiguous()
+    return features, features.stride(0), features.stride(1)
+
+
+def cost_volume_entropy(features, relproj, depth_values, groups, want_sim):
+    features = _f32(features)
+    features, bs, vs = _feature_strides(features)
+    depth_values = _f32(depth_values).contiguous()
+    require_cuda(relproj, depth_values)
+    if not features.is_cuda:
+        raise RuntimeError("mvsformer_b200 runs on CUDA tensors only; there is no CPU path")
+    b, v, c, h, w = features.shape
+    d = depth_values.shape[1]
+    entropy = torch.empty(b, v - 1, h, w, device=features.device, dtype=torch.float32)
+    sim = torch.empty(b, d, h, w, device=features.device, dtype=torch.float32) if want_sim else None
+    check(_lib.load().mvs_cost_volume_entropy(ptr(features), bs, vs, ptr(relproj), ptr(depth_values), ptr(entropy),
+                                              ptr(sim), b, v, c, groups, d, h, w, stream()), "mvs_cost_volume_entropy")
+    return entropy, sim
+
+
+def cost_volume_aggregate(features, relproj, depth_values, vis_weight, groups):
+    features = _f32(features)
+    features, bs, vs = _feature_strides(features)
+    depth_values = _f32(depth_values).contiguous()
+    require_cuda(relproj, depth_values, vis_weight)
+    b, v, c, h, w = features.shape
+    d = depth_values.shape[1]
+    volume = torch.empty(b, d, h, w, groups, device=features.device, dtype=torch.float32)
+    check(_lib.load().mvs_cost_volume_aggregate(ptr(features), bs, vs, ptr(relproj), ptr(depth_values), ptr(vis_weight),
+                                                ptr(volume), b, v, c, groups, d, h, w, stream()),
+          "mvs_cost_volume_aggregate")
+    return volume
+
+
+def argmax_gather(score, depth_values):
+    require_cuda(score, depth_values)
+    b, d, h, w = score.shape
+    out = torch.empty(b, h, w, device=score.device, dtype=torch.float32)
+    check(_lib.load().mvs_argmax_gather(ptr(score), ptr(depth_values), ptr(out), b, d, h, w, stream()), "mvs_argmax_gather")
+    return out
+
+
+def vis_weight(entropy_maps, params_host):
+    """entropy_maps [M,H,W] (device), params_host: float32 numpy array of MVS_VIS_PARAM_FLOATS."""
+    require_cuda(entropy_maps)
+    m, h, w = entropy_maps.shape
+    assert params_host.dtype == np.float32 and params_host.flags["C_CONTIGUOUS"]
+    out = torch.empty_like(entropy_maps)
+    check(_lib.load().mvs_vis_weight(ptr(entropy_maps), params_host.ctypes.data_as(ctypes.c_void_p), ptr(out), m, h, w,
+                                     stream()), "mvs_vis_weight")
+    return out
+
+
+def conv3d_cl(x, w_packed, shift, skip, stride, relu=True):
+    """x [B,D,H,W,Cin] -> [B,Do,Ho,Wo,Cout]; w_packed [kd,3,3,Cin,Cout]."""
+    require_cuda(x, w_packed, shift, skip)
+    b, d, h, w, cin = x.shape
+    kd, cout = w_packed.shape[0], w_packed.shape[4]
+    sd, sh, sw = stride
+    pd = kd // 2
+    do, ho, wo = (d + 2 * pd - kd) // sd + 1, (h - 1) // sh + 1, (w - 1) // sw + 1
+    y = torch.empty(b, do, ho, wo, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_cl(ptr(x), ptr(w_packed), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, kd,
+                                    sd, sh, sw, 1 if relu else 0, stream()), "mvs_conv3d_cl")
+    return y
+
+
+def deconv3d_cl(x, w_packed, shift, skip, sd, relu=True):
+    """ConvTranspose3d (kd,3,3), stride (sd,2,2), pad k//2, output_padding stride-1."""
+    require_cuda(x, w_packed, shift, skip)
+    b, d, h, w, cin = x.shape
+    kd, cout = w_packed.shape[0], w_packed.shape[4]
+    y = torch.empty(b, d * sd, h * 2, w * 2, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_deconv3d_cl(ptr(x), ptr(w_packed), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, kd,
+                                      sd, 1 if relu else 0, stream()), "mvs_deconv3d_cl")
+    return y
+
+
+def ncdhw_to_cl(x):
+    x = _f32(x).contiguous()
+    require_cuda(x)
+    b, c, d, h, w = x.shape
+    y = torch.empty(b, d, h, w, c, device=x.device, dtype=torch.float32)
+    check(_lib.load().mvs_ncdhw_to_cl(ptr(x), ptr(y), b, c, d, h, w, stream()), "mvs_ncdhw_to_cl")
+    return y
+
+
+def cl_to_ncdhw(x):
+    require_cuda(x)
+    b, d, h, w, c = x.shape
+    y = torch.empty(b, c, d, h, w, device=x.device, dtype=torch.float32)
+    check(_lib.load().mvs_cl_to_ncdhw(ptr(x), ptr(y), b, c, d, h, w, stream()), "mvs_cl_to_ncdhw")
+    return y
+
+
+def prob_conv_cl(x, w_host, bias_host, ksize):
+    require_cuda(x)
+    b, d, h, w, cin = x.shape
+    pre = torch.empty(b, d, h, w, device=x.device, dtype=torch.float32)
+    bias_p = bias_host.ctypes.data_as(ctypes.c_void_p) if bias_host is not None else None
+    check(_lib.load().mvs_prob_conv_cl(ptr(x), w_host.ctypes.data_as(ctypes.c_void_p), bias_p, ptr(pre), b, d, h, w, cin,
+                                       ksize, stream()), "mvs_prob_conv_cl")
+    return pre
+
+
+def regression_head(pre, depth_values, tmp, training, want_prob=True):
+    pre, depth_values = _f32(pre).contiguous(), _f32(depth_values).contiguous()
+    require_cuda(pre, depth_values)
+    b, d, h, w = pre.shape
+    if tuple(depth_values.shape) != (b, d, h, w):
+        raise RuntimeError("depth_values %s does not match prob volume %s" % (tuple(depth_values.shape), tuple(pre.shape)))
+    prob = torch.empty_like(pre) if want_prob else None
+    depth = torch.empty(b, h, w, device=pre.device, dtype=torch.float32)
+    conf = torch.empty(b, h, w, device=pre.device, dtype=torch.float32)
+    check(_lib.load().mvs_regression_head(ptr(pre), ptr(depth_values), float(tmp), 1 if training else 0, ptr(prob),
+                                          ptr(depth), ptr(conf), b, d, h, w, stream()), "mvs_regression_head")
+    return prob, depth, conf
+
+
+def depth_regression(p, depth_values):
+    p, depth_values = _f32(p).contiguous(), _f32(depth_values).contiguous()
+    require_cuda(p, depth_values)
+    b, d, h, w = p.shape
+    is_map = 1 if depth_values.dim() == 4 else 0
+    out = torch.empty(b, h, w, device=p.device, dtype=torch.float32)
+    check(_lib.load().mvs_depth_regression(ptr(p), ptr(depth_values), is_map, ptr(out), b, d, h, w, stream()),
+          "mvs_depth_regression")
+    return out
+
+
+def conf_regression(p, n):
+    p = _f32(p).contiguous()
+    require_cuda(p)
+    b, d, h, w = p.shape
+    out = torch.empty(b, h, w, device=p.device, dtype=torch.float32)
+    check(_lib.load().mvs_conf_regression(ptr(p), int(n), ptr(out), b, d, h, w, stream()), "mvs_conf_regression")
+    return out
+
+
+def init_range(cur_depth, ndepths, h, w, inverse):
+    cur_depth = _f32(cur_depth).contiguous()
+    require_cuda(cur_depth)
+    b, nd = cur_depth.shape
+    out = torch.empty(b, ndepths, h, w, device=cur_depth.device, dtype=torch.float32)
+    fn = _lib.load().mvs_init_inverse_range if inverse else _lib.load().mvs_init_range
+    check(fn(ptr(cur_depth), nd, ptr(out), b, ndepths, h, w, stream()), "mvs_init_range")
+    return out
+
+
+def schedule_inverse_range(depth, depth_hypo, ndepths, split_itv, h, w):
+    depth, depth_hypo = _f32(depth).contiguous(), _f32(depth_hypo).contiguous()
+    require_cuda(depth, depth_hypo)
+    b, dprev, h2, w2 = depth_hypo.shape
+    if (h2, w2) != (h // 2, w // 2) or tuple(depth.shape) != (b, h2, w2):
+        raise RuntimeError("schedule_inverse_range: previous-stage maps must be [B,%d,%d]" % (h // 2, w // 2))
+    out = torch.empty(b, ndepths, h, w, device=depth.device, dtype=torch.float32)
+    check(_lib.load().mvs_schedule_inverse_range(ptr(depth), ptr(depth_hypo), dprev, float(split_itv), ptr(out), b,
+                                                 ndepths, h, w, stream()), "mvs_schedule_inverse_range")
+    return out
+
+
+def schedule_range(cur_depth, ndepth, depth_interval_pixel, h, w):
+    cur_depth, itv = _f32(cur_depth).contiguous(), _f32(depth_interval_pixel).contiguous()
+    require_cuda(cur_depth, itv)
+    b = cur_depth.shape[0]
+    out = torch.empty(b, ndepth, h, w, device=cur_depth.device, dtype=torch.float32)
+    check(_lib.load().mvs_schedule_range(ptr(cur_depth), ptr(itv), ptr(out), b, ndepth, h, w, stream()), "mvs_schedule_range")
+    return out
+
+
+def confidence_accumulate(conf, acc, scale=1.0):
+    require_cuda(conf, acc)
+    b, h, w = conf.shape
+    check(_lib.load().mvs_confidence_accumulate(ptr(conf), h, w, ptr(acc), b, acc.shape[1], acc.shape[2], float(scale),
+                                                stream()), "mvs_confidence_accumulate")
+    return acc

@@ -1,0 +1,173 @@
+"""Drop-in mirror of the hot-path half of the reference's ``models/mvsformer_model.py``.
+
+* ``StageNet``     models/mvsformer_model.py:26-160 — same constructor, ``state_dict`` keys, forward
+                   signature and output dict; the whole forward is ten-odd kernel launches in
+                   libmvs_b200.so (fused warp + correlation, fused vis net, channels-last 3D CNN,
+                   fused head) and no PyTorch arithmetic.
+* ``CascadeMVS``   the cascade loop of ``TwinMVSNet.forward`` / ``DINOMVSNet.forward``
+                   (models/mvsformer_model.py:410-449 / :273-308) over pre-extracted per-stage
+                   features; ``fusions`` has the reference's name so ``fusions.*`` checkpoint
+                   entries load unchanged.
+* ``install_into(reference_module)``  swaps the reference's StageNet and schedulers for these,
+                   which is how ``models/mvsformer_model.py`` uses the engine as a drop-in
+                   (see INTEGRATION.md).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine
+from .module import (ConvBnReLU, CostRegNet, CostRegNet2D, CostRegNet3D, _FoldCache, _bn_scale_shift,
+                     init_inverse_range, init_range, schedule_inverse_range, schedule_range)
+
+
+class StageNet(nn.Module):
+    def __init__(self, args, ndepth, stage_idx):
+        super().__init__()
+        self.args = args
+        self.fusion_type = args.get("fusion_type", "cnn")
+        self.ndepth = ndepth
+        self.stage_idx = stage_idx
+        in_channels = args["base_ch"]
+        if self.fusion_type == "cnn":
+            model_th = args.get("model_th", 8)
+            self.vis = nn.Sequential(ConvBnReLU(1, 16), ConvBnReLU(16, 16), ConvBnReLU(16, 8), nn.Conv2d(8, 1, 1),
+                                     nn.Sigmoid())
+            if ndepth <= model_th:
+                self.cost_reg = CostRegNet3D(in_channels, args["base_ch"])
+            else:
+                self.cost_reg = CostRegNet(in_channels, args["base_ch"])
+        elif self.fusion_type in ("epipole", "epipoleV2"):
+            # present in the reference's code but used by no shipped config
+            raise NotImplementedError("fusion_type=%r is outside the accelerated path (only 'cnn' ships)" % self.fusion_type)
+        else:
+            raise NotImplementedError
+        self._vis_cache = _FoldCache()
+
+    # -- visibility-net parameters, BN folded, packed for mvs_vis_weight ---------------------------
+    def _vis_params_host(self):
+        def build():
+            chunks = []
+            for i in range(3):
+                blk = self.vis[i]
+                scale, shift = _bn_scale_shift(blk.bn)
+                w = blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)      # [Co,Ci,3,3]
+                chunks += [w.reshape(-1), shift.reshape(-1)]
+            last = self.vis[3]
+            chunks += [last.weight.detach().float().reshape(-1), last.bias.detach().float().reshape(-1)]
+            return np.ascontiguousarray(torch.cat(chunks).cpu().numpy().astype(np.float32))
+
+        tensors = []
+        for i in range(3):
+            blk = self.vis[i]
+            tensors += [blk.conv.weight, blk.bn.weight, blk.bn.bias, blk.bn.running_mean, blk.bn.running_var]
+        tensors += [self.vis[3].weight, self.vis[3].bias]
+        return self._vis_cache.get(tensors, build)
+
+    def build_cost_volume(self, features, proj_matrices, depth_values):
+        """models/mvsformer_model.py:52-105 -> (volume channels-last [B,D,H,W,G], sim_sum or None,
+        entropy [B,N,H,W], vis_weight [B,N,H,W])."""
+        if features.dim() != 5:
+            raise RuntimeError("features must be [B,V,C,H,W]")
+        b, v = features.shape[:2]
+        assert v == proj_matrices.shape[1], "Different number of images and projection matrices"
+        groups = self.args["base_ch"]
+        if features.shape[2] % groups:
+            raise RuntimeError("shape '[%d, %d, -1, ...]' is invalid for %d feature channels"
+                               % (b, groups, features.shape[2]))
+        if self.vis[0].bn.training:
+            raise NotImplementedError("StageNet: train-mode forward is not built in this round; call .eval()")
+        relproj = engine.relative_projections(proj_matrices)
+        entropy, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=not self.training)
+        h, w = entropy.shape[-2:]
+        weight = engine.vis_weight(entropy.view(b * (v - 1), h, w), self._vis_params_host()).view(b, v - 1, h, w)
+        volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups)
+        return volume, sim, entropy, weight
+
+    def forward(self, features, proj_matrices, depth_values, tmp=2.0):
+        """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W]."""
+        if self.args["depth_type"] not in ("ce", "was"):
+            raise NotImplementedError("depth_type=%r: only 'ce'/'was' heads are built (the shipped config uses 'ce')"
+                                      % self.args["depth_type"])
+        depth_values = depth_values.float().contiguous()
+        volume, sim, _, _ = self.build_cost_volume(features, proj_matrices, depth_values)
+        prob_volume_pre = self.cost_reg.forward_cl(volume)
+        if type(tmp) == list or type(tmp) == tuple:
+            tmp = tmp[self.stage_idx]
+        prob_volume, depth, conf = engine.regression_head(prob_volume_pre, depth_values, tmp, self.training)
+        outputs = {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
+                   "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
+        if not self.training:
+            outputs["sim_depth"] = engine.argmax_gather(sim, depth_values)
+        return outputs
+
+
+class CascadeMVS(nn.Module):
+    """Coarse-to-fine cascade over pre-extracted features (the body of ``TwinMVSNet.forward`` after
+    feature extraction, models/mvsformer_model.py:410-449)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.ndepths = args["ndepths"]
+        self.depth_interals_ratio = args["depth_interals_ratio"]
+        self.inverse_depth = args.get("inverse_depth", False)
+        self.fusions = nn.ModuleList([StageNet(args, self.ndepths[i], i) for i in range(len(self.ndepths))])
+
+    def forward(self, features, proj_matrices, depth_values, tmp=2.0, full_hw=None):
+        """features {"stageK": [B,V,C,h,w]}, proj_matrices {"stageK": [B,V,2,4,4]}, depth_values [B,ND]."""
+        nst = len(self.ndepths)
+        last_feat = features["stage%d" % nst]
+        b = last_feat.shape[0]
+        if full_hw is None:
+            full_hw = tuple(last_feat.shape[-2:])
+        outputs = {}
+        outputs_stage = None
+        use_conf = self.args["depth_type"] in ("ce", "mixup_ce")
+        prob_maps = torch.zeros(b, full_hw[0], full_hw[1], dtype=torch.float32, device=last_feat.device) if use_conf else None
+        depth_interval = depth_values[:, 1] - depth_values[:, 0]
+        for s in range(nst):
+            feats = features["stage%d" % (s + 1)]
+            h, w = feats.shape[-2:]
+            if s == 0:
+                rng = init_inverse_range if self.inverse_depth else init_range
+                depth_samples = rng(depth_values, self.ndepths[s], feats.device, torch.float32, h, w)
+            elif self.inverse_depth:
+                depth_samples = schedule_inverse_range(outputs_stage["depth"].detach(), outputs_stage["depth_values"],
+                                                       self.ndepths[s], self.depth_interals_ratio[s], h, w)
+            else:
+                depth_samples = schedule_range(outputs_stage["depth"].detach(), self.ndepths[s],
+                                               self.depth_interals_ratio[s] * depth_interval, h, w)
+            outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp)
+            outputs["stage%d" % (s + 1)] = outputs_stage
+            if use_conf:
+                conf = outputs_stage["photometric_confidence"]
+                engine.confidence_accumulate(conf, prob_maps, 1.0)
+                if tuple(conf.shape[-2:]) != tuple(full_hw):
+                    # the reference replaces the stage's confidence by its nearest upsampling (:439-441)
+                    up = torch.zeros_like(prob_maps)
+                    outputs_stage["photometric_confidence"] = engine.confidence_accumulate(conf, up, 1.0)
+            outputs.update(outputs_stage)
+        outputs["refined_depth"] = outputs_stage["depth"]
+        if use_conf:
+            outputs["photometric_confidence"] = prob_maps / nst
+        return outputs
+
+
+def install_into(reference_model_module, reference_module_module=None):
+    """Point the reference's ``models.mvsformer_model`` (already imported) at this engine: its
+    ``TwinMVSNet`` / ``DINOMVSNet`` then build our StageNet and call our schedulers, and their
+    checkpoints load unchanged.  See INTEGRATION.md."""
+    m = reference_model_module
+    m.StageNet = StageNet
+    m.init_inverse_range = init_inverse_range
+    m.init_range = init_range
+    m.schedule_inverse_range = schedule_inverse_range
+    m.schedule_range = schedule_range
+    m.CostRegNet, m.CostRegNet3D, m.CostRegNet2D = CostRegNet, CostRegNet3D, CostRegNet2D
+    if reference_module_module is not None:
+        for name in ("CostRegNet", "CostRegNet3D", "CostRegNet2D", "init_inverse_range", "init_range",
+                     "schedule_inverse_range", "schedule_range", "depth_regression", "conf_regression"):
+            setattr(reference_module_module, name, globals().get(name) or getattr(__import__(
+                "mvsformer_b200.module", fromlist=[name]), name))
+    return m

@@ -1,0 +1,196 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference on CPU.  TEST INFRASTRUCTURE.
+
+Run in the build container (where ``/root/reference`` exists):
+
+    python -m oracle.make_golden
+
+Inputs and weights are NOT stored: they are regenerated from ``mvsformer_b200.synthetic`` with the
+seeds recorded in each file (plus a checksum so a drifting RNG is detected, not silently
+compared).  Outputs are what the reference functions returned:
+
+* ``warp_*.npz``        models/warping.py:69-109,155-189
+* ``schedules.npz``     models/module.py:597-699
+* ``stage{1..4}.npz``   StageNet.forward (eval)  models/mvsformer_model.py:51-158
+* ``stage2_train.npz``  StageNet.forward (train mode: batch-stat BN, argmax depth)
+* ``cascade.npz``       the cascade loop models/mvsformer_model.py:410-449 driven over synthetic features
+                        (the loop is re-stated here in 15 lines because the reference only has it
+                        inline in TwinMVSNet.forward behind the ViT feature extractor)
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from mvsformer_b200 import synthetic as S  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+STAGE_ARGS = {"base_ch": 8, "fusion_type": "cnn", "depth_type": "ce"}
+
+
+def checksum(t):
+    return float(t.double().abs().sum())
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_warp(ns):
+    feats = S.make_features(2, 3, 24, 40, seed=5, stages=(3,), feat_chs=(0, 0, 0, 8))["stage4"]     # [2,3,8,24,40]
+    cams = S.make_cameras(2, 3, 24, 40)["stage4"]
+    # exaggerate the baseline so a good share of samples leaves the image
+    cams = cams.clone()
+    cams[:, 2, 0, 0, 3] += 150.0
+    O_compose = lambda p: _compose(p)
+    ref_p = O_compose(cams[:, 0])
+    dv_map = S.make_depth_range(2)[:, ::32][:, :6]                                                   # [2,6]
+    dv_px = dv_map.view(2, 6, 1, 1) * (1.0 + 0.1 * torch.rand(2, 6, 24, 40, generator=S._gen(3)))
+    out = {"seed": 5, "feat_checksum": checksum(feats)}
+    for v in (1, 2):
+        src_p = O_compose(cams[:, v])
+        w1, m1 = ns.warping.homo_warping_3D_with_mask(feats[:, v], src_p, ref_p, dv_map)
+        w2, m2 = ns.warping.homo_warping_3D_with_mask(feats[:, v], src_p, ref_p, dv_px)
+        w3 = ns.warping.homo_warping_3D(feats[:, v], src_p, ref_p, dv_px)
+        assert torch.equal(w2, w3)
+        out["warped_bd_v%d" % v] = np_(w1)
+        out["mask_bd_v%d" % v] = np_(m1)
+        out["warped_px_v%d" % v] = np_(w2)
+        out["mask_px_v%d" % v] = np_(m2)
+    np.savez_compressed(os.path.join(OUT, "warp.npz"), **out)
+
+
+def _compose(pair):
+    p = pair[:, 0].clone()
+    p[:, :3, :4] = torch.matmul(pair[:, 1, :3, :3], pair[:, 0, :3, :4])
+    return p
+
+
+def gen_schedules(ns):
+    M = ns.module
+    dv = S.make_depth_range(2)
+    g = S._gen(11)
+    out = {}
+    out["init_inverse_range"] = np_(M.init_inverse_range(dv, 32, "cpu", torch.float32, 8, 12))
+    out["init_range"] = np_(M.init_range(dv, 32, "cpu", torch.float32, 8, 12))
+    hyp = M.init_inverse_range(dv, 32, "cpu", torch.float32, 8, 12)
+    depth = 500.0 + 300.0 * torch.rand(2, 8, 12, generator=g)
+    out["sched_depth_in"] = np_(depth)
+    out["schedule_inverse_range"] = np_(M.schedule_inverse_range(depth, hyp, 16, 2.67, 16, 24))
+    out["schedule_range"] = np_(M.schedule_range(depth, 16, 2.67 * (dv[:, 1] - dv[:, 0]), 16, 24))
+    p = torch.softmax(3.0 * torch.randn(2, 32, 8, 12, generator=g), dim=1)
+    out["prob_in"] = np_(p)
+    out["depth_regression_map"] = np_(M.depth_regression(p, hyp))
+    out["depth_regression_vec"] = np_(M.depth_regression(p, dv[:, :32]))
+    for n in (2, 3, 4):
+        out["conf_regression_n%d" % n] = np_(M.conf_regression(p, n=n))
+    np.savez_compressed(os.path.join(OUT, "schedules.npz"), **out)
+
+
+def stage_inputs(stage, height, width, batch=1, views=3, seed=1234):
+    feats = S.make_features(batch, views, height, width, seed=seed, stages=(stage,))["stage%d" % (stage + 1)]
+    cams = S.make_cameras(batch, views, height, width)["stage%d" % (stage + 1)]
+    return feats, cams
+
+
+def gen_stages(ns):
+    R = ns.mvsformer_model
+    height, width = 128, 192
+    for s in range(4):
+        net = R.StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+        sd = S.fill_state_dict(net.state_dict(), seed=s)
+        net.load_state_dict(sd)
+        feats, cams = stage_inputs(s, height, width, batch=2 if s < 2 else 1)
+        hyp = S.narrow_hypotheses(s, height, width, feats.shape[0])
+        with torch.no_grad():
+            out = net(feats, cams, hyp, tmp=list(S.EVAL_TMP))
+        np.savez_compressed(
+            os.path.join(OUT, "stage%d.npz" % (s + 1)),
+            height=height, width=width, batch=feats.shape[0], views=3, weight_seed=s,
+            feat_checksum=checksum(feats), hyp_checksum=checksum(hyp),
+            **{k: np_(v) for k, v in out.items() if k != "depth_values"})
+    # training mode (batch-stat BN, argmax depth) for one stage
+    s = 1
+    net = R.StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).train()
+    sd = S.fill_state_dict(net.state_dict(), seed=s)
+    net.load_state_dict(sd)
+    feats, cams = stage_inputs(s, height, width, batch=2)
+    hyp = S.narrow_hypotheses(s, height, width, 2)
+    with torch.no_grad():
+        out = net(feats, cams, hyp, tmp=list(S.EVAL_TMP))
+    np.savez_compressed(os.path.join(OUT, "stage2_train.npz"), height=height, width=width, batch=2, views=3,
+                        weight_seed=s, feat_checksum=checksum(feats),
+                        **{k: np_(v) for k, v in out.items() if k != "depth_values"})
+
+
+def reference_cascade(ns, features, cams, depth_values, nets, tmp, ratios):
+    """The loop of models/mvsformer_model.py:410-449 (TwinMVSNet.forward after feature extraction),
+    calling the reference's own schedulers and StageNets."""
+    M = ns.module
+    outputs, last = {}, None
+    full_h, full_w = features["stage4"].shape[-2:]
+    prob_maps = torch.zeros(depth_values.shape[0], full_h, full_w)
+    for s in range(4):
+        f = features["stage%d" % (s + 1)]
+        h, w = f.shape[-2:]
+        if s == 0:
+            hyp = M.init_inverse_range(depth_values, S.NDEPTHS[s], "cpu", torch.float32, h, w)
+        else:
+            hyp = M.schedule_inverse_range(last["depth"].detach(), last["depth_values"], S.NDEPTHS[s], ratios[s], h, w)
+        last = nets[s](f, cams["stage%d" % (s + 1)], hyp, tmp=tmp)
+        conf = last["photometric_confidence"]
+        if conf.shape[-2:] != prob_maps.shape[-2:]:
+            conf = F.interpolate(conf.unsqueeze(1), [full_h, full_w], mode="nearest").squeeze(1)
+        prob_maps = prob_maps + conf
+        outputs["stage%d" % (s + 1)] = last
+    outputs["refined_depth"] = last["depth"]
+    outputs["photometric_confidence"] = prob_maps / 4
+    return outputs
+
+
+def gen_cascade(ns):
+    R = ns.mvsformer_model
+    height, width, batch, views = 128, 192, 1, 4
+    feats = S.make_features(batch, views, height, width, seed=77)
+    cams = S.make_cameras(batch, views, height, width)
+    dv = S.make_depth_range(batch)
+    nets = []
+    for s in range(4):
+        net = R.StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+        net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=10 + s))
+        nets.append(net)
+    with torch.no_grad():
+        out = reference_cascade(ns, feats, cams, dv, nets, list(S.EVAL_TMP), S.DEPTH_INTERVAL_RATIO)
+    blob = {"height": height, "width": width, "batch": batch, "views": views, "feat_seed": 77, "weight_seed0": 10,
+            "feat_checksum": checksum(feats["stage4"]),
+            "refined_depth": np_(out["refined_depth"]), "photometric_confidence": np_(out["photometric_confidence"])}
+    for s in range(4):
+        st = out["stage%d" % (s + 1)]
+        blob["stage%d_depth" % (s + 1)] = np_(st["depth"])
+        blob["stage%d_prob_volume_pre" % (s + 1)] = np_(st["prob_volume_pre"])
+        blob["stage%d_depth_values" % (s + 1)] = np_(st["depth_values"])
+        blob["stage%d_sim_depth" % (s + 1)] = np_(st["sim_depth"])
+    np.savez_compressed(os.path.join(OUT, "cascade.npz"), **blob)
+
+
+def main():
+    warnings.simplefilter("ignore")
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_import.load_reference()
+    gen_warp(ns)
+    gen_schedules(ns)
+    gen_stages(ns)
+    gen_cascade(ns)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
