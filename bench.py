@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — depth maps/s of the plane-sweep cascade on B200 (BASELINE.json metric, cfg 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one reference view: the 4-stage cascade (hypothesis
+schedule -> fused warp/correlation cost volume -> 3D-CNN -> softmax regression) at DTU test size
+1152x1536, 5 views, 192-depth range, ndepths 32/16/8/4, synthetic features / cameras / weights.
+Reference views are independent, so with N GPUs every rank runs its own reference views
+(weak scaling, no data-path collective); `value` = N*K / max-over-ranks(device time).
+
+Printed JSON line (rank 0): value (inputs resident in HBM), e2e (same call with pinned HOST
+inputs, H2D + D2H inside the timed region), roofline of the dominant kernel (live CUDA-event
+timing per kernel class), cpu_baseline (the CPU oracle port on a bounded sample), clocks.
+
+`--impl reference` times the reference's CPU arithmetic (the oracle port of the reference's own
+torch-CPU path: the reference is Python and cannot travel to the GPU box) on all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mvsformer_b200 import synthetic as S  # noqa: E402
+
+METRIC = "depth maps/sec @ DTU 1152x1536, 5 views, 192 depths; cost-vol Gvox/s"
+UNIT = "depth maps/s"
+HEIGHT, WIDTH, VIEWS = 1152, 1536, 5
+SAMPLE_H, SAMPLE_W = 256, 384          # bounded CPU sample (1/18 of the pixels of the full workload)
+CASCADE_ARGS = {"base_ch": 8, "fusion_type": "cnn", "depth_type": "ce", "ndepths": list(S.NDEPTHS),
+                "depth_interals_ratio": list(S.DEPTH_INTERVAL_RATIO), "inverse_depth": True}
+
+
+def workload_config(n_gpus):
+    return {"workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, "
+                        "feat ch 64/32/16/8, G=8, B=1 ref view per GPU per step" % (HEIGHT, WIDTH, VIEWS),
+            "precision": "fp32 features/volume/activations", "parallelism": "ref views sharded, %d rank(s), no collective" % n_gpus,
+            "l2_policy": "inputs 530 MB/step > 126 MB L2; every intermediate volume is rewritten each step"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel-class timing (CUDA events on torch's current stream = the launching stream)
+# ------------------------------------------------------------------------------------------------
+class KernelProfiler:
+    """Wraps the engine entry points with CUDA events and algorithmic byte / flop counters."""
+
+    def __init__(self):
+        self.records = {}
+        self._saved = {}
+
+    def _wrap(self, engine, name, cls, cost):
+        fn = getattr(engine, name)
+        self._saved[name] = fn
+
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            nbytes, flops = cost(out, *a, **k)
+            rec = self.records.setdefault(cls, {"events": [], "bytes": 0, "flops": 0, "launches": 0})
+            rec["events"].append((e0, e1))
+            rec["bytes"] += nbytes
+            rec["flops"] += flops
+            rec["launches"] += 1
+            return out
+
+        setattr(engine, name, wrapped)
+
+    def install(self, engine):
+        def numel_bytes(*ts):
+            return sum(4 * t.numel() for t in ts if t is not None and hasattr(t, "numel"))
+
+        def cv_cost(out, features, relproj, depth_values, *rest, **k):
+            b, v, c, h, w = features.shape
+            d = depth_values.shape[1]
+            return 4 * (b * v * c * h * w + b * d * h * w), 0      # features + hypotheses (outputs added below)
+
+        def ent_cost(out, features, relproj, depth_values, groups, want_sim):
+            base, _ = cv_cost(out, features, relproj, depth_values)
+            return base + numel_bytes(out[0], out[1]), 0
+
+        def agg_cost(out, features, relproj, depth_values, vis_weight, groups):
+            base, _ = cv_cost(out, features, relproj, depth_values)
+            return base + numel_bytes(out, vis_weight), 0
+
+        def conv_cost(out, x, w_packed, shift, skip, stride, relu=True):
+            taps_cin_cout = w_packed.numel()
+            return numel_bytes(x, out, skip, w_packed), 2 * taps_cin_cout * (out.numel() // out.shape[-1])
+
+        def deconv_cost(out, x, w_packed, shift, skip, sd, relu=True):
+            return numel_bytes(x, out, skip, w_packed), 2 * w_packed.numel() * (x.numel() // x.shape[-1])
+
+        def vis_cost(out, ent, params):
+            return numel_bytes(ent, out), 2 * 3608 * ent.numel()
+
+        def io_cost(out, *a, **k):
+            outs = out if isinstance(out, (tuple, list)) else (out,)
+            return numel_bytes(*outs) + numel_bytes(*[t for t in a if torch.is_tensor(t)]), 0
+
+        self._wrap(engine, "cost_volume_entropy", "cv_entropy(passA)", ent_cost)
+        self._wrap(engine, "cost_volume_aggregate", "cv_aggregate(passB)", agg_cost)
+        self._wrap(engine, "vis_weight", "vis_net", vis_cost)
+        self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
+        self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
+        for name in ("prob_conv_cl", "regression_head", "argmax_gather", "init_range", "schedule_inverse_range",
+                     "confidence_accumulate", "relative_projections"):
+            self._wrap(engine, name, "head+schedule", io_cost)
+
+    def uninstall(self, engine):
+        for name, fn in self._saved.items():
+            setattr(engine, name, fn)
+
+    def summary(self, steps):
+        out = {}
+        for cls, rec in self.records.items():
+            ms = sum(e0.elapsed_time(e1) for e0, e1 in rec["events"])
+            out[cls] = {"ms_per_step": ms / steps, "launches_per_step": rec["launches"] / steps,
+                        "alg_bytes_per_step": rec["bytes"] / steps, "alg_flops_per_step": rec["flops"] / steps,
+                        "avg_launch_ms": ms / max(rec["launches"], 1)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction
+# ------------------------------------------------------------------------------------------------
+def build_engine(device):
+    from mvsformer_b200.mvsformer_model import CascadeMVS
+    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
+    full = {}
+    for s in range(4):
+        sd = S.fill_state_dict(net.fusions[s].state_dict(), seed=s)
+        full.update({"fusions.%d.%s" % (s, k): v for k, v in sd.items()})
+    net.load_state_dict(full, strict=True)
+    return net.to(device)
+
+
+def host_inputs(height, width, views, seed, pin):
+    feats = S.make_features(1, views, height, width, seed=seed)
+    cams = S.make_cameras(1, views, height, width)
+    dv = S.make_depth_range(1)
+    if pin:
+        feats = {k: v.pin_memory() for k, v in feats.items()}
+        cams = {k: v.pin_memory() for k, v in cams.items()}
+        dv = dv.pin_memory()
+    return feats, cams, dv
+
+
+def cpu_cascade_rate(steps, warmup, threads):
+    """The reference's CPU arithmetic (oracle port) on the bounded sample; returns (maps/s scaled to
+    the full workload by pixel ratio, seconds per sample step)."""
+    from mvsformer_b200.mvsformer_model import CascadeMVS
+    from oracle import mvs_oracle as O
+    torch.set_num_threads(threads)
+    feats, cams, dv = host_inputs(SAMPLE_H, SAMPLE_W, VIEWS, 1234, pin=False)
+    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
+    sds = [S.fill_state_dict(net.fusions[s].state_dict(), seed=s) for s in range(4)]
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.cascade_forward(feats, cams, dv, sds)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.cascade_forward(feats, cams, dv, sds)
+        dt = (time.perf_counter() - t0) / steps
+    frac = (SAMPLE_H * SAMPLE_W) / float(HEIGHT * WIDTH)
+    return frac / dt, dt
+
+
+def sample_desc():
+    return ("4-stage cascade, %d views, 192-depth range, image %dx%d = 1/%d of the %dx%d pixels; rate scaled by the "
+            "pixel ratio" % (VIEWS, SAMPLE_H, SAMPLE_W, round(HEIGHT * WIDTH / (SAMPLE_H * SAMPLE_W)), HEIGHT, WIDTH))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    value, dt = cpu_cascade_rate(args.steps, max(args.warmup, 1), threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_engine(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from mvsformer_b200 import _lib, engine
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    net = build_engine(device)
+    feats_h, cams_h, dv_h = host_inputs(HEIGHT, WIDTH, VIEWS, 1234 + rank, pin=True)
+    feats_d = {k: v.to(device) for k, v in feats_h.items()}
+    cams_d = {k: v.to(device) for k, v in cams_h.items()}
+    dv_d = dv_h.to(device)
+    tmp = list(S.EVAL_TMP)
+    lib = _lib.load()
+
+    def step_resident():
+        return net(feats_d, cams_d, dv_d, tmp=tmp)
+
+    depth_host = torch.empty(1, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
+    conf_host = torch.empty(1, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        f = {k: v.to(device, non_blocking=True) for k, v in feats_h.items()}
+        c = {k: v.to(device, non_blocking=True) for k, v in cams_h.items()}
+        d = dv_h.to(device, non_blocking=True)
+        out = net(f, c, d, tmp=tmp)
+        depth_host.copy_(out["refined_depth"], non_blocking=True)
+        conf_host.copy_(out["photometric_confidence"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller consumes the depth map
+        return out
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.mvs_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), lib.mvs_launch_count() - l0
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms_total, launches = timed(step_resident, args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        ms_e2e, _ = timed(step_e2e, args.steps)
+
+        # per-kernel-class attribution (separate pass, same inputs)
+        prof = KernelProfiler()
+        prof.install(engine)
+        barrier()
+        psteps = min(args.steps, 5)
+        for _ in range(psteps):
+            step_resident()
+        barrier()
+        prof.uninstall(engine)
+        kernels = prof.summary(psteps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(4 * v.numel() for v in feats_h.values()) + sum(4 * v.numel() for v in cams_h.values()) + 4 * dv_h.numel()
+    d2h = 4 * (depth_host.numel() + conf_host.numel())
+    peaks = measured_peaks()
+
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    kd = kernels[dom]
+    if kd["alg_flops_per_step"] > 100 * kd["alg_bytes_per_step"]:
+        achieved = kd["alg_flops_per_step"] / (kd["ms_per_step"] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                "note": "fp32 math; peak = %s sustained cuBLAS bf16" % peaks["source"]}
+    else:
+        achieved = kd["alg_bytes_per_step"] / (kd["ms_per_step"] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "note": "peak = %s copy bandwidth" % peaks["source"]}
+    roof["avg_launch_ms"] = kd["avg_launch_ms"]
+    roof["share_of_step"] = kd["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())
+
+    # cost-volume build (pass A + vis net + pass B) against the HBM roofline — the north-star kernel
+    cv_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith("cv_") or k == "vis_net")
+    cv_bytes = S.cost_volume_algorithmic_bytes(VIEWS, HEIGHT, WIDTH)
+    cost_volume = {"ms_per_step": cv_ms, "gvox_per_s": S.voxels_per_ref_view(HEIGHT, WIDTH) / (cv_ms * 1e-3) / 1e9,
+                   "alg_bytes": cv_bytes, "achieved_gbs": cv_bytes / (cv_ms * 1e-3) / 1e9,
+                   "frac_of_hbm": cv_bytes / (cv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cost_volume": cost_volume,
+            "kernels": kernels}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_cascade_rate(3, 1, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc(),
+                                "seconds_per_sample_step": dt}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+    run_engine(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

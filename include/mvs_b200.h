@@ -39,6 +39,8 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------------ */
 int mvs_version(void);
 const char* mvs_last_error_string(void);
+/* Number of kernels this library has launched in this process (monotonic; used by bench.py). */
+long long mvs_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 int mvs_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

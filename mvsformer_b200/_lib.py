@@ -23,6 +23,7 @@ c_fl = ctypes.c_float
 _SIGNATURES = {
     "mvs_version": (c_i, []),
     "mvs_last_error_string": (ctypes.c_char_p, []),
+    "mvs_launch_count": (ctypes.c_longlong, []),
     "mvs_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
     "mvs_relative_projections": (c_i, [c_f, c_i, c_i, c_f, c_f]),
     "mvs_relative_projection_pair": (c_i, [c_f, c_f, c_i, c_f, c_f]),

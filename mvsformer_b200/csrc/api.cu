@@ -2,9 +2,13 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mvs {
+
+long long launches();
 
 static thread_local char g_error[512] = "no error";
 
@@ -15,9 +19,15 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 }  // namespace mvs
 
 extern "C" int mvs_version(void) { return 100; }   // 0.1.0
+
+extern "C" long long mvs_launch_count(void) { return mvs::launches(); }
 
 extern "C" const char* mvs_last_error_string(void) { return mvs::g_error; }
 

@@ -9,6 +9,7 @@
 namespace mvs {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // bumps the counter read by mvs_launch_count()
 
 #define MVS_REQUIRE(cond, ...)                      \
     do {                                            \
@@ -41,6 +42,7 @@ void set_error(const char* fmt, ...);
             ::mvs::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
             return MVS_ERR_CUDA;                                                            \
         }                                                                                   \
+        ::mvs::count_launch();                                                              \
     } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -12,6 +12,7 @@ compared).  Outputs are what the reference functions returned:
 * ``schedules.npz``     models/module.py:597-699
 * ``stage{1..4}.npz``   StageNet.forward (eval)  models/mvsformer_model.py:51-158
 * ``stage2_train.npz``  StageNet.forward (train mode: batch-stat BN, argmax depth)
+* ``state_dict_keys.json``  names/shapes of the 302 ``fusions.*`` checkpoint entries
 * ``cascade.npz``       the cascade loop models/mvsformer_model.py:410-449 driven over synthetic features
                         (the loop is re-stated here in 15 lines because the reference only has it
                         inline in TwinMVSNet.forward behind the ViT feature extractor)
@@ -179,6 +180,17 @@ def gen_cascade(ns):
     np.savez_compressed(os.path.join(OUT, "cascade.npz"), **blob)
 
 
+def gen_state_dict_keys(ns):
+    """Key names and shapes of ``fusions.*`` exactly as the reference's TwinMVSNet registers them
+    (models/mvsformer_model.py:347): the checkpoint contract of the drop-in modules."""
+    import json
+    R = ns.mvsformer_model
+    ml = torch.nn.ModuleList([R.StageNet(dict(STAGE_ARGS), S.NDEPTHS[i], i) for i in range(4)])
+    keys = {"fusions." + k: list(v.shape) for k, v in ml.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+
+
 def main():
     warnings.simplefilter("ignore")
     torch.set_num_threads(os.cpu_count())
@@ -188,6 +200,7 @@ def main():
     gen_schedules(ns)
     gen_stages(ns)
     gen_cascade(ns)
+    gen_state_dict_keys(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

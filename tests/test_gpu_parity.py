@@ -1,0 +1,284 @@
+"""GPU parity: every entry point of libmvs_b200.so (called through the C ABI via the Python mirror)
+against the CPU oracle on the same seeded inputs, and against the golden vectors produced by the
+unmodified reference (tests/golden, oracle/make_golden.py).
+
+Tolerances (fp32 path, stated per check):
+* index / mask outputs: agreement rate (pixels within 1 ulp of a border may flip)
+* sampled / correlated quantities: relative L1 <= 2e-5 on smooth features (white-noise features
+  amplify the 5e-5 px coordinate rounding of the reference's own normalise/un-normalise round trip)
+* depth maps: relative L1 <= 1e-3 is the north-star bar; we assert 1e-5 here.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mvsformer_b200 import engine, module as M, synthetic as S, warping as Wp
+from mvsformer_b200.mvsformer_model import CascadeMVS, StageNet
+from oracle import mvs_oracle as O
+from tests.helpers import STAGE_ARGS, checksum, load_golden, max_abs, rel_l1
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_reports_blackwell():
+    import ctypes
+    from mvsformer_b200 import _lib
+    lib = _lib.load()
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.mvs_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)))
+    assert maj.value == 10 and sm.value >= 100
+
+
+def test_relative_projections():
+    cams = S.make_cameras(2, 5, 128, 192)["stage3"]
+    got = engine.relative_projections(cu(cams)).cpu()
+    ref_p = O.compose_projection(cams[:, 0].double())
+    for v in range(1, 5):
+        rot, trans = O.relative_projection(O.compose_projection(cams[:, v].double()), ref_p)
+        want = torch.cat([rot, trans.unsqueeze(-1)], dim=-1).reshape(2, 12)
+        assert rel_l1(got[:, v - 1], want) < 1e-6
+
+
+def test_warp_vs_golden_and_oracle():
+    g = load_golden("warp.npz")
+    feats = S.make_features(2, 3, 24, 40, seed=5, stages=(3,), feat_chs=(0, 0, 0, 8))["stage4"]
+    assert checksum(feats) == pytest.approx(float(g["feat_checksum"]), rel=1e-12)
+    cams = S.make_cameras(2, 3, 24, 40)["stage4"].clone()
+    cams[:, 2, 0, 0, 3] += 150.0
+    ref_p = O.compose_projection(cams[:, 0])
+    dv_map = S.make_depth_range(2)[:, ::32][:, :6]
+    dv_px = dv_map.view(2, 6, 1, 1) * (1.0 + 0.1 * torch.rand(2, 6, 24, 40, generator=S._gen(3)))
+    for v in (1, 2):
+        src_p = O.compose_projection(cams[:, v])
+        for tag, dv in (("bd", dv_map), ("px", dv_px)):
+            warped, mask = Wp.homo_warping_3D_with_mask(cu(feats[:, v]), cu(src_p), cu(ref_p), cu(dv))
+            only = Wp.homo_warping_3D(cu(feats[:, v]), cu(src_p), cu(ref_p), cu(dv))
+            assert torch.equal(warped, only)
+            gw = torch.from_numpy(g["warped_%s_v%d" % (tag, v)])
+            gm = torch.from_numpy(g["mask_%s_v%d" % (tag, v)])
+            assert rel_l1(warped.cpu(), gw) < 2e-5
+            assert (mask.cpu() != gm).float().mean() < 2e-3
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+@pytest.mark.parametrize("smooth", [True, False])
+def test_cost_volume_parts(s, smooth):
+    """pass A (entropy, cosine similarity), vis net, pass B (aggregated volume) vs the oracle."""
+    height, width, batch, views = 128, 192, 2, 4
+    feats = S.make_features(batch, views, height, width, stages=(s,), smooth=smooth)["stage%d" % (s + 1)]
+    cams = S.make_cameras(batch, views, height, width)["stage%d" % (s + 1)]
+    hyp = S.narrow_hypotheses(s, height, width, batch)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+    sd = S.fill_state_dict(net.state_dict(), seed=s)
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    vol_o, sim_o, parts = O.build_cost_volume(feats, cams, hyp, sd, want_parts=True)
+    volume, sim, entropy, weight = net.build_cost_volume(cu(feats), cu(cams), cu(hyp))
+    tol = 2e-5 if smooth else 3e-4
+    ent_o = torch.cat(parts["entropy"], dim=1)
+    wgt_o = torch.cat(parts["weight"], dim=1)
+    assert rel_l1(entropy.cpu(), ent_o) < tol
+    assert rel_l1(weight.cpu(), wgt_o) < tol
+    assert rel_l1(sim.cpu(), sim_o) < tol
+    assert rel_l1(volume.cpu().permute(0, 4, 1, 2, 3), vol_o) < tol
+    # the vis net alone, on the oracle's entropy (isolates the fused 2D CNN)
+    b, n, h, w = ent_o.shape
+    w_only = engine.vis_weight(cu(ent_o.reshape(b * n, h, w).contiguous()), net._vis_params_host()).view(b, n, h, w)
+    assert rel_l1(w_only.cpu(), wgt_o) < 1e-5
+
+
+CONV_CASES = [
+    # cin, cout, kd, stride, D, H, W
+    (8, 16, 3, (2, 2, 2), 8, 16, 24),
+    (8, 16, 3, (1, 2, 2), 4, 16, 24),
+    (16, 16, 3, (1, 1, 1), 4, 10, 14),
+    (16, 32, 3, (2, 2, 2), 8, 8, 12),
+    (32, 32, 3, (1, 1, 1), 2, 6, 10),
+    (32, 64, 3, (1, 2, 2), 3, 6, 10),
+    (64, 64, 3, (1, 1, 1), 2, 5, 7),
+    (8, 16, 1, (1, 2, 2), 3, 16, 24),
+]
+
+
+@pytest.mark.parametrize("cin,cout,kd,stride,D,H,W", CONV_CASES)
+def test_conv3d_block(cin, cout, kd, stride, D, H, W):
+    g = S._gen(cin * 100 + cout + kd)
+    blk = M.Conv3d(cin, cout, kernel_size=(kd, 3, 3), stride=stride, padding=(kd // 2, 1, 1)).eval()
+    blk.load_state_dict(S.fill_state_dict(blk.state_dict(), seed=3))
+    x = torch.randn(2, cin, D, H, W, generator=g)
+    sd = blk.state_dict()
+    want = F.conv3d(x, sd["conv.weight"], stride=stride, padding=(kd // 2, 1, 1))
+    want = torch.relu(O._bn_eval(want, sd, "bn"))
+    got = blk.to(DEV)(cu(x)).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want) < 2e-6
+    # skip connection is added AFTER the activation
+    skip = torch.randn(want.shape, generator=g)
+    got2 = engine.cl_to_ncdhw(blk.forward_cl(engine.ncdhw_to_cl(cu(x)), skip=engine.ncdhw_to_cl(cu(skip)))).cpu()
+    assert rel_l1(got2, want + skip) < 2e-6
+
+
+DECONV_CASES = [
+    (64, 32, 3, 2, 2, 3, 5), (32, 16, 3, 2, 3, 6, 10), (16, 8, 3, 2, 4, 8, 12),
+    (64, 32, 3, 1, 2, 3, 5), (32, 16, 3, 1, 4, 6, 10), (16, 8, 3, 1, 4, 8, 12), (16, 8, 1, 1, 3, 8, 12),
+]
+
+
+@pytest.mark.parametrize("cin,cout,kd,sd,D,H,W", DECONV_CASES)
+def test_deconv3d_block(cin, cout, kd, sd, D, H, W):
+    g = S._gen(cin * 7 + cout + kd + sd)
+    blk = M._SeqDeconv(cin, cout, (kd, 3, 3), (sd, 2, 2), (kd // 2, 1, 1), (sd - 1, 1, 1)).eval()
+    blk.load_state_dict(S.fill_state_dict(blk.state_dict(), seed=4))
+    sdict = blk.state_dict()
+    x = torch.randn(2, cin, D, H, W, generator=g)
+    want = F.conv_transpose3d(x, sdict["0.weight"], stride=(sd, 2, 2), padding=(kd // 2, 1, 1), output_padding=(sd - 1, 1, 1))
+    want = torch.relu(O._bn_eval(want, sdict, "1"))
+    got = blk.to(DEV)(cu(x)).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("kind", ["CostRegNet", "CostRegNet3D", "CostRegNet2D"])
+def test_cost_reg_nets(kind):
+    g = S._gen(99)
+    net = getattr(M, kind)(8, 8).eval()
+    sd = S.fill_state_dict(net.state_dict(), seed=6)
+    net.load_state_dict(sd)
+    x = torch.randn(2, 8, 8, 16, 24, generator=g)
+    fn = {"CostRegNet": O.cost_reg_net, "CostRegNet3D": O.cost_reg_net_3d, "CostRegNet2D": O.cost_reg_net_2d}[kind]
+    want = fn(x, {"cost_reg." + k: v for k, v in sd.items()})
+    got = net.to(DEV)(cu(x)).cpu()
+    assert got.shape == want.shape == (2, 1, 8, 16, 24)
+    assert rel_l1(got, want) < 5e-6
+
+
+def test_cost_reg_rejects_bad_shapes():
+    net = M.CostRegNet(8, 8).eval().to(DEV)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 8, 8, 12, 24, device=DEV))          # H not divisible by 8 (reference: size mismatch)
+    with pytest.raises(NotImplementedError):
+        net.train()(torch.zeros(1, 8, 8, 16, 24, device=DEV))
+    with pytest.raises(RuntimeError):
+        M.depth_regression(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4))   # CPU tensors: no fallback
+
+
+def test_schedules_vs_golden():
+    g = load_golden("schedules.npz")
+    dv = cu(S.make_depth_range(2))
+    assert max_abs(M.init_inverse_range(dv, 32, DEV, torch.float32, 8, 12).cpu(), g["init_inverse_range"]) < 2e-4
+    assert max_abs(M.init_range(dv, 32, DEV, torch.float32, 8, 12).cpu(), g["init_range"]) < 2e-4
+    hyp = cu(torch.from_numpy(g["init_inverse_range"]))
+    depth = cu(torch.from_numpy(g["sched_depth_in"]))
+    assert rel_l1(M.schedule_inverse_range(depth, hyp, 16, 2.67, 16, 24).cpu(), g["schedule_inverse_range"]) < 1e-6
+    assert rel_l1(M.schedule_range(depth, 16, 2.67 * (dv[:, 1] - dv[:, 0]), 16, 24).cpu(), g["schedule_range"]) < 1e-6
+    p = cu(torch.from_numpy(g["prob_in"]))
+    assert rel_l1(M.depth_regression(p, hyp).cpu(), g["depth_regression_map"]) < 1e-6
+    assert rel_l1(M.depth_regression(p, dv[:, :32].contiguous()).cpu(), g["depth_regression_vec"]) < 1e-6
+    for n in (2, 3, 4):
+        assert rel_l1(M.conf_regression(p, n).cpu(), g["conf_regression_n%d" % n]) < 1e-6
+
+
+def test_regression_head_modes():
+    g = S._gen(21)
+    pre = 2.0 * torch.randn(2, 16, 12, 20, generator=g)
+    dv = S.narrow_hypotheses(1, 48, 80, 2)
+    for training in (False, True):
+        prob_o, depth_o, conf_o = O.regression_head(pre, dv, 5.0, training)
+        prob, depth, conf = engine.regression_head(cu(pre), cu(dv), 5.0, training)
+        assert rel_l1(prob.cpu(), prob_o) < 1e-6
+        assert rel_l1(conf.cpu(), conf_o) < 1e-6
+        if training:
+            assert torch.equal(depth.cpu(), depth_o)
+        else:
+            assert rel_l1(depth.cpu(), depth_o) < 1e-6
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_stagenet_vs_golden(s):
+    g = load_golden("stage%d.npz" % (s + 1))
+    batch = int(g["batch"])
+    height, width = 128, 192
+    feats = S.make_features(batch, 3, height, width, stages=(s,))["stage%d" % (s + 1)]
+    assert checksum(feats) == pytest.approx(float(g["feat_checksum"]), rel=1e-12)
+    cams = S.make_cameras(batch, 3, height, width)["stage%d" % (s + 1)]
+    hyp = S.narrow_hypotheses(s, height, width, batch)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=s), strict=True)
+    out = net.to(DEV)(cu(feats), cu(cams), cu(hyp), tmp=list(S.EVAL_TMP))
+    assert set(out) == {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre", "sim_depth"}
+    assert rel_l1(out["prob_volume_pre"].cpu(), g["prob_volume_pre"]) < 2e-5
+    assert rel_l1(out["prob_volume"].cpu(), g["prob_volume"]) < 2e-5
+    assert rel_l1(out["depth"].cpu(), g["depth"]) < 1e-5
+    assert rel_l1(out["photometric_confidence"].cpu(), g["photometric_confidence"]) < 2e-5
+    assert (out["sim_depth"].cpu() == torch.from_numpy(g["sim_depth"])).float().mean() > 0.995
+
+
+def test_cascade_vs_golden():
+    g = load_golden("cascade.npz")
+    height, width, batch, views = int(g["height"]), int(g["width"]), int(g["batch"]), int(g["views"])
+    feats = S.make_features(batch, views, height, width, seed=int(g["feat_seed"]))
+    cams = S.make_cameras(batch, views, height, width)
+    dv = S.make_depth_range(batch)
+    args = dict(STAGE_ARGS, ndepths=list(S.NDEPTHS), depth_interals_ratio=list(S.DEPTH_INTERVAL_RATIO), inverse_depth=True)
+    net = CascadeMVS(args).eval()
+    full = {}
+    for s in range(4):
+        sd = S.fill_state_dict(net.fusions[s].state_dict(), seed=int(g["weight_seed0"]) + s)
+        full.update({"fusions.%d.%s" % (s, k): v for k, v in sd.items()})
+    net.load_state_dict(full, strict=True)
+    net = net.to(DEV)
+    out = net({k: cu(v) for k, v in feats.items()}, {k: cu(v) for k, v in cams.items()}, cu(dv), tmp=list(S.EVAL_TMP))
+    for s in range(4):
+        st = out["stage%d" % (s + 1)]
+        assert rel_l1(st["depth_values"].cpu(), g["stage%d_depth_values" % (s + 1)]) < 1e-5
+        assert rel_l1(st["depth"].cpu(), g["stage%d_depth" % (s + 1)]) < 1e-5
+        assert rel_l1(st["prob_volume_pre"].cpu(), g["stage%d_prob_volume_pre" % (s + 1)]) < 1e-4
+    # north-star bar is 1e-3 relative L1 on the depth map
+    assert rel_l1(out["refined_depth"].cpu(), g["refined_depth"]) < 1e-5
+    assert rel_l1(out["photometric_confidence"].cpu(), g["photometric_confidence"]) < 2e-5
+
+
+def test_full_size_properties():
+    """BASELINE cfg 2 size (1152x1536, 5 views): size-independent properties of the cascade."""
+    height, width, batch, views = 1152, 1536, 1, 5
+    feats = {k: cu(v) for k, v in S.make_features(batch, views, height, width).items()}
+    cams = {k: cu(v) for k, v in S.make_cameras(batch, views, height, width).items()}
+    dv = cu(S.make_depth_range(batch))
+    args = dict(STAGE_ARGS, ndepths=list(S.NDEPTHS), depth_interals_ratio=list(S.DEPTH_INTERVAL_RATIO), inverse_depth=True)
+    net = CascadeMVS(args).eval()
+    full = {}
+    for s in range(4):
+        sd = S.fill_state_dict(net.fusions[s].state_dict(), seed=s)
+        full.update({"fusions.%d.%s" % (s, k): v for k, v in sd.items()})
+    net.load_state_dict(full)
+    net = net.to(DEV)
+    out = net(feats, cams, dv, tmp=list(S.EVAL_TMP))
+    torch.cuda.synchronize()
+    for s in range(4):
+        st = out["stage%d" % (s + 1)]
+        hyp = st["depth_values"]
+        assert torch.isfinite(st["prob_volume_pre"]).all()
+        # regression is a convex combination of the hypotheses
+        assert (st["depth"] <= hyp.max(dim=1)[0] * (1 + 1e-6)).all() and (st["depth"] >= hyp.min(dim=1)[0] * (1 - 1e-6)).all()
+        # softmax sums to one; confidence is its maximum
+        assert (st["prob_volume"].sum(dim=1) - 1).abs().max() < 1e-5
+        # hypotheses are monotone (inverse-depth schedule: far -> near)
+        assert (hyp[:, 1:] < hyp[:, :-1]).all()
+    assert out["refined_depth"].shape == (1, height, width)
+    conf = out["photometric_confidence"]
+    assert (conf > 0).all() and (conf <= 1 + 1e-6).all()
+    # permuting the source views must not change the aggregated volume (sum over views)
+    s = 3
+    net4 = net.fusions[s]
+    f4, c4, h4 = feats["stage4"], cams["stage4"], out["stage4"]["depth_values"]
+    perm = [0, 3, 1, 4, 2]
+    v1 = net4.build_cost_volume(f4, c4, h4)[0]
+    v2 = net4.build_cost_volume(f4[:, perm].contiguous(), c4[:, perm].contiguous(), h4)[0]
+    assert rel_l1(v2, v1) < 1e-6
