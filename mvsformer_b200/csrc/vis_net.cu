@@ -71,7 +71,7 @@ vis_net_kernel(const float* __restrict__ entropy, float* __restrict__ weight, in
         float acc[16];
 #pragma unroll
         for (int co = 0; co < 16; ++co) acc[co] = P.b2[co];
-#pragma unroll 1
+#pragma unroll
         for (int ci = 0; ci < 16; ++ci) {
             float in[9];
 #pragma unroll
@@ -94,7 +94,7 @@ vis_net_kernel(const float* __restrict__ entropy, float* __restrict__ weight, in
         float acc[8];
 #pragma unroll
         for (int co = 0; co < 8; ++co) acc[co] = P.b3[co];
-#pragma unroll 1
+#pragma unroll
         for (int ci = 0; ci < 16; ++ci) {
             float in[9];
 #pragma unroll
