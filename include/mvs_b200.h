@@ -96,6 +96,19 @@ int mvs_conv3d_cl(const float* x, const float* w_packed, const float* shift, con
                   int B, int D, int H, int W, int Cin, int Cout, int kd, int sd, int sh, int sw, int relu, void* stream);
 int mvs_deconv3d_cl(const float* x, const float* w_packed, const float* shift, const float* skip, float* y,
                     int B, int D, int H, int W, int Cin, int Cout, int kd, int sd, int relu, void* stream);
+/* Tensor-core (tcgen05, kind::tf32, fp32 accumulate in TMEM) implicit-GEMM variant of mvs_conv3d_cl
+ * for kernel (kd,3,3), stride sd in depth and shw (1 or 2) in both H and W.  Weights are packed by
+ * the caller in operand order  [Cout_tiles][kd][3 kh][Cin/CS][3 kw][CS/4][n_tile][4]  with
+ * CS = min(Cin, 32), rounded to TF32 (w_hi); w_lo = tf32(w - w_hi) selects the 3xTF32 mode
+ * (fp32-grade accuracy), NULL selects plain TF32 (cuDNN's default conv math on GPUs). */
+int mvs_conv3d_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
+                  float* y, int B, int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int sd, int shw,
+                  int relu, void* stream);
+/* Diagnostic: nk MMAs (M=128, N, K=8) over caller-made shared-memory operand images with explicit
+ * descriptor strides; dumps the 128 x N accumulator (used by tests to pin the operand layouts). */
+int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,
+                 unsigned a_sbo, unsigned b_lbo, unsigned b_sbo, int N, int nk, unsigned a_kstep,
+                 unsigned b_kstep, float* d_out, void* stream);
 /* Layout transforms at the module boundary (CostRegNet*.forward takes/returns NCDHW). */
 int mvs_ncdhw_to_cl(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);
 int mvs_cl_to_ncdhw(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);

@@ -240,3 +240,62 @@ def confidence_accumulate(conf, acc, scale=1.0):
     check(_lib.load().mvs_confidence_accumulate(ptr(conf), h, w, ptr(acc), b, acc.shape[1], acc.shape[2], float(scale),
                                                 stream()), "mvs_confidence_accumulate")
     return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) convolution path
+# ------------------------------------------------------------------------------------------------
+def round_tf32(t):
+    """Round-to-nearest (ties away) to TF32, the same as PTX cvt.rna.tf32.f32."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
+def tc_channel_slice(cin):
+    return 32 if cin >= 32 else cin
+
+
+def tc_n_tile(cout):
+    if cout <= 16:
+        return 16
+    return 32 if cout == 32 else 64
+
+
+def pack_tc_weights(w_packed, x3):
+    """w_packed [kd,3,3,Cin,Cout] (BN folded) -> operand-order arrays for mvs_conv3d_tc:
+    [Cout_tiles][kd][kh][Cin/CS][kw][CS/4][n_tile][4]; returns (w_hi, w_lo or None, n_tile)."""
+    kd, _, _, cin, cout = w_packed.shape
+    cs, nt = tc_channel_slice(cin), tc_n_tile(cout)
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt).permute(6, 0, 1, 3, 2, 4, 7, 5).contiguous()
+    hi = round_tf32(w)
+    lo = round_tf32(w - hi) if x3 else None
+    return hi, lo, nt
+
+
+def conv3d_tc(x, w_hi, w_lo, n_tile, cout, kd, shift, skip, stride, relu=True):
+    require_cuda(x, w_hi, w_lo, shift, skip)
+    b, d, h, w, cin = x.shape
+    sd, sh, sw = stride
+    if sh != sw:
+        raise RuntimeError("conv3d_tc: H and W strides must match")
+    pd = kd // 2
+    do, ho, wo = (d + 2 * pd - kd) // sd + 1, (h - 1) // sh + 1, (w - 1) // sw + 1
+    y = torch.empty(b, do, ho, wo, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_tc(ptr(x), ptr(w_hi), ptr(w_lo), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout,
+                                    n_tile, kd, sd, sh, 1 if relu else 0, stream()), "mvs_conv3d_tc")
+    return y
+
+
+def tc_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, n, nk, a_kstep, b_kstep):
+    require_cuda(a_img, b_img)
+    out = torch.empty(128, n, device=a_img.device, dtype=torch.float32)
+    check(_lib.load().mvs_tc_probe(ptr(a_img), a_img.numel() * 4, ptr(b_img), b_img.numel() * 4, a_lbo, a_sbo, b_lbo, b_sbo,
+                                   n, nk, a_kstep, b_kstep, ptr(out), stream()), "mvs_tc_probe")
+    return out

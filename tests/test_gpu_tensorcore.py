@@ -1,0 +1,83 @@
+"""tcgen05 tensor-core path: operand-layout probe and implicit-GEMM conv3d parity (GPU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mvsformer_b200 import engine, synthetic as S
+from tests.helpers import rel_l1
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _image(mat, lbo_rows):
+    """mat [R, K] (K multiple of 4) -> no-swizzle K-major operand image [K/4][lbo_rows][4]."""
+    r, k = mat.shape
+    img = torch.zeros(k // 4, lbo_rows, 4)
+    img[:, :r] = mat.reshape(r, k // 4, 4).permute(1, 0, 2)
+    return img.contiguous()
+
+
+@pytest.mark.parametrize("n", [16, 32, 64])
+def test_tc_probe_layout(n):
+    """D = A (128 x K) * B (n x K)^T with the plane layout [K/4][rows][4 floats]:
+    rows 16 B apart, SBO = 128 B between 8-row groups, LBO = plane pitch between 16-byte K chunks."""
+    g = S._gen(5 + n)
+    nk = 6
+    k = 8 * nk
+    a = engine.round_tf32(torch.randn(128, k, generator=g))
+    b = engine.round_tf32(torch.randn(n, k, generator=g))
+    rows_a, rows_b = 132, n
+    a_img, b_img = _image(a, rows_a), _image(b, rows_b)
+    want = a.double() @ b.double().t()
+    got = engine.tc_probe(a_img.to(DEV), b_img.to(DEV), rows_a * 16, 128, rows_b * 16, 128, n, nk,
+                          2 * rows_a * 16, 2 * rows_b * 16).cpu()
+    err = rel_l1(got, want)
+    if err > 1e-5:
+        # diagnose the convention before failing: try LBO/SBO swapped
+        alt = engine.tc_probe(a_img.to(DEV), b_img.to(DEV), 128, rows_a * 16, 128, rows_b * 16, n, nk,
+                              2 * rows_a * 16, 2 * rows_b * 16).cpu()
+        print("probe mismatch: rel_l1 %.3e; swapped LBO/SBO rel_l1 %.3e" % (err, rel_l1(alt, want)))
+        print("got[:4,:4]", got[:4, :4], "\nwant[:4,:4]", want[:4, :4].float())
+    assert err < 1e-5
+    # a row-shifted window of the same image (what the conv uses for the kw taps)
+    got2 = engine.tc_probe(a_img.to(DEV).view(-1)[8:].contiguous(), b_img.to(DEV), rows_a * 16, 128, rows_b * 16, 128, n, nk,
+                           2 * rows_a * 16, 2 * rows_b * 16).cpu()
+    a_shift = torch.cat([a[2:], torch.zeros(2, k)], dim=0)
+    assert rel_l1(got2[:126], (a_shift.double() @ b.double().t())[:126]) < 1e-5
+
+
+TC_CASES = [
+    # cin, cout, kd, stride, D, H, W
+    (8, 16, 3, (1, 2, 2), 4, 16, 24),
+    (8, 16, 3, (2, 2, 2), 8, 16, 24),
+    (16, 16, 3, (1, 1, 1), 4, 10, 14),
+    (16, 16, 1, (1, 1, 1), 1, 33, 47),
+    (16, 8, 1, (1, 1, 1), 1, 20, 20),
+    (16, 32, 3, (2, 2, 2), 8, 8, 12),
+    (16, 32, 3, (1, 2, 2), 4, 9, 13),
+    (32, 32, 3, (1, 1, 1), 2, 6, 10),
+    (32, 64, 3, (1, 2, 2), 3, 6, 10),
+    (64, 64, 3, (1, 1, 1), 2, 5, 7),
+    (16, 16, 3, (1, 1, 1), 2, 3, 300),
+]
+
+
+@pytest.mark.parametrize("x3", [False, True])
+@pytest.mark.parametrize("cin,cout,kd,stride,D,H,W", TC_CASES)
+def test_conv3d_tc(cin, cout, kd, stride, D, H, W, x3):
+    g = S._gen(cin * 100 + cout + kd + W)
+    w = torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = torch.randn(2, cin, D, H, W, generator=g)
+    want = torch.relu(F.conv3d(x.double(), w.double(), stride=stride, padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    w_packed = w.permute(2, 3, 4, 1, 0).contiguous().to(DEV)
+    hi, lo, nt = engine.pack_tc_weights(w_packed, x3)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.conv3d_tc(x_cl, hi, lo, nt, cout, kd, shift.to(DEV), skip_cl, stride, relu=True)
+    got = got.permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    tol = 1e-5 if x3 else 2e-3
+    assert rel_l1(got, want + skip.double()) < tol
