@@ -42,10 +42,15 @@ CASCADE_ARGS = {"base_ch": 8, "fusion_type": "cnn", "depth_type": "ce", "ndepths
                 "depth_interals_ratio": list(S.DEPTH_INTERVAL_RATIO), "inverse_depth": True}
 
 
+def conv_mode():
+    from mvsformer_b200 import config
+    return {"tf32x3": "3xTF32 tcgen05 (fp32-grade)", "tf32": "TF32 tcgen05", "fp32": "FP32 CUDA cores"}[config.conv_precision()]
+
+
 def workload_config(n_gpus):
     return {"workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, "
                         "feat ch 64/32/16/8, G=8, B=1 ref view per GPU per step" % (HEIGHT, WIDTH, VIEWS),
-            "precision": "fp32 features/volume/activations", "parallelism": "ref views sharded, %d rank(s), no collective" % n_gpus,
+            "precision": "fp32 features/volume/activations; conv math %s" % conv_mode(), "parallelism": "ref views sharded, %d rank(s), no collective" % n_gpus,
             "l2_policy": "inputs 530 MB/step > 126 MB L2; every intermediate volume is rewritten each step"}
 
 
@@ -157,8 +162,16 @@ class KernelProfiler:
         self._wrap(engine, "cost_volume_entropy", "cv_entropy(passA)", ent_cost)
         self._wrap(engine, "cost_volume_aggregate", "cv_aggregate(passB)", agg_cost)
         self._wrap(engine, "vis_weight", "vis_net", vis_cost)
+        def conv_tc_cost(out, x, w_hi, w_lo, n_tile, cout, kd, shift, skip, stride, relu=True):
+            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
+
+        def deconv_tc_cost(out, x, w_hi, w_lo, n_tile, cout, kd, shift, skip, sd, relu=True):
+            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (x.numel() // x.shape[-1])
+
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
+        self._wrap(engine, "conv3d_tc", "conv3d_tc", conv_tc_cost)
+        self._wrap(engine, "deconv3d_tc", "deconv3d_tc", deconv_tc_cost)
         for name in ("prob_conv_cl", "regression_head", "argmax_gather", "init_range", "schedule_inverse_range",
                      "confidence_accumulate", "relative_projections"):
             self._wrap(engine, name, "head+schedule", io_cost)

@@ -104,6 +104,12 @@ int mvs_deconv3d_cl(const float* x, const float* w_packed, const float* shift, c
 int mvs_conv3d_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
                   float* y, int B, int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int sd, int shw,
                   int relu, void* stream);
+/* Tensor-core variant of mvs_deconv3d_cl (same geometry).  Weights packed in operand order
+ * [Cout_tiles][kd][2 dy][Cin/CS][6 taps][CS/4][n_tile][4]; for dy = 0 the taps are
+ * (kh=1,kw=0..2),(kh=2,kw=0..2), for dy = 1 (kh=0,kw=0..2) followed by three unused slots. */
+int mvs_deconv3d_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
+                    float* y, int B, int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int sd,
+                    int relu, void* stream);
 /* Diagnostic: nk MMAs (M=128, N, K=8) over caller-made shared-memory operand images with explicit
  * descriptor strides; dumps the 128 x N accumulator (used by tests to pin the operand layouts). */
 int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,

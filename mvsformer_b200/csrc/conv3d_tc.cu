@@ -280,6 +280,220 @@ static int launch_tc(const float* x, const float* w_hi, const float* w_lo, const
     return MVS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// transposed convolution (ConvTranspose3d kernel (kd,3,3), stride (sd,2,2), pad k/2,
+// output_padding stride-1) in gather form.
+//
+// A CTA owns 128 consecutive *input* positions of one output depth slice zo, in the virtual index
+// j = y * (W + 1) + x, and produces the four output parity classes (2y+py, 2x+px) as four
+// accumulators in TMEM.  Output row parity fixes the kh taps and the input row they read
+// (py=0: kh=1 from row y; py=1: kh=2 from row y and kh=0 from row y+1), likewise in x
+// (px=0: kw=1 from x; px=1: kw=2 from x and kw=0 from x+1), so every one of the 9 in-plane taps
+// is exactly one MMA chain and nothing is predicated off.  Per (kz, dy, channel slice) one slab
+// of 129 virtual input voxels is staged; the x+1 tap is the +16 B window of the same slab.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int NT, bool X3>
+struct TcDeconvSmem {
+    static constexpr int NSPLIT = X3 ? 2 : 1;
+    static constexpr int CH = CIN / 4;
+    static constexpr int A_PLANE = CH * TC_SL;
+    static constexpr int B_TAP = CH * NT * 16;
+    static constexpr int B_BLOCK = 6 * B_TAP;                  // up to six taps per iteration
+    static __host__ __device__ constexpr int a_bytes() { return 2 * NSPLIT * A_PLANE; }
+    static __host__ __device__ constexpr int b_bytes() { return 2 * NSPLIT * B_BLOCK; }
+    static __host__ __device__ constexpr int total() { return a_bytes() + b_bytes() + 128; }
+};
+
+template <int CIN, int NT, bool X3>
+__global__ void __launch_bounds__(TC_THREADS)
+deconv3d_tc_kernel(const float* __restrict__ x, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
+                   const float* __restrict__ shift, const float* __restrict__ skip, float* __restrict__ y, TcDims d) {
+    using L = TcDeconvSmem<CIN, NT, X3>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + L::a_bytes();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::a_bytes() + L::b_bytes());
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : (4 * NT <= 64 ? 64 : (4 * NT <= 128 ? 128 : 256));
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int plane_idx = blockIdx.x / d.tiles_per_plane;          // b * Do + zo
+    const int tile = blockIdx.x - plane_idx * d.tiles_per_plane;
+    const int b = plane_idx / d.Do, zo = plane_idx - b * d.Do;
+    const int j0 = tile * 128;
+    const int co0 = blockIdx.y * NT;
+    const int pd = d.kd / 2;
+    const int nch = d.Cin / CIN;
+
+    // depth taps that feed this output slice: zo = iz * sd - pd + kz
+    int kzv[3], izv[3], nkz = 0;
+    for (int kz = 0; kz < d.kd; ++kz) {
+        const int t = zo + pd - kz;
+        if (t < 0 || (t % d.sd) != 0) continue;
+        const int iz = t / d.sd;
+        if (iz >= d.D) continue;
+        kzv[nkz] = kz; izv[nkz] = iz; ++nkz;
+    }
+    const int nit = nkz * 2 * nch;
+
+    int sy[2], sa[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int jv = j0 + tid + u * 128;
+        sy[u] = jv / d.PW;
+        sa[u] = jv - sy[u] * d.PW;
+    }
+    const int nslot_iters = (tid + 128 < 129) ? 2 : 1;
+    const size_t wtile = (size_t)d.kd * 2 * nch * (L::B_BLOCK / 4);          // floats per Cout tile
+    uint32_t started = 0;                                                    // per-class "accumulator written" bits (thread 0)
+
+    for (int it = 0; it < nit; ++it) {
+        const int buf = it & 1;
+        const int kzi = it / (2 * nch), rem = it - kzi * 2 * nch;
+        const int dy = rem / nch, ch = rem - dy * nch;
+        const int kz = kzv[kzi], iz = izv[kzi];
+        if (it >= 2) mbar_wait(&bars[buf], ((it >> 1) - 1) & 1);
+
+        // ---- stage A: input row y + dy ---------------------------------------------------------
+        {
+            uint8_t* dst_hi = sA + (size_t)(buf * L::NSPLIT + 0) * L::A_PLANE;
+            uint8_t* dst_lo = sA + (size_t)(buf * L::NSPLIT + (X3 ? 1 : 0)) * L::A_PLANE;
+            for (int u = 0; u < nslot_iters; ++u) {
+                const int slot = tid + u * 128;
+                const int yy = sy[u] + dy, xx = sa[u];
+                const bool ok = yy < d.H && xx < d.W;
+                const float4* src = reinterpret_cast<const float4*>(
+                    x + ((((size_t)b * d.D + iz) * d.H + (ok ? yy : 0)) * d.W + (ok ? xx : 0)) * d.Cin + ch * CIN);
+#pragma unroll
+                for (int q0 = 0; q0 < L::CH; q0 += 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q0 + q < L::CH) v[q] = ok ? __ldg(src + q0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q0 + q >= L::CH) continue;
+                        float4 hi = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+                        *reinterpret_cast<float4*>(dst_hi + (size_t)(q0 + q) * TC_SL + slot * 16) = hi;
+                        if (X3) {
+                            float4 lo = make_float4(to_tf32(v[q].x - hi.x), to_tf32(v[q].y - hi.y), to_tf32(v[q].z - hi.z),
+                                                    to_tf32(v[q].w - hi.w));
+                            *reinterpret_cast<float4*>(dst_lo + (size_t)(q0 + q) * TC_SL + slot * 16) = lo;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- stage B: six (dy = 0) or three (dy = 1) taps, packed [kz][dy][ch][tap][CH][NT][4] -----
+        const int ntaps = dy == 0 ? 6 : 3;
+        {
+            const size_t blk = ((size_t)kz * 2 + dy) * nch + ch;
+            float4* dst_hi = reinterpret_cast<float4*>(sB + (size_t)(buf * L::NSPLIT + 0) * L::B_BLOCK);
+            const float4* src_hi = reinterpret_cast<const float4*>(w_hi + (size_t)blockIdx.y * wtile) + blk * (L::B_BLOCK / 16);
+            for (int i = tid; i < ntaps * (L::B_TAP / 16); i += TC_THREADS) dst_hi[i] = __ldg(src_hi + i);
+            if (X3) {
+                float4* dst_lo = reinterpret_cast<float4*>(sB + (size_t)(buf * L::NSPLIT + 1) * L::B_BLOCK);
+                const float4* src_lo = reinterpret_cast<const float4*>(w_lo + (size_t)blockIdx.y * wtile) + blk * (L::B_BLOCK / 16);
+                for (int i = tid; i < ntaps * (L::B_TAP / 16); i += TC_THREADS) dst_lo[i] = __ldg(src_lo + i);
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const uint32_t a_hi = smem_u32(sA) + (uint32_t)(buf * L::NSPLIT + 0) * L::A_PLANE;
+            const uint32_t a_lo = smem_u32(sA) + (uint32_t)(buf * L::NSPLIT + (X3 ? 1 : 0)) * L::A_PLANE;
+            const uint32_t b_hi = smem_u32(sB) + (uint32_t)(buf * L::NSPLIT + 0) * L::B_BLOCK;
+            const uint32_t b_lo = smem_u32(sB) + (uint32_t)(buf * L::NSPLIT + (X3 ? 1 : 0)) * L::B_BLOCK;
+            for (int t = 0; t < ntaps; ++t) {
+                // tap order: dy = 0 -> (kh=1,kw=0..2), (kh=2,kw=0..2); dy = 1 -> (kh=0,kw=0..2)
+                const int kh = dy == 0 ? 1 + t / 3 : 0;
+                const int kw = t % 3;
+                const int py = (kh == 1) ? 0 : 1;
+                const int px = (kw == 1) ? 0 : 1;
+                const int sh = (kw == 0) ? 1 : 0;                   // kw = 0 reads input x + 1
+                const int cls = py * 2 + px;
+                const uint32_t dcol = tmem + (uint32_t)cls * NT;
+#pragma unroll
+                for (int kk = 0; kk < CIN / 8; ++kk) {
+                    const uint32_t ao = (uint32_t)sh * 16 + (uint32_t)(2 * kk) * TC_SL;
+                    const uint32_t bo = (uint32_t)t * L::B_TAP + (uint32_t)(2 * kk) * NT * 16;
+                    const uint32_t acc = (started >> cls) & 1u;
+                    started |= 1u << cls;
+                    const uint64_t adh = make_smem_desc(a_hi + ao, TC_SL, 128);
+                    const uint64_t bdh = make_smem_desc(b_hi + bo, NT * 16, 128);
+                    if (X3) {
+                        const uint64_t adl = make_smem_desc(a_lo + ao, TC_SL, 128);
+                        const uint64_t bdl = make_smem_desc(b_lo + bo, NT * 16, 128);
+                        mma_tf32_ss(dcol, adl, bdh, idesc, acc);
+                        mma_tf32_ss(dcol, adh, bdl, idesc, 1u);
+                        mma_tf32_ss(dcol, adh, bdh, idesc, 1u);
+                    } else {
+                        mma_tf32_ss(dcol, adh, bdh, idesc, acc);
+                    }
+                }
+            }
+            mma_commit(&bars[buf]);
+        }
+    }
+
+    const int last = nit - 1;
+    mbar_wait(&bars[last & 1], (last >> 1) & 1);
+    tc_fence_after_sync();
+    const int iy = sy[0], ix = sa[0];
+    const bool live = iy < d.H && ix < d.W;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+        float acc[NT];
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cls * NT + c0, acc + c0);
+        if (!live) continue;
+        const int oy = 2 * iy + (cls >> 1), ox = 2 * ix + (cls & 1);
+        const size_t o = ((((size_t)b * d.Do + zo) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0;
+#pragma unroll
+        for (int q = 0; q < NT / 4; ++q) {
+            if (co0 + q * 4 >= d.Cout) break;
+            float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            if (shift) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+            if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+            if (skip) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
+                r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+            reinterpret_cast<float4*>(y + o)[q] = r;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int CIN, int NT, bool X3>
+static int launch_deconv_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
+                            float* y, const TcDims& d, cudaStream_t st) {
+    using L = TcDeconvSmem<CIN, NT, X3>;
+    const size_t smem = L::total();
+    MVS_REQUIRE(smem <= 227 * 1024, "mvs_deconv3d_tc: needs %zu bytes of shared memory", smem);
+    auto kern = deconv3d_tc_kernel<CIN, NT, X3>;
+    MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((size_t)d.B * d.Do * d.tiles_per_plane), (unsigned)((d.Cout + NT - 1) / NT));
+    kern<<<grid, TC_THREADS, smem, st>>>(x, w_hi, w_lo, shift, skip, y, d);
+    MVS_LAUNCH_OK("deconv3d_tc_kernel");
+    return MVS_OK;
+}
+
 }  // namespace tc
 }  // namespace mvs
 
@@ -332,4 +546,37 @@ extern "C" int mvs_conv3d_tc(const float* x, const float* w_hi, const float* w_l
     MVS_TC_CASE(32, 64)
 #undef MVS_TC_CASE
     MVS_UNSUPPORTED("mvs_conv3d_tc: no tensor-core instantiation for Cin=%d, N tile=%d", Cin, n_tile);
+}
+
+extern "C" int mvs_deconv3d_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
+                               float* y, int B, int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int sd,
+                               int relu, void* stream) {
+    using namespace mvs;
+    using namespace mvs::tc;
+    MVS_REQUIRE(x && w_hi && y, "mvs_deconv3d_tc: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_deconv3d_tc: empty shape");
+    MVS_REQUIRE(kd == 1 || kd == 3, "mvs_deconv3d_tc: depth kernel size must be 1 or 3 (got %d)", kd);
+    MVS_REQUIRE(sd == 1 || sd == 2, "mvs_deconv3d_tc: depth stride must be 1 or 2");
+    MVS_REQUIRE(!(kd == 1 && sd != 1), "mvs_deconv3d_tc: kd = 1 requires sd = 1");
+    MVS_REQUIRE(Cout % 8 == 0 && Cout >= 8, "mvs_deconv3d_tc: Cout must be a multiple of 8 (got %d)", Cout);
+    TcDims d;
+    d.B = B; d.D = D; d.H = H; d.W = W;
+    d.Do = D * sd; d.Ho = 2 * H; d.Wo = 2 * W;
+    d.Cin = Cin; d.Cout = Cout; d.kd = kd; d.sd = sd; d.s2 = 1; d.relu = relu;
+    d.PW = W + 1;
+    d.tiles_per_plane = (int)(((int64_t)H * d.PW + 127) / 128);
+    MVS_REQUIRE((int64_t)B * d.Do * d.tiles_per_plane < 2147483647LL, "mvs_deconv3d_tc: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool x3 = (w_lo != nullptr);
+    const int cs = Cin >= 32 ? 32 : Cin;
+    MVS_REQUIRE(Cin % cs == 0 && (cs == 8 || cs == 16 || cs == 32), "mvs_deconv3d_tc: Cin must be 8, 16 or a multiple of 32 (got %d)", Cin);
+#define MVS_TCD_CASE(CIN, NT)                                                                                  \
+    if (cs == CIN && n_tile == NT)                                                                             \
+        return x3 ? launch_deconv_tc<CIN, NT, true>(x, w_hi, w_lo, shift, skip, y, d, st)                      \
+                  : launch_deconv_tc<CIN, NT, false>(x, w_hi, w_lo, shift, skip, y, d, st);
+    MVS_TCD_CASE(16, 16)
+    MVS_TCD_CASE(32, 16)
+    MVS_TCD_CASE(32, 32)
+#undef MVS_TCD_CASE
+    MVS_UNSUPPORTED("mvs_deconv3d_tc: no tensor-core instantiation for Cin=%d, N tile=%d", Cin, n_tile);
 }

