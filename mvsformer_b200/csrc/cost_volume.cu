@@ -15,6 +15,8 @@
 // Roofline: algorithmic HBM bytes per stage = 4 [(N+1) C h w + D h w + G D h w];
 // the sampling itself is bounded by L1/LSU throughput (4 taps x C x 4 B per (view, d, pixel)).
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -212,6 +214,24 @@ static int check_cv_args(const char* fn, const float* features, const float* rel
     return MVS_OK;
 }
 
+// TMA-staged production kernels (cost_volume_tma.cu); return 1 when the shape is not covered.
+int cost_volume_tma_entropy(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
+                            const float* depth, float* entropy, float* sim_sum, int B, int V, int C, int G, int D, int H, int W,
+                            cudaStream_t st);
+int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
+                              const float* depth, const float* vis_weight, float* volume, int B, int V, int C, int G, int D,
+                              int H, int W, cudaStream_t st);
+
+// MVS_K1_IMPL=generic forces the generic (non-TMA) kernels, for A/B parity runs.
+static bool use_tma_kernels() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("MVS_K1_IMPL");
+        cached = (e && strcmp(e, "generic") == 0) ? 0 : 1;
+    }
+    return cached == 1;
+}
+
 }  // namespace mvs
 
 extern "C" int mvs_cost_volume_entropy(const float* features, int64_t batch_stride, int64_t view_stride,
@@ -220,6 +240,11 @@ extern "C" int mvs_cost_volume_entropy(const float* features, int64_t batch_stri
     int rc = mvs::check_cv_args("mvs_cost_volume_entropy", features, relproj, depth, B, V, C, G, D, H, W);
     if (rc) return rc;
     MVS_REQUIRE(entropy, "mvs_cost_volume_entropy: null entropy output");
+    if (mvs::use_tma_kernels()) {
+        rc = mvs::cost_volume_tma_entropy(features, batch_stride, view_stride, relproj, depth, entropy, sim_sum, B, V, C, G, D, H,
+                                          W, (cudaStream_t)stream);
+        if (rc <= 0) return rc;
+    }
     mvs::CvParams p{features, batch_stride, view_stride, relproj, depth, V - 1, C, G, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     return sim_sum ? mvs::dispatch_entropy<true>(p, entropy, sim_sum, B, st)
@@ -233,6 +258,11 @@ extern "C" int mvs_cost_volume_aggregate(const float* features, int64_t batch_st
     if (rc) return rc;
     MVS_REQUIRE(vis_weight && volume, "mvs_cost_volume_aggregate: null pointer");
     if (G != 8) MVS_UNSUPPORTED("mvs_cost_volume_aggregate: only G = 8 groups is built (got %d)", G);
+    if (mvs::use_tma_kernels()) {
+        rc = mvs::cost_volume_tma_aggregate(features, batch_stride, view_stride, relproj, depth, vis_weight, volume, B, V, C, G, D,
+                                            H, W, (cudaStream_t)stream);
+        if (rc <= 0) return rc;
+    }
     mvs::CvParams p{features, batch_stride, view_stride, relproj, depth, V - 1, C, G, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     dim3 block(32, 8);
