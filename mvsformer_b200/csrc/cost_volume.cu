@@ -224,12 +224,8 @@ int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64
 
 // MVS_K1_IMPL=generic forces the generic (non-TMA) kernels, for A/B parity runs.
 static bool use_tma_kernels() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("MVS_K1_IMPL");
-        cached = (e && strcmp(e, "generic") == 0) ? 0 : 1;
-    }
-    return cached == 1;
+    const char* e = getenv("MVS_K1_IMPL");
+    return !(e && strcmp(e, "generic") == 0);
 }
 
 }  // namespace mvs

@@ -157,7 +157,10 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
         if (tid == 0) {
             float mx = FLT_MAX, my = FLT_MAX;
             for (int w = 0; w < 8; ++w) { mx = fminf(mx, s_red[w * 2]); my = fminf(my, s_red[w * 2 + 1]); }
-            const int bx0 = mx < 1e7f ? (int)floorf(mx) : 0;
+            // The TMA unit requires the innermost start coordinate to be 16-byte aligned (a multiple of 4
+            // floats; negative values are fine) — measured on B200: any other value raises "illegal
+            // instruction".  Round the box origin down; BW carries the 3 columns of slack.
+            const int bx0 = mx < 1e7f ? ((int)floorf(mx) & ~3) : 0;
             const int by0 = my < 1e7f ? (int)floorf(my) : 0;
             s_org[0] = bx0; s_org[1] = by0;
             mbar_expect_tx(bar, CC * PLANE * 4);
