@@ -141,7 +141,7 @@ class KernelProfiler:
             base, _ = cv_cost(out, features, relproj, depth_values)
             return base + numel_bytes(out[0], out[1]), 0
 
-        def agg_cost(out, features, relproj, depth_values, vis_weight, groups):
+        def agg_cost(out, features, relproj, depth_values, vis_weight, groups, round_tf32=False):
             base, _ = cv_cost(out, features, relproj, depth_values)
             return base + numel_bytes(out, vis_weight), 0
 
@@ -168,6 +168,14 @@ class KernelProfiler:
         def deconv_tc_cost(out, x, w_hi, w_lo, n_tile, cout, kd, shift, skip, sd, relu=True):
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (x.numel() // x.shape[-1])
 
+        def conv_tcz_cost(out, x, w_tcz, n_tile, cout, kd, shift, skip, shw, relu=True):
+            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
+
+        def deconv_tcz_cost(out, x, w_tcz, n_tile, cout, kd, shift, skip, relu=True):
+            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (x.numel() // x.shape[-1])
+
+        self._wrap(engine, "conv3d_tcz", "conv3d_tcz", conv_tcz_cost)
+        self._wrap(engine, "deconv3d_tcz", "deconv3d_tcz", deconv_tcz_cost)
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
         self._wrap(engine, "conv3d_tc", "conv3d_tc", conv_tc_cost)
@@ -313,18 +321,16 @@ def run_engine(args, rank, world, local_rank):
     def step_resident():
         return net(feats_d, cams_d, dv_d, tmp=tmp)
 
-    depth_host = torch.empty(1, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
-    conf_host = torch.empty(1, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
+    from mvsformer_b200.pipeline import StreamedCascade
+    streamer = StreamedCascade(net, device, tmp)
 
-    def step_e2e():
-        f = {k: v.to(device, non_blocking=True) for k, v in feats_h.items()}
-        c = {k: v.to(device, non_blocking=True) for k, v in cams_h.items()}
-        d = dv_h.to(device, non_blocking=True)
-        out = net(f, c, d, tmp=tmp)
-        depth_host.copy_(out["refined_depth"], non_blocking=True)
-        conf_host.copy_(out["photometric_confidence"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller consumes the depth map
-        return out
+    def run_e2e(steps):
+        """The public host-to-host call: pinned HOST features in, HOST depth + confidence out;
+        uploads of view i+1 and downloads of view i-1 overlap the compute of view i."""
+        checksum = 0.0
+        for depth_h, conf_h in streamer.run((feats_h, cams_h, dv_h) for _ in range(steps)):
+            checksum += float(depth_h[0, 0, 0])          # the caller touches every result
+        return checksum
 
     def timed(fn, steps):
         barrier()
@@ -348,9 +354,17 @@ def run_engine(args, rank, world, local_rank):
             sampler.start()
         ms_total, launches = timed(step_resident, args.steps)
         clocks = sampler.stop() if rank == 0 else None
-        for _ in range(max(1, args.warmup // 2)):
-            step_e2e()
-        ms_e2e, _ = timed(step_e2e, args.steps)
+        run_e2e(max(2, args.warmup // 2))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_e2e(args.steps)
+        e1.record()
+        barrier()
+        ms_t = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(ms_t.item())
 
         # per-kernel-class attribution (separate pass, same inputs)
         prof = KernelProfiler()
@@ -371,8 +385,7 @@ def run_engine(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(4 * v.numel() for v in feats_h.values()) + sum(4 * v.numel() for v in cams_h.values()) + 4 * dv_h.numel()
-    d2h = 4 * (depth_host.numel() + conf_host.numel())
+    h2d, d2h = streamer.h2d_bytes, streamer.d2h_bytes
     peaks = measured_peaks()
 
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
@@ -400,7 +413,8 @@ def run_engine(args, rank, world, local_rank):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "mvsformer_b200.pipeline.StreamedCascade.run (copy stream prefetch + pinned result ring)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cost_volume": cost_volume,
             "kernels": kernels}
     if world == 1 and not args.no_cpu_baseline:

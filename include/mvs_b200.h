@@ -73,6 +73,10 @@ int mvs_cost_volume_entropy(const float* features, int64_t batch_stride, int64_t
 int mvs_cost_volume_aggregate(const float* features, int64_t batch_stride, int64_t view_stride,
                               const float* relproj, const float* depth, const float* vis_weight,
                               float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream);
+/* Same, with the volume rounded to TF32 on store (operand of the TF32 tensor-core 3D CNN). */
+int mvs_cost_volume_aggregate_tf32(const float* features, int64_t batch_stride, int64_t view_stride,
+                                   const float* relproj, const float* depth, const float* vis_weight,
+                                   float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream);
 /* sim_depth = depth[argmax_d sim_sum] (:151-156).  out [B,H,W]. */
 int mvs_argmax_gather(const float* score, const float* depth, float* out, int B, int D, int H, int W, void* stream);
 
@@ -110,6 +114,15 @@ int mvs_conv3d_tc(const float* x, const float* w_hi, const float* w_lo, const fl
 int mvs_deconv3d_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
                     float* y, int B, int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int sd,
                     int relu, void* stream);
+/* Depth-fused, cp.async-pipelined TF32 kernels for depth-unstrided layers (sd = 1; conv3d_tcz.cu).
+ * Inputs must already be TF32-rounded (outputs of these kernels, of mvs_cost_volume_aggregate with
+ * round_tf32 = 1, or of mvs_ncdhw_to_cl_tf32); outputs are TF32-rounded.  Weights (TF32-rounded):
+ *   conv   [Cout_tiles][3 kh][Cin/CS][kd][3 kw][CS/4][n_tile][4]
+ *   deconv [Cout_tiles][2 dy][Cin/CS][kd][6 taps][CS/4][n_tile][4]   (tap order as mvs_deconv3d_tc) */
+int mvs_conv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                   int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
+int mvs_deconv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                     int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
 /* Diagnostic: nk MMAs (M=128, N, K=8) over caller-made shared-memory operand images with explicit
  * descriptor strides; dumps the 128 x N accumulator (used by tests to pin the operand layouts). */
 int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,
@@ -117,6 +130,7 @@ int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_byte
                  unsigned b_kstep, float* d_out, void* stream);
 /* Layout transforms at the module boundary (CostRegNet*.forward takes/returns NCDHW). */
 int mvs_ncdhw_to_cl(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);
+int mvs_ncdhw_to_cl_tf32(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);   /* + TF32 rounding */
 int mvs_cl_to_ncdhw(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);
 
 /* ---- A7/A8. prob conv + head: models/module.py:493,582; models/mvsformer_model.py:110-125 ----

@@ -47,6 +47,13 @@ void count_launch();   // bumps the counter read by mvs_launch_count()
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// fp32 -> TF32 (round to nearest, ties away; low 13 mantissa bits cleared)
+__device__ __forceinline__ float round_to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Plane-sweep sampling geometry shared by the warp and cost-volume kernels.
 // Mirrors models/warping.py:84-96 followed by ATen's grid_sampler (bilinear, zeros,

@@ -226,7 +226,7 @@ deconv3d_cl_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 constexpr int TR_VOX = 64;
 
 __global__ void __launch_bounds__(256)
-ncdhw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int64_t S) {
+ncdhw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int64_t S, int round_tf32) {
     extern __shared__ float s_t[];   // [C][TR_VOX + 1]
     const int b = blockIdx.y;
     const int64_t s0 = (int64_t)blockIdx.x * TR_VOX;
@@ -238,7 +238,9 @@ ncdhw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ y, int C, in
     __syncthreads();
     for (int i = threadIdx.x; i < n * C; i += blockDim.x) {
         const int s = i / C, c = i % C;
-        y[((int64_t)b * S + s0 + s) * C + c] = s_t[c * (TR_VOX + 1) + s];
+        float v = s_t[c * (TR_VOX + 1) + s];
+        if (round_tf32) v = round_to_tf32(v);
+        y[((int64_t)b * S + s0 + s) * C + c] = v;
     }
 }
 
@@ -337,16 +339,24 @@ extern "C" int mvs_deconv3d_cl(const float* x, const float* w, const float* shif
     MVS_DISPATCH_CIN(launch_deconv, 8)
 }
 
-extern "C" int mvs_ncdhw_to_cl(const float* x, float* y, int B, int C, int D, int H, int W, void* stream) {
+static int ncdhw_to_cl_impl(const float* x, float* y, int B, int C, int D, int H, int W, int round_tf32, void* stream) {
     using namespace mvs;
     MVS_REQUIRE(x && y, "mvs_ncdhw_to_cl: null pointer");
     MVS_REQUIRE(B >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1 && B <= 65535, "mvs_ncdhw_to_cl: bad shape");
     const int64_t S = (int64_t)D * H * W;
     const size_t smem = (size_t)C * (TR_VOX + 1) * sizeof(float);
     MVS_REQUIRE(smem <= 48 * 1024, "mvs_ncdhw_to_cl: C = %d too large", C);
-    ncdhw_to_cl_kernel<<<dim3(cdiv(S, TR_VOX), B), 256, smem, (cudaStream_t)stream>>>(x, y, C, S);
+    ncdhw_to_cl_kernel<<<dim3(cdiv(S, TR_VOX), B), 256, smem, (cudaStream_t)stream>>>(x, y, C, S, round_tf32);
     MVS_LAUNCH_OK("ncdhw_to_cl_kernel");
     return MVS_OK;
+}
+
+extern "C" int mvs_ncdhw_to_cl(const float* x, float* y, int B, int C, int D, int H, int W, void* stream) {
+    return ncdhw_to_cl_impl(x, y, B, C, D, H, W, 0, stream);
+}
+
+extern "C" int mvs_ncdhw_to_cl_tf32(const float* x, float* y, int B, int C, int D, int H, int W, void* stream) {
+    return ncdhw_to_cl_impl(x, y, B, C, D, H, W, 1, stream);
 }
 
 extern "C" int mvs_cl_to_ncdhw(const float* x, float* y, int B, int C, int D, int H, int W, void* stream) {

@@ -1,0 +1,494 @@
+// conv3d_tcz.cu — second-generation tcgen05 convolution kernels for the depth-unstrided layers
+// (CostRegNet3D, models/module.py:550-594: every layer of cascade stages 3-4, 93 % of the 3D-CNN
+// FLOPs, and the 2D visibility net run as kd = 1): TF32 operands, fp32 accumulation in TMEM.
+//
+// What changes against conv3d_tc.cu (which stays for depth-strided layers and the 3xTF32 mode):
+//   * depth fusion — a CTA owns 128 virtual voxels of ALL output depth slices of its z-chunk, one
+//     TMEM accumulator per slice.  A staged input slab (iz, kh) feeds the three kw taps of up to
+//     three output slices (kz = iz - oz + 1), so every slab is staged once instead of three times
+//     and carries 3x the MMA work per barrier; zero-padding slices in z are never staged or
+//     multiplied at all.
+//   * asynchronous staging — activations are already TF32-rounded by their producer (this
+//     kernel's own epilogue, the cost-volume kernel, the layout kernel), so operands go
+//     global -> shared with cp.async (16 B, zero-fill for padding) through a 4-stage ring;
+//     three iterations of loads are in flight per CTA while the tensor core works.
+//   * weights of one (kh, channel-slice) group — all kz, kw taps — are fetched once per group and
+//     reused across the depth slices.
+// Operand layouts, descriptors and the virtual-index trick are those of conv3d_tc.cu.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace mvs {
+namespace tc {
+
+constexpr int TZ_THREADS = 128;
+constexpr int TZ_SLOTS = 132;
+constexpr int TZ_SL = TZ_SLOTS * 16;
+constexpr int TZ_STAGES = 4;
+
+struct TzDims {
+    int B, D, H, W, Ho, Wo, Cin, Cout;
+    int kd;                  // 1 or 3 (depth stride is 1)
+    int s2;                  // conv: stride 2 in y and x
+    int relu;
+    int PW, tiles_per_plane;
+    int zc;                  // output depth slices per CTA
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TAPS = weight taps staged per (kh | dy, channel-slice) group and depth tap: conv 3 (kw), deconv 6.
+template <int CS, int NT, int TAPS, int NPLANES>
+struct TzSmem {
+    static constexpr int CH = CS / 4;
+    static constexpr int A_STAGE = NPLANES * CH * TZ_SL;
+    static constexpr int B_TAP = CH * NT * 16;
+    static __host__ __device__ constexpr int b_group(int kd) { return kd * TAPS * B_TAP; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward convolution, kernel (kd,3,3), stride (1, s, s)
+// ------------------------------------------------------------------------------------------------
+template <int CS, int NT, bool S2>
+__global__ void __launch_bounds__(TZ_THREADS)
+conv3d_tcz_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                  const float* __restrict__ skip, float* __restrict__ y, TzDims d) {
+    constexpr int NPL = S2 ? 2 : 1;
+    using L = TzSmem<CS, NT, 3, NPL>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int bgroup = L::b_group(d.kd);
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;                 // weight-buffer ring (see header)
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TZ_STAGES * L::A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)br * bgroup);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ncols = d.zc * NT;
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : (ncols <= 256 ? 256 : 512)));
+    if (tid == 0) {
+        for (int s = 0; s < TZ_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int b = blockIdx.z;
+    const int tile = blockIdx.x;
+    const int z0 = blockIdx.y * d.zc;                          // first output slice of this CTA
+    const int nz = min(d.zc, d.D - z0);
+    const int co_tile = 0;                                     // Cout tiles are folded into gridDim.x by the host
+    (void)co_tile;
+    const int j0 = (tile % d.tiles_per_plane) * 128;
+    const int ct = tile / d.tiles_per_plane;                   // Cout tile
+    const int co0 = ct * NT;
+    const int pd = d.kd / 2;
+    const int nch = d.Cin / CS;
+
+    // input slices that feed this z-chunk
+    const int iz_lo = max(z0 - pd, 0), iz_hi = min(z0 + nz - 1 + pd, d.D - 1);
+    const int niz = iz_hi - iz_lo + 1;
+    const int ngroups = 3 * nch;                               // (kh, channel slice)
+    const int nit = ngroups * niz;
+    const int glen = br == 2 ? niz : 1;                        // iterations sharing one weight buffer
+
+    int sy[2], sa[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int jv = j0 + tid + u * 128;
+        sy[u] = jv / d.PW;
+        sa[u] = jv - sy[u] * d.PW;
+    }
+    const int nslot_iters = (tid + 128 < 130) ? 2 : 1;
+    const float* wt = w + (size_t)ct * ngroups * (bgroup / 4);
+
+    auto issue = [&](int it) {
+        const int g = it / niz, iz = iz_lo + (it - g * niz);
+        const int kh = g / nch, ch = g - kh * nch;
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+            for (int u = 0; u < nslot_iters; ++u) {
+                const int slot = tid + u * 128;
+                const int yy = S2 ? 2 * sy[u] + kh - 1 : sy[u] + kh - 1;
+                const int xx = S2 ? (p == 0 ? 2 * sa[u] : 2 * sa[u] - 1) : sa[u] - 1;
+                const bool ok = yy >= 0 && yy < d.H && xx >= 0 && xx < d.W;
+                const float* src = x + ((((size_t)b * d.D + iz) * d.H + (ok ? yy : 0)) * d.W + (ok ? xx : 0)) * d.Cin + ch * CS;
+                const uint32_t dst = a_base + (uint32_t)p * L::CH * TZ_SL + slot * 16;
+#pragma unroll
+                for (int q = 0; q < L::CH; ++q) cp_async16(dst + q * TZ_SL, src + q * 4, ok ? 16u : 0u);
+            }
+        }
+        // weights: once per group (glen > 1) or with every iteration (glen == 1)
+        if (glen == 1 || it == g * niz) {
+            const int slot_b = glen == 1 ? it % TZ_STAGES : g % 2;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)slot_b * bgroup;
+            const float4* srcb = reinterpret_cast<const float4*>(wt) + (size_t)g * (bgroup / 16);
+            for (int i = tid; i < bgroup / 16; i += TZ_THREADS) cp_async16(b_base + i * 16, srcb + i, 16u);
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < TZ_STAGES - 1; ++i) {
+        if (i < nit) issue(i);
+        cp_async_commit();
+    }
+
+    uint32_t started = 0;                                      // per-slice "accumulator written" bits (thread 0)
+    for (int it = 0; it < nit; ++it) {
+        const int nx = it + TZ_STAGES - 1;
+        if (nx < nit) {
+            // stage of iteration nx was last read by the MMAs of iteration it-1
+            if (it >= 1) mbar_wait(&bars[(it - 1) % TZ_STAGES], ((it - 1) / TZ_STAGES) & 1);
+            issue(nx);
+        }
+        cp_async_commit();
+        cp_async_wait<TZ_STAGES - 1>();                        // this thread's copies of iteration `it` have landed
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const int g = it / niz, iz = iz_lo + (it - g * niz);
+            const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)(glen == 1 ? it % TZ_STAGES : g % 2) * bgroup;
+            for (int kz = 0; kz < d.kd; ++kz) {
+                const int oz = iz + pd - kz;                   // output slice fed through depth tap kz
+                if (oz < z0 || oz >= z0 + nz) continue;
+                const uint32_t dcol = tmem + (uint32_t)(oz - z0) * NT;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int p = S2 ? (kw == 1 ? 0 : 1) : 0;
+                    const int sh = S2 ? (kw == 2 ? 1 : 0) : kw;
+                    const uint32_t aoff = (uint32_t)p * L::CH * TZ_SL + (uint32_t)sh * 16;
+#pragma unroll
+                    for (int kk = 0; kk < CS / 8; ++kk) {
+                        const uint32_t acc = (started >> (oz - z0)) & 1u;
+                        started |= 1u << (oz - z0);
+                        const uint64_t ad = make_smem_desc(a_base + aoff + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
+                        const uint64_t bd = make_smem_desc(b_base + (uint32_t)(kz * 3 + kw) * L::B_TAP + (uint32_t)(2 * kk) * NT * 16, NT * 16, 128);
+                        mma_tf32_ss(dcol, ad, bd, idesc, acc);
+                    }
+                }
+            }
+            mma_commit(&bars[it % TZ_STAGES]);
+        }
+    }
+
+    const int last = nit - 1;
+    mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
+    tc_fence_after_sync();
+    const int oy = sy[0], ox = sa[0];
+    const bool live = oy < d.Ho && ox < d.Wo;
+    for (int zi = 0; zi < nz; ++zi) {
+        float acc[NT];
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + zi * NT + c0, acc + c0);
+        if (!live) continue;
+        const size_t o = ((((size_t)b * d.D + z0 + zi) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0;
+#pragma unroll
+        for (int q = 0; q < NT / 4; ++q) {
+            if (co0 + q * 4 >= d.Cout) break;
+            float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            if (shift) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+            if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+            if (skip) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
+                r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+            // consumers read this tensor as a TF32 operand: round once here
+            r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+            reinterpret_cast<float4*>(y + o)[q] = r;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// transposed convolution, kernel (kd,3,3), stride (1,2,2): four output parity classes per slice
+// ------------------------------------------------------------------------------------------------
+template <int CS, int NT>
+__global__ void __launch_bounds__(TZ_THREADS)
+deconv3d_tcz_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                    const float* __restrict__ skip, float* __restrict__ y, TzDims d) {
+    using L = TzSmem<CS, NT, 6, 1>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int bgroup = L::b_group(d.kd);
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TZ_STAGES * L::A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)br * bgroup);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ncols = d.zc * 4 * NT;
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : (ncols <= 256 ? 256 : 512)));
+    if (tid == 0) {
+        for (int s = 0; s < TZ_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int b = blockIdx.z;
+    const int z0 = blockIdx.y * d.zc;
+    const int nz = min(d.zc, d.D - z0);
+    const int j0 = (blockIdx.x % d.tiles_per_plane) * 128;
+    const int ct = blockIdx.x / d.tiles_per_plane;
+    const int co0 = ct * NT;
+    const int pd = d.kd / 2;
+    const int nch = d.Cin / CS;
+    const int iz_lo = max(z0 - pd, 0), iz_hi = min(z0 + nz - 1 + pd, d.D - 1);
+    const int niz = iz_hi - iz_lo + 1;
+    const int ngroups = 2 * nch;                               // (dy, channel slice)
+    const int nit = ngroups * niz;
+    const int glen = br == 2 ? niz : 1;
+
+    int sy[2], sa[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int jv = j0 + tid + u * 128;
+        sy[u] = jv / d.PW;
+        sa[u] = jv - sy[u] * d.PW;
+    }
+    const int nslot_iters = (tid + 128 < 129) ? 2 : 1;
+    const float* wt = w + (size_t)ct * ngroups * (bgroup / 4);
+
+    auto issue = [&](int it) {
+        const int g = it / niz, iz = iz_lo + (it - g * niz);
+        const int dy = g / nch, ch = g - dy * nch;
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+        for (int u = 0; u < nslot_iters; ++u) {
+            const int slot = tid + u * 128;
+            const int yy = sy[u] + dy, xx = sa[u];
+            const bool ok = yy < d.H && xx < d.W;
+            const float* src = x + ((((size_t)b * d.D + iz) * d.H + (ok ? yy : 0)) * d.W + (ok ? xx : 0)) * d.Cin + ch * CS;
+            const uint32_t dst = a_base + slot * 16;
+#pragma unroll
+            for (int q = 0; q < L::CH; ++q) cp_async16(dst + q * TZ_SL, src + q * 4, ok ? 16u : 0u);
+        }
+        if (glen == 1 || it == g * niz) {
+            const int slot_b = glen == 1 ? it % TZ_STAGES : g % 2;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)slot_b * bgroup;
+            const float4* srcb = reinterpret_cast<const float4*>(wt) + (size_t)g * (bgroup / 16);
+            for (int i = tid; i < bgroup / 16; i += TZ_THREADS) cp_async16(b_base + i * 16, srcb + i, 16u);
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < TZ_STAGES - 1; ++i) {
+        if (i < nit) issue(i);
+        cp_async_commit();
+    }
+
+    uint32_t started = 0;                                      // bit (slice * 4 + class)
+    for (int it = 0; it < nit; ++it) {
+        const int nx = it + TZ_STAGES - 1;
+        if (nx < nit) {
+            if (it >= 1) mbar_wait(&bars[(it - 1) % TZ_STAGES], ((it - 1) / TZ_STAGES) & 1);
+            issue(nx);
+        }
+        cp_async_commit();
+        cp_async_wait<TZ_STAGES - 1>();
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const int g = it / niz, iz = iz_lo + (it - g * niz);
+            const int dy = g / nch;
+            const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)(glen == 1 ? it % TZ_STAGES : g % 2) * bgroup;
+            const int ntaps = dy == 0 ? 6 : 3;
+            for (int kz = 0; kz < d.kd; ++kz) {
+                const int oz = iz - pd + kz;                   // zo = iz - pd + kz (depth stride 1)
+                if (oz < z0 || oz >= z0 + nz) continue;
+                for (int t = 0; t < ntaps; ++t) {
+                    const int kh = dy == 0 ? 1 + t / 3 : 0;
+                    const int kw = t % 3;
+                    const int cls = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);
+                    const int sh = (kw == 0) ? 1 : 0;
+                    const int slot_acc = (oz - z0) * 4 + cls;
+                    const uint32_t dcol = tmem + (uint32_t)slot_acc * NT;
+#pragma unroll
+                    for (int kk = 0; kk < CS / 8; ++kk) {
+                        const uint32_t acc = (started >> slot_acc) & 1u;
+                        started |= 1u << slot_acc;
+                        const uint64_t ad = make_smem_desc(a_base + (uint32_t)sh * 16 + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
+                        const uint64_t bd = make_smem_desc(b_base + (uint32_t)(kz * 6 + t) * L::B_TAP + (uint32_t)(2 * kk) * NT * 16, NT * 16, 128);
+                        mma_tf32_ss(dcol, ad, bd, idesc, acc);
+                    }
+                }
+            }
+            mma_commit(&bars[it % TZ_STAGES]);
+        }
+    }
+
+    const int last = nit - 1;
+    mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
+    tc_fence_after_sync();
+    const int iy = sy[0], ix = sa[0];
+    const bool live = iy < d.H && ix < d.W;
+    for (int zi = 0; zi < nz; ++zi) {
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+            float acc[NT];
+#pragma unroll
+            for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (zi * 4 + cls) * NT + c0, acc + c0);
+            if (!live) continue;
+            const int oy = 2 * iy + (cls >> 1), ox = 2 * ix + (cls & 1);
+            const size_t o = ((((size_t)b * d.D + z0 + zi) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0;
+#pragma unroll
+            for (int q = 0; q < NT / 4; ++q) {
+                if (co0 + q * 4 >= d.Cout) break;
+                float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+                if (shift) {
+                    const float4 s = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                    r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+                }
+                if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                if (skip) {
+                    const float4 s = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
+                    r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+                }
+                r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+                reinterpret_cast<float4*>(y + o)[q] = r;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <int CS, int NT, bool S2>
+static int launch_conv_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, const TzDims& d,
+                           cudaStream_t st) {
+    using L = TzSmem<CS, NT, 3, S2 ? 2 : 1>;
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;
+    const size_t smem = (size_t)TZ_STAGES * L::A_STAGE + (size_t)br * L::b_group(d.kd) + 128;
+    MVS_REQUIRE(smem <= 227 * 1024, "mvs_conv3d_tcz: needs %zu bytes of shared memory", smem);
+    auto kern = conv3d_tcz_kernel<CS, NT, S2>;
+    MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (d.Cout + NT - 1) / NT;
+    dim3 grid((unsigned)(d.tiles_per_plane * ntiles), (unsigned)((d.D + d.zc - 1) / d.zc), (unsigned)d.B);
+    kern<<<grid, TZ_THREADS, smem, st>>>(x, w, shift, skip, y, d);
+    MVS_LAUNCH_OK("conv3d_tcz_kernel");
+    return MVS_OK;
+}
+
+template <int CS, int NT>
+static int launch_deconv_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, const TzDims& d,
+                             cudaStream_t st) {
+    using L = TzSmem<CS, NT, 6, 1>;
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;
+    const size_t smem = (size_t)TZ_STAGES * L::A_STAGE + (size_t)br * L::b_group(d.kd) + 128;
+    MVS_REQUIRE(smem <= 227 * 1024, "mvs_deconv3d_tcz: needs %zu bytes of shared memory", smem);
+    auto kern = deconv3d_tcz_kernel<CS, NT>;
+    MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (d.Cout + NT - 1) / NT;
+    dim3 grid((unsigned)(d.tiles_per_plane * ntiles), (unsigned)((d.D + d.zc - 1) / d.zc), (unsigned)d.B);
+    kern<<<grid, TZ_THREADS, smem, st>>>(x, w, shift, skip, y, d);
+    MVS_LAUNCH_OK("deconv3d_tcz_kernel");
+    return MVS_OK;
+}
+
+// Depth slices per CTA: the largest divisor of D whose accumulators fit the 512 TMEM columns and
+// whose operand rings fit shared memory.  Chunks of >= 3 slices share one weight buffer per group
+// (2-deep ring); shorter chunks reload weights with every iteration (ring of TZ_STAGES).
+static int pick_zc(int D, int cols_per_slice, size_t a_bytes, size_t bgroup) {
+    for (int zc = D < 8 ? D : 8; zc >= 1; --zc) {
+        if (D % zc) continue;
+        if (zc * cols_per_slice > 512) continue;
+        const int br = zc >= 3 ? 2 : TZ_STAGES;
+        if (a_bytes + (size_t)br * bgroup + 128 <= 227 * 1024) return zc;
+    }
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace mvs
+
+extern "C" int mvs_conv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                              int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream) {
+    using namespace mvs;
+    using namespace mvs::tc;
+    MVS_REQUIRE(x && w && y, "mvs_conv3d_tcz: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && B <= 65535, "mvs_conv3d_tcz: bad shape");
+    MVS_REQUIRE(kd == 1 || kd == 3, "mvs_conv3d_tcz: depth kernel size must be 1 or 3 (got %d)", kd);
+    MVS_REQUIRE(shw == 1 || shw == 2, "mvs_conv3d_tcz: in-plane stride must be 1 or 2");
+    MVS_REQUIRE(Cout % 8 == 0 && Cout >= 8, "mvs_conv3d_tcz: Cout must be a multiple of 8 (got %d)", Cout);
+    const int cs = Cin >= 32 ? 32 : Cin;
+    MVS_REQUIRE(Cin % cs == 0 && (cs == 8 || cs == 16 || cs == 32), "mvs_conv3d_tcz: Cin must be 8, 16 or a multiple of 32 (got %d)", Cin);
+    TzDims d;
+    d.B = B; d.D = D; d.H = H; d.W = W;
+    d.Ho = (H - 1) / shw + 1; d.Wo = (W - 1) / shw + 1;
+    d.Cin = Cin; d.Cout = Cout; d.kd = kd; d.s2 = shw == 2; d.relu = relu;
+    d.PW = d.s2 ? d.Wo + 1 : d.Wo + 2;
+    d.tiles_per_plane = (int)(((int64_t)d.Ho * d.PW + 127) / 128);
+    const size_t a_bytes = (size_t)TZ_STAGES * (d.s2 ? 2 : 1) * (cs / 4) * TZ_SL;
+    const size_t bgroup = (size_t)kd * 3 * (cs / 4) * n_tile * 16;
+    d.zc = pick_zc(D, n_tile, a_bytes, bgroup);
+    if (d.zc == 0) MVS_UNSUPPORTED("mvs_conv3d_tcz: no depth chunking fits D=%d with N tile %d", D, n_tile);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_TZ_CASE(CS_, NT_)                                                                          \
+    if (cs == CS_ && n_tile == NT_)                                                                    \
+        return d.s2 ? launch_conv_tcz<CS_, NT_, true>(x, w, shift, skip, y, d, st)                     \
+                    : launch_conv_tcz<CS_, NT_, false>(x, w, shift, skip, y, d, st);
+    MVS_TZ_CASE(8, 16)
+    MVS_TZ_CASE(16, 16)
+    MVS_TZ_CASE(16, 32)
+    MVS_TZ_CASE(32, 16)
+    MVS_TZ_CASE(32, 32)
+    MVS_TZ_CASE(32, 64)
+#undef MVS_TZ_CASE
+    MVS_UNSUPPORTED("mvs_conv3d_tcz: no instantiation for Cin=%d, N tile=%d", Cin, n_tile);
+}
+
+extern "C" int mvs_deconv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                                int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream) {
+    using namespace mvs;
+    using namespace mvs::tc;
+    MVS_REQUIRE(x && w && y, "mvs_deconv3d_tcz: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && B <= 65535, "mvs_deconv3d_tcz: bad shape");
+    MVS_REQUIRE(kd == 1 || kd == 3, "mvs_deconv3d_tcz: depth kernel size must be 1 or 3 (got %d)", kd);
+    MVS_REQUIRE(Cout % 8 == 0 && Cout >= 8, "mvs_deconv3d_tcz: Cout must be a multiple of 8 (got %d)", Cout);
+    const int cs = Cin >= 32 ? 32 : Cin;
+    MVS_REQUIRE(Cin % cs == 0 && (cs == 16 || cs == 32), "mvs_deconv3d_tcz: Cin must be 16 or a multiple of 32 (got %d)", Cin);
+    TzDims d;
+    d.B = B; d.D = D; d.H = H; d.W = W;
+    d.Ho = 2 * H; d.Wo = 2 * W;
+    d.Cin = Cin; d.Cout = Cout; d.kd = kd; d.s2 = 1; d.relu = relu;
+    d.PW = W + 1;
+    d.tiles_per_plane = (int)(((int64_t)H * d.PW + 127) / 128);
+    const size_t a_bytes = (size_t)TZ_STAGES * (cs / 4) * TZ_SL;
+    const size_t bgroup = (size_t)kd * 6 * (cs / 4) * n_tile * 16;
+    d.zc = pick_zc(D, 4 * n_tile, a_bytes, bgroup);
+    if (d.zc == 0) MVS_UNSUPPORTED("mvs_deconv3d_tcz: no depth chunking fits D=%d with N tile %d", D, n_tile);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_TZD_CASE(CS_, NT_) \
+    if (cs == CS_ && n_tile == NT_) return launch_deconv_tcz<CS_, NT_>(x, w, shift, skip, y, d, st);
+    MVS_TZD_CASE(16, 16)
+    MVS_TZD_CASE(32, 16)
+    MVS_TZD_CASE(32, 32)
+#undef MVS_TZD_CASE
+    MVS_UNSUPPORTED("mvs_deconv3d_tcz: no instantiation for Cin=%d, N tile=%d", Cin, n_tile);
+}

@@ -114,7 +114,7 @@ cv_entropy_kernel(CvParams p, float* __restrict__ entropy, float* __restrict__ s
 // ------------------------------------------------------------------------------------------
 template <int G_T, int CPG_T>
 __global__ void __launch_bounds__(256)
-cv_aggregate_kernel(CvParams p, const float* __restrict__ vis_weight, float* __restrict__ volume) {
+cv_aggregate_kernel(CvParams p, const float* __restrict__ vis_weight, float* __restrict__ volume, int round_tf32) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int b = blockIdx.z / p.D, k = blockIdx.z % p.D;
@@ -150,14 +150,19 @@ cv_aggregate_kernel(CvParams p, const float* __restrict__ vis_weight, float* __r
         }
     }
     const float inv = 1.0f / (wsum + 1e-6f);          // :105
+#pragma unroll
+    for (int g = 0; g < G_T; ++g) {
+        acc[g] *= inv;
+        if (round_tf32) acc[g] = round_to_tf32(acc[g]);
+    }
     float* out = volume + ((((int64_t)b * p.D + k) * p.H + y) * p.W + x) * G_T;
     if (G_T % 4 == 0) {
 #pragma unroll
         for (int g = 0; g < G_T; g += 4)
-            *reinterpret_cast<float4*>(out + g) = make_float4(acc[g] * inv, acc[g + 1] * inv, acc[g + 2] * inv, acc[g + 3] * inv);
+            *reinterpret_cast<float4*>(out + g) = make_float4(acc[g], acc[g + 1], acc[g + 2], acc[g + 3]);
     } else {
 #pragma unroll
-        for (int g = 0; g < G_T; ++g) out[g] = acc[g] * inv;
+        for (int g = 0; g < G_T; ++g) out[g] = acc[g];
     }
 }
 
@@ -220,7 +225,7 @@ int cost_volume_tma_entropy(const float* features, int64_t batch_stride, int64_t
                             cudaStream_t st);
 int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
                               const float* depth, const float* vis_weight, float* volume, int B, int V, int C, int G, int D,
-                              int H, int W, cudaStream_t st);
+                              int H, int W, int round_tf32, cudaStream_t st);
 
 // MVS_K1_IMPL=generic forces the generic (non-TMA) kernels, for A/B parity runs.
 static bool use_tma_kernels() {
@@ -247,16 +252,16 @@ extern "C" int mvs_cost_volume_entropy(const float* features, int64_t batch_stri
                    : mvs::dispatch_entropy<false>(p, entropy, nullptr, B, st);
 }
 
-extern "C" int mvs_cost_volume_aggregate(const float* features, int64_t batch_stride, int64_t view_stride,
-                                         const float* relproj, const float* depth, const float* vis_weight,
-                                         float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream) {
+static int cost_volume_aggregate_impl(const float* features, int64_t batch_stride, int64_t view_stride,
+                                      const float* relproj, const float* depth, const float* vis_weight,
+                                      float* volume, int B, int V, int C, int G, int D, int H, int W, int round_tf32, void* stream) {
     int rc = mvs::check_cv_args("mvs_cost_volume_aggregate", features, relproj, depth, B, V, C, G, D, H, W);
     if (rc) return rc;
     MVS_REQUIRE(vis_weight && volume, "mvs_cost_volume_aggregate: null pointer");
     if (G != 8) MVS_UNSUPPORTED("mvs_cost_volume_aggregate: only G = 8 groups is built (got %d)", G);
     if (mvs::use_tma_kernels()) {
         rc = mvs::cost_volume_tma_aggregate(features, batch_stride, view_stride, relproj, depth, vis_weight, volume, B, V, C, G, D,
-                                            H, W, (cudaStream_t)stream);
+                                            H, W, round_tf32, (cudaStream_t)stream);
         if (rc <= 0) return rc;
     }
     mvs::CvParams p{features, batch_stride, view_stride, relproj, depth, V - 1, C, G, D, H, W};
@@ -264,14 +269,26 @@ extern "C" int mvs_cost_volume_aggregate(const float* features, int64_t batch_st
     dim3 block(32, 8);
     dim3 grid(mvs::cdiv(W, 32), mvs::cdiv(H, 8), B * D);
     switch (C / G) {
-        case 1: mvs::cv_aggregate_kernel<8, 1><<<grid, block, 0, st>>>(p, vis_weight, volume); break;
-        case 2: mvs::cv_aggregate_kernel<8, 2><<<grid, block, 0, st>>>(p, vis_weight, volume); break;
-        case 4: mvs::cv_aggregate_kernel<8, 4><<<grid, block, 0, st>>>(p, vis_weight, volume); break;
-        case 8: mvs::cv_aggregate_kernel<8, 8><<<grid, block, 0, st>>>(p, vis_weight, volume); break;
-        default: mvs::cv_aggregate_kernel<8, 0><<<grid, block, 0, st>>>(p, vis_weight, volume); break;
+        case 1: mvs::cv_aggregate_kernel<8, 1><<<grid, block, 0, st>>>(p, vis_weight, volume, round_tf32); break;
+        case 2: mvs::cv_aggregate_kernel<8, 2><<<grid, block, 0, st>>>(p, vis_weight, volume, round_tf32); break;
+        case 4: mvs::cv_aggregate_kernel<8, 4><<<grid, block, 0, st>>>(p, vis_weight, volume, round_tf32); break;
+        case 8: mvs::cv_aggregate_kernel<8, 8><<<grid, block, 0, st>>>(p, vis_weight, volume, round_tf32); break;
+        default: mvs::cv_aggregate_kernel<8, 0><<<grid, block, 0, st>>>(p, vis_weight, volume, round_tf32); break;
     }
     MVS_LAUNCH_OK("cv_aggregate_kernel");
     return MVS_OK;
+}
+
+extern "C" int mvs_cost_volume_aggregate(const float* features, int64_t batch_stride, int64_t view_stride,
+                                         const float* relproj, const float* depth, const float* vis_weight,
+                                         float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream) {
+    return cost_volume_aggregate_impl(features, batch_stride, view_stride, relproj, depth, vis_weight, volume, B, V, C, G, D, H, W, 0, stream);
+}
+
+extern "C" int mvs_cost_volume_aggregate_tf32(const float* features, int64_t batch_stride, int64_t view_stride,
+                                              const float* relproj, const float* depth, const float* vis_weight,
+                                              float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream) {
+    return cost_volume_aggregate_impl(features, batch_stride, view_stride, relproj, depth, vis_weight, volume, B, V, C, G, D, H, W, 1, stream);
 }
 
 extern "C" int mvs_argmax_gather(const float* score, const float* depth, float* out, int B, int D, int H, int W,

@@ -43,6 +43,7 @@ struct K1Params {
     float* sim_sum;          // pass A out [B, D, H, W] (SIM)
     const float* vis_weight; // pass B in  [B, N, H, W]
     float* volume;           // pass B out [B, D, H, W, 8]
+    int round_tf32;          // pass B: round the stored volume to TF32
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -301,9 +302,14 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
         const float inv = 1.0f / (wsum + 1e-6f);
 #pragma unroll
         for (int j = 0; j < KPT; ++j) {
+#pragma unroll
+            for (int g = 0; g < (PASS_B ? G : 1); ++g) {
+                acc[g][j] *= inv;
+                if (p.round_tf32) acc[g][j] = tc::to_tf32(acc[g][j]);
+            }
             float* out = p.volume + (((int64_t)b * D + dg * KPT + j) * hw + pixoff) * G;
-            *reinterpret_cast<float4*>(out) = make_float4(acc[0][j] * inv, acc[PASS_B ? 1 : 0][j] * inv, acc[PASS_B ? 2 : 0][j] * inv, acc[PASS_B ? 3 : 0][j] * inv);
-            *reinterpret_cast<float4*>(out + 4) = make_float4(acc[PASS_B ? 4 : 0][j] * inv, acc[PASS_B ? 5 : 0][j] * inv, acc[PASS_B ? 6 : 0][j] * inv, acc[PASS_B ? 7 : 0][j] * inv);
+            *reinterpret_cast<float4*>(out) = make_float4(acc[0][j], acc[PASS_B ? 1 : 0][j], acc[PASS_B ? 2 : 0][j], acc[PASS_B ? 3 : 0][j]);
+            *reinterpret_cast<float4*>(out + 4) = make_float4(acc[PASS_B ? 4 : 0][j], acc[PASS_B ? 5 : 0][j], acc[PASS_B ? 6 : 0][j], acc[PASS_B ? 7 : 0][j]);
         }
     } else if (SIM) {
 #pragma unroll
@@ -383,16 +389,16 @@ int cost_volume_tma_entropy(const float* features, int64_t batch_stride, int64_t
                             cudaStream_t st) {
     const int64_t hw = (int64_t)H * W;
     if (G != 8 || (W % 4) != 0 || view_stride != C * hw || batch_stride != V * C * hw || ((uintptr_t)features & 15)) return 1;
-    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, entropy, sim_sum, nullptr, nullptr};
+    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, entropy, sim_sum, nullptr, nullptr, 0};
     return sim_sum ? k1::dispatch<false, true>(p, B, C, D, st) : k1::dispatch<false, false>(p, B, C, D, st);
 }
 
 int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
                               const float* depth, const float* vis_weight, float* volume, int B, int V, int C, int G, int D,
-                              int H, int W, cudaStream_t st) {
+                              int H, int W, int round_tf32, cudaStream_t st) {
     const int64_t hw = (int64_t)H * W;
     if (G != 8 || (W % 4) != 0 || view_stride != C * hw || batch_stride != V * C * hw || ((uintptr_t)features & 15)) return 1;
-    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, nullptr, nullptr, vis_weight, volume};
+    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, nullptr, nullptr, vis_weight, volume, round_tf32};
     return k1::dispatch<true, false>(p, B, C, D, st);
 }
 

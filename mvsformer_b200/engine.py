@@ -78,7 +78,7 @@ def cost_volume_entropy(features, relproj, depth_values, groups, want_sim):
     return entropy, sim
 
 
-def cost_volume_aggregate(features, relproj, depth_values, vis_weight, groups):
+def cost_volume_aggregate(features, relproj, depth_values, vis_weight, groups, round_tf32=False):
     features = _f32(features)
     features, bs, vs = _feature_strides(features)
     depth_values = _f32(depth_values).contiguous()
@@ -86,9 +86,9 @@ def cost_volume_aggregate(features, relproj, depth_values, vis_weight, groups):
     b, v, c, h, w = features.shape
     d = depth_values.shape[1]
     volume = torch.empty(b, d, h, w, groups, device=features.device, dtype=torch.float32)
-    check(_lib.load().mvs_cost_volume_aggregate(ptr(features), bs, vs, ptr(relproj), ptr(depth_values), ptr(vis_weight),
-                                                ptr(volume), b, v, c, groups, d, h, w, stream()),
-          "mvs_cost_volume_aggregate")
+    fn = _lib.load().mvs_cost_volume_aggregate_tf32 if round_tf32 else _lib.load().mvs_cost_volume_aggregate
+    check(fn(ptr(features), bs, vs, ptr(relproj), ptr(depth_values), ptr(vis_weight), ptr(volume), b, v, c, groups, d, h, w,
+             stream()), "mvs_cost_volume_aggregate")
     return volume
 
 
@@ -142,12 +142,13 @@ def deconv3d_cl(x, w_packed, shift, skip, sd, relu=True):
     return y
 
 
-def ncdhw_to_cl(x):
+def ncdhw_to_cl(x, round_tf32=False):
     x = _f32(x).contiguous()
     require_cuda(x)
     b, c, d, h, w = x.shape
     y = torch.empty(b, d, h, w, c, device=x.device, dtype=torch.float32)
-    check(_lib.load().mvs_ncdhw_to_cl(ptr(x), ptr(y), b, c, d, h, w, stream()), "mvs_ncdhw_to_cl")
+    fn = _lib.load().mvs_ncdhw_to_cl_tf32 if round_tf32 else _lib.load().mvs_ncdhw_to_cl
+    check(fn(ptr(x), ptr(y), b, c, d, h, w, stream()), "mvs_ncdhw_to_cl")
     return y
 
 
@@ -333,3 +334,84 @@ def tc_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, n, nk, a_kstep, b_kstep):
     check(_lib.load().mvs_tc_probe(ptr(a_img), a_img.numel() * 4, ptr(b_img), b_img.numel() * 4, a_lbo, a_sbo, b_lbo, b_sbo,
                                    n, nk, a_kstep, b_kstep, ptr(out), stream()), "mvs_tc_probe")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# depth-fused, cp.async-pipelined TF32 kernels (conv3d_tcz.cu) for depth-unstrided layers
+# ------------------------------------------------------------------------------------------------
+def tcz_n_tile(cout, stride2=False, transposed=False):
+    if cout <= 16:
+        return 16
+    if cout == 32 or stride2 or transposed:
+        return 32
+    return 64
+
+
+def tcz_supported(cin, cout, d, kd, stride2=False, transposed=False):
+    """Mirror of the shape rules of mvs_conv3d_tcz / mvs_deconv3d_tcz (depth stride 1)."""
+    if not (cin in (8, 16) or cin % 32 == 0) or cout % 8 or cout > 64 or d > 8:
+        return False
+    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2, transposed)
+    if transposed:
+        if (cs, nt) not in ((16, 16), (32, 16), (32, 32)):
+            return False
+        cols = 4 * nt
+    else:
+        if (cs, nt) not in ((8, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64)):
+            return False
+        cols = nt
+    return any(d % zc == 0 and zc * cols <= 512 for zc in range(1, d + 1))
+
+
+def pack_tcz_weights(w_packed, stride2):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][3 kh][Cin/CS][kd][3 kw][CS/4][n_tile][4], TF32-rounded."""
+    kd, _, _, cin, cout = w_packed.shape
+    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2)
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt).permute(6, 1, 3, 0, 2, 4, 7, 5).contiguous()
+    return round_tf32(w), nt
+
+
+def pack_tcz_deconv_weights(w_packed):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][2 dy][Cin/CS][kd][6 taps][CS/4][n_tile][4], TF32-rounded."""
+    kd, _, _, cin, cout = w_packed.shape
+    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, transposed=True)
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt)               # [kz, kh, kw, ch, q, e, tile, n]
+    out = torch.zeros(ntiles, 2, cin // cs, kd, 6, cs // 4, nt, 4, device=w.device, dtype=w.dtype)
+    taps = {0: [(1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2)], 1: [(0, 0), (0, 1), (0, 2)]}
+    for dy, lst in taps.items():
+        for t, (kh, kw) in enumerate(lst):
+            out[:, dy, :, :, t] = w[:, kh, kw].permute(4, 1, 0, 2, 5, 3)      # [tile, ch, kz, q, n, e]
+    return round_tf32(out.contiguous()), nt
+
+
+def conv3d_tcz(x, w_tcz, n_tile, cout, kd, shift, skip, shw, relu=True):
+    require_cuda(x, w_tcz, shift, skip)
+    b, d, h, w, cin = x.shape
+    ho, wo = (h - 1) // shw + 1, (w - 1) // shw + 1
+    y = torch.empty(b, d, ho, wo, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_tcz(ptr(x), ptr(w_tcz), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
+                                     shw, 1 if relu else 0, stream()), "mvs_conv3d_tcz")
+    return y
+
+
+def deconv3d_tcz(x, w_tcz, n_tile, cout, kd, shift, skip, relu=True):
+    require_cuda(x, w_tcz, shift, skip)
+    b, d, h, w, cin = x.shape
+    y = torch.empty(b, d, h * 2, w * 2, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_deconv3d_tcz(ptr(x), ptr(w_tcz), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
+                                       1 if relu else 0, stream()), "mvs_deconv3d_tcz")
+    return y

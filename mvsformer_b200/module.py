@@ -76,6 +76,10 @@ def _tc_eligible(cin, cout, transposed):
 
 def _run_conv(cache, x, w, shift, skip, stride, relu):
     kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    if (config.conv_precision() == "tf32" and stride[0] == 1 and stride[1] == stride[2]
+            and engine.tcz_supported(cin, cout, x.shape[1], kd, stride[1] == 2)):
+        wz, nt = cache.get_derived("tcz_s%d" % stride[1], lambda v: engine.pack_tcz_weights(v[0], stride[1] == 2))
+        return engine.conv3d_tcz(x, wz, nt, cout, kd, shift, skip, stride[1], relu)
     if stride[1] == stride[2] and _tc_eligible(cin, cout, False):
         x3 = config.conv_precision() == "tf32x3"
         hi, lo, nt = cache.get_derived("tc_x3" if x3 else "tc", lambda v: engine.pack_tc_weights(v[0], x3))
@@ -85,6 +89,9 @@ def _run_conv(cache, x, w, shift, skip, stride, relu):
 
 def _run_deconv(cache, x, w, shift, skip, sd, relu):
     kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    if config.conv_precision() == "tf32" and sd == 1 and engine.tcz_supported(cin, cout, x.shape[1], kd, transposed=True):
+        wz, nt = cache.get_derived("tczd", lambda v: engine.pack_tcz_deconv_weights(v[0]))
+        return engine.deconv3d_tcz(x, wz, nt, cout, kd, shift, skip, relu)
     if _tc_eligible(cin, cout, True):
         x3 = config.conv_precision() == "tf32x3"
         hi, lo, nt = cache.get_derived("tcd_x3" if x3 else "tcd", lambda v: engine.pack_tc_deconv_weights(v[0], x3))
@@ -154,7 +161,7 @@ class Conv3d(nn.Module):
         return _run_conv(self._fold, x, w, shift, skip, _triple(self.conv.stride), self.relu)
 
     def forward(self, x):
-        return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x)))
+        return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32")))
 
     def init_weights(self, init_method):
         _init_uniform(self.conv, init_method)
@@ -188,7 +195,7 @@ class Deconv3d(nn.Module):
         return _run_deconv(self._fold, x, w, shift, skip, sd, self.relu)
 
     def forward(self, x):
-        return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x)))
+        return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32")))
 
     def init_weights(self, init_method):
         _init_uniform(self.conv, init_method)
@@ -255,7 +262,7 @@ class _SeqDeconv(nn.Sequential):
         return _run_deconv(self._fold, x, w, shift, skip, sd, True)
 
     def forward(self, x):
-        return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x)))
+        return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32")))
 
 
 class _ProbCache(_FoldCache):
@@ -307,7 +314,7 @@ class _RegNetBase(nn.Module):
         return y
 
     def forward(self, x):
-        out = self.forward_cl(engine.ncdhw_to_cl(x))
+        out = self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32"))
         if out.dim() == 4:
             return out.unsqueeze(1)
         return engine.cl_to_ncdhw(out)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import config, engine
 from .module import (ConvBnReLU, CostRegNet, CostRegNet2D, CostRegNet3D, _FoldCache, _bn_scale_shift,
                      init_inverse_range, init_range, schedule_inverse_range, schedule_range)
 
@@ -81,7 +81,8 @@ class StageNet(nn.Module):
         entropy, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=not self.training)
         h, w = entropy.shape[-2:]
         weight = engine.vis_weight(entropy.view(b * (v - 1), h, w), self._vis_params_host()).view(b, v - 1, h, w)
-        volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups)
+        volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups,
+                                              round_tf32=config.conv_precision() == "tf32")
         return volume, sim, entropy, weight
 
     def forward(self, features, proj_matrices, depth_values, tmp=2.0):

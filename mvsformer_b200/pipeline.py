@@ -1,0 +1,83 @@
+"""Host-side streaming executor for the cascade: the call a user makes to turn HOST feature maps of
+a list of reference views into HOST depth maps.
+
+The reference's driver (test.py:232-251) moves one sample to the GPU, runs the model,
+synchronises and copies every output back, strictly in sequence.  Here the three legs overlap:
+
+* a copy stream uploads the pinned inputs of reference view i+1 while view i computes,
+* the compute stream runs the cascade (all kernels of libmvs_b200.so),
+* the depth map and confidence of view i are downloaded into a ring of pinned buffers right
+  behind the compute, and handed to the caller one step later, so the host never stalls the GPU.
+
+Only depth and confidence cross PCIe on the way back (14 MB at 1152x1536) — not the per-stage
+probability volumes the reference's ``tensor2numpy(outputs)`` drags along (test.py:251).
+"""
+import torch
+
+
+class StreamedCascade:
+    def __init__(self, net, device, tmp, ring=2):
+        self.net = net
+        self.device = torch.device(device)
+        self.tmp = tmp
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ring = ring
+        self._out = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _upload(self, sample):
+        """sample = (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
+        feats, cams, dv = sample
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            f = {k: v.to(self.device, non_blocking=True) for k, v in feats.items()}
+            c = {k: v.to(self.device, non_blocking=True) for k, v in cams.items()}
+            d = dv.to(self.device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        for t in list(f.values()) + list(c.values()) + [d]:
+            t.record_stream(main)                      # consumed on the compute stream
+        self.h2d_bytes = sum(4 * v.numel() for v in feats.values()) + sum(4 * v.numel() for v in cams.values()) + 4 * dv.numel()
+        return f, c, d, ready
+
+    def _ring_buffers(self, depth, conf):
+        if self._out is None or self._out[0][0].shape != depth.shape:
+            self._out = [(torch.empty(depth.shape, dtype=torch.float32).pin_memory(),
+                          torch.empty(conf.shape, dtype=torch.float32).pin_memory(), torch.cuda.Event())
+                         for _ in range(self.ring)]
+        return self._out
+
+    def run(self, samples):
+        """Iterates over host samples; yields (depth, confidence) pinned host tensors, valid until
+        ``ring`` further results have been produced."""
+        main = torch.cuda.current_stream(self.device)
+        it = iter(samples)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        staged = self._upload(nxt)
+        pending = []
+        i = 0
+        with torch.no_grad():
+            while staged is not None:
+                f, c, d, ready = staged
+                nxt = next(it, None)
+                staged = self._upload(nxt) if nxt is not None else None      # overlaps with this view's compute
+                main.wait_event(ready)
+                out = self.net(f, c, d, tmp=self.tmp)
+                bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
+                hd, hc, done = bufs[i % self.ring]
+                hd.copy_(out["refined_depth"], non_blocking=True)
+                hc.copy_(out["photometric_confidence"], non_blocking=True)
+                done.record(main)
+                self.d2h_bytes = 4 * (hd.numel() + hc.numel())
+                pending.append((hd, hc, done))
+                if len(pending) >= self.ring:                                # hand out the oldest result
+                    od, oc, oe = pending.pop(0)
+                    oe.synchronize()
+                    yield od, oc
+                i += 1
+        for od, oc, oe in pending:
+            oe.synchronize()
+            yield od, oc

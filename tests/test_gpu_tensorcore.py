@@ -130,3 +130,81 @@ def test_cost_reg_precision_modes(kind, mode, tol):
     finally:
         config.set_conv_precision(old)
     assert rel_l1(got, want) < tol
+
+
+TCZ_CASES = [
+    # cin, cout, kd, shw, D, H, W
+    (8, 16, 3, 2, 4, 16, 24), (16, 16, 3, 1, 4, 10, 14), (16, 16, 1, 1, 1, 33, 47), (16, 8, 1, 1, 1, 20, 20),
+    (16, 32, 3, 2, 4, 9, 13), (32, 32, 3, 1, 8, 6, 10), (32, 64, 3, 2, 3, 6, 10), (64, 64, 3, 1, 2, 5, 7),
+    (64, 64, 3, 1, 8, 5, 7), (16, 16, 3, 1, 2, 3, 300), (16, 16, 3, 1, 5, 7, 9),
+]
+
+
+@pytest.mark.parametrize("cin,cout,kd,shw,D,H,W", TCZ_CASES)
+def test_conv3d_tcz(cin, cout, kd, shw, D, H, W):
+    assert engine.tcz_supported(cin, cout, D, kd, shw == 2)
+    g = S._gen(cin * 100 + cout + kd + W + D)
+    w = engine.round_tf32(torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = engine.round_tf32(torch.randn(2, cin, D, H, W, generator=g))          # producer-rounded operand
+    want = torch.relu(F.conv3d(x.double(), w.double(), stride=(1, shw, shw), padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    wz, nt = engine.pack_tcz_weights(w.permute(2, 3, 4, 1, 0).contiguous().to(DEV), shw == 2)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.conv3d_tcz(x_cl, wz, nt, cout, kd, shift.to(DEV), skip_cl, shw, relu=True).permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got, engine.round_tf32(got))                            # output is TF32-rounded
+    assert rel_l1(got, want + skip.double()) < 5e-4                            # exact products; only the output rounding (2^-11)
+
+
+TCZD_CASES = [(64, 32, 3, 4, 3, 5), (64, 32, 3, 8, 3, 5), (32, 16, 3, 4, 6, 10), (16, 8, 3, 4, 8, 12), (16, 8, 1, 3, 8, 12),
+              (32, 16, 3, 8, 5, 200), (16, 8, 3, 8, 4, 6), (16, 8, 3, 1, 9, 9)]
+
+
+@pytest.mark.parametrize("cin,cout,kd,D,H,W", TCZD_CASES)
+def test_deconv3d_tcz(cin, cout, kd, D, H, W):
+    assert engine.tcz_supported(cin, cout, D, kd, transposed=True)
+    g = S._gen(cin * 7 + cout + kd + W + D)
+    w = engine.round_tf32(torch.randn(cin, cout, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9 / 4)) ** 0.5)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = engine.round_tf32(torch.randn(2, cin, D, H, W, generator=g))
+    want = torch.relu(F.conv_transpose3d(x.double(), w.double(), stride=(1, 2, 2), padding=(kd // 2, 1, 1),
+                                         output_padding=(0, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    wz, nt = engine.pack_tcz_deconv_weights(w.permute(2, 3, 4, 0, 1).contiguous().to(DEV))
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.deconv3d_tcz(x_cl, wz, nt, cout, kd, shift.to(DEV), skip_cl, relu=True).permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want + skip.double()) < 5e-4
+
+
+def test_cascade_tf32_meets_north_star_tolerance():
+    """TF32 tensor-core convolutions (the bench default): refined depth within 1e-3 relative L1 of the
+    reference's golden output (BASELINE.json north_star tolerance)."""
+    from mvsformer_b200 import config
+    from mvsformer_b200.mvsformer_model import CascadeMVS
+    from tests.helpers import STAGE_ARGS, load_golden
+    g = load_golden("cascade.npz")
+    height, width, batch, views = int(g["height"]), int(g["width"]), int(g["batch"]), int(g["views"])
+    feats = S.make_features(batch, views, height, width, seed=int(g["feat_seed"]))
+    cams = S.make_cameras(batch, views, height, width)
+    dv = S.make_depth_range(batch)
+    args = dict(STAGE_ARGS, ndepths=list(S.NDEPTHS), depth_interals_ratio=list(S.DEPTH_INTERVAL_RATIO), inverse_depth=True)
+    net = CascadeMVS(args).eval()
+    full = {}
+    for s in range(4):
+        sd = S.fill_state_dict(net.fusions[s].state_dict(), seed=int(g["weight_seed0"]) + s)
+        full.update({"fusions.%d.%s" % (s, k): v for k, v in sd.items()})
+    net.load_state_dict(full, strict=True)
+    net = net.to(DEV)
+    old = config.conv_precision()
+    try:
+        config.set_conv_precision("tf32")
+        out = net({k: v.to(DEV) for k, v in feats.items()}, {k: v.to(DEV) for k, v in cams.items()}, dv.to(DEV), tmp=list(S.EVAL_TMP))
+    finally:
+        config.set_conv_precision(old)
+    err = rel_l1(out["refined_depth"].cpu(), g["refined_depth"])
+    print("tf32 refined_depth rel-L1 = %.3e" % err)
+    assert err < 1e-3
