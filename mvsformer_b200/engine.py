@@ -347,20 +347,31 @@ def tcz_n_tile(cout, stride2=False, transposed=False):
     return 64
 
 
+def _tcz_pick_zc(d, cols_per_slice, a_bytes, bgroup):
+    """Mirror of pick_zc() in conv3d_tcz.cu: depth slices per CTA (0 = does not fit)."""
+    for zc in range(min(d, 8), 0, -1):
+        if d % zc or zc * cols_per_slice > 512:
+            continue
+        ring = 2 if zc >= 3 else 4
+        if a_bytes + ring * bgroup + 128 <= 227 * 1024:
+            return zc
+    return 0
+
+
 def tcz_supported(cin, cout, d, kd, stride2=False, transposed=False):
     """Mirror of the shape rules of mvs_conv3d_tcz / mvs_deconv3d_tcz (depth stride 1)."""
-    if not (cin in (8, 16) or cin % 32 == 0) or cout % 8 or cout > 64 or d > 8:
+    if not (cin in (8, 16) or cin % 32 == 0) or cout % 8 or cout > 64:
         return False
     cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2, transposed)
     if transposed:
         if (cs, nt) not in ((16, 16), (32, 16), (32, 32)):
             return False
-        cols = 4 * nt
+        a_bytes, bgroup, cols = 4 * (cs // 4) * 2112, kd * 6 * (cs // 4) * nt * 16, 4 * nt
     else:
         if (cs, nt) not in ((8, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64)):
             return False
-        cols = nt
-    return any(d % zc == 0 and zc * cols <= 512 for zc in range(1, d + 1))
+        a_bytes, bgroup, cols = 4 * (2 if stride2 else 1) * (cs // 4) * 2112, kd * 3 * (cs // 4) * nt * 16, nt
+    return _tcz_pick_zc(d, cols, a_bytes, bgroup) > 0
 
 
 def pack_tcz_weights(w_packed, stride2):
