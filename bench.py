@@ -162,6 +162,8 @@ class KernelProfiler:
         self._wrap(engine, "cost_volume_entropy", "cv_entropy(passA)", ent_cost)
         self._wrap(engine, "cost_volume_aggregate", "cv_aggregate(passB)", agg_cost)
         self._wrap(engine, "vis_weight", "vis_net", vis_cost)
+        self._wrap(engine, "vis_first_cl", "vis_net(thin layers)", io_cost)
+        self._wrap(engine, "vis_last_cl", "vis_net(thin layers)", io_cost)
         def conv_tc_cost(out, x, w_hi, w_lo, n_tile, cout, kd, shift, skip, stride, relu=True):
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
 

@@ -86,6 +86,11 @@ int mvs_argmax_gather(const float* score, const float* depth, float* out, int B,
  *   w1[16][9] b1[16] w2[16][16][9] b2[16] w3[8][16][9] b3[8] w4[8] b4[1]   (3641 floats). */
 #define MVS_VIS_PARAM_FLOATS (16 * 9 + 16 + 16 * 16 * 9 + 16 + 8 * 16 * 9 + 8 + 8 + 1)
 int mvs_vis_weight(const float* entropy, const float* params_host, float* weight, int M, int H, int W, void* stream);
+/* Tensor-core route of the same net (TF32 conv mode): first layer (1->16, params [host] w1[16][9] b1[16])
+ * to channels-last TF32 [M,H,W,16]; the 16->16 and 16->8 layers run through mvs_conv3d_tcz (kd = 1,
+ * D = M); last layer (params [host] w4[8] b4) + sigmoid from channels-last [M,H,W,8]. */
+int mvs_vis_first_cl(const float* entropy, const float* params_host, float* out, int M, int H, int W, void* stream);
+int mvs_vis_last_cl(const float* act, const float* params_host, float* weight, int M, int H, int W, void* stream);
 
 /* ---- A7. 3D-CNN layers: models/module.py:83-159 (Conv3d / Deconv3d blocks), :469-594 --------
  * Channels-last activations.  y = act(conv(x) + shift) (+ skip);  BN (eval) is folded by the

@@ -33,6 +33,8 @@ _SIGNATURES = {
     "mvs_cost_volume_aggregate_tf32": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "mvs_argmax_gather": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "mvs_vis_weight": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "mvs_vis_first_cl": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "mvs_vis_last_cl": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "mvs_conv3d_cl": (c_i, [c_f] * 5 + [c_i] * 11 + [c_f]),
     "mvs_deconv3d_cl": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_conv3d_tc": (c_i, [c_f] * 6 + [c_i] * 11 + [c_f]),

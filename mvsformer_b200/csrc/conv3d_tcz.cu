@@ -15,6 +15,8 @@
 //   * weights of one (kh, channel-slice) group — all kz, kw taps — are fetched once per group and
 //     reused across the depth slices.
 // Operand layouts, descriptors and the virtual-index trick are those of conv3d_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -345,34 +347,62 @@ deconv3d_tcz_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     const int last = nit - 1;
     mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
     tc_fence_after_sync();
+    // Epilogue.  The skip tensor does not depend on the MMAs: its loads for the next group of
+    // accumulators are issued before the current group is drained, so their latency is hidden.
     const int iy = sy[0], ix = sa[0];
     const bool live = iy < d.H && ix < d.W;
-    for (int zi = 0; zi < nz; ++zi) {
+    constexpr int U = 64 / NT;                                  // accumulators per prefetch group (<= 16 float4)
+    const int nacc = nz * 4;
+    float4 skA[U][NT / 4], skB[U][NT / 4];                      // ping-pong register buffers (static indexing)
+    auto out_index = [&](int a) -> size_t {
+        const int zi = a >> 2, cls = a & 3;
+        return ((((size_t)b * d.D + z0 + zi) * d.Ho + 2 * iy + (cls >> 1)) * d.Wo + 2 * ix + (cls & 1)) * d.Cout + co0;
+    };
+    auto prefetch = [&](int a0, float4 (&buf)[U][NT / 4]) {
+        if (!skip || !live) return;
 #pragma unroll
-        for (int cls = 0; cls < 4; ++cls) {
-            float acc[NT];
+        for (int u = 0; u < U; ++u) {
+            if (a0 + u < nacc) {
+                const float4* sp = reinterpret_cast<const float4*>(skip + out_index(a0 + u));
 #pragma unroll
-            for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (zi * 4 + cls) * NT + c0, acc + c0);
-            if (!live) continue;
-            const int oy = 2 * iy + (cls >> 1), ox = 2 * ix + (cls & 1);
-            const size_t o = ((((size_t)b * d.D + z0 + zi) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0;
-#pragma unroll
-            for (int q = 0; q < NT / 4; ++q) {
-                if (co0 + q * 4 >= d.Cout) break;
-                float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-                if (shift) {
-                    const float4 s = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
-                    r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
-                }
-                if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-                if (skip) {
-                    const float4 s = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
-                    r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
-                }
-                r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
-                reinterpret_cast<float4*>(y + o)[q] = r;
+                for (int q = 0; q < NT / 4; ++q)
+                    if (co0 + q * 4 < d.Cout) buf[u][q] = __ldg(sp + q);
             }
         }
+    };
+    auto drain = [&](int a0, float4 (&buf)[U][NT / 4]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (a0 + u < nacc) {                                 // uniform across the CTA
+                float acc[NT];
+#pragma unroll
+                for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (a0 + u) * NT + c0, acc + c0);
+                if (live) {
+                    const size_t o = out_index(a0 + u);
+#pragma unroll
+                    for (int q = 0; q < NT / 4; ++q) {
+                        if (co0 + q * 4 < d.Cout) {
+                            float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+                            if (shift) {
+                                const float4 sft = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                                r.x += sft.x; r.y += sft.y; r.z += sft.z; r.w += sft.w;
+                            }
+                            if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                            if (skip) { r.x += buf[u][q].x; r.y += buf[u][q].y; r.z += buf[u][q].z; r.w += buf[u][q].w; }
+                            r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+                            reinterpret_cast<float4*>(y + o)[q] = r;
+                        }
+                    }
+                }
+            }
+        }
+    };
+    prefetch(0, skA);
+    for (int a0 = 0; a0 < nacc; a0 += 2 * U) {
+        if (a0 + U < nacc) prefetch(a0 + U, skB);
+        drain(a0, skA);
+        if (a0 + 2 * U < nacc) prefetch(a0 + 2 * U, skA);
+        if (a0 + U < nacc) drain(a0 + U, skB);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -411,17 +441,33 @@ static int launch_deconv_tcz(const float* x, const float* w, const float* shift,
     return MVS_OK;
 }
 
-// Depth slices per CTA: the largest divisor of D whose accumulators fit the 512 TMEM columns and
-// whose operand rings fit shared memory.  Chunks of >= 3 slices share one weight buffer per group
-// (2-deep ring); shorter chunks reload weights with every iteration (ring of TZ_STAGES).
-static int pick_zc(int D, int cols_per_slice, size_t a_bytes, size_t bgroup) {
+// Depth slices per CTA.  Candidates are the divisors of D whose accumulators fit TMEM and whose
+// operand rings fit shared memory.  Among them take the largest one that (a) leaves room for
+// several co-resident CTAs per SM (accumulator columns <= max_cols, default 128 of the 512), so
+// one CTA's epilogue overlaps another's MMAs, and (b) still launches >= min_ctas CTAs (default two
+// per SM) so small layers fill the machine; relax (b), then (a), if nothing qualifies.
+// Chunks of >= 3 slices share one weight buffer per group (2-deep ring); shorter chunks reload
+// weights with every iteration (ring of TZ_STAGES).  MVS_TCZ_MAX_COLS / MVS_TCZ_MIN_CTAS override.
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int pick_zc(int D, int cols_per_slice, size_t a_bytes, size_t bgroup, int64_t ctas_per_slice) {
+    const int max_cols = env_int("MVS_TCZ_MAX_COLS", 128);
+    const int min_ctas = env_int("MVS_TCZ_MIN_CTAS", 296);
+    int best_fit = 0, best_cols = 0, best_all = 0;
     for (int zc = D < 8 ? D : 8; zc >= 1; --zc) {
         if (D % zc) continue;
         if (zc * cols_per_slice > 512) continue;
         const int br = zc >= 3 ? 2 : TZ_STAGES;
-        if (a_bytes + (size_t)br * bgroup + 128 <= 227 * 1024) return zc;
+        if (a_bytes + (size_t)br * bgroup + 128 > 227 * 1024) continue;
+        if (!best_fit) best_fit = zc;
+        const bool cols_ok = zc * cols_per_slice <= max_cols;
+        if (cols_ok && !best_cols) best_cols = zc;
+        if (cols_ok && ctas_per_slice * (D / zc) >= min_ctas && !best_all) best_all = zc;
     }
-    return 0;
+    return best_all ? best_all : (best_cols ? best_cols : best_fit);
 }
 
 }  // namespace tc
@@ -446,7 +492,7 @@ extern "C" int mvs_conv3d_tcz(const float* x, const float* w, const float* shift
     d.tiles_per_plane = (int)(((int64_t)d.Ho * d.PW + 127) / 128);
     const size_t a_bytes = (size_t)TZ_STAGES * (d.s2 ? 2 : 1) * (cs / 4) * TZ_SL;
     const size_t bgroup = (size_t)kd * 3 * (cs / 4) * n_tile * 16;
-    d.zc = pick_zc(D, n_tile, a_bytes, bgroup);
+    d.zc = pick_zc(D, n_tile, a_bytes, bgroup, (int64_t)B * d.tiles_per_plane * ((Cout + n_tile - 1) / n_tile));
     if (d.zc == 0) MVS_UNSUPPORTED("mvs_conv3d_tcz: no depth chunking fits D=%d with N tile %d", D, n_tile);
     cudaStream_t st = (cudaStream_t)stream;
 #define MVS_TZ_CASE(CS_, NT_)                                                                          \
@@ -481,7 +527,7 @@ extern "C" int mvs_deconv3d_tcz(const float* x, const float* w, const float* shi
     d.tiles_per_plane = (int)(((int64_t)H * d.PW + 127) / 128);
     const size_t a_bytes = (size_t)TZ_STAGES * (cs / 4) * TZ_SL;
     const size_t bgroup = (size_t)kd * 6 * (cs / 4) * n_tile * 16;
-    d.zc = pick_zc(D, 4 * n_tile, a_bytes, bgroup);
+    d.zc = pick_zc(D, 4 * n_tile, a_bytes, bgroup, (int64_t)B * d.tiles_per_plane * ((Cout + n_tile - 1) / n_tile));
     if (d.zc == 0) MVS_UNSUPPORTED("mvs_deconv3d_tcz: no depth chunking fits D=%d with N tile %d", D, n_tile);
     cudaStream_t st = (cudaStream_t)stream;
 #define MVS_TZD_CASE(CS_, NT_) \

@@ -111,6 +111,26 @@ def vis_weight(entropy_maps, params_host):
     return out
 
 
+def vis_first_cl(entropy_maps, params_host):
+    """[M,H,W] -> channels-last TF32 [M,H,W,16] (first vis layer)."""
+    require_cuda(entropy_maps)
+    m, h, w = entropy_maps.shape
+    out = torch.empty(m, h, w, 16, device=entropy_maps.device, dtype=torch.float32)
+    check(_lib.load().mvs_vis_first_cl(ptr(entropy_maps), params_host.ctypes.data_as(ctypes.c_void_p), ptr(out), m, h, w,
+                                       stream()), "mvs_vis_first_cl")
+    return out
+
+
+def vis_last_cl(act, params_host):
+    """channels-last [M,H,W,8] -> sigmoid(1x1 conv) [M,H,W] (last vis layer)."""
+    require_cuda(act)
+    m, h, w, _ = act.shape
+    out = torch.empty(m, h, w, device=act.device, dtype=torch.float32)
+    check(_lib.load().mvs_vis_last_cl(ptr(act), params_host.ctypes.data_as(ctypes.c_void_p), ptr(out), m, h, w, stream()),
+          "mvs_vis_last_cl")
+    return out
+
+
 def conv3d_cl(x, w_packed, shift, skip, stride, relu=True):
     """x [B,D,H,W,Cin] -> [B,Do,Ho,Wo,Cout]; w_packed [kd,3,3,Cin,Cout]."""
     require_cuda(x, w_packed, shift, skip)

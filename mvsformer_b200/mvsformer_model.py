@@ -64,6 +64,37 @@ class StageNet(nn.Module):
         tensors += [self.vis[3].weight, self.vis[3].bias]
         return self._vis_cache.get(tensors, build)
 
+    def _vis_params_tc(self):
+        """Operands of the tensor-core route: host params of the thin first / last layers and the
+        TF32 operand-order weights of the 16->16 and 16->8 layers (BN folded)."""
+        def build(_):
+            host = self._vis_params_host()
+            first = np.ascontiguousarray(host[:16 * 9 + 16])
+            last = np.ascontiguousarray(host[-9:])
+            mids = []
+            for i in (1, 2):
+                blk = self.vis[i]
+                scale, shift = _bn_scale_shift(blk.bn)
+                w = blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)          # [Co,Ci,3,3]
+                w_packed = w.permute(2, 3, 1, 0).unsqueeze(0).contiguous()              # [kd=1,3,3,Ci,Co]
+                wz, nt = engine.pack_tcz_weights(w_packed, False)
+                mids.append((wz, nt, w.shape[0], shift.contiguous()))
+            return first, mids, last
+        self._vis_params_host()                                   # refreshes the cache key
+        return self._vis_cache.get_derived("tc", build)
+
+    def _vis_weight(self, entropy):
+        """entropy [B,N,H,W] -> visibility weight [B,N,H,W] (models/mvsformer_model.py:91)."""
+        b, n, h, w = entropy.shape
+        maps = entropy.view(b * n, h, w)
+        if config.conv_precision() == "tf32" and engine.tcz_supported(16, 16, b * n, 1):
+            first, mids, last = self._vis_params_tc()
+            x = engine.vis_first_cl(maps, first).view(1, b * n, h, w, 16)
+            for wz, nt, cout, shift in mids:
+                x = engine.conv3d_tcz(x, wz, nt, cout, 1, shift, None, 1, True)
+            return engine.vis_last_cl(x.view(b * n, h, w, 8), last).view(b, n, h, w)
+        return engine.vis_weight(maps, self._vis_params_host()).view(b, n, h, w)
+
     def build_cost_volume(self, features, proj_matrices, depth_values):
         """models/mvsformer_model.py:52-105 -> (volume channels-last [B,D,H,W,G], sim_sum or None,
         entropy [B,N,H,W], vis_weight [B,N,H,W])."""
@@ -79,8 +110,7 @@ class StageNet(nn.Module):
             raise NotImplementedError("StageNet: train-mode forward is not built in this round; call .eval()")
         relproj = engine.relative_projections(proj_matrices)
         entropy, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=not self.training)
-        h, w = entropy.shape[-2:]
-        weight = engine.vis_weight(entropy.view(b * (v - 1), h, w), self._vis_params_host()).view(b, v - 1, h, w)
+        weight = self._vis_weight(entropy)
         volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups,
                                               round_tf32=config.conv_precision() == "tf32")
         return volume, sim, entropy, weight

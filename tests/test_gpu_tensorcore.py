@@ -215,3 +215,30 @@ def test_tcz_shape_rules_fall_back():
     generic tensor-core kernel, not rejected."""
     assert not engine.tcz_supported(64, 64, 2, 3)
     assert engine.tcz_supported(64, 64, 4, 3) and engine.tcz_supported(16, 16, 1, 1)
+
+
+def test_vis_net_tensor_core_route():
+    """StageNet.vis through the TF32 tensor-core route (first / last layers streaming, middle layers as
+    kd = 1 implicit GEMMs with the views as depth axis) vs the oracle's fp32 visibility net."""
+    from mvsformer_b200 import config
+    from mvsformer_b200.mvsformer_model import StageNet
+    from oracle import mvs_oracle as O
+    from tests.helpers import STAGE_ARGS
+    g = S._gen(77)
+    net = StageNet(dict(STAGE_ARGS), 8, 2).eval()
+    sd = S.fill_state_dict(net.state_dict(), seed=5)
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    for (b, n, h, w) in [(1, 4, 40, 56), (2, 3, 17, 130), (1, 10, 24, 32)]:
+        ent = 2.0 * torch.rand(b, n, h, w, generator=g)
+        want = O.vis_weight(ent.view(b * n, 1, h, w), sd, "vis").view(b, n, h, w)
+        old = config.conv_precision()
+        try:
+            config.set_conv_precision("tf32")
+            got = net._vis_weight(ent.to(DEV)).cpu()
+            config.set_conv_precision("fp32")
+            exact = net._vis_weight(ent.to(DEV)).cpu()
+        finally:
+            config.set_conv_precision(old)
+        assert rel_l1(exact, want) < 1e-5
+        assert rel_l1(got, want) < 2e-3
