@@ -119,7 +119,8 @@ class KernelProfiler:
             out = fn(*a, **k)
             e1.record()
             nbytes, flops = cost(out, *a, **k)
-            rec = self.records.setdefault(cls, {"events": [], "bytes": 0, "flops": 0, "launches": 0})
+            name_cls = cls(*a, **k) if callable(cls) else cls
+            rec = self.records.setdefault(name_cls, {"events": [], "bytes": 0, "flops": 0, "launches": 0})
             rec["events"].append((e0, e1))
             rec["bytes"] += nbytes
             rec["flops"] += flops
@@ -176,7 +177,9 @@ class KernelProfiler:
         def deconv_tcz_cost(out, x, w_tcz, n_tile, cout, kd, shift, skip, relu=True):
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (x.numel() // x.shape[-1])
 
-        self._wrap(engine, "conv3d_tcz", "conv3d_tcz", conv_tcz_cost)
+        # kd = 1 calls are the two middle layers of the visibility net
+        self._wrap(engine, "conv3d_tcz", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcz",
+                   conv_tcz_cost)
         self._wrap(engine, "deconv3d_tcz", "deconv3d_tcz", deconv_tcz_cost)
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
@@ -298,9 +301,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def profile_traffic(kernel_family):
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu --set full capture
+    (profiles/r01_traffic.json, written by scripts/summarise_ncu.py); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(kernel_family)
+
+
 def run_engine(args, rank, world, local_rank):
     import torch.distributed as dist
-    from mvsformer_b200 import _lib, engine
+    from mvsformer_b200 import _lib, config, engine
+    from mvsformer_b200.sharding import shard_ref_views
+
+    # bench default: TF32 tensor-core convolutions (cuDNN's default conv math for the reference on a
+    # GPU); tests/test_gpu_tensorcore.py::test_cascade_tf32_meets_north_star_tolerance gates it.
+    config.set_conv_precision(os.environ.get("MVS_CONV_PRECISION", "tf32"))
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -313,7 +331,9 @@ def run_engine(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     net = build_engine(device)
-    feats_h, cams_h, dv_h = host_inputs(HEIGHT, WIDTH, VIEWS, 1234 + rank, pin=True)
+    # each rank owns the reference views i % world == rank of a virtual list; no data-path collective
+    my_views = shard_ref_views(world * (args.steps + args.warmup), rank, world)
+    feats_h, cams_h, dv_h = host_inputs(HEIGHT, WIDTH, VIEWS, 1234 + my_views[0], pin=True)
     feats_d = {k: v.to(device) for k, v in feats_h.items()}
     cams_d = {k: v.to(device) for k, v in cams_h.items()}
     dv_d = dv_h.to(device)
@@ -395,24 +415,25 @@ def run_engine(args, rank, world, local_rank):
     if kd["alg_flops_per_step"] > 100 * kd["alg_bytes_per_step"]:
         achieved = kd["alg_flops_per_step"] / (kd["ms_per_step"] * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None,
-                "note": "fp32 math; peak = %s sustained cuBLAS bf16" % peaks["source"]}
+                "frac": achieved / peaks["bf16_tflops"], "traffic": profile_traffic(dom),
+                "note": "conv math %s; peak = %s sustained cuBLAS bf16 (dense TF32 peak is half of it)" % (conv_mode(), peaks["source"])}
     else:
         achieved = kd["alg_bytes_per_step"] / (kd["ms_per_step"] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "note": "peak = %s copy bandwidth" % peaks["source"]}
+                "frac": achieved / peaks["hbm_gbs"], "traffic": profile_traffic(dom), "note": "peak = %s copy bandwidth" % peaks["source"]}
     roof["avg_launch_ms"] = kd["avg_launch_ms"]
     roof["share_of_step"] = kd["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())
 
     # cost-volume build (pass A + vis net + pass B) against the HBM roofline — the north-star kernel
-    cv_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith("cv_") or k == "vis_net")
+    cv_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith("cv_") or k.startswith("vis_net"))
     cv_bytes = S.cost_volume_algorithmic_bytes(VIEWS, HEIGHT, WIDTH)
     cost_volume = {"ms_per_step": cv_ms, "gvox_per_s": S.voxels_per_ref_view(HEIGHT, WIDTH) / (cv_ms * 1e-3) / 1e9,
                    "alg_bytes": cv_bytes, "achieved_gbs": cv_bytes / (cv_ms * 1e-3) / 1e9,
                    "frac_of_hbm": cv_bytes / (cv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if config.conv_precision() == "fp32" else "f32 (conv MMA operands %s, fp32 accumulate)" % config.conv_precision(),
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,

@@ -443,7 +443,7 @@ static int launch_deconv_tcz(const float* x, const float* w, const float* shift,
 
 // Depth slices per CTA.  Candidates are the divisors of D whose accumulators fit TMEM and whose
 // operand rings fit shared memory.  Among them take the largest one that (a) leaves room for
-// several co-resident CTAs per SM (accumulator columns <= max_cols, default 128 of the 512), so
+// several co-resident CTAs per SM (accumulator columns <= max_cols, default 256 of the 512), so
 // one CTA's epilogue overlaps another's MMAs, and (b) still launches >= min_ctas CTAs (default two
 // per SM) so small layers fill the machine; relax (b), then (a), if nothing qualifies.
 // Chunks of >= 3 slices share one weight buffer per group (2-deep ring); shorter chunks reload
@@ -454,7 +454,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int pick_zc(int D, int cols_per_slice, size_t a_bytes, size_t bgroup, int64_t ctas_per_slice) {
-    const int max_cols = env_int("MVS_TCZ_MAX_COLS", 128);
+    const int max_cols = env_int("MVS_TCZ_MAX_COLS", 256);
     const int min_ctas = env_int("MVS_TCZ_MIN_CTAS", 296);
     int best_fit = 0, best_cols = 0, best_all = 0;
     for (int zc = D < 8 ? D : 8; zc >= 1; --zc) {
