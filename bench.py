@@ -180,6 +180,11 @@ class KernelProfiler:
         # kd = 1 calls are the two middle layers of the visibility net
         self._wrap(engine, "conv3d_tcz", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcz",
                    conv_tcz_cost)
+        def conv_tcr_cost(out, x, w_tcr, n_tile, cout, kd, shift, skip, relu=True):
+            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
+
+        self._wrap(engine, "conv3d_tcr", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcr",
+                   conv_tcr_cost)
         self._wrap(engine, "deconv3d_tcz", "deconv3d_tcz", deconv_tcz_cost)
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)

@@ -128,6 +128,10 @@ int mvs_conv3d_tcz(const float* x, const float* w, const float* shift, const flo
                    int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
 int mvs_deconv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
                      int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
+/* Row-tiled variant of mvs_conv3d_tcz for wide stride-1 layers (Cin <= 32): R rows x 128 columns x zc
+ * slices per CTA, all taps resident.  Weights (TF32): [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4]. */
+int mvs_conv3d_tcr(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                   int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
 /* Diagnostic: nk MMAs (M=128, N, K=8) over caller-made shared-memory operand images with explicit
  * descriptor strides; dumps the 128 x N accumulator (used by tests to pin the operand layouts). */
 int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,

@@ -72,9 +72,7 @@ __device__ __forceinline__ void project(const RelProj& m, const PixelRay& ray, f
 }
 
 // CPG channels per group (G = 8 groups), DG depth groups x KPT hypotheses per thread (D = DG*KPT),
-// BW x BH source box, NCH channel chunks.  Work items (view, chunk) are software-pipelined over two
-// tile buffers: while item w is sampled, the TMA load of item w+1 (next chunk, or chunk 0 of the
-// next view, whose geometry is computed first) is already in flight.
+// BW x BH source box, NCH channel chunks.
 template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM>
 __global__ void __launch_bounds__(256)
 cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
@@ -84,16 +82,15 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     constexpr int CPC = PASS_B ? CPG : CPG / NCH;                // c' per chunk
     constexpr int GPC = PASS_B ? G / NCH : G;                    // groups per chunk
     constexpr int PLANE = BH * BW;
-    constexpr int TILE = CC * PLANE;                             // floats per tile buffer
     static_assert(CPC * GPC == CC && CPC >= 1 && GPC >= 1, "chunking");
 
     extern __shared__ __align__(128) uint8_t smem[];
-    float* tiles = reinterpret_cast<float*>(smem);               // [2][CC][BH][BW]
-    float* s_ref = tiles + 2 * TILE;                             // [C][TP]
+    float* tile = reinterpret_cast<float*>(smem);                // [CC][BH][BW]
+    float* s_ref = tile + CC * PLANE;                            // [C][TP]
     float* s_col = s_ref + C * TP;                               // [D][TP] (pass A)
-    float* s_red = s_col + (PASS_B ? 0 : D * TP);                // [8][2]
+    float* s_red = s_col + (PASS_B ? 0 : D * TP);                // [8][4]
     int* s_org = reinterpret_cast<int*>(s_red + 32);             // bx0, by0
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_org + 2);     // [2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_org + 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dg = tid / TP, pix = tid - dg * TP;
@@ -106,7 +103,7 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     const float half_w = (float)((p.W - 1) / 2.0), half_h = (float)((p.H - 1) / 2.0);
     const float inv_cpg = 1.0f / (float)CPG;
 
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     for (int i = tid; i < C * TP; i += 256) {
         const int c = i / TP, q = i - c * TP;
         const int qx = blockIdx.x * 32 + (q & 31), qy = blockIdx.y * TH + (q >> 5);
@@ -134,13 +131,14 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
         for (int g = 0; g < (PASS_B ? G : 1); ++g) acc[g][j] = 0.0f;
     }
     float wsum = 0.0f;
+    uint32_t phase = 0;
 
-    // Geometry of one source view: sample positions of this thread's hypotheses, the CTA-wide
-    // bounding-box origin (two block barriers), and the per-hypothesis cache (box offset or -1 =
-    // footprint outside the box, bilinear fractions).
-    auto geometry = [&](int v, int (&off)[KPT], float (&fx)[KPT], float (&fy)[KPT], int& bx0, int& by0) {
+    for (int v = 0; v < p.N; ++v) {
         const RelProj m = load_relproj(p.relproj + ((int64_t)b * p.N + v) * 12);
         const PixelRay ray = pixel_ray(m, (float)x, (float)y);
+        const float* src = ref + (int64_t)(v + 1) * C * hw;
+
+        // ---- 1. sample positions of my hypotheses and the CTA's bounding box -------------------
         float ix[KPT], iy[KPT];
         float bminx = FLT_MAX, bminy = FLT_MAX;
 #pragma unroll
@@ -156,18 +154,25 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
             bminy = fminf(bminy, __shfl_xor_sync(0xffffffffu, bminy, o));
         }
         if (lane == 0) { s_red[warp * 2] = bminx; s_red[warp * 2 + 1] = bminy; }
-        __syncthreads();
+        __syncthreads();                                          // also: previous view's tile fully consumed
         if (tid == 0) {
             float mx = FLT_MAX, my = FLT_MAX;
             for (int w = 0; w < 8; ++w) { mx = fminf(mx, s_red[w * 2]); my = fminf(my, s_red[w * 2 + 1]); }
             // The TMA unit requires the innermost start coordinate to be 16-byte aligned (a multiple of 4
             // floats; negative values are fine) — measured on B200: any other value raises "illegal
             // instruction".  Round the box origin down; BW carries the 3 columns of slack.
-            s_org[0] = mx < 1e7f ? ((int)floorf(mx) & ~3) : 0;
-            s_org[1] = my < 1e7f ? (int)floorf(my) : 0;
+            const int bx0 = mx < 1e7f ? ((int)floorf(mx) & ~3) : 0;
+            const int by0 = my < 1e7f ? (int)floorf(my) : 0;
+            s_org[0] = bx0; s_org[1] = by0;
+            mbar_expect_tx(bar, CC * PLANE * 4);
+            tma_load_5d(tile, &tmap, bar, bx0, by0, 0, 0, b * p.V + v + 1);
         }
         __syncthreads();
-        bx0 = s_org[0]; by0 = s_org[1];
+        const int bx0 = s_org[0], by0 = s_org[1];
+
+        // ---- 2. per-hypothesis cache: box offset (or -1 = outside the box) and fractions ---------
+        int off[KPT];
+        float fx[KPT], fy[KPT];
 #pragma unroll
         for (int j = 0; j < KPT; ++j) {
             const bool sane = live && fabsf(ix[j]) < 1e7f && fabsf(iy[j]) < 1e7f;
@@ -176,23 +181,6 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
             const int lx = sane ? (int)x0 - bx0 : -1, ly = sane ? (int)y0 - by0 : -1;
             off[j] = (lx >= 0 && lx + 1 < BW && ly >= 0 && ly + 1 < BH) ? ly * BW + lx : -1;
         }
-    };
-    auto issue_tma = [&](int item, int v, int ch, int bx0, int by0) {      // thread 0 only
-        mbar_expect_tx(&bars[item & 1], TILE * 4);
-        tma_load_5d(tiles + (size_t)(item & 1) * TILE, &tmap, &bars[item & 1], bx0, by0, PASS_B ? 0 : ch * CPC,
-                    PASS_B ? ch * GPC : 0, b * p.V + v + 1);
-    };
-
-    int off[KPT], offn[KPT];
-    float fx[KPT], fy[KPT], fxn[KPT], fyn[KPT];
-    int bx0, by0, bx0n = 0, by0n = 0;
-    geometry(0, off, fx, fy, bx0, by0);
-    if (tid == 0) issue_tma(0, 0, 0, bx0, by0);
-    uint32_t phase0 = 0, phase1 = 0;
-    int item = 0;
-
-    for (int v = 0; v < p.N; ++v) {
-        const float* src = ref + (int64_t)(v + 1) * C * hw;
         float wv = 0.0f;
         if (PASS_B) {
             wv = live ? __ldg(p.vis_weight + ((int64_t)b * p.N + v) * hw + pixoff) : 0.0f;
@@ -202,21 +190,18 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
 #pragma unroll
         for (int j = 0; j < KPT; ++j) sview[j] = 0.0f;
 
+        // ---- 3. channel chunks -------------------------------------------------------------------
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch, ++item) {
-            // ---- prefetch the next work item into the other buffer (its last reader was item-1) ----------
-            if (ch + 1 < NCH) {
-                __syncthreads();
-                if (tid == 0) issue_tma(item + 1, v, ch + 1, bx0, by0);
-            } else if (v + 1 < p.N) {
-                geometry(v + 1, offn, fxn, fyn, bx0n, by0n);              // contains the block barriers
-                if (tid == 0) issue_tma(item + 1, v + 1, 0, bx0n, by0n);
-            } else {
-                __syncthreads();
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (ch > 0) {
+                __syncthreads();                                  // previous chunk consumed
+                if (tid == 0) {
+                    mbar_expect_tx(bar, CC * PLANE * 4);
+                    tma_load_5d(tile, &tmap, bar, bx0, by0, PASS_B ? 0 : ch * CPC, PASS_B ? ch * GPC : 0, b * p.V + v + 1);
+                }
             }
-            // ---- wait for this item's tile ------------------------------------------------------------------
-            if (item & 1) { mbar_wait(&bars[1], phase1); phase1 ^= 1u; } else { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
-            const float* tile = tiles + (size_t)(item & 1) * TILE;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
             const int cp0 = PASS_B ? 0 : ch * CPC, g0 = PASS_B ? ch * GPC : 0;
 #pragma unroll
             for (int j = 0; j < KPT; ++j) {
@@ -256,8 +241,6 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
                     }
                 } else {
                     // predicated global path: the reference's per-tap bounds checks, any geometry
-                    const RelProj m = load_relproj(p.relproj + ((int64_t)b * p.N + v) * 12);
-                    const PixelRay ray = pixel_ray(m, (float)x, (float)y);
                     const float dep = __ldg(p.depth + ((int64_t)b * D + dg * KPT + j) * hw + pixoff);
                     const Taps tp = make_taps(m, ray, dep, p.H, p.W, half_w, half_h);
                     if (PASS_B) {
@@ -294,7 +277,7 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
             }
         }
 
-        // ---- pass A: entropy of softmax over the full depth column ---------------------------------------
+        // ---- 4. pass A: entropy of softmax over the full depth column ---------------------------------
         if (!PASS_B) {
 #pragma unroll
             for (int j = 0; j < KPT; ++j) s_col[(dg * KPT + j) * TP + pix] = sview[j] * inv_cpg;
@@ -312,10 +295,6 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
                 p.entropy[((int64_t)b * p.N + v) * hw + pixoff] = ent;
             }
         }
-        // the next view's geometry becomes current
-#pragma unroll
-        for (int j = 0; j < KPT; ++j) { off[j] = offn[j]; fx[j] = fxn[j]; fy[j] = fyn[j]; }
-        bx0 = bx0n; by0 = by0n;
     }
 
     if (!live) return;
@@ -378,7 +357,7 @@ template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool S
 static int launch(const K1Params& p, int B, cudaStream_t st) {
     constexpr int G = 8, C = G * CPG, D = DG * KPT, TP = 256 / DG, TH = 8 / DG, CC = C / NCH;
     constexpr int CPC = PASS_B ? CPG : CPG / NCH, GPC = PASS_B ? G / NCH : G;
-    const size_t smem = (size_t)(2 * CC * BH * BW + C * TP + (PASS_B ? 0 : D * TP) + 32 + 2) * 4 + 32;
+    const size_t smem = (size_t)(CC * BH * BW + C * TP + (PASS_B ? 0 : D * TP) + 32 + 2) * 4 + 16;
     CUtensorMap map;
     int rc = make_feature_map(&map, p.feat, B * p.V, G, CPG, p.H, p.W, BW, BH, CPC, GPC);
     if (rc) return rc;
@@ -394,8 +373,8 @@ static int launch(const K1Params& p, int B, cudaStream_t st) {
 // They only steer how many samples take the fast path; any geometry stays correct.
 template <bool PASS_B, bool SIM>
 static int dispatch(const K1Params& p, int B, int C, int D, cudaStream_t st) {
-    if (C == 64 && D == 32) return launch<8, 4, 8, 112, 8, 8, PASS_B, SIM>(p, B, st);
-    if (C == 32 && D == 16) return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
+    if (C == 64 && D == 32) return launch<8, 4, 8, 112, 8, 4, PASS_B, SIM>(p, B, st);
+    if (C == 32 && D == 16) return launch<4, 2, 8, 64, 12, 1, PASS_B, SIM>(p, B, st);
     if (C == 16 && D == 8) return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
     if (C == 8 && D == 4) return launch<1, 1, 4, 48, 16, 1, PASS_B, SIM>(p, B, st);
     return 1;   // not covered: caller uses the generic kernels

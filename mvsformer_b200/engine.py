@@ -446,3 +446,38 @@ def deconv3d_tcz(x, w_tcz, n_tile, cout, kd, shift, skip, relu=True):
     check(_lib.load().mvs_deconv3d_tcz(ptr(x), ptr(w_tcz), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
                                        1 if relu else 0, stream()), "mvs_deconv3d_tcz")
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# row-tiled TF32 kernel (conv3d_tcr) for wide stride-1 layers
+# ------------------------------------------------------------------------------------------------
+def tcr_supported(cin, cout, w, stride2=False):
+    """Stride-1 layers with Cin <= 32 whose width wastes <= 15 % in 128-column blocks."""
+    if stride2 or cin not in (8, 16, 32) or cout % 8 or cout > 32:
+        return False
+    blocks = (w + 127) // 128
+    return (blocks * 128 - w) <= 0.15 * w
+
+
+def pack_tcr_weights(w_packed):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4], TF32-rounded."""
+    kd, _, _, cin, cout = w_packed.shape
+    nt = 16 if cout <= 16 else 32
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    w = w.reshape(kd, 3, 3, cin // 4, 4, ntiles, nt).permute(5, 0, 1, 2, 3, 6, 4).contiguous()
+    return round_tf32(w), nt
+
+
+def conv3d_tcr(x, w_tcr, n_tile, cout, kd, shift, skip, relu=True):
+    require_cuda(x, w_tcr, shift, skip)
+    b, d, h, w, cin = x.shape
+    y = torch.empty(b, d, h, w, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_tcr(ptr(x), ptr(w_tcr), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
+                                     1 if relu else 0, stream()), "mvs_conv3d_tcr")
+    return y

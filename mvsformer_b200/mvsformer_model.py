@@ -78,7 +78,8 @@ class StageNet(nn.Module):
                 w = blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)          # [Co,Ci,3,3]
                 w_packed = w.permute(2, 3, 1, 0).unsqueeze(0).contiguous()              # [kd=1,3,3,Ci,Co]
                 wz, nt = engine.pack_tcz_weights(w_packed, False)
-                mids.append((wz, nt, w.shape[0], shift.contiguous()))
+                wr, ntr = engine.pack_tcr_weights(w_packed)
+                mids.append((wz, nt, w.shape[0], shift.contiguous(), wr, ntr))
             return first, mids, last
         self._vis_params_host()                                   # refreshes the cache key
         return self._vis_cache.get_derived("tc", build)
@@ -90,8 +91,11 @@ class StageNet(nn.Module):
         if config.conv_precision() == "tf32" and engine.tcz_supported(16, 16, b * n, 1):
             first, mids, last = self._vis_params_tc()
             x = engine.vis_first_cl(maps, first).view(1, b * n, h, w, 16)
-            for wz, nt, cout, shift in mids:
-                x = engine.conv3d_tcz(x, wz, nt, cout, 1, shift, None, 1, True)
+            for wz, nt, cout, shift, wr, ntr in mids:
+                if engine.tcr_supported(16, cout, w):
+                    x = engine.conv3d_tcr(x, wr, ntr, cout, 1, shift, None, True)
+                else:
+                    x = engine.conv3d_tcz(x, wz, nt, cout, 1, shift, None, 1, True)
             return engine.vis_last_cl(x.view(b * n, h, w, 8), last).view(b, n, h, w)
         return engine.vis_weight(maps, self._vis_params_host()).view(b, n, h, w)
 

@@ -242,3 +242,23 @@ def test_vis_net_tensor_core_route():
             config.set_conv_precision(old)
         assert rel_l1(exact, want) < 1e-5
         assert rel_l1(got, want) < 2e-3
+
+
+TCR_CASES = [(16, 16, 3, 4, 6, 128), (16, 16, 1, 4, 9, 256), (16, 8, 1, 5, 7, 130), (32, 32, 3, 4, 5, 128), (8, 16, 3, 3, 4, 140),
+             (16, 32, 3, 8, 3, 128), (16, 16, 3, 1, 2, 384)]
+
+
+@pytest.mark.parametrize("cin,cout,kd,D,H,W", TCR_CASES)
+def test_conv3d_tcr(cin, cout, kd, D, H, W):
+    g = S._gen(cin * 100 + cout + kd + W + D + 1)     # includes partial 128-column blocks (W = 130, 140)
+    w = engine.round_tf32(torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = engine.round_tf32(torch.randn(2, cin, D, H, W, generator=g))
+    want = torch.relu(F.conv3d(x.double(), w.double(), padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    wr, nt = engine.pack_tcr_weights(w.permute(2, 3, 4, 1, 0).contiguous().to(DEV))
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.conv3d_tcr(x_cl, wr, nt, cout, kd, shift.to(DEV), skip_cl, relu=True).permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want + skip.double()) < 5e-4
