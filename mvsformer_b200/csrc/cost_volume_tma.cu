@@ -73,8 +73,9 @@ __device__ __forceinline__ void project(const RelProj& m, const PixelRay& ray, f
 
 // CPG channels per group (G = 8 groups), DG depth groups x KPT hypotheses per thread (D = DG*KPT),
 // BW x BH source box, NCH channel chunks.
-template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM>
-__global__ void __launch_bounds__(256)
+// MINB = CTAs per SM the register allocation must allow (co-resident CTAs hide each other's TMA waits).
+template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, int MINB = (CPG == 1 ? 3 : 2)>
+__global__ void __launch_bounds__(256, MINB)
 cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     constexpr int G = 8, C = G * CPG, D = DG * KPT;
     constexpr int TP = 256 / DG, TH = 8 / DG;                    // pixels per CTA, tile height (width 32)
@@ -374,7 +375,7 @@ static int launch(const K1Params& p, int B, cudaStream_t st) {
 template <bool PASS_B, bool SIM>
 static int dispatch(const K1Params& p, int B, int C, int D, cudaStream_t st) {
     if (C == 64 && D == 32) return launch<8, 4, 8, 112, 8, 4, PASS_B, SIM>(p, B, st);
-    if (C == 32 && D == 16) return launch<4, 2, 8, 64, 12, 1, PASS_B, SIM>(p, B, st);
+    if (C == 32 && D == 16) return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
     if (C == 16 && D == 8) return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
     if (C == 8 && D == 4) return launch<1, 1, 4, 48, 16, 1, PASS_B, SIM>(p, B, st);
     return 1;   // not covered: caller uses the generic kernels
