@@ -381,7 +381,7 @@ def run_engine(args, rank, world, local_rank):
             sampler.start()
         ms_total, launches = timed(step_resident, args.steps)
         clocks = sampler.stop() if rank == 0 else None
-        run_e2e(max(2, args.warmup // 2))
+        run_e2e(max(3, args.warmup))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -22,6 +22,8 @@
 // pass B chunks over groups.  Both are boxes of the same 5-D tensor map.
 #include <cuda.h>
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -372,12 +374,35 @@ static int launch(const K1Params& p, int B, cudaStream_t st) {
 
 // Box sizes: 32-pixel-wide tile + the sweep of the hypotheses along the epipolar line + slack.
 // They only steer how many samples take the fast path; any geometry stays correct.
+// Depth groups per stage (threads = 256 / DG pixels x DG groups).  More groups = fewer hypotheses and
+// registers per thread, more and smaller CTAs (better wave quantisation on 148 SMs).  Defaults were
+// measured on B200; MVS_K1_DG="s1,s2,s3,s4" overrides them for experiments.
+static void depth_groups(int dg[4]) {
+    dg[0] = 8; dg[1] = 2; dg[2] = 1; dg[3] = 1;
+    const char* e = getenv("MVS_K1_DG");
+    if (e) sscanf(e, "%d,%d,%d,%d", &dg[0], &dg[1], &dg[2], &dg[3]);
+}
+
 template <bool PASS_B, bool SIM>
 static int dispatch(const K1Params& p, int B, int C, int D, cudaStream_t st) {
-    if (C == 64 && D == 32) return launch<8, 4, 8, 112, 8, 4, PASS_B, SIM>(p, B, st);
-    if (C == 32 && D == 16) return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
-    if (C == 16 && D == 8) return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
-    if (C == 8 && D == 4) return launch<1, 1, 4, 48, 16, 1, PASS_B, SIM>(p, B, st);
+    int dg[4];
+    depth_groups(dg);
+    if (C == 64 && D == 32) {
+        if (dg[0] == 4) return launch<8, 4, 8, 112, 8, 4, PASS_B, SIM>(p, B, st);
+        return launch<8, 8, 4, 112, 8, 4, PASS_B, SIM>(p, B, st);
+    }
+    if (C == 32 && D == 16) {
+        if (dg[1] == 4) return launch<4, 4, 4, 64, 8, 2, PASS_B, SIM>(p, B, st);
+        return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
+    }
+    if (C == 16 && D == 8) {
+        if (dg[2] == 2) return launch<2, 2, 4, 48, 12, 1, PASS_B, SIM>(p, B, st);
+        return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
+    }
+    if (C == 8 && D == 4) {
+        if (dg[3] == 2) return launch<1, 2, 2, 48, 12, 1, PASS_B, SIM>(p, B, st);
+        return launch<1, 1, 4, 48, 16, 1, PASS_B, SIM>(p, B, st);
+    }
     return 1;   // not covered: caller uses the generic kernels
 }
 
