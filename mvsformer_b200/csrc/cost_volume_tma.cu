@@ -378,7 +378,7 @@ static int launch(const K1Params& p, int B, cudaStream_t st) {
 // registers per thread, more and smaller CTAs (better wave quantisation on 148 SMs).  Defaults were
 // measured on B200; MVS_K1_DG="s1,s2,s3,s4" overrides them for experiments.
 static void depth_groups(int dg[4]) {
-    dg[0] = 8; dg[1] = 2; dg[2] = 1; dg[3] = 1;
+    dg[0] = 8; dg[1] = 4; dg[2] = 2; dg[3] = 1;
     const char* e = getenv("MVS_K1_DG");
     if (e) sscanf(e, "%d,%d,%d,%d", &dg[0], &dg[1], &dg[2], &dg[3]);
 }
@@ -392,12 +392,12 @@ static int dispatch(const K1Params& p, int B, int C, int D, cudaStream_t st) {
         return launch<8, 8, 4, 112, 8, 4, PASS_B, SIM>(p, B, st);
     }
     if (C == 32 && D == 16) {
-        if (dg[1] == 4) return launch<4, 4, 4, 64, 8, 2, PASS_B, SIM>(p, B, st);
-        return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
+        if (dg[1] == 2) return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
+        return launch<4, 4, 4, 64, 8, 2, PASS_B, SIM>(p, B, st);
     }
     if (C == 16 && D == 8) {
-        if (dg[2] == 2) return launch<2, 2, 4, 48, 12, 1, PASS_B, SIM>(p, B, st);
-        return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
+        if (dg[2] == 1) return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
+        return launch<2, 2, 4, 48, 12, 1, PASS_B, SIM>(p, B, st);
     }
     if (C == 8 && D == 4) {
         if (dg[3] == 2) return launch<1, 2, 2, 48, 12, 1, PASS_B, SIM>(p, B, st);
