@@ -328,6 +328,8 @@ def run_engine(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's optional version/debug banner goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
@@ -452,7 +454,7 @@ def run_engine(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "api": "mvsformer_b200.pipeline.StreamedCascade.run (copy stream prefetch + pinned result ring)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cost_volume": cost_volume,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "cost_volume": cost_volume,
             "kernels": kernels}
     if world == 1 and not args.no_cpu_baseline:
         threads = best_thread_count()
