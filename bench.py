@@ -350,14 +350,15 @@ def run_engine(args, rank, world, local_rank):
     def step_resident():
         return net(feats_d, cams_d, dv_d, tmp=tmp)
 
-    from mvsformer_b200.pipeline import StreamedCascade
+    from mvsformer_b200.pipeline import PackedSample, StreamedCascade
     streamer = StreamedCascade(net, device, tmp)
+    packed = PackedSample(feats_h, cams_h, dv_h)          # one pinned buffer -> one DMA per reference view
 
     def run_e2e(steps):
         """The public host-to-host call: pinned HOST features in, HOST depth + confidence out;
         uploads of view i+1 and downloads of view i-1 overlap the compute of view i."""
         checksum = 0.0
-        for depth_h, conf_h in streamer.run((feats_h, cams_h, dv_h) for _ in range(steps)):
+        for depth_h, conf_h in streamer.run(packed for _ in range(steps)):
             checksum += float(depth_h[0, 0, 0])          # the caller touches every result
         return checksum
 

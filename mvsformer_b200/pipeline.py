@@ -15,6 +15,35 @@ probability volumes the reference's ``tensor2numpy(outputs)`` drags along (test.
 import torch
 
 
+class PackedSample:
+    """One reference view's inputs packed into a single pinned host buffer, so the upload is ONE
+    DMA transfer instead of one per tensor (per-copy gaps cost ~10 % of PCIe bandwidth at 531 MB)."""
+
+    def __init__(self, features, proj_matrices, depth_values):
+        parts = [("f", k, v) for k, v in features.items()] + [("c", k, v) for k, v in proj_matrices.items()] + \
+                [("d", "", depth_values)]
+        self.layout, total = [], 0
+        for kind, key, t in parts:
+            n = t.numel()
+            self.layout.append((kind, key, tuple(t.shape), total, n))
+            total += (n + 63) // 64 * 64                      # keep every tensor 256-byte aligned
+        self.flat = torch.empty(total, dtype=torch.float32).pin_memory()
+        for (kind, key, shape, off, n), (_, _, t) in zip(self.layout, parts):
+            self.flat[off:off + n].copy_(t.reshape(-1).float())
+
+    def unpack(self, flat):
+        feats, cams, dv = {}, {}, None
+        for kind, key, shape, off, n in self.layout:
+            view = flat[off:off + n].view(shape)
+            if kind == "f":
+                feats[key] = view
+            elif kind == "c":
+                cams[key] = view
+            else:
+                dv = view
+        return feats, cams, dv
+
+
 class StreamedCascade:
     def __init__(self, net, device, tmp, ring=2):
         self.net = net
@@ -27,9 +56,18 @@ class StreamedCascade:
         self.d2h_bytes = 0
 
     def _upload(self, sample):
-        """sample = (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
-        feats, cams, dv = sample
+        """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
         main = torch.cuda.current_stream(self.device)
+        if isinstance(sample, PackedSample):
+            with torch.cuda.stream(self.copy_stream):
+                dflat = sample.flat.to(self.device, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_stream)
+            dflat.record_stream(main)
+            f, c, d = sample.unpack(dflat)
+            self.h2d_bytes = 4 * sample.flat.numel()
+            return f, c, d, ready
+        feats, cams, dv = sample
         with torch.cuda.stream(self.copy_stream):
             f = {k: v.to(self.device, non_blocking=True) for k, v in feats.items()}
             c = {k: v.to(self.device, non_blocking=True) for k, v in cams.items()}

@@ -312,3 +312,54 @@ def test_full_size_properties():
     v1 = net4.build_cost_volume(f4, c4, h4)[0]
     v2 = net4.build_cost_volume(f4[:, perm].contiguous(), c4[:, perm].contiguous(), h4)[0]
     assert rel_l1(v2, v1) < 1e-6
+
+
+@pytest.mark.parametrize("batch,views,height,width", [(1, 2, 64, 96), (2, 11, 64, 128), (1, 4, 64, 104)])
+def test_stagenet_odd_shapes_vs_oracle(batch, views, height, width):
+    """Single source view, 10 source views (T&T), batch 2, and a width whose stage-4 row is not a
+    multiple of 32 / TMA-friendly (generic kernels): every stage against the oracle."""
+    for s in (0, 3):
+        h, w = S.stage_hw(height, width, s)
+        if s == 0 and (h % 8 or w % 8):
+            continue
+        feats = S.make_features(batch, views, height, width, stages=(s,), seed=31 + s)["stage%d" % (s + 1)]
+        cams = S.make_cameras(batch, views, height, width)["stage%d" % (s + 1)]
+        hyp = S.narrow_hypotheses(s, height, width, batch)
+        net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+        sd = S.fill_state_dict(net.state_dict(), seed=s)
+        net.load_state_dict(sd)
+        want = O.stage_forward(feats, cams, hyp, sd, S.NDEPTHS[s], S.EVAL_TMP[s])
+        out = net.to(DEV)(cu(feats), cu(cams), cu(hyp), tmp=list(S.EVAL_TMP))
+        assert rel_l1(out["prob_volume_pre"].cpu(), want["prob_volume_pre"]) < 5e-5
+        assert rel_l1(out["depth"].cpu(), want["depth"]) < 1e-5
+        assert rel_l1(out["photometric_confidence"].cpu(), want["photometric_confidence"]) < 5e-5
+
+
+def test_half_precision_features_are_upcast():
+    """AMP callers hand fp16 features (mvsformer_model.py:68,78 upcasts to fp32 inside autocast(False))."""
+    s, height, width = 3, 64, 96
+    feats = S.make_features(1, 3, height, width, stages=(s,))["stage4"].half()
+    cams = S.make_cameras(1, 3, height, width)["stage4"]
+    hyp = S.narrow_hypotheses(s, height, width, 1)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+    sd = S.fill_state_dict(net.state_dict(), seed=s)
+    net.load_state_dict(sd)
+    want = O.stage_forward(feats.float(), cams, hyp, sd, S.NDEPTHS[s], S.EVAL_TMP[s])
+    out = net.to(DEV)(cu(feats), cu(cams), cu(hyp), tmp=list(S.EVAL_TMP))
+    assert rel_l1(out["depth"].cpu(), want["depth"]) < 1e-5
+
+
+def test_non_contiguous_feature_views():
+    """features assembled by torch.stack of per-view tensors with a non-dense batch stride fall back to
+    the generic (non-TMA) kernels and give the same volume."""
+    s, height, width = 2, 64, 96
+    feats = S.make_features(2, 3, height, width, stages=(s,))["stage3"]
+    padded = torch.zeros(2, 4, *feats.shape[2:])
+    padded[:, :3] = feats
+    view = padded.to(DEV)[:, :3]                      # batch stride = 4*C*h*w, view stride = C*h*w
+    cams = S.make_cameras(2, 3, height, width)["stage3"]
+    hyp = S.narrow_hypotheses(s, height, width, 2)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval().to(DEV)
+    a = net.build_cost_volume(view, cu(cams), cu(hyp))[0]
+    b = net.build_cost_volume(cu(feats), cu(cams), cu(hyp))[0]
+    assert torch.equal(a, b)
