@@ -52,6 +52,8 @@ class StreamedCascade:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ring = ring
         self._out = None
+        self._dev_ring = None            # [(device flat buffer, "consumed" event)] for PackedSample uploads
+        self._up = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -59,14 +61,22 @@ class StreamedCascade:
         """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
         main = torch.cuda.current_stream(self.device)
         if isinstance(sample, PackedSample):
+            # persistent device staging ring (no allocator traffic): slot i % 2 is overwritten only
+            # after the compute that read it (two uploads ago) has been enqueued and finished
+            n = sample.flat.numel()
+            if self._dev_ring is None or self._dev_ring[0][0].numel() != n:
+                self._dev_ring = [[torch.empty(n, dtype=torch.float32, device=self.device), None] for _ in range(2)]
+            slot = self._dev_ring[self._up % 2]
+            self._up += 1
             with torch.cuda.stream(self.copy_stream):
-                dflat = sample.flat.to(self.device, non_blocking=True)
+                if slot[1] is not None:
+                    self.copy_stream.wait_event(slot[1])
+                slot[0].copy_(sample.flat, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
-            dflat.record_stream(main)
-            f, c, d = sample.unpack(dflat)
-            self.h2d_bytes = 4 * sample.flat.numel()
-            return f, c, d, ready
+            f, c, d = sample.unpack(slot[0])
+            self.h2d_bytes = 4 * n
+            return f, c, d, ready, slot
         feats, cams, dv = sample
         with torch.cuda.stream(self.copy_stream):
             f = {k: v.to(self.device, non_blocking=True) for k, v in feats.items()}
@@ -77,7 +87,7 @@ class StreamedCascade:
         for t in list(f.values()) + list(c.values()) + [d]:
             t.record_stream(main)                      # consumed on the compute stream
         self.h2d_bytes = sum(4 * v.numel() for v in feats.values()) + sum(4 * v.numel() for v in cams.values()) + 4 * dv.numel()
-        return f, c, d, ready
+        return f, c, d, ready, None
 
     def _ring_buffers(self, depth, conf):
         if self._out is None or self._out[0][0].shape != depth.shape:
@@ -99,11 +109,14 @@ class StreamedCascade:
         i = 0
         with torch.no_grad():
             while staged is not None:
-                f, c, d, ready = staged
+                f, c, d, ready, slot = staged
                 nxt = next(it, None)
                 staged = self._upload(nxt) if nxt is not None else None      # overlaps with this view's compute
                 main.wait_event(ready)
                 out = self.net(f, c, d, tmp=self.tmp)
+                if slot is not None:                                         # staging slot may be refilled after this
+                    slot[1] = torch.cuda.Event()
+                    slot[1].record(main)
                 bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
                 hd, hc, done = bufs[i % self.ring]
                 hd.copy_(out["refined_depth"], non_blocking=True)
