@@ -191,7 +191,7 @@ class KernelProfiler:
         self._wrap(engine, "conv3d_tc", "conv3d_tc", conv_tc_cost)
         self._wrap(engine, "deconv3d_tc", "deconv3d_tc", deconv_tc_cost)
         for name in ("prob_conv_cl", "regression_head", "argmax_gather", "init_range", "schedule_inverse_range",
-                     "confidence_accumulate", "relative_projections"):
+                     "confidence_accumulate", "confidence_upsample_accumulate", "relative_projections"):
             self._wrap(engine, name, "head+schedule", io_cost)
 
     def uninstall(self, engine):

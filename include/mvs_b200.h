@@ -171,6 +171,10 @@ int mvs_schedule_range(const float* depth, const float* interval, float* out, in
 /* Nearest-neighbour upsample + accumulate of the per-stage confidence (mvsformer_model.py:438-442):
  * acc[B,H,W] += scale * conf[B,h,w] (nearest, F.interpolate semantics). */
 int mvs_confidence_accumulate(const float* conf, int h, int w, float* acc, int B, int H, int W, float scale, void* stream);
+/* Same in one pass, also writing the nearest-upsampled stage confidence up[B,H,W] (the value the
+ * reference stores back into outputs_stage['photometric_confidence'], mvsformer_model.py:439-441). */
+int mvs_confidence_upsample_accumulate(const float* conf, int h, int w, float* up, float* acc, int B, int H, int W,
+                                       float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "mvs_schedule_inverse_range": (c_i, [c_f, c_f, c_i, c_fl, c_f] + [c_i] * 4 + [c_f]),
     "mvs_schedule_range": (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f]),
     "mvs_confidence_accumulate": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_fl, c_f]),
+    "mvs_confidence_upsample_accumulate": (c_i, [c_f, c_i, c_i, c_f, c_f, c_i, c_i, c_i, c_fl, c_f]),
 }
 
 

@@ -87,8 +87,6 @@ conv3d_tcz_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     const int tile = blockIdx.x;
     const int z0 = blockIdx.y * d.zc;                          // first output slice of this CTA
     const int nz = min(d.zc, d.D - z0);
-    const int co_tile = 0;                                     // Cout tiles are folded into gridDim.x by the host
-    (void)co_tile;
     const int j0 = (tile % d.tiles_per_plane) * 128;
     const int ct = tile / d.tiles_per_plane;                   // Cout tile
     const int co0 = ct * NT;

@@ -218,8 +218,8 @@ schedule_kernel(const float* __restrict__ depth, const float* __restrict__ hypo,
     }
 }
 
-__global__ void confidence_accumulate_kernel(const float* __restrict__ conf, int h, int w, float* __restrict__ acc, int H,
-                                             int W, float scale, int64_t total) {
+__global__ void confidence_accumulate_kernel(const float* __restrict__ conf, int h, int w, float* __restrict__ acc,
+                                             float* __restrict__ up, int H, int W, float scale, int64_t total) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t o = i;
@@ -229,7 +229,9 @@ __global__ void confidence_accumulate_kernel(const float* __restrict__ conf, int
     // F.interpolate(mode='nearest'): src = floor(dst * in/out) computed in fp32
     const int sy = min((int)floorf((float)y * ((float)h / (float)H)), h - 1);
     const int sx = min((int)floorf((float)x * ((float)w / (float)W)), w - 1);
-    acc[o] += scale * __ldg(conf + (b * h + sy) * (int64_t)w + sx);
+    const float c = __ldg(conf + (b * h + sy) * (int64_t)w + sx);
+    acc[o] += scale * c;
+    if (up) up[o] = c;                          // the stage's own confidence, nearest-upsampled (:439-441)
 }
 
 static int check_map_args(const char* fn, const void* a, const void* b, const void* c, int B, int D, int H, int W) {
@@ -348,7 +350,18 @@ extern "C" int mvs_confidence_accumulate(const float* conf, int h, int w, float*
     MVS_REQUIRE(conf && acc, "mvs_confidence_accumulate: null pointer");
     MVS_REQUIRE(B >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "mvs_confidence_accumulate: empty shape");
     const int64_t total = (int64_t)B * H * W;
-    confidence_accumulate_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, H, W, scale, total);
+    confidence_accumulate_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, nullptr, H, W, scale, total);
+    MVS_LAUNCH_OK("confidence_accumulate_kernel");
+    return MVS_OK;
+}
+
+extern "C" int mvs_confidence_upsample_accumulate(const float* conf, int h, int w, float* up, float* acc, int B, int H, int W,
+                                                  float scale, void* stream) {
+    using namespace mvs;
+    MVS_REQUIRE(conf && acc && up, "mvs_confidence_upsample_accumulate: null pointer");
+    MVS_REQUIRE(B >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "mvs_confidence_upsample_accumulate: empty shape");
+    const int64_t total = (int64_t)B * H * W;
+    confidence_accumulate_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, up, H, W, scale, total);
     MVS_LAUNCH_OK("confidence_accumulate_kernel");
     return MVS_OK;
 }

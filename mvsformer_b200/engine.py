@@ -255,6 +255,16 @@ def schedule_range(cur_depth, ndepth, depth_interval_pixel, h, w):
     return out
 
 
+def confidence_upsample_accumulate(conf, acc, scale=1.0):
+    """acc += scale * nearest_upsample(conf); returns the upsampled stage confidence."""
+    require_cuda(conf, acc)
+    b, h, w = conf.shape
+    up = torch.empty_like(acc)
+    check(_lib.load().mvs_confidence_upsample_accumulate(ptr(conf), h, w, ptr(up), ptr(acc), b, acc.shape[1], acc.shape[2],
+                                                         float(scale), stream()), "mvs_confidence_upsample_accumulate")
+    return up
+
+
 def confidence_accumulate(conf, acc, scale=1.0):
     require_cuda(conf, acc)
     b, h, w = conf.shape

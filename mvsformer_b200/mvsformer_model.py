@@ -177,11 +177,11 @@ class CascadeMVS(nn.Module):
             outputs["stage%d" % (s + 1)] = outputs_stage
             if use_conf:
                 conf = outputs_stage["photometric_confidence"]
-                engine.confidence_accumulate(conf, prob_maps, 1.0)
                 if tuple(conf.shape[-2:]) != tuple(full_hw):
                     # the reference replaces the stage's confidence by its nearest upsampling (:439-441)
-                    up = torch.zeros_like(prob_maps)
-                    outputs_stage["photometric_confidence"] = engine.confidence_accumulate(conf, up, 1.0)
+                    outputs_stage["photometric_confidence"] = engine.confidence_upsample_accumulate(conf, prob_maps, 1.0)
+                else:
+                    engine.confidence_accumulate(conf, prob_maps, 1.0)
             outputs.update(outputs_stage)
         outputs["refined_depth"] = outputs_stage["depth"]
         if use_conf:
