@@ -137,6 +137,10 @@ int mvs_conv3d_tcr(const float* x, const float* w, const float* shift, const flo
 int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,
                  unsigned a_sbo, unsigned b_lbo, unsigned b_sbo, int N, int nk, unsigned a_kstep,
                  unsigned b_kstep, float* d_out, void* stream);
+/* Same with the A operand staged smem -> TMEM by tcgen05.cp.128x256b and read from tensor memory. */
+int mvs_tc_probe_ts(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,
+                    unsigned a_sbo, unsigned b_lbo, unsigned b_sbo, int N, int nk, unsigned a_kstep,
+                    unsigned b_kstep, unsigned a_shift_bytes, float* d_out, void* stream);
 /* Layout transforms at the module boundary (CostRegNet*.forward takes/returns NCDHW). */
 int mvs_ncdhw_to_cl(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);
 int mvs_ncdhw_to_cl_tf32(const float* x, float* y, int B, int C, int D, int H, int W, void* stream);   /* + TF32 rounding */

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "mvs_deconv3d_tcz": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_ncdhw_to_cl_tf32": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "mvs_tc_probe": (c_i, [c_f, c_i, c_f, c_i] + [ctypes.c_uint] * 4 + [c_i, c_i, ctypes.c_uint, ctypes.c_uint, c_f, c_f]),
+    "mvs_tc_probe_ts": (c_i, [c_f, c_i, c_f, c_i] + [ctypes.c_uint] * 4 + [c_i, c_i, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, c_f, c_f]),
     "mvs_ncdhw_to_cl": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "mvs_cl_to_ncdhw": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "mvs_prob_conv_cl": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f]),

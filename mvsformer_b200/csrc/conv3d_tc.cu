@@ -81,6 +81,53 @@ tc_probe_kernel(const float* __restrict__ a_img, int a_bytes, const float* __res
     if (threadIdx.x < 32) tmem_dealloc(tmem, 64);
 }
 
+// Probe of the A-from-TMEM path: each K step's A slice is first copied smem -> TMEM with
+// tcgen05.cp.128x256b (descriptor start shifted by `a_shift_bytes`, as the conv kernels do for the
+// kw taps), then multiplied with tcgen05.mma (A in TMEM, B in smem).
+__global__ void __launch_bounds__(TC_THREADS)
+tc_probe_ts_kernel(const float* __restrict__ a_img, int a_bytes, const float* __restrict__ b_img, int b_bytes, uint32_t a_lbo,
+                   uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, int N, int nk, uint32_t a_kstep, uint32_t b_kstep,
+                   uint32_t a_shift_bytes, float* __restrict__ d_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    float* sa = reinterpret_cast<float*>(smem);
+    float* sb = reinterpret_cast<float*>(smem + ((a_bytes + 127) / 128) * 128);
+    for (int i = threadIdx.x; i < a_bytes / 4; i += TC_THREADS) sa[i] = a_img[i];
+    for (int i = threadIdx.x; i < b_bytes / 4; i += TC_THREADS) sb[i] = b_img[i];
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 256);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a_tmem = tmem + 64;                        // A slices live behind the accumulator columns
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, N);
+        for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = make_smem_desc(smem_u32(sa) + k * a_kstep + a_shift_bytes, a_lbo, a_sbo);
+            tmem_cp_128x256b(a_tmem + k * 8, ad);
+        }
+        for (int k = 0; k < nk; ++k) {
+            const uint64_t bd = make_smem_desc(smem_u32(sb) + k * b_kstep, b_lbo, b_sbo);
+            mma_tf32_ts(tmem, a_tmem + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after_sync();
+    const int warp = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int i = 0; i < 16; ++i) d_out[(size_t)threadIdx.x * N + c0 + i] = v[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+}
+
 // ------------------------------------------------------------------------------------------------
 // convolution
 // ------------------------------------------------------------------------------------------------
@@ -509,6 +556,21 @@ extern "C" int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img,
     tc::tc_probe_kernel<<<1, tc::TC_THREADS, smem, (cudaStream_t)stream>>>(a_img, a_bytes, b_img, b_bytes, a_lbo, a_sbo, b_lbo,
                                                                            b_sbo, N, nk, a_kstep, b_kstep, d_out);
     MVS_LAUNCH_OK("tc_probe_kernel");
+    return MVS_OK;
+}
+
+extern "C" int mvs_tc_probe_ts(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,
+                               unsigned a_sbo, unsigned b_lbo, unsigned b_sbo, int N, int nk, unsigned a_kstep,
+                               unsigned b_kstep, unsigned a_shift_bytes, float* d_out, void* stream) {
+    using namespace mvs;
+    MVS_REQUIRE(a_img && b_img && d_out, "mvs_tc_probe_ts: null pointer");
+    MVS_REQUIRE(N >= 16 && N <= 64 && N % 16 == 0 && nk >= 1 && nk <= 16, "mvs_tc_probe_ts: bad N/nk");
+    MVS_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0 && a_bytes + b_bytes + 256 <= 200 * 1024, "mvs_tc_probe_ts: bad image sizes");
+    const size_t smem = (size_t)((a_bytes + 127) / 128) * 128 + b_bytes + 128;
+    MVS_CUDA_OK(cudaFuncSetAttribute(tc::tc_probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::tc_probe_ts_kernel<<<1, tc::TC_THREADS, smem, (cudaStream_t)stream>>>(a_img, a_bytes, b_img, b_bytes, a_lbo, a_sbo, b_lbo,
+                                                                              b_sbo, N, nk, a_kstep, b_kstep, a_shift_bytes, d_out);
+    MVS_LAUNCH_OK("tc_probe_ts_kernel");
     return MVS_OK;
 }
 

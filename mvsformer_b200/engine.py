@@ -491,3 +491,11 @@ def conv3d_tcr(x, w_tcr, n_tile, cout, kd, shift, skip, relu=True):
     check(_lib.load().mvs_conv3d_tcr(ptr(x), ptr(w_tcr), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
                                      1 if relu else 0, stream()), "mvs_conv3d_tcr")
     return y
+
+
+def tc_probe_ts(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, n, nk, a_kstep, b_kstep, a_shift_bytes=0):
+    require_cuda(a_img, b_img)
+    out = torch.empty(128, n, device=a_img.device, dtype=torch.float32)
+    check(_lib.load().mvs_tc_probe_ts(ptr(a_img), a_img.numel() * 4, ptr(b_img), b_img.numel() * 4, a_lbo, a_sbo, b_lbo, b_sbo,
+                                      n, nk, a_kstep, b_kstep, a_shift_bytes, ptr(out), stream()), "mvs_tc_probe_ts")
+    return out

@@ -262,3 +262,21 @@ def test_conv3d_tcr(cin, cout, kd, D, H, W):
     got = engine.conv3d_tcr(x_cl, wr, nt, cout, kd, shift.to(DEV), skip_cl, relu=True).permute(0, 4, 1, 2, 3).cpu()
     assert got.shape == want.shape
     assert rel_l1(got, want + skip.double()) < 5e-4
+
+
+@pytest.mark.parametrize("n,shift", [(16, 0), (16, 2), (32, 1), (64, 0)])
+def test_tc_probe_a_from_tmem(n, shift):
+    """A operand copied smem -> TMEM (tcgen05.cp.128x256b, row-shifted descriptor) and read from TMEM by
+    tcgen05.mma: D = A[shift:shift+128] * B^T."""
+    g = S._gen(50 + n + shift)
+    nk = 6
+    k = 8 * nk
+    a = engine.round_tf32(torch.randn(132, k, generator=g))
+    b = engine.round_tf32(torch.randn(n, k, generator=g))
+    a_img, b_img = _image(a, 132), _image(b, n)
+    want = a[shift:shift + 128].double() @ b.double().t()
+    got = engine.tc_probe_ts(a_img.to(DEV), b_img.to(DEV), 132 * 16, 128, n * 16, 128, n, nk, 2 * 132 * 16, 2 * n * 16, shift * 16).cpu()
+    err = rel_l1(got, want)
+    if err > 1e-5:
+        print("TS probe mismatch", err, got[:3, :4], want[:3, :4].float())
+    assert err < 1e-5
