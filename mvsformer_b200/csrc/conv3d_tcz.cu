@@ -433,19 +433,14 @@ conv3d_tcr_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     const int b_bytes = d.kd * 9 * B_TAP;
     uint8_t* sA = smem;
     uint8_t* sB = smem + TZ_STAGES * A_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_bytes);                 // [TZ_STAGES] stage free + [1] all done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    // TMEM: R*zc accumulators of NT columns, then two A-operand buffers of 3 kw shifts x CS columns.
-    // The A slab of an iteration is copied smem -> TMEM once (tcgen05.cp) and every tap's MMA reads it
-    // from tensor memory; only the 0.5-2 KB weight tile is fetched from shared memory per MMA.  (With
-    // both operands in smem the kernel was bound by re-reading the 4 KB A tile for each of the 27 taps.)
-    const int acc_cols = d.R * d.zc * NT;
-    const int ncols = acc_cols + 2 * 3 * CS;
+    const int ncols = d.R * d.zc * NT;
     const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : (ncols <= 256 ? 256 : 512)));
     if (tid == 0) {
-        for (int s = 0; s <= TZ_STAGES; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < TZ_STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
@@ -512,15 +507,6 @@ conv3d_tcr_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
             const int iz = iz_lo + it / niy, iy = iy_lo + it % niy;
             const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * A_STAGE;
             const uint32_t b_base = smem_u32(sB);
-            const uint32_t a_t = tmem + (uint32_t)acc_cols + (uint32_t)(it & 1) * (3 * CS);
-            // slab -> TMEM: 3 kw windows x CS/8 K-steps of 128 rows x 8 columns
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                for (int kk = 0; kk < CS / 8; ++kk)
-                    tmem_cp_128x256b(a_t + (uint32_t)(kw * (CS / 8) + kk) * 8,
-                                     make_smem_desc(a_base + (uint32_t)kw * 16 + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128));
-            mma_commit(&bars[it % TZ_STAGES]);                     // the smem stage is free once the copies retire
             for (int kz = 0; kz < d.kd; ++kz) {
                 const int oz = iz + pd - kz;
                 if (oz < z0 || oz >= z0 + nz) continue;
@@ -535,17 +521,19 @@ conv3d_tcr_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
                         for (int kk = 0; kk < CS / 8; ++kk) {
                             const uint32_t acc = (started >> slot_acc) & 1u;
                             started |= 1u << slot_acc;
+                            const uint64_t ad = make_smem_desc(a_base + (uint32_t)kw * 16 + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
                             const uint64_t bd = make_smem_desc(b_base + (uint32_t)((kz * 3 + kh) * 3 + kw) * B_TAP + (uint32_t)(2 * kk) * NT * 16, NT * 16, 128);
-                            mma_tf32_ts(dcol, a_t + (uint32_t)(kw * (CS / 8) + kk) * 8, bd, idesc, acc);
+                            mma_tf32_ss(dcol, ad, bd, idesc, acc);
                         }
                     }
                 }
             }
-            if (it == nit - 1) mma_commit(&bars[TZ_STAGES]);       // everything issued so far has completed
+            mma_commit(&bars[it % TZ_STAGES]);
         }
     }
 
-    mbar_wait(&bars[TZ_STAGES], 0);
+    const int last = nit - 1;
+    mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
     tc_fence_after_sync();
     const int ox = x0 + tid;
     const bool live = ox < d.W;
