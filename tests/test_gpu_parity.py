@@ -363,3 +363,61 @@ def test_non_contiguous_feature_views():
     a = net.build_cost_volume(view, cu(cams), cu(hyp))[0]
     b = net.build_cost_volume(cu(feats), cu(cams), cu(hyp))[0]
     assert torch.equal(a, b)
+
+
+def _cascade(seed0=0):
+    args = dict(STAGE_ARGS, ndepths=list(S.NDEPTHS), depth_interals_ratio=list(S.DEPTH_INTERVAL_RATIO), inverse_depth=True)
+    net = CascadeMVS(args).eval()
+    full, sds = {}, []
+    for s in range(4):
+        sd = S.fill_state_dict(net.fusions[s].state_dict(), seed=seed0 + s)
+        sds.append(sd)
+        full.update({"fusions.%d.%s" % (s, k): v for k, v in sd.items()})
+    net.load_state_dict(full, strict=True)
+    return net.to(DEV), sds
+
+
+def test_baseline_cfg1_plumbing_case():
+    """BASELINE.json configs[0]: 2 source views, 32 hypotheses, 320x256 image, single cascade stage
+    (stage-1 features [1,3,64,32,40]) — the reference's CPU-runnable case, against the oracle."""
+    height, width = 256, 320
+    feats = S.make_features(1, 3, height, width, stages=(0,), seed=2024)["stage1"]
+    cams = S.make_cameras(1, 3, height, width)["stage1"]
+    dv = S.make_depth_range(1)
+    hyp = O.init_inverse_range(dv, 32, 32, 40)
+    net = StageNet(dict(STAGE_ARGS), 32, 0).eval()
+    sd = S.fill_state_dict(net.state_dict(), seed=0)
+    net.load_state_dict(sd)
+    want = O.stage_forward(feats, cams, hyp, sd, 32, 5.0)
+    got_hyp = M.init_inverse_range(cu(dv), 32, DEV, torch.float32, 32, 40)
+    assert max_abs(got_hyp.cpu(), hyp) < 2e-4
+    out = net.to(DEV)(cu(feats), cu(cams), got_hyp, tmp=5.0)
+    assert rel_l1(out["depth"].cpu(), want["depth"]) < 1e-5
+    assert rel_l1(out["prob_volume"].cpu(), want["prob_volume"]) < 5e-5
+    assert (out["sim_depth"].cpu() == want["sim_depth"]).float().mean() > 0.995
+
+
+@pytest.mark.parametrize("name,batch,views,height,width", [("cfg3 BlendedMVS", 4, 7, 576, 768), ("cfg4 T&T @1088", 1, 11, 1088, 1920)])
+def test_baseline_cfg3_cfg4_properties(name, batch, views, height, width):
+    """BASELINE.json configs[2] (B=4, 7 views, 576x768) and configs[3] (11 views, 1088x1920: 1056 is not
+    runnable by the reference): size-independent properties of the full cascade."""
+    net, _ = _cascade()
+    feats = {k: cu(v) for k, v in S.make_features(batch, views, height, width, seed=9).items()}
+    cams = {k: cu(v) for k, v in S.make_cameras(batch, views, height, width).items()}
+    dv = cu(S.make_depth_range(batch))
+    out = net(feats, cams, dv, tmp=list(S.EVAL_TMP))
+    torch.cuda.synchronize()
+    assert out["refined_depth"].shape == (batch, height, width)
+    for s in range(4):
+        st = out["stage%d" % (s + 1)]
+        hyp = st["depth_values"]
+        assert torch.isfinite(st["prob_volume_pre"]).all()
+        assert (st["depth"] <= hyp.max(dim=1)[0] * (1 + 1e-6)).all() and (st["depth"] >= hyp.min(dim=1)[0] * (1 - 1e-6)).all()
+        assert (st["prob_volume"].sum(dim=1) - 1).abs().max() < 1e-5
+    conf = out["photometric_confidence"]
+    assert (conf > 0).all() and (conf <= 1 + 1e-6).all()
+    # batch items are independent: item 0 alone reproduces item 0 of the batch
+    if batch > 1:
+        one = net({k: v[:1].contiguous() for k, v in feats.items()}, {k: v[:1].contiguous() for k, v in cams.items()},
+                  dv[:1].contiguous(), tmp=list(S.EVAL_TMP))
+        assert rel_l1(one["refined_depth"], out["refined_depth"][:1]) < 1e-6
