@@ -391,7 +391,7 @@ def test_baseline_cfg1_plumbing_case():
     want = O.stage_forward(feats, cams, hyp, sd, 32, 5.0)
     got_hyp = M.init_inverse_range(cu(dv), 32, DEV, torch.float32, 32, 40)
     assert max_abs(got_hyp.cpu(), hyp) < 2e-4
-    out = net.to(DEV)(cu(feats), cu(cams), got_hyp, tmp=5.0)
+    out = net.to(DEV)(cu(feats), cu(cams), cu(hyp), tmp=5.0)       # same hypothesis values on both sides (sim_depth is an exact gather)
     assert rel_l1(out["depth"].cpu(), want["depth"]) < 1e-5
     assert rel_l1(out["prob_volume"].cpu(), want["prob_volume"]) < 5e-5
     assert (out["sim_depth"].cpu() == want["sim_depth"]).float().mean() > 0.995
