@@ -729,6 +729,11 @@ extern "C" int mvs_conv3d_tcr(const float* x, const float* w, const float* shift
     while (D % zc) --zc;
     int R = 256 / (zc * n_tile);
     if (R > 2) R = 2;            // measured: 2 rows (more, smaller CTAs) beats 4 on B200
+    if (kd == 1) {               // 2D layers (visibility net): slices share nothing, spend the accumulators on rows
+        zc = 1;
+        R = 128 / n_tile;
+        if (R > 8) R = 8;
+    }
     if (R < 1) { R = 1; while (zc > 1 && zc * n_tile > 512) --zc; }
     R = env_int("MVS_TCR_ROWS", R);
     MVS_REQUIRE(R * zc * n_tile <= 512 && R * zc <= 32, "mvs_conv3d_tcr: accumulators do not fit TMEM (R=%d zc=%d N=%d)", R, zc, n_tile);
