@@ -76,7 +76,7 @@ __device__ __forceinline__ void project(const RelProj& m, const PixelRay& ray, f
 // CPG channels per group (G = 8 groups), DG depth groups x KPT hypotheses per thread (D = DG*KPT),
 // BW x BH source box, NCH channel chunks.
 // MINB = CTAs per SM the register allocation must allow (co-resident CTAs hide each other's TMA waits).
-template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, int MINB = (CPG == 1 ? 3 : 2)>
+template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, int MINB = (CPG == 1 ? (PASS_B ? 3 : 4) : 2)>
 __global__ void __launch_bounds__(256, MINB)
 cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     constexpr int G = 8, C = G * CPG, D = DG * KPT;
