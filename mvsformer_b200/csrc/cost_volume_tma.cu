@@ -60,21 +60,33 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-// Sample position of (pixel ray, depth): identical arithmetic to make_taps() in common.cuh.
+// a / b with a correctly rounded reciprocal rb = RN(1/b): q = RN(a*rb); r = a - b*q (exact, one FMA);
+// RN(q + r*rb).  This is the refinement IEEE division itself uses (Markstein), so the quotient is the
+// correctly rounded one — bit-identical to __fdiv_rn for operands in the normal range (checked
+// exhaustively on random operands against exact rational arithmetic) — but the reciprocal is shared:
+// one for both projected coordinates, one per kernel for the image-size constants.  Samples whose
+// coordinates leave the normal range fail the `sane` test and take the predicated global path, which
+// uses plain IEEE divisions (make_taps).
+__device__ __forceinline__ float div_by(float a, float b, float rb) {
+    const float q = __fmul_rn(a, rb);
+    const float r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, rb, q);
+}
+
+// Sample position of (pixel ray, depth): the arithmetic of make_taps() in common.cuh.
 __device__ __forceinline__ void project(const RelProj& m, const PixelRay& ray, float depth, int H, int W, float half_w,
-                                        float half_h, float* ix, float* iy) {
+                                        float half_h, float rcp_half_w, float rcp_half_h, float* ix, float* iy) {
     const float qx = __fadd_rn(__fmul_rn(ray.x, depth), m.t0);
     const float qy = __fadd_rn(__fmul_rn(ray.y, depth), m.t1);
     const float qz = __fadd_rn(__fmul_rn(ray.z, depth), m.t2);
     const float den = __fadd_rn(qz, 1e-6f);
-    const float gx = __fadd_rn(__fdiv_rn(__fdiv_rn(qx, den), half_w), -1.0f);
-    const float gy = __fadd_rn(__fdiv_rn(__fdiv_rn(qy, den), half_h), -1.0f);
+    const float rden = __frcp_rn(den);
+    const float gx = __fadd_rn(div_by(div_by(qx, den, rden), half_w, rcp_half_w), -1.0f);
+    const float gy = __fadd_rn(div_by(div_by(qy, den, rden), half_h, rcp_half_h), -1.0f);
     *ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
     *iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
 }
 
-// CPG channels per group (G = 8 groups), DG depth groups x KPT hypotheses per thread (D = DG*KPT),
-// BW x BH source box, NCH channel chunks.
 // MINB = CTAs per SM the register allocation must allow (co-resident CTAs hide each other's TMA waits).
 template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, int MINB = (CPG == 1 ? (PASS_B ? 3 : 4) : 2)>
 __global__ void __launch_bounds__(256, MINB)
@@ -104,6 +116,7 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     const int pixoff = live ? y * p.W + x : 0;
     const float* ref = p.feat + (int64_t)b * p.V * C * hw;
     const float half_w = (float)((p.W - 1) / 2.0), half_h = (float)((p.H - 1) / 2.0);
+    const float rcp_half_w = __frcp_rn(half_w), rcp_half_h = __frcp_rn(half_h);
     const float inv_cpg = 1.0f / (float)CPG;
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -147,7 +160,7 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
 #pragma unroll
         for (int j = 0; j < KPT; ++j) {
             const float dep = __ldg(p.depth + ((int64_t)b * D + dg * KPT + j) * hw + pixoff);
-            project(m, ray, dep, p.H, p.W, half_w, half_h, &ix[j], &iy[j]);
+            project(m, ray, dep, p.H, p.W, half_w, half_h, rcp_half_w, rcp_half_h, &ix[j], &iy[j]);
             const bool sane = live && fabsf(ix[j]) < 1e7f && fabsf(iy[j]) < 1e7f;      // false for NaN / inf too
             if (sane) { bminx = fminf(bminx, ix[j]); bminy = fminf(bminy, iy[j]); }
         }
