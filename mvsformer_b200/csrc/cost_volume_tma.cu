@@ -385,37 +385,23 @@ static int launch(const K1Params& p, int B, cudaStream_t st) {
     return MVS_OK;
 }
 
-// Box sizes: 32-pixel-wide tile + the sweep of the hypotheses along the epipolar line + slack.
-// They only steer how many samples take the fast path; any geometry stays correct.
-// Depth groups per stage (threads = 256 / DG pixels x DG groups).  More groups = fewer hypotheses and
-// registers per thread, more and smaller CTAs (better wave quantisation on 148 SMs).  Defaults were
-// measured on B200; MVS_K1_DG="s1,s2,s3,s4" overrides them for experiments.
-static void depth_groups(int dg[4]) {
-    dg[0] = 8; dg[1] = 4; dg[2] = 2; dg[3] = 1;
-    const char* e = getenv("MVS_K1_DG");
-    if (e) sscanf(e, "%d,%d,%d,%d", &dg[0], &dg[1], &dg[2], &dg[3]);
-}
-
+// Box sizes BW x BH: the 32-pixel-wide tile + the sweep of the hypotheses along the epipolar line +
+// the spread of the per-pixel hypotheses inside the tile + 3 columns of alignment slack.  They only
+// steer how many samples take the fast path; any geometry stays correct (and bit-identical).  Measured
+// on the bench workload (scripts/box_coverage.py, scripts/box_sweep.py): 128x10 / 64x8 / 64x12 / 80x16
+// cover 99.7-100 % of the samples of every view; the first-round 112x8 / 48x12 / 48x16 boxes covered
+// only 88-99 % at stages 3-4 and cost 0.39 ms per reference view in predicated global taps.  A row
+// pitch that is a multiple of 32 floats also keeps image rows on the same banks (stage 1: 1.25 instead
+// of 1.49 shared-memory wavefronts per load).
+// Depth groups per stage (threads = 256 / DG pixels x DG groups): 8/4/2/1, i.e. four hypotheses per
+// thread at every stage.  More groups = fewer registers per thread and more, smaller CTAs (better wave
+// quantisation on 148 SMs); 4/2/1/2 groups were measured 5-20 % slower on B200 and are no longer built.
 template <bool PASS_B, bool SIM>
 static int dispatch(const K1Params& p, int B, int C, int D, cudaStream_t st) {
-    int dg[4];
-    depth_groups(dg);
-    if (C == 64 && D == 32) {
-        if (dg[0] == 4) return launch<8, 4, 8, 112, 8, 4, PASS_B, SIM>(p, B, st);
-        return launch<8, 8, 4, 112, 8, 4, PASS_B, SIM>(p, B, st);
-    }
-    if (C == 32 && D == 16) {
-        if (dg[1] == 2) return launch<4, 2, 8, 64, 12, 2, PASS_B, SIM>(p, B, st);
-        return launch<4, 4, 4, 64, 8, 2, PASS_B, SIM>(p, B, st);
-    }
-    if (C == 16 && D == 8) {
-        if (dg[2] == 1) return launch<2, 1, 8, 48, 16, 1, PASS_B, SIM>(p, B, st);
-        return launch<2, 2, 4, 48, 12, 1, PASS_B, SIM>(p, B, st);
-    }
-    if (C == 8 && D == 4) {
-        if (dg[3] == 2) return launch<1, 2, 2, 48, 12, 1, PASS_B, SIM>(p, B, st);
-        return launch<1, 1, 4, 48, 16, 1, PASS_B, SIM>(p, B, st);
-    }
+    if (C == 64 && D == 32) return launch<8, 8, 4, 128, 10, 4, PASS_B, SIM>(p, B, st);
+    if (C == 32 && D == 16) return launch<4, 4, 4, 64, 8, 2, PASS_B, SIM>(p, B, st);
+    if (C == 16 && D == 8) return launch<2, 2, 4, 64, 12, 1, PASS_B, SIM>(p, B, st);
+    if (C == 8 && D == 4) return launch<1, 1, 4, 80, 16, 1, PASS_B, SIM>(p, B, st);
     return 1;   // not covered: caller uses the generic kernels
 }
 
