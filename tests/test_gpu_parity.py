@@ -124,6 +124,33 @@ def test_cost_volume_wild_geometry(s):
     assert rel_l1(volume.cpu().permute(0, 4, 1, 2, 3), vol_o) < 1e-4
 
 
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_cost_volume_is_deterministic_under_allocator_churn(s):
+    """The cost-volume build must give bit-identical results call after call, also when every output
+    and scratch buffer lands on recycled memory that holds NaNs (no read of uninitialised memory, no
+    race between the TMA-staged tiles and their consumers)."""
+    height, width, batch, views = 128, 192, 2, 4
+    feats = cu(S.make_features(batch, views, height, width, stages=(s,))["stage%d" % (s + 1)])
+    cams = cu(S.make_cameras(batch, views, height, width)["stage%d" % (s + 1)])
+    hyp = cu(S.narrow_hypotheses(s, height, width, batch))
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=s))
+    net = net.to(DEV)
+    first = None
+    gen = torch.Generator().manual_seed(5)
+    for it in range(12):
+        # poison the caching allocator's free blocks with NaNs of assorted sizes
+        junk = [torch.full((int(n),), float("nan"), device=DEV) for n in torch.randint(1 << 8, 1 << 20, (6,), generator=gen)]
+        del junk
+        out = [t.clone() for t in net.build_cost_volume(feats, cams, hyp)]
+        assert all(torch.isfinite(t).all() for t in out)
+        if first is None:
+            first = out
+        else:
+            for a, b in zip(out, first):
+                assert torch.equal(a, b), "iteration %d differs from the first call" % it
+
+
 CONV_CASES = [
     # cin, cout, kd, stride, D, H, W
     (8, 16, 3, (2, 2, 2), 8, 16, 24),
