@@ -11,8 +11,70 @@ synchronises and copies every output back, strictly in sequence.  Here the three
 
 Only depth and confidence cross PCIe on the way back (14 MB at 1152x1536) — not the per-stage
 probability volumes the reference's ``tensor2numpy(outputs)`` drags along (test.py:251).
+
+``FeatureCache`` + ``StreamedCascade.run_scan`` add the first "next" row of SURVEY.md §8f: inside a
+scan every image is the reference view once and a source view of ~4 neighbours
+(datasets/general_eval.py:71), so the reference re-extracts (and this engine would re-upload) each
+view's feature maps ~5 times.  The cache keeps per-view feature maps resident in HBM (49 DTU views
+x 106 MB = 5.2 GB of the 180 GB), uploads a view the first time a sample names it, and assembles
+the dense ``[1,V,C,h,w]`` operand of the cost-volume kernels by a device-side gather.
 """
+from collections import OrderedDict
+
 import torch
+
+
+class ScanSample:
+    """One reference view of a scan: ``view_ids[0]`` is the reference view, the rest its source
+    views; ``load(view_id)`` returns that view's PINNED host features ``{"stageK": [C,h,w]}`` and is
+    only called for views that are not resident; cameras / depth range as in ``StageNet.forward``
+    (``proj_matrices["stageK"]`` is ``[1,V,2,4,4]`` in ``view_ids`` order)."""
+
+    def __init__(self, view_ids, load, proj_matrices, depth_values):
+        self.view_ids = list(view_ids)
+        self.load = load
+        self.proj_matrices = proj_matrices
+        self.depth_values = depth_values
+
+
+class FeatureCache:
+    """Slot allocator (LRU) over per-stage device pools ``[capacity, C, h, w]``.  Pure bookkeeping:
+    the pools are created by ``StreamedCascade`` on first use, so this class is testable on CPU."""
+
+    def __init__(self, capacity):
+        if capacity < 2:
+            raise ValueError("FeatureCache needs at least 2 slots")
+        self.capacity = capacity
+        self.slot_of = OrderedDict()          # view id -> slot, least recently used first
+        self.free = list(range(capacity - 1, -1, -1))
+        self.hits = 0
+        self.misses = 0
+
+    def lookup(self, view_id):
+        """Slot of a resident view (and mark it most recently used), else None."""
+        slot = self.slot_of.get(view_id)
+        if slot is not None:
+            self.slot_of.move_to_end(view_id)
+            self.hits += 1
+        return slot
+
+    def reserve(self, view_id, pinned=()):
+        """Slot for a view that is about to be uploaded; evicts the least recently used view that
+        is not in ``pinned``.  Returns (slot, evicted_view_or_None)."""
+        self.misses += 1
+        evicted = None
+        if self.free:
+            slot = self.free.pop()
+        else:
+            for cand in self.slot_of:
+                if cand not in pinned:
+                    evicted = cand
+                    break
+            if evicted is None:
+                raise RuntimeError("FeatureCache: capacity %d is too small for the views pinned by one sample" % self.capacity)
+            slot = self.slot_of.pop(evicted)
+        self.slot_of[view_id] = slot
+        return slot, evicted
 
 
 class PackedSample:
@@ -56,6 +118,10 @@ class StreamedCascade:
         self._up = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.cache = None                # FeatureCache bookkeeping (run_scan)
+        self._pools = None               # {"stageK": [capacity, C, h, w]} device pools
+        self._gathered = None            # {"stageK": [1, V, C, h, w]} dense operand of the current sample
+        self._gather_done = None         # event: last gather has read the pools
 
     def _upload(self, sample):
         """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
@@ -88,6 +154,88 @@ class StreamedCascade:
             t.record_stream(main)                      # consumed on the compute stream
         self.h2d_bytes = sum(4 * v.numel() for v in feats.values()) + sum(4 * v.numel() for v in cams.values()) + 4 * dv.numel()
         return f, c, d, ready, None
+
+    # -- scan mode: per-view feature cache ----------------------------------------------------------
+    def _stage_scan(self, sample):
+        """Upload the views of ``sample`` that are not resident (copy stream) and return what the
+        gather needs.  Slots of views this sample uses are pinned against eviction."""
+        cache = self.cache
+        slots, uploaded = [], 0
+        with torch.cuda.stream(self.copy_stream):
+            for vid in sample.view_ids:
+                slot = cache.lookup(vid)
+                if slot is None:
+                    slot, evicted = cache.reserve(vid, pinned=sample.view_ids)
+                    feats = sample.load(vid)
+                    if self._pools is None:
+                        self._pools = {k: torch.empty((cache.capacity,) + tuple(v.shape), dtype=torch.float32, device=self.device)
+                                       for k, v in feats.items()}
+                    if evicted is not None and self._gather_done is not None:
+                        self.copy_stream.wait_event(self._gather_done)   # the evicted view may still be read by a gather
+                    for k, v in feats.items():
+                        self._pools[k][slot].copy_(v, non_blocking=True)
+                        uploaded += 4 * v.numel()
+                slots.append(slot)
+            cams = {k: v.to(self.device, non_blocking=True) for k, v in sample.proj_matrices.items()}
+            dv = sample.depth_values.to(self.device, non_blocking=True)
+            uploaded += sum(4 * v.numel() for v in sample.proj_matrices.values()) + 4 * sample.depth_values.numel()
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        main = torch.cuda.current_stream(self.device)
+        for t in list(cams.values()) + [dv]:
+            t.record_stream(main)
+        return slots, cams, dv, ready, uploaded
+
+    def _gather(self, slots):
+        """Dense [1,V,C,h,w] operand from the pools (device-side copy on the compute stream)."""
+        if self._gathered is None or next(iter(self._gathered.values())).shape[1] != len(slots):
+            self._gathered = {k: torch.empty((1, len(slots)) + tuple(p.shape[1:]), dtype=torch.float32, device=self.device)
+                              for k, p in self._pools.items()}
+        for k, p in self._pools.items():
+            dst = self._gathered[k][0]
+            for j, slot in enumerate(slots):
+                dst[j].copy_(p[slot], non_blocking=True)                     # device-to-device, stream ordered
+        self._gather_done = torch.cuda.Event()
+        self._gather_done.record(torch.cuda.current_stream(self.device))
+        return self._gathered
+
+    def run_scan(self, samples, capacity=64):
+        """Like ``run`` for ``ScanSample``s that share views: each view's features cross PCIe once
+        (while resident).  Yields (depth, confidence) pinned host tensors, one step behind the GPU."""
+        main = torch.cuda.current_stream(self.device)
+        if self.cache is None or self.cache.capacity != capacity:
+            self.cache, self._pools, self._gathered, self._gather_done = FeatureCache(capacity), None, None, None
+        it = iter(samples)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        staged = self._stage_scan(nxt)
+        pending = []
+        i = 0
+        with torch.no_grad():
+            while staged is not None:
+                slots, c, d, ready, uploaded = staged
+                main.wait_event(ready)
+                f = self._gather(slots)                                      # reads the pools before the next upload may evict
+                self.h2d_bytes = uploaded
+                nxt = next(it, None)
+                staged = self._stage_scan(nxt) if nxt is not None else None  # overlaps with this view's compute
+                out = self.net(f, c, d, tmp=self.tmp)
+                bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
+                hd, hc, done = bufs[i % self.ring]
+                hd.copy_(out["refined_depth"], non_blocking=True)
+                hc.copy_(out["photometric_confidence"], non_blocking=True)
+                done.record(main)
+                self.d2h_bytes = 4 * (hd.numel() + hc.numel())
+                pending.append((hd, hc, done))
+                if len(pending) >= self.ring:
+                    od, oc, oe = pending.pop(0)
+                    oe.synchronize()
+                    yield od, oc
+                i += 1
+        for od, oc, oe in pending:
+            oe.synchronize()
+            yield od, oc
 
     def _ring_buffers(self, depth, conf):
         if self._out is None or self._out[0][0].shape != depth.shape:

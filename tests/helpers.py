@@ -6,6 +6,7 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STAGE_ARGS = {"base_ch": 8, "fusion_type": "cnn", "depth_type": "ce"}
+CASCADE_ARGS = dict(STAGE_ARGS, ndepths=[32, 16, 8, 4], depth_interals_ratio=[4.0, 2.67, 1.5, 1.0], inverse_depth=True)
 
 
 def load_golden(name):

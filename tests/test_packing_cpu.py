@@ -88,3 +88,20 @@ def test_packed_sample_roundtrip():
     assert all(torch.equal(f[k], feats[k]) for k in feats) and all(torch.equal(c[k], cams[k]) for k in cams)
     assert torch.equal(d, dv)
     assert all(off % 64 == 0 for _, _, _, off, _ in ps.layout)      # 256-byte aligned views (TMA needs 16)
+
+
+def test_feature_cache_lru_and_pinning():
+    from mvsformer_b200.pipeline import FeatureCache
+    c = FeatureCache(3)
+    assert [c.reserve(v)[0] for v in "abc"] == [0, 1, 2]
+    assert c.lookup("a") == 0 and c.lookup("zz") is None
+    slot, evicted = c.reserve("d")                        # LRU is now b
+    assert (slot, evicted) == (1, "b")
+    slot, evicted = c.reserve("e", pinned=("c", "e"))     # c is LRU but pinned -> a goes
+    assert (slot, evicted) == (0, "a")
+    assert c.lookup("c") == 2 and c.hits == 2 and c.misses == 5
+    import pytest
+    with pytest.raises(RuntimeError):
+        c.reserve("f", pinned=("c", "d", "e"))
+    with pytest.raises(ValueError):
+        FeatureCache(1)
