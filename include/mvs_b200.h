@@ -180,6 +180,58 @@ int mvs_confidence_accumulate(const float* conf, int h, int w, float* acc, int B
 int mvs_confidence_upsample_accumulate(const float* conf, int h, int w, float* up, float* acc, int B, int H, int W,
                                        float scale, void* stream);
 
+/* ---- training path: train-mode forward + backward of StageNet (SURVEY.md 8b "Autograd") -------
+ * The reference trains through torch autograd over models/mvsformer_model.py:61-125; the Python
+ * mirror wraps the entry points below in torch.autograd.Function (mvsformer_b200/autograd.py).
+ * In training the per-view correlation IS materialised (it is an autograd-saved tensor in the
+ * reference too) as corr [B,N,D,H,W,G] channels-last; N = V-1 source views. */
+/* corr_v = mean_c' ref * warped_v (mvsformer_model.py:70-79).  features/strides as mvs_cost_volume_entropy. */
+int mvs_group_corr_fwd(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
+                       const float* depth, float* corr, int B, int V, int C, int G, int D, int H, int W, void* stream);
+/* Gradient w.r.t. the features of all views (the sampling grid is built under no_grad, warping.py:79):
+ * gcorr [B,N,D,H,W,G] -> gfeat [B,V,C,H,W] dense, ZEROED by the caller, accumulated with fp32 atomics. */
+int mvs_group_corr_bwd(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
+                       const float* depth, const float* gcorr, float* gfeat, int B, int V, int C, int G, int D, int H,
+                       int W, void* stream);
+/* entropy [BN,H,W] of softmax_d(sum_g corr) (mvsformer_model.py:87-90; no gradient: the input is detached). */
+int mvs_corr_entropy(const float* corr, float* entropy, int BN, int G, int D, int H, int W, void* stream);
+/* volume [B,D,H,W,G] = sum_v corr_v w_v / (sum_v w_v + 1e-6), weight [B,N,H,W] (mvsformer_model.py:101-105), and its backward. */
+int mvs_aggregate_fwd(const float* corr, const float* weight, float* volume, int B, int N, int G, int D, int H, int W,
+                      void* stream);
+int mvs_aggregate_bwd(const float* gvol, const float* corr, const float* weight, float* gcorr, float* gweight, int B, int N,
+                      int G, int D, int H, int W, void* stream);
+/* Train-mode BatchNorm over channels-last x [M,C] (nn.BatchNorm2d/3d inside ConvBnReLU / Conv3d / Deconv3d,
+ * models/module.py:83-197).  sums: 2C doubles, ZEROED by the caller (sum, sum of squares); with SyncBatchNorm
+ * the caller all-reduces sums and passes the global count.  mean_invstd: 2C floats.  running_* updated in
+ * place (NULL to skip): r = (1-momentum) r + momentum * batch value, unbiased variance. */
+int mvs_bn_stats(const float* x, double* sums, int64_t M, int C, void* stream);
+int mvs_bn_finalize(const double* sums, double count, float eps, float momentum, float* mean_invstd, float* running_mean,
+                    float* running_var, int C, void* stream);
+/* y = act((x - mean) * invstd * gamma + beta) (+ skip after the activation, module.py:500-502). */
+int mvs_bn_act_fwd(const float* x, const float* mean_invstd, const float* gamma, const float* beta, const float* skip,
+                   float* y, int64_t M, int C, int relu, void* stream);
+/* Backward: sums (2C doubles, ZEROED by the caller) <- (d gamma, d beta); then
+ * gx = gamma * invstd * (g - dbeta/count - xhat * dgamma/count), g = gy masked by the ReLU. */
+int mvs_bn_act_bwd_reduce(const float* gy, const float* x, const float* mean_invstd, const float* gamma, const float* beta,
+                          double* sums, int64_t M, int C, int relu, void* stream);
+int mvs_bn_act_bwd_apply(const float* gy, const float* x, const float* mean_invstd, const float* gamma, const float* beta,
+                         const double* sums, double count, float* gx, int64_t M, int C, int relu, void* stream);
+/* Weight gradient of a (kd,k,k) conv / transposed conv (k in {1,3}, padding k/2), packed layout
+ * dw [kd][k][k][Cin][Cout], ZEROED by the caller.  `small` lives on the strided grid, `big` on the fine
+ * one (big position = small position * stride - pad + tap):
+ *   conv   (small_is_cout = 1): small = grad of the output [.., Cout], big = the input [.., Cin]
+ *   deconv (small_is_cout = 0): small = the input [.., Cin],  big = grad of the output [.., Cout] */
+int mvs_conv_wgrad_cl(const float* small, const float* big, float* dw, int B, int Ds, int Hs, int Ws, int Db, int Hb,
+                      int Wb, int Cs, int Cb, int kd, int khw, int sd, int shw, int small_is_cout, void* stream);
+/* Few-channel convolution with DEVICE weights w [kd*k*k][Cin][Cout], bias [Cout] or NULL; stride 1, padding k/2;
+ * act 0 none, 1 ReLU, 2 sigmoid (vis net 1->16 and 8->1, `prob` 8->1, and their data gradients). */
+int mvs_thin_conv_cl(const float* x, const float* w, const float* bias, float* y, int B, int D, int H, int W, int Cin,
+                     int Cout, int kd, int khw, int act, void* stream);
+/* gx = gy * y * (1 - y) over n elements. */
+int mvs_sigmoid_bwd(const float* gy, const float* y, float* gx, int64_t n, void* stream);
+/* p = softmax_d(pre) on [B,D,H,W]: gpre = p * (gp - sum_d gp * p)  (mvsformer_model.py:111). */
+int mvs_softmax_bwd(const float* gp, const float* p, float* gpre, int B, int D, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

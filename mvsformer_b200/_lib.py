@@ -19,6 +19,7 @@ c_f = ctypes.c_void_p      # device / host float pointers travel as void*
 c_i = ctypes.c_int
 c_l = ctypes.c_int64
 c_fl = ctypes.c_float
+c_d = ctypes.c_double
 
 _SIGNATURES = {
     "mvs_version": (c_i, []),
@@ -57,6 +58,21 @@ _SIGNATURES = {
     "mvs_schedule_range": (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f]),
     "mvs_confidence_accumulate": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_fl, c_f]),
     "mvs_confidence_upsample_accumulate": (c_i, [c_f, c_i, c_i, c_f, c_f, c_i, c_i, c_i, c_fl, c_f]),
+    # training path (train.cu)
+    "mvs_group_corr_fwd": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
+    "mvs_group_corr_bwd": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
+    "mvs_corr_entropy": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
+    "mvs_aggregate_fwd": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
+    "mvs_aggregate_bwd": (c_i, [c_f] * 5 + [c_i] * 6 + [c_f]),
+    "mvs_bn_stats": (c_i, [c_f, c_f, c_l, c_i, c_f]),
+    "mvs_bn_finalize": (c_i, [c_f, c_d, c_fl, c_fl, c_f, c_f, c_f, c_i, c_f]),
+    "mvs_bn_act_fwd": (c_i, [c_f] * 6 + [c_l, c_i, c_i, c_f]),
+    "mvs_bn_act_bwd_reduce": (c_i, [c_f] * 6 + [c_l, c_i, c_i, c_f]),
+    "mvs_bn_act_bwd_apply": (c_i, [c_f] * 6 + [c_d, c_f, c_l, c_i, c_i, c_f]),
+    "mvs_conv_wgrad_cl": (c_i, [c_f, c_f, c_f] + [c_i] * 14 + [c_f]),
+    "mvs_thin_conv_cl": (c_i, [c_f] * 4 + [c_i] * 9 + [c_f]),
+    "mvs_sigmoid_bwd": (c_i, [c_f, c_f, c_f, c_l, c_f]),
+    "mvs_softmax_bwd": (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f]),
 }
 
 

@@ -37,7 +37,7 @@ def _nvcc():
 
 
 def _newest_header():
-    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [__file__]
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inl")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [__file__]
     return max(os.path.getmtime(h) for h in hdrs)
 
 

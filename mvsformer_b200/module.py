@@ -12,14 +12,15 @@ arithmetic runs in libmvs_b200.so on channels-last activations.  Reference lines
 * ``depth_regression`` ... ``schedule_range``   models/module.py:597-699
 
 Eval-mode BatchNorm is folded into the convolution (scale into the packed weights, shift as a
-per-channel bias) once per parameter version.  Train-mode forward (batch statistics + autograd)
-is not built yet and raises ``NotImplementedError`` instead of silently using another path.
+per-channel bias) once per parameter version.  In training (``module.training``) every block
+runs through ``mvsformer_b200.autograd``: raw FP32 convolution -> batch-statistics BatchNorm (running
+statistics updated in place) -> ReLU (+ skip), with a hand-written backward.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
-from . import config, engine
+from . import autograd, config, engine
 
 
 def _versions(*tensors):
@@ -125,11 +126,11 @@ def _triple(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
 
 
-def _require_eval(mod):
-    if mod.training:
-        raise NotImplementedError(
-            "%s: train-mode forward (batch-statistics BatchNorm + backward) is not built in this round; "
-            "call .eval(). No fallback path is taken." % type(mod).__name__)
+def _train_block(mod, conv, bn, x, skip, transposed, stride, relu):
+    """Training forward of one conv(+BN+ReLU) block (autograd.conv_bn_act)."""
+    if bn is None:
+        raise NotImplementedError("%s without BatchNorm is not built for training" % type(mod).__name__)
+    return autograd.conv_bn_act(x, conv, bn, skip, transposed, stride, relu)
 
 
 class Conv3d(nn.Module):
@@ -158,12 +159,15 @@ class Conv3d(nn.Module):
 
     def forward_cl(self, x, skip=None):
         """Channels-last forward: x [B,D,H,W,Cin]; ``skip`` is added after the activation."""
-        _require_eval(self)
         self._check_geometry()
+        if self.training:
+            return _train_block(self, self.conv, self.bn, x, skip, False, _triple(self.conv.stride), self.relu)
         w, shift = self.packed()
         return _run_conv(self._fold, x, w, shift, skip, _triple(self.conv.stride), self.relu)
 
     def forward(self, x):
+        if self.training:                  # differentiable layout change (torch owns the permutes)
+            return self.forward_cl(x.float().permute(0, 2, 3, 4, 1).contiguous()).permute(0, 4, 1, 2, 3)
         return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32")))
 
     def init_weights(self, init_method):
@@ -192,12 +196,15 @@ class Deconv3d(nn.Module):
         return self._fold.get(tensors, lambda: _pack_conv(self.conv, self.bn, True))
 
     def forward_cl(self, x, skip=None):
-        _require_eval(self)
         sd = _deconv_depth_stride(self.conv)
+        if self.training:
+            return _train_block(self, self.conv, self.bn, x, skip, True, (sd, 2, 2), self.relu)
         w, shift = self.packed()
         return _run_deconv(self._fold, x, w, shift, skip, sd, self.relu)
 
     def forward(self, x):
+        if self.training:                  # differentiable layout change (torch owns the permutes)
+            return self.forward_cl(x.float().permute(0, 2, 3, 4, 1).contiguous()).permute(0, 4, 1, 2, 3)
         return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32")))
 
     def init_weights(self, init_method):
@@ -236,9 +243,19 @@ class ConvBnReLU(nn.Module):
                               bias=False)
         self.bn = nn.BatchNorm2d(out_channels)
 
+    def forward_cl(self, x):
+        """x channels-last [B,1,H,W,Cin] (a depth-1 volume) -> [B,1,H,W,Cout]; FP32 conv, BatchNorm with batch
+        statistics in training / running statistics in eval, ReLU (autograd.conv_bn_act)."""
+        k, st, pd, dl = (tuple(self.conv.kernel_size), tuple(self.conv.stride), tuple(self.conv.padding),
+                         tuple(self.conv.dilation))
+        if k != (3, 3) or st != (1, 1) or pd != (1, 1) or dl != (1, 1):
+            raise NotImplementedError("ConvBnReLU: only 3x3 / stride 1 / pad 1 is built, got k=%s s=%s p=%s d=%s" % (k, st, pd, dl))
+        return autograd.conv_bn_act(x, self.conv, self.bn, None, False, (1, 1, 1), True)
+
     def forward(self, x):
-        raise NotImplementedError("ConvBnReLU runs fused inside StageNet.vis (mvs_vis_weight); a standalone 2D "
-                                  "conv block is outside the accelerated path")
+        """Standalone use (NCHW in / out).  Inside ``StageNet.vis`` the eval path is one fused kernel instead."""
+        y = self.forward_cl(x.float().permute(0, 2, 3, 1).unsqueeze(1).contiguous())
+        return y.squeeze(1).permute(0, 3, 1, 2)
 
 
 class _SeqDeconv(nn.Sequential):
@@ -259,12 +276,15 @@ class _SeqDeconv(nn.Sequential):
                               lambda: _pack_conv(conv, bn, True))
 
     def forward_cl(self, x, skip=None):
-        _require_eval(self)
         sd = _deconv_depth_stride(self[0])
+        if self.training:
+            return _train_block(self, self[0], self[1], x, skip, True, (sd, 2, 2), True)
         w, shift = self.packed()
         return _run_deconv(self._fold, x, w, shift, skip, sd, True)
 
     def forward(self, x):
+        if self.training:                  # differentiable layout change (torch owns the permutes)
+            return self.forward_cl(x.float().permute(0, 2, 3, 4, 1).contiguous()).permute(0, 4, 1, 2, 3)
         return engine.cl_to_ncdhw(self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32")))
 
 
@@ -297,6 +317,8 @@ class _RegNetBase(nn.Module):
 
     def _prob_cl(self, y):
         conv = self.prob
+        if self.training:
+            return autograd.thin_conv_module(y, conv).squeeze(-1)
         if not hasattr(self, "_prob_cache"):
             object.__setattr__(self, "_prob_cache", _ProbCache())
         w_host, b_host = self._prob_cache.get([conv.weight, conv.bias], lambda: _prob_host(conv))
@@ -304,7 +326,6 @@ class _RegNetBase(nn.Module):
 
     def forward_cl(self, x):
         """x: channels-last cost volume [B,D,H,W,Cin] -> prob_volume_pre [B,D,H,W]."""
-        _require_eval(self)
         b, d, h, w, _ = x.shape
         sd = self._depth_stride
         if h % 8 or w % 8 or (sd == 2 and d % 8):
@@ -317,6 +338,9 @@ class _RegNetBase(nn.Module):
         return y
 
     def forward(self, x):
+        if self.training:
+            out = self.forward_cl(x.float().permute(0, 2, 3, 4, 1).contiguous())
+            return out.unsqueeze(1) if out.dim() == 4 else out.permute(0, 4, 1, 2, 3)
         out = self.forward_cl(engine.ncdhw_to_cl(x, config.conv_precision() == "tf32"))
         if out.dim() == 4:
             return out.unsqueeze(1)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import config, engine
+from . import autograd, config, engine
 from .module import (ConvBnReLU, CostRegNet, CostRegNet2D, CostRegNet3D, _FoldCache, _bn_scale_shift,
                      init_inverse_range, init_range, schedule_inverse_range, schedule_range)
 
@@ -110,8 +110,6 @@ class StageNet(nn.Module):
         if features.shape[2] % groups:
             raise RuntimeError("shape '[%d, %d, -1, ...]' is invalid for %d feature channels"
                                % (b, groups, features.shape[2]))
-        if self.vis[0].bn.training:
-            raise NotImplementedError("StageNet: train-mode forward is not built in this round; call .eval()")
         relproj = engine.relative_projections(proj_matrices)
         entropy, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=not self.training)
         weight = self._vis_weight(entropy)
@@ -119,12 +117,44 @@ class StageNet(nn.Module):
                                               round_tf32=config.conv_precision() == "tf32")
         return volume, sim, entropy, weight
 
+    def _vis_weight_train(self, entropy):
+        """Training form of ``self.vis`` (batch-statistics BatchNorm, autograd): the reference calls the
+        net once per source view (mvsformer_model.py:91), so statistics are per view.  entropy [B,H,W]."""
+        x = entropy.contiguous().unsqueeze(1).unsqueeze(-1)                  # depth-1 volume [B,1,H,W,1]
+        for i in range(3):
+            x = self.vis[i].forward_cl(x)
+        return autograd.thin_conv_module(x, self.vis[3], act=2).squeeze(-1).squeeze(1)      # sigmoid -> [B,H,W]
+
+    def _forward_train(self, features, proj_matrices, depth_values, tmp):
+        """models/mvsformer_model.py:51-158 with ``self.training``: differentiable w.r.t. the features, the
+        visibility net and the regulariser; argmax depth; no similarity branch."""
+        if features.dim() != 5:
+            raise RuntimeError("features must be [B,V,C,H,W]")
+        assert features.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
+        groups = self.args["base_ch"]
+        if features.shape[2] % groups:
+            raise RuntimeError("shape '[%d, %d, -1, ...]' is invalid for %d feature channels"
+                               % (features.shape[0], groups, features.shape[2]))
+        relproj = engine.relative_projections(proj_matrices)
+        corr = autograd.group_correlation(features, relproj, depth_values, groups)          # [B,N,D,H,W,G]
+        entropy = autograd.corr_entropy(corr.detach())                                      # [B,N,H,W], :88 detach
+        weight = torch.stack([self._vis_weight_train(entropy[:, v]) for v in range(entropy.shape[1])], dim=1)
+        volume = autograd.aggregate(corr, weight)
+        prob_volume_pre = self.cost_reg.forward_cl(volume)
+        prob_volume, depth, conf = autograd.train_head(prob_volume_pre, depth_values, tmp)
+        return {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
+                "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
+
     def forward(self, features, proj_matrices, depth_values, tmp=2.0):
         """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W]."""
         if self.args["depth_type"] not in ("ce", "was"):
             raise NotImplementedError("depth_type=%r: only 'ce'/'was' heads are built (the shipped config uses 'ce')"
                                       % self.args["depth_type"])
         depth_values = depth_values.float().contiguous()
+        if self.training:
+            if type(tmp) == list or type(tmp) == tuple:
+                tmp = tmp[self.stage_idx]
+            return self._forward_train(features, proj_matrices, depth_values, tmp)
         volume, sim, _, _ = self.build_cost_volume(features, proj_matrices, depth_values)
         prob_volume_pre = self.cost_reg.forward_cl(volume)
         if type(tmp) == list or type(tmp) == tuple:

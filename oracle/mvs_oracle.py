@@ -225,7 +225,7 @@ def build_cost_volume(features, proj_matrices, depth_values, sd, groups=8, train
         corr = group_correlation(ref, warped, groups)
         if not training:
             sim_sum = sim_sum + cosine_similarity_volume(ref, warped, groups)
-        ent = view_entropy(corr)
+        ent = view_entropy(corr.detach())                                # :88 detaches the softmax input
         wgt = vis_weight(ent, sd, "vis", training)
         vol_sum = vol_sum + corr * wgt.unsqueeze(1)                      # :101
         w_sum = w_sum + wgt                                              # :102

@@ -14,8 +14,8 @@ def load_golden(name):
 
 
 def rel_l1(a, b):
-    a = torch.as_tensor(a).double()
-    b = torch.as_tensor(b).double()
+    a = torch.as_tensor(a).detach().double()
+    b = torch.as_tensor(b).detach().double()
     return float((a - b).abs().mean() / b.abs().mean().clamp_min(1e-30))
 
 

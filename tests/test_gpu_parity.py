@@ -220,8 +220,6 @@ def test_cost_reg_rejects_bad_shapes():
     net = M.CostRegNet(8, 8).eval().to(DEV)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 8, 8, 12, 24, device=DEV))          # H not divisible by 8 (reference: size mismatch)
-    with pytest.raises(NotImplementedError):
-        net.train()(torch.zeros(1, 8, 8, 16, 24, device=DEV))
     with pytest.raises(RuntimeError):
         M.depth_regression(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4))   # CPU tensors: no fallback
 

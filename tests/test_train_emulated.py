@@ -1,0 +1,308 @@
+"""Training path on the CPU emulation harness (tests/emu): the per-thread kernel bodies of
+csrc/train_kernels.cuh — the same source the CUDA library is built from — are run thread by thread
+on host memory, driven through the package's own autograd layer, and compared with torch autograd
+over the oracle.  This checks index arithmetic, formulas, weight re-packing for the data-gradient
+kernels and the autograd wiring without a GPU; the CUDA launch itself is covered by
+tests/test_gpu_train.py.  The emulation library is test infrastructure: the product never loads it.
+"""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mvsformer_b200 import _lib, autograd, engine
+from mvsformer_b200 import module as M
+from mvsformer_b200 import synthetic as S
+from mvsformer_b200.mvsformer_model import StageNet
+from oracle import mvs_oracle as O
+from tests.emu import build_emu
+from tests.helpers import STAGE_ARGS, rel_l1
+
+_EMU_SYMBOLS = [
+    "mvs_last_error_string", "mvs_launch_count", "mvs_conv3d_cl", "mvs_deconv3d_cl", "mvs_group_corr_fwd",
+    "mvs_group_corr_bwd", "mvs_corr_entropy", "mvs_aggregate_fwd", "mvs_aggregate_bwd", "mvs_bn_stats", "mvs_bn_finalize",
+    "mvs_bn_act_fwd", "mvs_bn_act_bwd_reduce", "mvs_bn_act_bwd_apply", "mvs_conv_wgrad_cl", "mvs_thin_conv_cl",
+    "mvs_sigmoid_bwd", "mvs_softmax_bwd"]
+
+
+def _host_only(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        assert not t.is_cuda and t.dtype in (torch.float32, torch.float64) and t.is_contiguous(), (t.dtype, t.stride())
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    """Points the package's ctypes layer at the CPU emulation library for the duration of a test."""
+    lib = ctypes.CDLL(build_emu.build())
+    for name in _EMU_SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = _lib._SIGNATURES[name]
+    monkeypatch.setattr(_lib, "load", lambda: lib)
+    monkeypatch.setattr(_lib, "require_cuda", _host_only)
+    monkeypatch.setattr(_lib, "stream", lambda: None)
+    monkeypatch.setattr(engine, "require_cuda", _host_only)
+    monkeypatch.setattr(engine, "stream", lambda: None)
+
+    def relproj(proj):
+        b, v = proj.shape[:2]
+        ref = O.compose_projection(proj[:, 0].double())
+        rows = []
+        for i in range(1, v):
+            rot, trans = O.relative_projection(O.compose_projection(proj[:, i].double()), ref)
+            rows.append(torch.cat([rot, trans.unsqueeze(-1)], dim=-1).reshape(b, 12))
+        return torch.stack(rows, dim=1).float().contiguous()
+
+    def head(pre, depth_values, tmp, training, want_prob=True):
+        prob, depth, conf = O.regression_head(pre.detach(), depth_values, tmp, training)
+        return prob.contiguous(), depth.contiguous(), conf.contiguous()
+
+    monkeypatch.setattr(engine, "relative_projections", relproj)
+    monkeypatch.setattr(engine, "regression_head", head)
+    return lib
+
+
+def _case(batch=2, views=3, chans=16, depth=4, height=8, width=16, seed=0):
+    g = S._gen(seed)
+    feats = torch.nn.functional.avg_pool2d(torch.randn(batch * views, chans, height + 4, width + 4, generator=g), 5, 1)
+    feats = feats.view(batch, views, chans, height, width).contiguous()
+    cams = S.make_cameras(batch, views, height * 8, width * 8)["stage1"]
+    hyp = (500.0 + 60.0 * torch.arange(depth).view(1, depth, 1, 1)
+           + 20.0 * torch.rand(batch, depth, height, width, generator=g)).contiguous()
+    return feats, cams, hyp
+
+
+def _oracle_corr(feats, cams, hyp, groups):
+    ref_p = O.compose_projection(cams[:, 0])
+    out = []
+    for v in range(1, feats.shape[1]):
+        warped, _ = O.homo_warping_3D_with_mask(feats[:, v], O.compose_projection(cams[:, v]), ref_p, hyp)
+        out.append(O.group_correlation(feats[:, 0], warped, groups))              # [B,G,D,H,W]
+    return torch.stack(out, dim=1)                                                 # [B,N,G,D,H,W]
+
+
+def test_group_correlation_forward_backward(emu):
+    feats, cams, hyp = _case()
+    relproj = engine.relative_projections(cams)
+    f1 = feats.clone().requires_grad_(True)
+    corr = autograd.group_correlation(f1, relproj, hyp, 8)                        # [B,N,D,H,W,G]
+    f2 = feats.clone().requires_grad_(True)
+    want = _oracle_corr(f2, cams, hyp, 8).permute(0, 1, 3, 4, 5, 2)
+    assert rel_l1(corr, want) < 1e-5
+    gout = torch.randn(corr.shape, generator=S._gen(1))
+    corr.backward(gout)
+    want.backward(gout)
+    assert rel_l1(f1.grad[:, 0], f2.grad[:, 0]) < 1e-5                            # reference-view gradient
+    assert rel_l1(f1.grad[:, 1:], f2.grad[:, 1:]) < 1e-5                          # scattered source-view gradients
+    ent = autograd.corr_entropy(corr.detach())
+    want_ent = torch.stack([O.view_entropy(want.detach()[:, v].permute(0, 4, 1, 2, 3)).squeeze(1)
+                            for v in range(want.shape[1])], dim=1)
+    assert rel_l1(ent, want_ent) < 1e-5
+
+
+def test_group_correlation_wide_baseline_taps_outside(emu):
+    """Samples that leave the source image (zero padding) must neither read nor scatter out of bounds."""
+    feats, cams, hyp = _case(views=4, seed=3)
+    cams = cams.clone()
+    cams[:, 2, 0, 0, 3] += 400.0                                                   # push a view far sideways
+    cams[:, 3, 0, 2, 3] -= 900.0                                                   # and one behind the scene
+    relproj = engine.relative_projections(cams)
+    f1 = feats.clone().requires_grad_(True)
+    corr = autograd.group_correlation(f1, relproj, hyp, 8)
+    f2 = feats.clone().requires_grad_(True)
+    want = _oracle_corr(f2, cams, hyp, 8).permute(0, 1, 3, 4, 5, 2)
+    assert rel_l1(corr, want) < 1e-5
+    corr.sum().backward()
+    want.sum().backward()
+    assert rel_l1(f1.grad, f2.grad) < 1e-5
+
+
+def test_aggregate_forward_backward(emu):
+    g = S._gen(5)
+    corr = torch.randn(2, 3, 4, 6, 8, 8, generator=g).requires_grad_(True)         # [B,N,D,H,W,G]
+    weight = torch.rand(2, 3, 6, 8, generator=g).requires_grad_(True)
+    vol = autograd.aggregate(corr, weight)
+    c2, w2 = corr.detach().clone().requires_grad_(True), weight.detach().clone().requires_grad_(True)
+    want = (c2 * w2.view(2, 3, 1, 6, 8, 1)).sum(1) / (w2.sum(1).view(2, 1, 6, 8, 1) + 1e-6)
+    assert rel_l1(vol, want) < 1e-6
+    gout = torch.randn(vol.shape, generator=g)
+    vol.backward(gout)
+    want.backward(gout)
+    assert rel_l1(corr.grad, c2.grad) < 1e-5
+    assert rel_l1(weight.grad, w2.grad) < 1e-4
+
+
+def _torch_block(x, conv, bn, skip, transposed, stride, relu, out_pad):
+    """The reference block on NCDHW tensors: conv / conv_transpose -> BatchNorm(batch stats) -> ReLU (+ skip)."""
+    w = conv.weight if conv.weight.dim() == 5 else conv.weight.unsqueeze(2)
+    pad = tuple(k // 2 for k in w.shape[2:])
+    if transposed:
+        y = F.conv_transpose3d(x, w, stride=stride, padding=pad, output_padding=out_pad)
+    else:
+        y = F.conv3d(x, w, stride=stride, padding=pad)
+    y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
+    if relu:
+        y = torch.relu(y)
+    return y if skip is None else y + skip
+
+
+@pytest.mark.parametrize("name,cin,cout,kernel,stride,transposed", [
+    ("conv_s1", 8, 16, (3, 3, 3), (1, 1, 1), False),
+    ("conv_s2", 8, 16, (3, 3, 3), (2, 2, 2), False),
+    ("conv_s122", 16, 32, (3, 3, 3), (1, 2, 2), False),
+    ("conv_k133_s122", 8, 16, (1, 3, 3), (1, 2, 2), False),
+    ("deconv_s2", 16, 8, (3, 3, 3), (2, 2, 2), True),
+    ("deconv_s122", 32, 16, (3, 3, 3), (1, 2, 2), True),
+    ("deconv_k133", 16, 8, (1, 3, 3), (1, 2, 2), True),
+    ("thin_2d_1to16", 1, 16, (1, 3, 3), (1, 1, 1), False),
+])
+def test_conv_bn_act_block(emu, name, cin, cout, kernel, stride, transposed):
+    g = S._gen(11)
+    pad = tuple(k // 2 for k in kernel)
+    out_pad = tuple(s - 1 for s in stride)
+    if transposed:
+        conv = torch.nn.ConvTranspose3d(cin, cout, kernel, stride=stride, padding=pad, output_padding=out_pad, bias=False)
+    else:
+        conv = torch.nn.Conv3d(cin, cout, kernel, stride=stride, padding=pad, bias=False)
+    bn = torch.nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.2)
+        bn.weight.copy_(0.5 + torch.rand(cout, generator=g))
+        bn.bias.copy_(torch.randn(cout, generator=g) * 0.3)
+        bn.running_mean.copy_(torch.randn(cout, generator=g) * 0.1)
+        bn.running_var.copy_(0.5 + torch.rand(cout, generator=g))
+    d_in = 4 if kernel[0] == 3 else 1
+    x = torch.randn(2, cin, d_in, 6, 8, generator=g)
+    # reference (torch autograd, NCDHW), on clones of the module state
+    import copy
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    xr = x.clone().requires_grad_(True)
+    want0 = _torch_block(xr, conv_r, bn_r, None, transposed, stride, True, out_pad)
+    skip = torch.randn(want0.shape, generator=g)
+    sr = skip.clone().requires_grad_(True)
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    want = _torch_block(xr, conv_r, bn_r, sr, transposed, stride, True, out_pad)
+    # ours (channels-last)
+    xo = x.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    so = skip.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    got = autograd.conv_bn_act(xo, conv, bn, so, transposed, stride, True)
+    assert rel_l1(got.permute(0, 4, 1, 2, 3), want) < 1e-5
+    assert rel_l1(bn.running_mean, bn_r.running_mean) < 1e-5 and rel_l1(bn.running_var, bn_r.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == 1
+    gout = torch.randn(want.shape, generator=g)
+    want.backward(gout)
+    got.backward(gout.permute(0, 2, 3, 4, 1).contiguous())
+    assert rel_l1(conv.weight.grad, conv_r.weight.grad) < 2e-4
+    assert rel_l1(bn.weight.grad, bn_r.weight.grad) < 2e-4 and rel_l1(bn.bias.grad, bn_r.bias.grad) < 2e-4
+    assert rel_l1(xo.grad.permute(0, 4, 1, 2, 3), xr.grad) < 2e-4
+    assert rel_l1(so.grad.permute(0, 4, 1, 2, 3), sr.grad) < 1e-6
+
+
+def test_conv_bn_act_frozen_statistics(emu):
+    """BatchNorm in eval inside a training graph: running statistics, treated as constants by the backward."""
+    g = S._gen(12)
+    conv = torch.nn.Conv3d(8, 8, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm3d(8).eval()
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.randn(8, generator=g) * 0.1)
+        bn.running_var.copy_(0.5 + torch.rand(8, generator=g))
+    x = torch.randn(1, 8, 2, 6, 8, generator=g)
+    xr = x.clone().requires_grad_(True)
+    want = _torch_block(xr, conv, bn, None, False, (1, 1, 1), True, None)
+    want.sum().backward()
+    gw = conv.weight.grad.clone()
+    conv.weight.grad = None
+    xo = x.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    got = autograd.conv_bn_act(xo, conv, bn, None, False, (1, 1, 1), True)
+    got.sum().backward()
+    assert rel_l1(got.permute(0, 4, 1, 2, 3), want) < 1e-5
+    assert rel_l1(conv.weight.grad, gw) < 1e-4
+    assert rel_l1(xo.grad.permute(0, 4, 1, 2, 3), xr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,k,bias,act", [(8, 1, 3, False, 0), (8, 1, 1, True, 0), (8, 1, 1, True, 2)])
+def test_thin_conv_module(emu, cin, cout, k, bias, act):
+    g = S._gen(13)
+    conv = torch.nn.Conv3d(cin, cout, k, padding=k // 2, bias=bias)
+    x = torch.randn(2, cin, 3, 5, 7, generator=g)
+    xr = x.clone().requires_grad_(True)
+    want = conv(xr)
+    if act == 2:
+        want = torch.sigmoid(want)
+    gout = torch.randn(want.shape, generator=g)
+    want.backward(gout)
+    ref_grads = [conv.weight.grad.clone(), conv.bias.grad.clone() if bias else None]
+    conv.zero_grad()
+    xo = x.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    got = autograd.thin_conv_module(xo, conv, act)
+    got.backward(gout.permute(0, 2, 3, 4, 1).contiguous())
+    assert rel_l1(got.permute(0, 4, 1, 2, 3), want) < 1e-5
+    assert rel_l1(conv.weight.grad, ref_grads[0]) < 1e-4
+    if bias:
+        assert rel_l1(conv.bias.grad, ref_grads[1]) < 1e-4
+    assert rel_l1(xo.grad.permute(0, 4, 1, 2, 3), xr.grad) < 1e-4
+
+
+def test_softmax_head_backward(emu):
+    g = S._gen(14)
+    pre = torch.randn(2, 6, 5, 7, generator=g).requires_grad_(True)
+    dv = torch.rand(2, 6, 5, 7, generator=g) + 1.0
+    prob, depth, conf = autograd.train_head(pre, dv, 1.0)
+    p2 = pre.detach().clone().requires_grad_(True)
+    want = torch.softmax(p2, dim=1)
+    gout = torch.randn(prob.shape, generator=g)
+    prob.backward(gout)
+    want.backward(gout)
+    assert not depth.requires_grad and not conf.requires_grad
+    assert rel_l1(pre.grad, p2.grad) < 1e-5
+
+
+def _stage_pair(stage, ndepth, height, width, batch=2):
+    feats, cams, hyp = _case(batch=batch, views=3, chans=S.FEAT_CHS[stage], depth=ndepth, height=height, width=width,
+                             seed=20 + stage)
+    net = StageNet(dict(STAGE_ARGS), ndepth, stage).train()
+    sd = S.fill_state_dict(net.state_dict(), seed=30 + stage)
+    net.load_state_dict(sd)
+    return net, sd, feats, cams, hyp
+
+
+@pytest.mark.parametrize("stage,ndepth", [(1, 16), (3, 4)])
+def test_stagenet_training_step_matches_oracle_autograd(emu, stage, ndepth):
+    """Whole StageNet.forward in training + backward of a cross-entropy loss on prob_volume_pre
+    (models/losses.py:340-341) against torch autograd over the oracle restatement."""
+    net, sd, feats, cams, hyp = _stage_pair(stage, ndepth, 8, 16)
+    f1 = feats.clone().requires_grad_(True)
+    out = net(f1, cams, hyp, tmp=list(S.EVAL_TMP))
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    sd2 = dict(sd)
+    sd2.update(params)
+    f2 = feats.clone().requires_grad_(True)
+    want = O.stage_forward(f2, cams, hyp, sd2, ndepth, S.EVAL_TMP[stage], training=True)
+    assert rel_l1(out["prob_volume_pre"], want["prob_volume_pre"]) < 1e-4
+    assert (out["depth"] == want["depth"]).float().mean() > 0.98                    # argmax ties aside
+    target = torch.randint(0, ndepth, (feats.shape[0], 8, 16), generator=S._gen(7))
+    F.cross_entropy(out["prob_volume_pre"], target).backward()
+    F.cross_entropy(want["prob_volume_pre"], target).backward()
+    assert rel_l1(f1.grad, f2.grad) < 2e-3
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        if name == "cost_reg.prob.bias":           # d CE / d (bias added to every logit) is exactly 0: rounding noise only
+            assert float(p.grad.abs().max()) < 1e-6
+            continue
+        assert rel_l1(p.grad, params[name].grad) < 5e-3, name
+    # running statistics moved (momentum 0.1) and the counters advanced once per call
+    assert int(net.cost_reg.conv1.bn.num_batches_tracked) == 1
+    assert int(net.vis[0].bn.num_batches_tracked) == feats.shape[1] - 1            # one call per source view
+
+
+def test_cost_reg_training_ncdhw_interface(emu):
+    """CostRegNet3D.forward (NCDHW in / out) in training is differentiable end to end."""
+    g = S._gen(15)
+    net = M.CostRegNet3D(8, 8).train()
+    x = torch.randn(1, 8, 2, 8, 16, generator=g, requires_grad=True)
+    y = net(x)
+    assert y.shape == (1, 1, 2, 8, 16)
+    y.square().mean().backward()
+    assert x.grad is not None and all(p.grad is not None for p in net.parameters())
