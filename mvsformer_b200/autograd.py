@@ -245,8 +245,12 @@ class _ConvBnAct(torch.autograd.Function):
             track = bn.track_running_stats and bn.running_mean is not None
             _call("mvs_bn_finalize", _p(sums), float(m * world), float(bn.eps), float(bn.momentum), _p(mean_invstd),
                   _p(bn.running_mean if track else None), _p(bn.running_var if track else None), c)
-            if track and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+            if track:
+                # the kernel wrote through raw pointers: tell torch (the eval path's fold cache keys on versions)
+                torch.autograd.graph.increment_version(bn.running_mean)
+                torch.autograd.graph.increment_version(bn.running_var)
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
         else:                                   # frozen BN inside a training graph: running statistics
             mean_invstd = torch.cat([bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + bn.eps)]).contiguous()
         y = torch.empty_like(conv)

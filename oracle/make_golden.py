@@ -12,6 +12,8 @@ compared).  Outputs are what the reference functions returned:
 * ``schedules.npz``     models/module.py:597-699
 * ``stage{1..4}.npz``   StageNet.forward (eval)  models/mvsformer_model.py:51-158
 * ``stage2_train.npz``  StageNet.forward (train mode: batch-stat BN, argmax depth)
+* ``stage{2,4}_train_grads.npz``  gradients of a cross-entropy loss on ``prob_volume_pre`` (models/losses.py:340-341)
+                        through StageNet.forward in train mode, from torch autograd over the reference
 * ``state_dict_keys.json``  names/shapes of the 302 ``fusions.*`` checkpoint entries
 * ``cascade.npz``       the cascade loop models/mvsformer_model.py:410-449 driven over synthetic features
                         (the loop is re-stated here in 15 lines because the reference only has it
@@ -130,6 +132,47 @@ def gen_stages(ns):
                         **{k: np_(v) for k, v in out.items() if k != "depth_values"})
 
 
+TRAIN_GRAD_FULL = ("vis.0.conv.weight", "vis.0.bn.weight", "vis.2.bn.bias", "vis.3.weight", "vis.3.bias",
+                   "cost_reg.conv1.conv.weight", "cost_reg.conv1.bn.weight", "cost_reg.conv2.bn.bias",
+                   "cost_reg.prob.weight")
+
+
+def train_target(stage, batch, h, w):
+    """Synthetic ground-truth hypothesis index per pixel (the role of gt_index_volume, models/losses.py:338)."""
+    return torch.randint(0, S.NDEPTHS[stage], (batch, h, w), generator=S._gen(700 + stage))
+
+
+def gen_train_grads(ns):
+    """Backward of the training branch: reference StageNet.train(), loss = CE(prob_volume_pre, target)."""
+    R = ns.mvsformer_model
+    height, width = 64, 96
+    for s in (1, 3):
+        net = R.StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).train()
+        sd = S.fill_state_dict(net.state_dict(), seed=50 + s)
+        net.load_state_dict(sd)
+        feats, cams = stage_inputs(s, height, width, batch=2, seed=77 + s)
+        hyp = S.narrow_hypotheses(s, height, width, 2)
+        feats = feats.clone().requires_grad_(True)
+        out = net(feats, cams, hyp, tmp=list(S.EVAL_TMP))
+        target = train_target(s, 2, feats.shape[-2], feats.shape[-1])
+        loss = F.cross_entropy(out["prob_volume_pre"], target)
+        loss.backward()
+        grads = {"grad_features": np_(feats.grad), "loss": float(loss), "prob_volume_pre": np_(out["prob_volume_pre"])}
+        names = []
+        for name, p in net.named_parameters():
+            names.append(name)
+            grads["abs_sum/" + name] = float(p.grad.double().abs().sum())
+            grads["sum/" + name] = float(p.grad.double().sum())
+            if name in TRAIN_GRAD_FULL or name.endswith("conv11.0.weight") or name.endswith("conv11.conv.weight"):
+                grads["grad/" + name] = np_(p.grad)
+        for name, buf in net.named_buffers():
+            if "running" in name and (name.startswith("vis.0") or name.startswith("cost_reg.conv1.")):
+                grads["buf/" + name] = np_(buf)
+        np.savez_compressed(os.path.join(OUT, "stage%d_train_grads.npz" % (s + 1)), height=height, width=width, batch=2,
+                            views=3, weight_seed=50 + s, feat_seed=77 + s, feat_checksum=checksum(feats),
+                            param_names=np.array(names), **grads)
+
+
 def reference_cascade(ns, features, cams, depth_values, nets, tmp, ratios):
     """The loop of models/mvsformer_model.py:410-449 (TwinMVSNet.forward after feature extraction),
     calling the reference's own schedulers and StageNets."""
@@ -200,6 +243,7 @@ def main():
     gen_schedules(ns)
     gen_stages(ns)
     gen_cascade(ns)
+    gen_train_grads(ns)
     gen_state_dict_keys(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

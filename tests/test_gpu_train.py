@@ -1,0 +1,213 @@
+"""GPU parity of the training path (SURVEY.md §8b "Autograd", BASELINE cfg 5): train-mode forward and
+backward through the C ABI on the device, against torch autograd over the CPU oracle and against
+gradients recorded from the unmodified reference (tests/golden/stage{2,4}_train_grads.npz).
+
+Tolerances: forward volumes 1e-4 rel-L1 (batch statistics amplify fp32 summation-order noise), data
+and weight gradients 5e-3 rel-L1 (fp32 atomics, different accumulation order than torch's CPU
+kernels); the same kernel bodies are checked to 1e-5 / 2e-4 by the CPU emulation tests.
+"""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mvsformer_b200 import autograd, engine
+from mvsformer_b200 import module as M
+from mvsformer_b200 import synthetic as S
+from mvsformer_b200.mvsformer_model import CascadeMVS, StageNet
+from oracle import mvs_oracle as O
+from tests.helpers import CASCADE_ARGS, STAGE_ARGS, rel_l1
+from tests.test_oracle_golden import _train_grad_case
+from tests.test_train_emulated import _case, _oracle_corr, _torch_block
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def test_group_correlation_forward_backward_gpu():
+    feats, cams, hyp = _case(batch=2, views=4, chans=32, depth=8, height=16, width=24, seed=2)
+    cams = cams.clone()
+    cams[:, 3, 0, 0, 3] += 400.0                                          # one view partly outside the image
+    relproj = engine.relative_projections(cu(cams))
+    f1 = cu(feats).requires_grad_(True)
+    corr = autograd.group_correlation(f1, relproj, cu(hyp), 8)
+    f2 = feats.clone().requires_grad_(True)
+    want = _oracle_corr(f2, cams, hyp, 8).permute(0, 1, 3, 4, 5, 2)
+    assert rel_l1(corr.cpu(), want) < 2e-5
+    gout = torch.randn(want.shape, generator=S._gen(1))
+    corr.backward(cu(gout))
+    want.backward(gout)
+    assert rel_l1(f1.grad.cpu(), f2.grad) < 1e-4
+    ent = autograd.corr_entropy(corr.detach())
+    want_ent = torch.stack([O.view_entropy(want.detach()[:, v].permute(0, 4, 1, 2, 3)).squeeze(1)
+                            for v in range(want.shape[1])], dim=1)
+    assert rel_l1(ent.cpu(), want_ent) < 1e-4
+
+
+def test_aggregate_forward_backward_gpu():
+    g = S._gen(5)
+    corr = torch.randn(2, 3, 4, 16, 24, 8, generator=g)
+    weight = torch.rand(2, 3, 16, 24, generator=g)
+    c1, w1 = cu(corr).requires_grad_(True), cu(weight).requires_grad_(True)
+    vol = autograd.aggregate(c1, w1)
+    c2, w2 = corr.clone().requires_grad_(True), weight.clone().requires_grad_(True)
+    want = (c2 * w2.view(2, 3, 1, 16, 24, 1)).sum(1) / (w2.sum(1).view(2, 1, 16, 24, 1) + 1e-6)
+    assert rel_l1(vol.cpu(), want) < 1e-6
+    gout = torch.randn(want.shape, generator=g)
+    vol.backward(cu(gout))
+    want.backward(gout)
+    assert rel_l1(c1.grad.cpu(), c2.grad) < 1e-5
+    assert rel_l1(w1.grad.cpu(), w2.grad) < 1e-4
+
+
+@pytest.mark.parametrize("name,cin,cout,kernel,stride,transposed", [
+    ("conv_s1", 16, 16, (3, 3, 3), (1, 1, 1), False),
+    ("conv_s2", 8, 16, (3, 3, 3), (2, 2, 2), False),
+    ("conv_s122", 32, 64, (3, 3, 3), (1, 2, 2), False),
+    ("conv_wide", 64, 64, (3, 3, 3), (1, 1, 1), False),
+    ("deconv_s2", 64, 32, (3, 3, 3), (2, 2, 2), True),
+    ("deconv_s122", 16, 8, (3, 3, 3), (1, 2, 2), True),
+    ("thin_2d_1to16", 1, 16, (1, 3, 3), (1, 1, 1), False),
+    ("vis_2d_16to8", 16, 8, (1, 3, 3), (1, 1, 1), False),
+])
+def test_conv_bn_act_block_gpu(name, cin, cout, kernel, stride, transposed):
+    g = S._gen(11)
+    pad = tuple(k // 2 for k in kernel)
+    out_pad = tuple(s - 1 for s in stride)
+    if transposed:
+        conv = torch.nn.ConvTranspose3d(cin, cout, kernel, stride=stride, padding=pad, output_padding=out_pad, bias=False)
+    else:
+        conv = torch.nn.Conv3d(cin, cout, kernel, stride=stride, padding=pad, bias=False)
+    bn = torch.nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.2)
+        bn.weight.copy_(0.5 + torch.rand(cout, generator=g))
+        bn.bias.copy_(torch.randn(cout, generator=g) * 0.3)
+    x = torch.randn(2, cin, 4 if kernel[0] == 3 else 1, 16, 24, generator=g)
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    xr = x.clone().requires_grad_(True)
+    probe = _torch_block(xr, copy.deepcopy(conv), copy.deepcopy(bn), None, transposed, stride, True, out_pad)
+    skip = torch.randn(probe.shape, generator=g)
+    sr = skip.clone().requires_grad_(True)
+    want = _torch_block(xr, conv_r, bn_r, sr, transposed, stride, True, out_pad)
+    conv, bn = conv.to(DEV), bn.to(DEV)
+    xo = cu(x.permute(0, 2, 3, 4, 1).contiguous()).requires_grad_(True)
+    so = cu(skip.permute(0, 2, 3, 4, 1).contiguous()).requires_grad_(True)
+    got = autograd.conv_bn_act(xo, conv, bn, so, transposed, stride, True)
+    assert rel_l1(got.permute(0, 4, 1, 2, 3).cpu(), want) < 1e-4
+    assert rel_l1(bn.running_mean.cpu(), bn_r.running_mean) < 1e-4 and rel_l1(bn.running_var.cpu(), bn_r.running_var) < 1e-4
+    gout = torch.randn(want.shape, generator=g)
+    want.backward(gout)
+    got.backward(cu(gout.permute(0, 2, 3, 4, 1).contiguous()))
+    assert rel_l1(conv.weight.grad.cpu(), conv_r.weight.grad) < 5e-3
+    assert rel_l1(bn.weight.grad.cpu(), bn_r.weight.grad) < 5e-3 and rel_l1(bn.bias.grad.cpu(), bn_r.bias.grad) < 5e-3
+    assert rel_l1(xo.grad.permute(0, 4, 1, 2, 3).cpu(), xr.grad) < 5e-3
+    assert rel_l1(so.grad.permute(0, 4, 1, 2, 3).cpu(), sr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("s", [1, 3])
+def test_stagenet_training_step_vs_reference_gradients(s):
+    """StageNet.train() forward + backward of CE(prob_volume_pre) on the GPU vs the gradients torch
+    autograd produced through the UNMODIFIED reference (oracle/make_golden.py::gen_train_grads)."""
+    g, feats, cams, hyp, sd, target = _train_grad_case(s)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).train()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    f1 = cu(feats).requires_grad_(True)
+    out = net(f1, cu(cams), cu(hyp), tmp=list(S.EVAL_TMP))
+    assert set(out) == {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre"}
+    assert rel_l1(out["prob_volume_pre"].cpu(), g["prob_volume_pre"]) < 1e-4
+    loss = F.cross_entropy(out["prob_volume_pre"], cu(target))
+    assert float(loss.detach()) == pytest.approx(float(g["loss"]), rel=1e-4)
+    loss.backward()
+    assert rel_l1(f1.grad.cpu(), g["grad_features"]) < 5e-3
+    for name, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        if name == "cost_reg.prob.bias":
+            assert float(p.grad.abs().max()) < 1e-5
+            continue
+        tol = 3e-2 if name.startswith("vis.") else 5e-3
+        assert float(p.grad.double().abs().sum()) == pytest.approx(float(g["abs_sum/" + name]), rel=tol), name
+        if "grad/" + name in g.files:
+            assert rel_l1(p.grad.cpu(), g["grad/" + name]) < tol, name
+    for name, buf in net.named_buffers():
+        if "buf/" + name in g.files:
+            assert rel_l1(buf.cpu(), g["buf/" + name]) < 1e-4, name
+
+
+def test_eval_after_training_uses_updated_statistics():
+    """.train() steps move the running statistics in place; .eval() then folds the NEW statistics (cache
+    keyed on tensor versions) and takes the fused inference path again."""
+    s = 3
+    _, feats, cams, hyp, sd, target = _train_grad_case(s)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        before = net(cu(feats), cu(cams), cu(hyp), tmp=1.0)["prob_volume_pre"].clone()
+    net.train()
+    F.cross_entropy(net(cu(feats), cu(cams), cu(hyp))["prob_volume_pre"], cu(target)).backward()
+    net.eval()
+    with torch.no_grad():
+        after = net(cu(feats), cu(cams), cu(hyp), tmp=1.0)["prob_volume_pre"]
+    sd_now = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    want = O.stage_forward(feats, cams, hyp, sd_now, S.NDEPTHS[s], 1.0)["prob_volume_pre"]
+    assert rel_l1(after.cpu(), want) < 2e-3                      # TF32-or-better conv mode of the eval path
+    assert rel_l1(after.cpu(), before.cpu()) > 1e-3              # the statistics really changed
+
+
+def test_cascade_training_step_cfg5_size():
+    """BASELINE cfg 5 per-GPU shape (1 reference + 4 source views, 512x640, 4-stage cascade) in training:
+    one forward + backward over all four stages; gradients finite and non-zero for every parameter and for
+    the features; a small step of the stage-1 parameters along their negative gradient lowers the stage-1
+    loss (first-order property; later stages see argmax-dependent hypotheses, so only stage 1 is smooth)."""
+    height, width, batch, views = 512, 640, 1, 5
+    feats = {k: cu(v).requires_grad_(True) for k, v in S.make_features(batch, views, height, width, seed=9).items()}
+    cams = {k: cu(v) for k, v in S.make_cameras(batch, views, height, width).items()}
+    dv = cu(S.make_depth_range(batch))
+    net = CascadeMVS(dict(CASCADE_ARGS)).train().to(DEV)
+    targets = [cu(torch.randint(0, S.NDEPTHS[s], (batch,) + S.stage_hw(height, width, s), generator=S._gen(s)))
+               for s in range(4)]
+
+    def losses():
+        out = net(feats, cams, dv)
+        return [F.cross_entropy(out["stage%d" % (s + 1)]["prob_volume_pre"], targets[s]) for s in range(4)]
+
+    first = losses()
+    sum(first).backward()
+    torch.cuda.synchronize()
+    for name, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        if not name.endswith("prob.bias"):
+            assert float(p.grad.abs().sum()) > 0, name
+    for k, f in feats.items():
+        assert f.grad is not None and torch.isfinite(f.grad).all() and float(f.grad.abs().sum()) > 0, k
+    stage1 = list(net.fusions[0].parameters())
+    gnorm = sum(float(p.grad.double().pow(2).sum()) for p in stage1) ** 0.5
+    with torch.no_grad():
+        for p in stage1:
+            p -= (1e-2 / gnorm) * p.grad
+        second = losses()
+    assert float(second[0]) < float(first[0])
+
+
+def test_cost_reg_training_ncdhw_interface_gpu():
+    g = S._gen(15)
+    net = M.CostRegNet(8, 8).train().to(DEV)
+    x = cu(torch.randn(1, 8, 8, 16, 24, generator=g)).requires_grad_(True)
+    y = net(x)
+    assert y.shape == (1, 1, 8, 16, 24)
+    y.square().mean().backward()
+    assert x.grad is not None and all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+def test_training_path_rejects_cpu_tensors():
+    net = StageNet(dict(STAGE_ARGS), 4, 3).train()
+    feats, cams, hyp = _case(batch=1, views=3, chans=8, depth=4, height=8, width=16)
+    with pytest.raises(RuntimeError):
+        net(feats, cams, hyp)                                    # CPU tensors: no fallback

@@ -100,3 +100,46 @@ def test_cascade_golden():
         assert rel_l1(out["stage%d" % (s + 1)]["depth"], g["stage%d_depth" % (s + 1)]) < 1e-6
     assert rel_l1(out["refined_depth"], g["refined_depth"]) < 1e-6
     assert rel_l1(out["photometric_confidence"], g["photometric_confidence"]) < 1e-5
+
+
+def _train_grad_case(s):
+    """Inputs of oracle/make_golden.py::gen_train_grads, regenerated from the recorded seeds."""
+    from tests.helpers import reference_state_dict_template
+
+    g = load_golden("stage%d_train_grads.npz" % (s + 1))
+    height, width, batch = int(g["height"]), int(g["width"]), int(g["batch"])
+    feats = S.make_features(batch, 3, height, width, seed=int(g["feat_seed"]), stages=(s,))["stage%d" % (s + 1)]
+    assert checksum(feats) == pytest.approx(float(g["feat_checksum"]), rel=1e-12)
+    cams = S.make_cameras(batch, 3, height, width)["stage%d" % (s + 1)]
+    hyp = S.narrow_hypotheses(s, height, width, batch)
+    sd = S.fill_state_dict(reference_state_dict_template(s, S.NDEPTHS[s]), seed=int(g["weight_seed"]))
+    target = torch.randint(0, S.NDEPTHS[s], (batch, feats.shape[-2], feats.shape[-1]), generator=S._gen(700 + s))
+    return g, feats, cams, hyp, sd, target
+
+
+@pytest.mark.parametrize("s", [1, 3])
+def test_training_gradients_golden(s):
+    """torch autograd over the oracle restatement == torch autograd over the unmodified reference
+    (train mode, CE loss on prob_volume_pre): pins the gradient oracle used by the training-path tests."""
+    g, feats, cams, hyp, sd, target = _train_grad_case(s)
+    feats = feats.clone().requires_grad_(True)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.dtype.is_floating_point and "running" not in k}
+    sd2 = dict(sd)
+    sd2.update(params)
+    out = O.stage_forward(feats, cams, hyp, sd2, S.NDEPTHS[s], S.EVAL_TMP[s], training=True)
+    assert rel_l1(out["prob_volume_pre"], g["prob_volume_pre"]) < 1e-5
+    loss = torch.nn.functional.cross_entropy(out["prob_volume_pre"], target)
+    assert float(loss.detach()) == pytest.approx(float(g["loss"]), rel=1e-5)
+    loss.backward()
+    assert rel_l1(feats.grad, g["grad_features"]) < 1e-4
+    for name in [str(n) for n in g["param_names"]]:
+        if name == "cost_reg.prob.bias":
+            continue                                        # exactly zero in exact arithmetic (softmax shift invariance)
+        want_abs = float(g["abs_sum/" + name])
+        got_abs = float(params[name].grad.double().abs().sum())
+        # the visibility net's gradients are ~1e-6 sums with heavy cancellation: 1e-2; everything else 2e-3
+        tol = 1e-2 if name.startswith("vis.") else 2e-3
+        assert got_abs == pytest.approx(want_abs, rel=tol), name
+        if "grad/" + name in g.files:
+            assert rel_l1(params[name].grad, g["grad/" + name]) < tol, name
