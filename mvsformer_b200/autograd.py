@@ -170,7 +170,9 @@ def _pack(weight, transposed):
 
 
 def _unpack(dwp, transposed):
-    return (dwp.permute(3, 4, 0, 1, 2) if transposed else dwp.permute(4, 3, 0, 1, 2)).contiguous()
+    """packed [kd,kh,kw,Cin,Cout] -> torch layout, with canonical strides (DDP's bucket views expect them)."""
+    src = dwp.permute(3, 4, 0, 1, 2) if transposed else dwp.permute(4, 3, 0, 1, 2)
+    return torch.empty(src.shape, device=dwp.device, dtype=dwp.dtype).copy_(src)
 
 
 def _fat(cin, cout):
@@ -334,7 +336,7 @@ class _ThinConv(torch.autograd.Function):
         gweight = None
         if ctx.needs_input_grad[1]:
             dwp = conv_wgrad(g, x, kd, khw, 1, 1, small_is_cout=True)            # [kd,k,k,Cin,Cout]
-            gweight = dwp.permute(4, 3, 0, 1, 2).contiguous()
+            gweight = _unpack(dwp, False)
         gx = None
         if ctx.needs_input_grad[0]:
             wd = w_taps.view(kd, khw, khw, cin, cout).flip(0, 1, 2).permute(0, 1, 2, 4, 3).contiguous()

@@ -5,63 +5,23 @@ over the oracle.  This checks index arithmetic, formulas, weight re-packing for 
 kernels and the autograd wiring without a GPU; the CUDA launch itself is covered by
 tests/test_gpu_train.py.  The emulation library is test infrastructure: the product never loads it.
 """
-import ctypes
-
 import pytest
 import torch
 import torch.nn.functional as F
 
-from mvsformer_b200 import _lib, autograd, engine
+from mvsformer_b200 import autograd, engine
 from mvsformer_b200 import module as M
 from mvsformer_b200 import synthetic as S
 from mvsformer_b200.mvsformer_model import StageNet
 from oracle import mvs_oracle as O
-from tests.emu import build_emu
+from tests.emu import harness
 from tests.helpers import STAGE_ARGS, rel_l1
-
-_EMU_SYMBOLS = [
-    "mvs_last_error_string", "mvs_launch_count", "mvs_conv3d_cl", "mvs_deconv3d_cl", "mvs_group_corr_fwd",
-    "mvs_group_corr_bwd", "mvs_corr_entropy", "mvs_aggregate_fwd", "mvs_aggregate_bwd", "mvs_bn_stats", "mvs_bn_finalize",
-    "mvs_bn_act_fwd", "mvs_bn_act_bwd_reduce", "mvs_bn_act_bwd_apply", "mvs_conv_wgrad_cl", "mvs_thin_conv_cl",
-    "mvs_sigmoid_bwd", "mvs_softmax_bwd"]
-
-
-def _host_only(*tensors):
-    for t in tensors:
-        if t is None:
-            continue
-        assert not t.is_cuda and t.dtype in (torch.float32, torch.float64) and t.is_contiguous(), (t.dtype, t.stride())
 
 
 @pytest.fixture()
 def emu(monkeypatch):
     """Points the package's ctypes layer at the CPU emulation library for the duration of a test."""
-    lib = ctypes.CDLL(build_emu.build())
-    for name in _EMU_SYMBOLS:
-        fn = getattr(lib, name)
-        fn.restype, fn.argtypes = _lib._SIGNATURES[name]
-    monkeypatch.setattr(_lib, "load", lambda: lib)
-    monkeypatch.setattr(_lib, "require_cuda", _host_only)
-    monkeypatch.setattr(_lib, "stream", lambda: None)
-    monkeypatch.setattr(engine, "require_cuda", _host_only)
-    monkeypatch.setattr(engine, "stream", lambda: None)
-
-    def relproj(proj):
-        b, v = proj.shape[:2]
-        ref = O.compose_projection(proj[:, 0].double())
-        rows = []
-        for i in range(1, v):
-            rot, trans = O.relative_projection(O.compose_projection(proj[:, i].double()), ref)
-            rows.append(torch.cat([rot, trans.unsqueeze(-1)], dim=-1).reshape(b, 12))
-        return torch.stack(rows, dim=1).float().contiguous()
-
-    def head(pre, depth_values, tmp, training, want_prob=True):
-        prob, depth, conf = O.regression_head(pre.detach(), depth_values, tmp, training)
-        return prob.contiguous(), depth.contiguous(), conf.contiguous()
-
-    monkeypatch.setattr(engine, "relative_projections", relproj)
-    monkeypatch.setattr(engine, "regression_head", head)
-    return lib
+    return harness.install(monkeypatch.setattr)
 
 
 def _case(batch=2, views=3, chans=16, depth=4, height=8, width=16, seed=0):
