@@ -229,6 +229,10 @@ int mvs_thin_conv_cl(const float* x, const float* w, const float* bias, float* y
                      int Cout, int kd, int khw, int act, void* stream);
 /* gx = gy * y * (1 - y) over n elements. */
 int mvs_sigmoid_bwd(const float* gy, const float* y, float* gx, int64_t n, void* stream);
+/* Backward of mvs_homo_warp w.r.t. src_fea (F.grid_sample's input gradient, warping.py:105): gwarped [B,C,D,H,W]
+ * -> gsrc [B,C,H,W], ZEROED by the caller, fp32 atomics. */
+int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, const float* depth, int depth_is_map, float* gsrc,
+                      int B, int C, int D, int H, int W, void* stream);
 /* p = softmax_d(pre) on [B,D,H,W]: gpre = p * (gp - sum_d gp * p)  (mvsformer_model.py:111). */
 int mvs_softmax_bwd(const float* gp, const float* p, float* gpre, int B, int D, int H, int W, void* stream);
 

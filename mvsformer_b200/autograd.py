@@ -159,6 +159,40 @@ def aggregate(corr, weight):
     return _Aggregate.apply(corr.contiguous(), weight.contiguous())
 
 
+class _HomoWarp(torch.autograd.Function):
+    """homo_warping_3D[_with_mask] (models/warping.py:69-109): differentiable w.r.t. src_fea, as the
+    reference's F.grid_sample is; the grid (cameras, depth) is built under no_grad there (:79)."""
+
+    @staticmethod
+    def forward(ctx, src_fea, relproj, depth_values, want_mask):
+        warped, mask = engine.homo_warp(src_fea, relproj, depth_values, want_mask)
+        ctx.save_for_backward(relproj, depth_values)
+        ctx.src_shape = tuple(src_fea.shape)
+        if mask is not None:
+            ctx.mark_non_differentiable(mask)
+            return warped, mask
+        return warped, None
+
+    @staticmethod
+    def backward(ctx, gwarped, _gmask):
+        relproj, depth_values = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        gwarped = gwarped.contiguous()
+        depth_values = depth_values.float().contiguous()
+        _lib.require_cuda(gwarped, relproj, depth_values)
+        b, c, h, w = ctx.src_shape
+        d = depth_values.shape[1]
+        gsrc = torch.zeros(b, c, h, w, device=gwarped.device, dtype=torch.float32)
+        _call("mvs_homo_warp_bwd", _p(gwarped), _p(relproj), _p(depth_values), 1 if depth_values.dim() == 4 else 0,
+              _p(gsrc), b, c, d, h, w)
+        return gsrc, None, None, None
+
+
+def homo_warp(src_fea, relproj, depth_values, want_mask):
+    return _HomoWarp.apply(engine._f32(src_fea), relproj, depth_values, want_mask)
+
+
 # ------------------------------------------------------------------------------------------------
 # conv / transposed conv  ->  BatchNorm (batch statistics)  ->  ReLU  (+ skip)
 # ------------------------------------------------------------------------------------------------

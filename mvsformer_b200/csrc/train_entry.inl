@@ -174,3 +174,12 @@ extern "C" int mvs_softmax_bwd(const float* gp, const float* p, float* gpre, int
     SoftmaxBwd f{gp, p, gpre, B, D, (int64_t)H * W};
     return launch_flat(f, (int64_t)B * H * W, stream, "softmax_bwd");
 }
+
+extern "C" int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, const float* depth, int depth_is_map,
+                                 float* gsrc, int B, int C, int D, int H, int W, void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(gwarped && relproj && depth && gsrc, "mvs_homo_warp_bwd: null pointer");
+    MVS_REQUIRE(B >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_homo_warp_bwd: empty shape");
+    HomoWarpBwd f{gwarped, relproj, depth, depth_is_map, gsrc, B, C, D, H, W};
+    return launch_flat(f, (int64_t)B * D * H * W, stream, "homo_warp_bwd");
+}

@@ -421,6 +421,34 @@ __device__ __forceinline__ void softmax_bwd_thread(const float* __restrict__ gp,
     }
 }
 
+// Backward of the materialising warp (mvs_homo_warp; models/warping.py:105 F.grid_sample) w.r.t.
+// the source feature: gsrc[b][c][tap] += gwarped[b][c][k][y][x] * weight(tap).  gsrc [B,C,H,W]
+// zero-initialised by the caller; one thread per (b, k, y, x).
+__device__ __forceinline__ void homo_warp_bwd_thread(const float* __restrict__ gwarped, const float* __restrict__ relproj,
+                                                     const float* __restrict__ depth, int depth_is_map,
+                                                     float* __restrict__ gsrc, int B, int C, int D, int H, int W,
+                                                     int64_t tid) {
+    const int64_t hw = (int64_t)H * W;
+    if (tid >= (int64_t)B * D * hw) return;
+    const int x = (int)(tid % W), y = (int)((tid / W) % H);
+    const int k = (int)((tid / hw) % D), b = (int)(tid / (hw * D));
+    const RelProj m = load_relproj(relproj + (int64_t)b * 12);
+    const PixelRay ray = pixel_ray(m, (float)x, (float)y);
+    const float dep = depth_is_map ? __ldg(depth + ((int64_t)b * D + k) * hw + (int64_t)y * W + x)
+                                   : __ldg(depth + (int64_t)b * D + k);
+    const Taps t = make_taps(m, ray, dep, H, W, (float)((W - 1) / 2.0), (float)((H - 1) / 2.0));
+    const float* gp = gwarped + (((int64_t)b * C) * D + k) * hw + (int64_t)y * W + x;
+    float* plane = gsrc + (int64_t)b * C * hw;
+    for (int c = 0; c < C; ++c, plane += hw) {
+        const float g = __ldg(gp + (int64_t)c * D * hw);
+        if (g == 0.0f) continue;
+        if (t.w00 != 0.0f) MVS_ATOMIC_ADD_F(plane + t.o00, g * t.w00);
+        if (t.w01 != 0.0f) MVS_ATOMIC_ADD_F(plane + t.o01, g * t.w01);
+        if (t.w10 != 0.0f) MVS_ATOMIC_ADD_F(plane + t.o10, g * t.w10);
+        if (t.w11 != 0.0f) MVS_ATOMIC_ADD_F(plane + t.o11, g * t.w11);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Functors: one per kernel, called as f(tid, nthreads) by launch_flat (train.cu: a __global__
 // wrapper; tests/emu/emu.cpp: a loop over tid).
@@ -477,6 +505,10 @@ struct ThinConv {
 struct SigmoidBwd {
     const float *gy, *y; float* gx; int64_t n;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { sigmoid_bwd_thread(gy, y, gx, n, tid); }
+};
+struct HomoWarpBwd {
+    const float *gwarped, *relproj, *depth; int depth_is_map; float* gsrc; int B, C, D, H, W;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { homo_warp_bwd_thread(gwarped, relproj, depth, depth_is_map, gsrc, B, C, D, H, W, tid); }
 };
 struct SoftmaxBwd {
     const float *gp, *p; float* gpre; int B, D; int64_t hw;

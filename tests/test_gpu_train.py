@@ -211,3 +211,26 @@ def test_training_path_rejects_cpu_tensors():
     feats, cams, hyp = _case(batch=1, views=3, chans=8, depth=4, height=8, width=16)
     with pytest.raises(RuntimeError):
         net(feats, cams, hyp)                                    # CPU tensors: no fallback
+
+
+def test_homo_warping_is_differentiable_wrt_source_features():
+    """homo_warping_3D_with_mask / homo_warping_3D backward (F.grid_sample input gradient, warping.py:105)."""
+    from mvsformer_b200 import warping as W
+
+    feats, cams, hyp = _case(batch=2, views=2, chans=8, depth=4, height=16, width=24, seed=17)
+    cams = cams.clone()
+    cams[:, 1, 0, 0, 3] += 250.0
+    src_p, ref_p = O.compose_projection(cams[:, 1]), O.compose_projection(cams[:, 0])
+    for dv in (hyp, hyp[:, :, 0, 0].contiguous()):
+        s1 = cu(feats[:, 1].contiguous()).requires_grad_(True)
+        warped, mask = W.homo_warping_3D_with_mask(s1, cu(src_p), cu(ref_p), cu(dv))
+        s2 = feats[:, 1].clone().requires_grad_(True)
+        want, want_mask = O.homo_warping_3D_with_mask(s2, src_p, ref_p, dv)
+        gout = torch.randn(want.shape, generator=S._gen(2))
+        warped.backward(cu(gout))
+        want.backward(gout)
+        assert rel_l1(warped.cpu(), want) < 1e-5 and mask.dtype == torch.bool
+        assert rel_l1(s1.grad.cpu(), s2.grad) < 1e-4
+    s3 = cu(feats[:, 1].contiguous()).requires_grad_(True)
+    W.homo_warping_3D(s3, cu(src_p), cu(ref_p), cu(hyp)).sum().backward()
+    assert s3.grad is not None and torch.isfinite(s3.grad).all()

@@ -266,3 +266,24 @@ def test_cost_reg_training_ncdhw_interface(emu):
     assert y.shape == (1, 1, 2, 8, 16)
     y.square().mean().backward()
     assert x.grad is not None and all(p.grad is not None for p in net.parameters())
+
+
+@pytest.mark.parametrize("depth_is_map", [0, 1])
+def test_homo_warp_backward_kernel(emu, depth_is_map):
+    """mvs_homo_warp_bwd (gradient of homo_warping_3D w.r.t. src_fea) vs torch autograd through the oracle warp."""
+    from mvsformer_b200 import _lib
+
+    feats, cams, hyp = _case(batch=2, views=2, chans=6, depth=3, height=8, width=12, seed=17)
+    cams = cams.clone()
+    cams[:, 1, 0, 0, 3] += 250.0
+    dv = hyp if depth_is_map else hyp[:, :, 0, 0].contiguous()
+    src = feats[:, 1].clone().requires_grad_(True)
+    src_p, ref_p = O.compose_projection(cams[:, 1]), O.compose_projection(cams[:, 0])
+    warped, _ = O.homo_warping_3D_with_mask(src, src_p, ref_p, dv)
+    gout = torch.randn(warped.shape, generator=S._gen(2))
+    warped.backward(gout)
+    relproj = engine.relative_projections(cams)[:, 0].contiguous()
+    gsrc = torch.zeros_like(feats[:, 1])
+    _lib.check(emu.mvs_homo_warp_bwd(_lib.ptr(gout.contiguous()), _lib.ptr(relproj), _lib.ptr(dv), depth_is_map, _lib.ptr(gsrc),
+                                     2, 6, 3, 8, 12, None), "mvs_homo_warp_bwd")
+    assert rel_l1(gsrc, src.grad) < 1e-5
