@@ -295,6 +295,8 @@ def measured_peaks():
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    from mvsformer_b200 import config
+    config.set_conv_precision(os.environ.get("MVS_CONV_PRECISION", "tf32"))     # same `config` as the engine arm
     threads = best_thread_count()
     value, dt = cpu_cascade_rate(args.steps, max(args.warmup, 1), threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
