@@ -312,7 +312,8 @@ class _RegNetBase(nn.Module):
         y = self.conv7.forward_cl(y, skip=c4)
         y = self.conv9.forward_cl(y, skip=c2)
         if not isinstance(self.inner, nn.Identity):
-            raise NotImplementedError("in_channels != base_channels (1x1x1 `inner` projection) is not built")
+            # 1x1x1 projection of the input skip when in_channels != base_channels (module.py:486-489, :502)
+            c0 = autograd.thin_conv_module(c0, self.inner)
         return self.conv11.forward_cl(y, skip=c0)
 
     def _prob_cl(self, y):

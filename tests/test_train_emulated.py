@@ -287,3 +287,36 @@ def test_homo_warp_backward_kernel(emu, depth_is_map):
     _lib.check(emu.mvs_homo_warp_bwd(_lib.ptr(gout.contiguous()), _lib.ptr(relproj), _lib.ptr(dv), depth_is_map, _lib.ptr(gsrc),
                                      2, 6, 3, 8, 12, None), "mvs_homo_warp_bwd")
     assert rel_l1(gsrc, src.grad) < 1e-5
+
+
+def test_cost_reg_inner_projection(emu):
+    """CostRegNet3D(in_channels != base_channel): the input skip goes through the 1x1x1 `inner` conv
+    (models/module.py:486-489, :502); training forward + backward vs torch autograd over the same weights."""
+    g = S._gen(16)
+    net = M.CostRegNet3D(16, 8).train()
+    assert isinstance(net.inner, torch.nn.Conv3d)
+    sd = S.fill_state_dict(net.state_dict(), seed=61)
+    net.load_state_dict(sd)
+    x = torch.randn(1, 16, 2, 8, 16, generator=g)
+    x1 = x.clone().requires_grad_(True)
+    y = net(x1)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    sdr = {"cost_reg." + k: v for k, v in {**sd, **params}.items()}
+    x2 = x.clone().requires_grad_(True)
+    p = "cost_reg."
+    st, op = (1, 2, 2), (0, 1, 1)
+    c2 = O._conv_block(O._conv_block(x2, sdr, p + "conv1", st, True), sdr, p + "conv2", 1, True)
+    c4 = O._conv_block(O._conv_block(c2, sdr, p + "conv3", st, True), sdr, p + "conv4", 1, True)
+    z = O._conv_block(O._conv_block(c4, sdr, p + "conv5", st, True), sdr, p + "conv6", 1, True)
+    z = c4 + O._deconv_block(z, sdr, p + "conv7.0.weight", p + "conv7.1", st, op, True)
+    z = c2 + O._deconv_block(z, sdr, p + "conv9.0.weight", p + "conv9.1", st, op, True)
+    z = F.conv3d(x2, sdr[p + "inner.weight"], sdr[p + "inner.bias"]) + \
+        O._deconv_block(z, sdr, p + "conv11.0.weight", p + "conv11.1", st, op, True)
+    want = F.conv3d(z, sdr[p + "prob.weight"], sdr[p + "prob.bias"])
+    assert rel_l1(y, want) < 1e-4
+    gout = torch.randn(want.shape, generator=g)
+    y.backward(gout)
+    want.backward(gout)
+    assert rel_l1(x1.grad, x2.grad) < 2e-3
+    assert rel_l1(net.inner.weight.grad, params["inner.weight"].grad) < 2e-3
+    assert rel_l1(net.inner.bias.grad, params["inner.bias"].grad) < 2e-3
