@@ -308,6 +308,54 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def measure_train_step(device, steps=5, warmup=3):
+    """Extra key (NOT the headline): one training step at BASELINE cfg 5's per-GPU shape — 1 reference + 4
+    source views, 512x640, 4-stage cascade in .train() (batch-statistics BN), cross-entropy on every stage's
+    prob_volume_pre, backward through the hand-written kernels (mvsformer_b200/autograd.py), SGD update.
+    Synthetic features / targets resident in HBM; CUDA events; FP32 CUDA-core first version."""
+    import torch.nn.functional as F
+    from mvsformer_b200.mvsformer_model import CascadeMVS
+
+    height, width, views = 512, 640, 5
+    feats = {k: v.to(device).requires_grad_(True) for k, v in S.make_features(1, views, height, width, seed=5).items()}
+    cams = {k: v.to(device) for k, v in S.make_cameras(1, views, height, width).items()}
+    dv = S.make_depth_range(1).to(device)
+    net = CascadeMVS(dict(CASCADE_ARGS)).train().to(device)
+    targets = [torch.randint(0, S.NDEPTHS[s], (1,) + S.stage_hw(height, width, s), generator=S._gen(s)).to(device)
+               for s in range(4)]
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        for f in feats.values():
+            f.grad = None
+        out = net(feats, cams, dv)
+        loss = sum(F.cross_entropy(out["stage%d" % (s + 1)]["prob_volume_pre"], targets[s]) for s in range(4))
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    from mvsformer_b200 import _lib
+    first = None
+    for i in range(warmup):
+        loss = step()
+        first = float(loss) if first is None else first
+    torch.cuda.synchronize()
+    l0 = _lib.load().mvs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "ref_views_per_s": 1e3 / ms, "steps": steps, "warmup": warmup,
+            "launches_per_step": (_lib.load().mvs_launch_count() - l0) / steps,
+            "loss_first": first, "loss_last": float(loss),
+            "config": "cfg 5 per-GPU shape: B=1, 5 views, 512x640, 4-stage cascade, train mode, CE loss on 4 stages, "
+                      "SGD; fp32 CUDA-core kernels; features given (backbone out of scope)"}
+
+
 def profile_traffic(kernel_family):
     """DRAM bytes per launch of the dominant kernel family from the committed ncu --set full capture
     (profiles/r01_traffic.json, written by scripts/summarise_ncu.py); None when not captured."""
@@ -498,6 +546,11 @@ def run_engine(args, rank, world, local_rank):
         v, dt = cpu_cascade_rate(3, 1, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
                                 "sample": sample_desc(), "seconds_per_sample_step": dt}
+    if world == 1 and not args.no_train_step:
+        try:                                   # last on purpose: nothing above depends on it
+            line["train_step_cfg5"] = measure_train_step(device)
+        except Exception as exc:               # report, never lose the headline line
+            line["train_step_cfg5"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -510,6 +563,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
