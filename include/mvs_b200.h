@@ -201,16 +201,21 @@ int mvs_aggregate_fwd(const float* corr, const float* weight, float* volume, int
 int mvs_aggregate_bwd(const float* gvol, const float* corr, const float* weight, float* gcorr, float* gweight, int B, int N,
                       int G, int D, int H, int W, void* stream);
 /* Train-mode BatchNorm over channels-last x [M,C] (nn.BatchNorm2d/3d inside ConvBnReLU / Conv3d / Deconv3d,
- * models/module.py:83-197).  sums: 2C doubles, ZEROED by the caller (sum, sum of squares); with SyncBatchNorm
- * the caller all-reduces sums and passes the global count.  mean_invstd: 2C floats.  running_* updated in
- * place (NULL to skip): r = (1-momentum) r + momentum * batch value, unbiased variance. */
+ * models/module.py:83-197).  sums: MVS_BN_REPLICAS x 2C doubles, ZEROED by the caller: the reduction kernels
+ * spread their fp64 atomics over the replicas, mvs_bn_collapse folds them into the first 2C doubles (sum, sum of
+ * squares), which is what finalize / apply read; with SyncBatchNorm the caller all-reduces those 2C doubles and
+ * passes the global count.  mean_invstd: 2C floats.  running_* updated in place (NULL to skip):
+ * r = (1-momentum) r + momentum * batch value, unbiased variance. */
+#define MVS_BN_REPLICAS 32
 int mvs_bn_stats(const float* x, double* sums, int64_t M, int C, void* stream);
-int mvs_bn_finalize(const double* sums, double count, float eps, float momentum, float* mean_invstd, float* running_mean,
-                    float* running_var, int C, void* stream);
+int mvs_bn_collapse(double* sums, int C, void* stream);
+/* replicas: MVS_BN_REPLICAS straight after mvs_bn_stats (finalize folds the copies itself), 1 after mvs_bn_collapse. */
+int mvs_bn_finalize(const double* sums, int replicas, double count, float eps, float momentum, float* mean_invstd,
+                    float* running_mean, float* running_var, int C, void* stream);
 /* y = act((x - mean) * invstd * gamma + beta) (+ skip after the activation, module.py:500-502). */
 int mvs_bn_act_fwd(const float* x, const float* mean_invstd, const float* gamma, const float* beta, const float* skip,
                    float* y, int64_t M, int C, int relu, void* stream);
-/* Backward: sums (2C doubles, ZEROED by the caller) <- (d gamma, d beta); then
+/* Backward: sums (MVS_BN_REPLICAS x 2C doubles, ZEROED by the caller; mvs_bn_collapse afterwards) <- (d gamma, d beta); then
  * gx = gamma * invstd * (g - dbeta/count - xhat * dgamma/count), g = gy masked by the ReLU. */
 int mvs_bn_act_bwd_reduce(const float* gy, const float* x, const float* mean_invstd, const float* gamma, const float* beta,
                           double* sums, int64_t M, int C, int relu, void* stream);

@@ -65,7 +65,8 @@ _SIGNATURES = {
     "mvs_aggregate_fwd": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
     "mvs_aggregate_bwd": (c_i, [c_f] * 5 + [c_i] * 6 + [c_f]),
     "mvs_bn_stats": (c_i, [c_f, c_f, c_l, c_i, c_f]),
-    "mvs_bn_finalize": (c_i, [c_f, c_d, c_fl, c_fl, c_f, c_f, c_f, c_i, c_f]),
+    "mvs_bn_collapse": (c_i, [c_f, c_i, c_f]),
+    "mvs_bn_finalize": (c_i, [c_f, c_i, c_d, c_fl, c_fl, c_f, c_f, c_f, c_i, c_f]),
     "mvs_bn_act_fwd": (c_i, [c_f] * 6 + [c_l, c_i, c_i, c_f]),
     "mvs_bn_act_bwd_reduce": (c_i, [c_f] * 6 + [c_l, c_i, c_i, c_f]),
     "mvs_bn_act_bwd_apply": (c_i, [c_f] * 6 + [c_d, c_f, c_l, c_i, c_i, c_f]),

@@ -24,8 +24,46 @@ import torch.nn as nn
 from . import _lib, engine
 
 
+_PROFILE = None          # {entry point: [(start event, end event), ...]} while profile_kernels() is active
+
+
+class profile_kernels:
+    """``with profile_kernels() as prof: step()`` then ``prof.summary()`` -> {entry point: (ms, launches)} from
+    CUDA events recorded around every training-path launch on the current stream (bench / scripts only)."""
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = self.events = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _PROFILE.setdefault(self.name, []).append((self.start, end))
+
+
 def _call(name, *args):
-    _lib.check(getattr(_lib.load(), name)(*args, _lib.stream()), name)
+    with _timed(name):
+        _lib.check(getattr(_lib.load(), name)(*args, _lib.stream()), name)
 
 
 def _p(t):
@@ -86,12 +124,21 @@ def aggregate_bwd(gvol, corr, weight):
     return gcorr, gweight
 
 
+BN_REPLICAS = 32          # MVS_BN_REPLICAS of include/mvs_b200.h
+
+
+def _reduction_buffer(channels, device):
+    """Zeroed accumulators of the BatchNorm reductions: BN_REPLICAS copies of 2C doubles (see mvs_bn_stats)."""
+    return torch.zeros(BN_REPLICAS * 2 * channels, device=device, dtype=torch.float64)
+
+
 def channel_sums(x, channels):
     """x [M,C] channels-last (any leading shape) -> float64 [2C]: per-channel sum and sum of squares."""
     _lib.require_cuda(x)
-    sums = torch.zeros(2 * channels, device=x.device, dtype=torch.float64)
+    sums = _reduction_buffer(channels, x.device)
     _call("mvs_bn_stats", _p(x), _p(sums), x.numel() // channels, channels)
-    return sums
+    _call("mvs_bn_collapse", _p(sums), channels)
+    return sums[:2 * channels]
 
 
 def thin_conv(x, w_taps, bias, kd, khw, act):
@@ -220,9 +267,11 @@ def _raw_conv(x, wp, transposed, stride):
     if transposed:
         if not _fat(cin, cout):
             raise NotImplementedError("transposed conv %d->%d channels is not built" % (cin, cout))
-        return engine.deconv3d_cl(x, wp, None, None, stride[0], relu=False)
+        with _timed("mvs_deconv3d_cl"):
+            return engine.deconv3d_cl(x, wp, None, None, stride[0], relu=False)
     if kh == 3 and _fat(cin, cout):
-        return engine.conv3d_cl(x, wp, None, None, stride, relu=False)
+        with _timed("mvs_conv3d_cl"):
+            return engine.conv3d_cl(x, wp, None, None, stride, relu=False)
     if tuple(stride) != (1, 1, 1):
         raise NotImplementedError("strided conv %d->%d channels (kernel %d) is not built" % (cin, cout, kh))
     return thin_conv(x, wp.view(-1, cin, cout), None, kd, kh, 0)
@@ -273,13 +322,16 @@ class _ConvBnAct(torch.autograd.Function):
         if bn.training:
             if bn.momentum is None:
                 raise NotImplementedError("BatchNorm with cumulative moving average (momentum=None) is not built")
-            sums = channel_sums(conv, c)
             world = _world(bn)
+            sums, replicas = _reduction_buffer(c, x.device), BN_REPLICAS
+            _call("mvs_bn_stats", _p(conv), _p(sums), m, c)
             if world > 1:                      # SyncBatchNorm: same spatial size on every rank (DDP)
+                _call("mvs_bn_collapse", _p(sums), c)
+                sums, replicas = sums[:2 * c], 1
                 dist.all_reduce(sums)
             mean_invstd = torch.empty(2 * c, device=x.device, dtype=torch.float32)
             track = bn.track_running_stats and bn.running_mean is not None
-            _call("mvs_bn_finalize", _p(sums), float(m * world), float(bn.eps), float(bn.momentum), _p(mean_invstd),
+            _call("mvs_bn_finalize", _p(sums), replicas, float(m * world), float(bn.eps), float(bn.momentum), _p(mean_invstd),
                   _p(bn.running_mean if track else None), _p(bn.running_var if track else None), c)
             if track:
                 # the kernel wrote through raw pointers: tell torch (the eval path's fold cache keys on versions)
@@ -304,9 +356,11 @@ class _ConvBnAct(torch.autograd.Function):
         _lib.require_cuda(gy)
         c = conv.shape[-1]
         m = conv.numel() // c
-        sums = torch.zeros(2 * c, device=gy.device, dtype=torch.float64)
+        sums = _reduction_buffer(c, gy.device)
         _call("mvs_bn_act_bwd_reduce", _p(gy), _p(conv), _p(mean_invstd), _p(gamma), _p(beta), _p(sums), m, c,
               1 if relu else 0)
+        _call("mvs_bn_collapse", _p(sums), c)
+        sums = sums[:2 * c]
         ggamma, gbeta = sums[:c].float(), sums[c:].float()          # this rank's share (DDP averages them)
         if batch_stats:
             if world > 1:

@@ -7,6 +7,8 @@
 //   template <class F> int launch_flat(const F& f, int64_t nthreads, void* stream, const char* name);
 // which runs f(tid, T) for tid in [0, T), T = nthreads rounded up to a multiple of 256.
 
+#include <stdlib.h>
+
 namespace mvs {
 namespace train {
 
@@ -16,7 +18,7 @@ static inline bool pow2_le_256(int c) { return c >= 1 && c <= 256 && (c & (c - 1
 // multiple of 256 (hence of every supported channel count)
 static inline int64_t reduce_threads(int64_t elems) {
     int64_t t = (elems + 15) / 16;
-    const int64_t cap = 148 * 8 * 256;
+    const int64_t cap = 148 * 4 * 256;
     if (t > cap) t = cap;
     if (t < 256) t = 256;
     return (t + 255) / 256 * 256;
@@ -90,12 +92,20 @@ extern "C" int mvs_bn_stats(const float* x, double* sums, int64_t M, int C, void
     return launch_flat(f, reduce_threads(M * C), stream, "bn_stats");
 }
 
-extern "C" int mvs_bn_finalize(const double* sums, double count, float eps, float momentum, float* mean_invstd,
-                               float* running_mean, float* running_var, int C, void* stream) {
+extern "C" int mvs_bn_collapse(double* sums, int C, void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(sums && C >= 1, "mvs_bn_collapse: null pointer or C < 1");
+    BnCollapse f{sums, C};
+    return launch_flat(f, 2 * C, stream, "bn_collapse");
+}
+
+extern "C" int mvs_bn_finalize(const double* sums, int replicas, double count, float eps, float momentum,
+                               float* mean_invstd, float* running_mean, float* running_var, int C, void* stream) {
     using namespace mvs::train;
     MVS_REQUIRE(sums && mean_invstd, "mvs_bn_finalize: null pointer");
     MVS_REQUIRE(count >= 1.0 && C >= 1, "mvs_bn_finalize: bad count / C");
-    BnFinalize f{sums, count, eps, momentum, mean_invstd, running_mean, running_var, C};
+    MVS_REQUIRE(replicas == 1 || replicas == MVS_BN_REPLICAS, "mvs_bn_finalize: replicas must be 1 or %d", MVS_BN_REPLICAS);
+    BnFinalize f{sums, replicas, count, eps, momentum, mean_invstd, running_mean, running_var, C};
     return launch_flat(f, C, stream, "bn_finalize");
 }
 
@@ -140,12 +150,42 @@ extern "C" int mvs_conv_wgrad_cl(const float* small, const float* big, float* dw
     MVS_REQUIRE((Db + sd - 1) / sd == Ds && (Hb + shw - 1) / shw == Hs && (Wb + shw - 1) / shw == Ws,
                 "mvs_conv_wgrad_cl: grids [%d,%d,%d] and [%d,%d,%d] do not match strides (%d,%d,%d)", Ds, Hs, Ws, Db, Hb,
                 Wb, sd, shw, shw);
-    WgradDims d{B, Ds, Hs, Ws, Db, Hb, Wb, Cs, Cb, kd, khw, sd, shw, small_is_cout ? 1 : 0};
-    const int ts = Cs % 4 == 0 ? 4 : 1, tb = Cb % 4 == 0 ? 4 : 1;
-    const int64_t threads = (int64_t)kd * khw * khw * (Cs / ts) * (Cb / tb) * B * Ds * Hs;
-    if (ts == 4 && tb == 4) return launch_flat(ConvWgrad<4, 4>{small, big, dw, d}, threads, stream, "conv_wgrad<4,4>");
-    if (ts == 4) return launch_flat(ConvWgrad<4, 1>{small, big, dw, d}, threads, stream, "conv_wgrad<4,1>");
-    if (tb == 4) return launch_flat(ConvWgrad<1, 4>{small, big, dw, d}, threads, stream, "conv_wgrad<1,4>");
+    // register tile of a thread: 8x8 channels (four 128-bit loads per 64 FMAs) when both channel counts allow,
+    // else 4 or 1 per side.  The first version (4x4 tile, scalar loads) was load-instruction bound:
+    // 13 of 40 ms of a cfg-5 training step (profiles/r01_train_step_entry_points_final.json).
+    // MVS_WGRAD_TILE=4 caps the tile at 4 per side (64 registers, 4x the threads) for A/B measurements.
+    int tmax = 8;
+    if (const char* env = getenv("MVS_WGRAD_TILE")) tmax = atoi(env);
+    const int ts = (Cs % 8 == 0 && tmax >= 8) ? 8 : (Cs % 4 == 0 && tmax >= 4 ? 4 : 1);
+    const int tb = (Cb % 8 == 0 && tmax >= 8) ? 8 : (Cb % 4 == 0 && tmax >= 4 ? 4 : 1);
+    MVS_REQUIRE((ts == 1 || ((uintptr_t)small & 15) == 0) && (tb == 1 || ((uintptr_t)big & 15) == 0),
+                "mvs_conv_wgrad_cl: tensors with a multiple of 4 channels must be 16-byte aligned");
+    const int64_t ntasks = (int64_t)kd * khw * khw * (Cs / ts) * (Cb / tb), nrows = (int64_t)B * Ds * Hs;
+    // Work split.  A thread owns (tap, channel tile) x a unit of voxels and ends with ts*tb atomics.  Aim at
+    // ~512k threads: layers with many (row, task) pairs take several rows per thread (fewer atomics), layers
+    // with few split each row into x segments (more threads; the serial loop over x is the latency chain).
+    // MVS_WGRAD_ROWS / MVS_WGRAD_XSEG override (tests).
+    const int64_t target = 512 * 1024;
+    int64_t rpt = ntasks * nrows / target, xseg = Ws;
+    if (rpt < 1) {
+        rpt = 1;
+        const int64_t want_seg = target / (ntasks * nrows);          // >= 1 here
+        xseg = (Ws + want_seg - 1) / want_seg;
+        if (xseg < 16) xseg = 16;
+    }
+    if (const char* env = getenv("MVS_WGRAD_ROWS")) rpt = atoi(env);
+    if (const char* env = getenv("MVS_WGRAD_XSEG")) xseg = atoi(env);
+    if (rpt < 1) rpt = 1;
+    if (rpt > 32) rpt = 32;
+    if (rpt > nrows) rpt = nrows;
+    if (xseg < 1 || xseg > Ws) xseg = Ws;
+    WgradDims d{B, Ds, Hs, Ws, Db, Hb, Wb, Cs, Cb, kd, khw, sd, shw, small_is_cout ? 1 : 0, (int)rpt, (int)xseg};
+    const int64_t threads = ntasks * ((nrows + rpt - 1) / rpt) * ((Ws + xseg - 1) / xseg);
+#define MVS_WGRAD_CASE(A, Bt) \
+    if (ts == A && tb == Bt) return launch_flat(ConvWgrad<A, Bt>{small, big, dw, d}, threads, stream, "conv_wgrad<" #A "," #Bt ">")
+    MVS_WGRAD_CASE(8, 8); MVS_WGRAD_CASE(8, 4); MVS_WGRAD_CASE(4, 8); MVS_WGRAD_CASE(4, 4);
+    MVS_WGRAD_CASE(8, 1); MVS_WGRAD_CASE(1, 8); MVS_WGRAD_CASE(4, 1); MVS_WGRAD_CASE(1, 4);
+#undef MVS_WGRAD_CASE
     return launch_flat(ConvWgrad<1, 1>{small, big, dw, d}, threads, stream, "conv_wgrad<1,1>");
 }
 

@@ -205,6 +205,12 @@ __device__ __forceinline__ void aggregate_bwd_thread(const float* __restrict__ g
 // BatchNorm (training) over channels-last data x[M][C]:  nthreads % C == 0, so a thread always
 // sees channel tid % C and consecutive threads read consecutive floats.
 // ------------------------------------------------------------------------------------------
+// The fp64 atomics of a reduction are spread over MVS_BN_REPLICAS copies of the 2C accumulators
+// (replica = (tid / C) % R, so the 32 lanes of a warp hit 32 different addresses); bn_collapse
+// folds the copies into replica 0, which is what finalize / apply / the host read.  Measured on
+// B200 (profiles/r01_train_step_entry_points.json): the un-replicated version spent 10 of 41 ms of
+// a training step in same-address fp64 atomics.
+#define MVS_BN_REPLICAS 32
 __device__ __forceinline__ void bn_stats_thread(const float* __restrict__ x, double* __restrict__ sums, int64_t M, int C,
                                                 int64_t tid, int64_t nthreads) {
     const int64_t total = M * C;
@@ -216,20 +222,34 @@ __device__ __forceinline__ void bn_stats_thread(const float* __restrict__ x, dou
     }
     if (tid < total) {
         const int c = (int)(tid % C);
-        MVS_ATOMIC_ADD_D(sums + c, s);
-        MVS_ATOMIC_ADD_D(sums + C + c, q);
+        double* rep = sums + ((tid / C) % MVS_BN_REPLICAS) * 2 * C;
+        MVS_ATOMIC_ADD_D(rep + c, s);
+        MVS_ATOMIC_ADD_D(rep + C + c, q);
     }
+}
+
+// sums[0][i] += sum_{r >= 1} sums[r][i], one thread per i < 2C
+__device__ __forceinline__ void bn_collapse_thread(double* __restrict__ sums, int C, int64_t tid) {
+    if (tid >= 2 * C) return;
+    double t = sums[tid];
+    for (int r = 1; r < MVS_BN_REPLICAS; ++r) t += sums[(int64_t)r * 2 * C + tid];
+    sums[tid] = t;
 }
 
 // sums[2C] (sum, sum of squares over `count` samples) -> mean_invstd[2C]; updates the running
 // statistics in place when given (momentum m: r = (1-m) r + m * batch, unbiased batch variance).
-__device__ __forceinline__ void bn_finalize_thread(const double* __restrict__ sums, double count, float eps, float momentum,
-                                                   float* __restrict__ mean_invstd, float* __restrict__ running_mean,
-                                                   float* __restrict__ running_var, int C, int64_t tid) {
+// `replicas` = how many copies of the accumulators to fold (MVS_BN_REPLICAS straight after mvs_bn_stats,
+// 1 after an explicit mvs_bn_collapse, e.g. around the SyncBatchNorm all-reduce).
+__device__ __forceinline__ void bn_finalize_thread(const double* __restrict__ sums, int replicas, double count, float eps,
+                                                   float momentum, float* __restrict__ mean_invstd,
+                                                   float* __restrict__ running_mean, float* __restrict__ running_var, int C,
+                                                   int64_t tid) {
     if (tid >= C) return;
     const int c = (int)tid;
-    const double mean = sums[c] / count;
-    double var = sums[C + c] / count - mean * mean;
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < replicas; ++r) { s += sums[(int64_t)r * 2 * C + c]; q += sums[(int64_t)r * 2 * C + C + c]; }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
     mean_invstd[c] = (float)mean;
     mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -273,8 +293,9 @@ __device__ __forceinline__ void bn_act_bwd_reduce_thread(const float* __restrict
         dg += (double)g * (double)xh;
         db += (double)g;
     }
-    MVS_ATOMIC_ADD_D(sums + c, dg);
-    MVS_ATOMIC_ADD_D(sums + C + c, db);
+    double* rep = sums + ((tid / C) % MVS_BN_REPLICAS) * 2 * C;
+    MVS_ATOMIC_ADD_D(rep + c, dg);
+    MVS_ATOMIC_ADD_D(rep + C + c, db);
 }
 
 // gx = gamma * invstd * (g - dbeta/count - xhat * dgamma/count), one thread per element
@@ -306,7 +327,26 @@ __device__ __forceinline__ void bn_act_bwd_apply_thread(const float* __restrict_
 struct WgradDims {
     int B, Ds, Hs, Ws, Db, Hb, Wb, Cs, Cb;
     int kd, khw, sd, shw, small_is_cout;
+    int rpt;   // rows of the small grid per thread (consecutive rows; fewer, fatter threads = fewer atomics)
+    int xseg;  // x positions of a row per thread (rows are split into ceil(Ws / xseg) segments when there are
+               // too few (row, task) pairs to fill the GPU); xseg >= Ws = whole rows
 };
+
+// T consecutive floats; 128-bit loads when T is a multiple of 4 (the caller guarantees 16-byte alignment:
+// channel counts that are multiples of 4 and 16-byte aligned tensors)
+template <int T>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float* out) {
+    if (T % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < T / 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+            out[q * 4 + 0] = v.x; out[q * 4 + 1] = v.y; out[q * 4 + 2] = v.z; out[q * 4 + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < T; ++i) out[i] = __ldg(p + i);
+    }
+}
 
 template <int TS, int TB>
 __device__ __forceinline__ void conv_wgrad_thread(const float* __restrict__ small, const float* __restrict__ big,
@@ -315,39 +355,57 @@ __device__ __forceinline__ void conv_wgrad_thread(const float* __restrict__ smal
     const int ntaps = d.kd * d.khw * d.khw;
     const int64_t ntasks = (int64_t)ntaps * nts * ntb;
     const int64_t nrows = (int64_t)d.B * d.Ds * d.Hs;
-    if (tid >= ntasks * nrows) return;
+    const int64_t nchunks = (nrows + d.rpt - 1) / d.rpt;
+    const int nseg = (d.Ws + d.xseg - 1) / d.xseg;
+    if (tid >= ntasks * nchunks * nseg) return;
     int64_t task = tid % ntasks;
-    int64_t row = tid / ntasks;
+    const int64_t unit = tid / ntasks;
+    const int seg = (int)(unit % nseg);
+    const int64_t row0 = (unit / nseg) * d.rpt;
     const int tb = (int)(task % ntb); task /= ntb;
     const int ts = (int)(task % nts); task /= nts;
     const int tap = (int)task;
     const int kx = tap % d.khw, ky = (tap / d.khw) % d.khw, kz = tap / (d.khw * d.khw);
-    const int y = (int)(row % d.Hs); row /= d.Hs;
-    const int z = (int)(row % d.Ds);
-    const int b = (int)(row / d.Ds);
-    const int bz = z * d.sd - d.kd / 2 + kz;
-    const int by = y * d.shw - d.khw / 2 + ky;
-    if (bz < 0 || bz >= d.Db || by < 0 || by >= d.Hb) return;
-    const float* ps = small + ((((int64_t)b * d.Ds + z) * d.Hs + y) * d.Ws) * d.Cs + ts * TS;
-    const float* pb = big + ((((int64_t)b * d.Db + bz) * d.Hb + by) * d.Wb) * d.Cb + tb * TB;
+    // x range of this thread with the fine-grid position bx = x*shw - pad + kx inside [0, Wb): no
+    // bounds test in the inner loop, so it unrolls and keeps several independent loads in flight
+    // (measured on B200: the branchy one-load-at-a-time loop was latency bound, 13 of 41 ms per step)
+    const int pad = d.khw / 2;
+    int xa = (pad - kx > 0) ? 1 : 0;                              // ceil((pad - kx) / shw) for pad - kx in {-1, 0, 1}
+    const int last = d.Wb - 1 + pad - kx;                         // largest admissible x*shw
+    int xb = last < 0 ? 0 : last / d.shw + 1;
+    if (xb > d.Ws) xb = d.Ws;
+    if (xa < seg * d.xseg) xa = seg * d.xseg;
+    if (xb > (seg + 1) * d.xseg) xb = (seg + 1) * d.xseg;
+    if (xa >= xb) return;
     float acc[TS][TB];
 #pragma unroll
     for (int i = 0; i < TS; ++i)
 #pragma unroll
         for (int j = 0; j < TB; ++j) acc[i][j] = 0.0f;
-    for (int x = 0; x < d.Ws; ++x) {
-        const int bx = x * d.shw - d.khw / 2 + kx;
-        if (bx < 0 || bx >= d.Wb) continue;
-        float a[TS], c[TB];
+    bool any = false;
+    for (int64_t row = row0; row < row0 + d.rpt && row < nrows; ++row) {
+        const int y = (int)(row % d.Hs);
+        const int z = (int)((row / d.Hs) % d.Ds);
+        const int b = (int)(row / ((int64_t)d.Hs * d.Ds));
+        const int bz = z * d.sd - d.kd / 2 + kz;
+        const int by = y * d.shw - pad + ky;
+        if (bz < 0 || bz >= d.Db || by < 0 || by >= d.Hb) continue;
+        any = true;
+        const float* ps = small + ((((int64_t)b * d.Ds + z) * d.Hs + y) * d.Ws) * d.Cs + ts * TS;
+        const float* pb = big + ((((int64_t)b * d.Db + bz) * d.Hb + by) * d.Wb + (kx - pad)) * d.Cb + tb * TB;
+        const int64_t bstep = (int64_t)d.shw * d.Cb;
+#pragma unroll 2
+        for (int x = xa; x < xb; ++x) {
+            float a[TS], c[TB];
+            load_vec<TS>(ps + (int64_t)x * d.Cs, a);
+            load_vec<TB>(pb + x * bstep, c);
 #pragma unroll
-        for (int i = 0; i < TS; ++i) a[i] = __ldg(ps + (int64_t)x * d.Cs + i);
+            for (int i = 0; i < TS; ++i)
 #pragma unroll
-        for (int j = 0; j < TB; ++j) c[j] = __ldg(pb + (int64_t)bx * d.Cb + j);
-#pragma unroll
-        for (int i = 0; i < TS; ++i)
-#pragma unroll
-            for (int j = 0; j < TB; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+                for (int j = 0; j < TB; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+        }
     }
+    if (!any) return;
     const int cin = d.small_is_cout ? d.Cb : d.Cs, cout = d.small_is_cout ? d.Cs : d.Cb;
     float* base = dw + (int64_t)tap * cin * cout;
 #pragma unroll
@@ -477,9 +535,13 @@ struct BnStats {
     const float* x; double* sums; int64_t M; int C;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t nthreads) const { bn_stats_thread(x, sums, M, C, tid, nthreads); }
 };
+struct BnCollapse {
+    double* sums; int C;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { bn_collapse_thread(sums, C, tid); }
+};
 struct BnFinalize {
-    const double* sums; double count; float eps, momentum; float *mean_invstd, *running_mean, *running_var; int C;
-    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { bn_finalize_thread(sums, count, eps, momentum, mean_invstd, running_mean, running_var, C, tid); }
+    const double* sums; int replicas; double count; float eps, momentum; float *mean_invstd, *running_mean, *running_var; int C;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { bn_finalize_thread(sums, replicas, count, eps, momentum, mean_invstd, running_mean, running_var, C, tid); }
 };
 struct BnActFwd {
     const float *x, *mean_invstd, *gamma, *beta, *skip; float* y; int64_t M; int C, relu;

@@ -15,6 +15,7 @@
 
 #include "../../include/mvs_b200.h"
 
+struct float4 { float x, y, z, w; };
 #define __device__
 #define __forceinline__ inline
 #define __restrict__

@@ -320,3 +320,28 @@ def test_cost_reg_inner_projection(emu):
     assert rel_l1(x1.grad, x2.grad) < 2e-3
     assert rel_l1(net.inner.weight.grad, params["inner.weight"].grad) < 2e-3
     assert rel_l1(net.inner.bias.grad, params["inner.bias"].grad) < 2e-3
+
+
+@pytest.mark.parametrize("rows,xseg,width,tile", [("3", "0", 8, "8"), ("32", "0", 8, "4"), ("1", "3", 8, "8"), ("2", "5", 7, "4"),
+                                                  ("1", "1", 1, "8"), ("1", "0", 8, "1")])
+def test_wgrad_work_split(emu, monkeypatch, rows, xseg, width, tile):
+    """mvs_conv_wgrad_cl with several rows of the strided grid per thread (large layers; ragged last chunk,
+    chunks spanning batch items) and with rows split into x segments (small layers; odd widths, width 1)
+    gives the same weight gradient."""
+    monkeypatch.setenv("MVS_WGRAD_ROWS", rows)
+    monkeypatch.setenv("MVS_WGRAD_XSEG", xseg)
+    monkeypatch.setenv("MVS_WGRAD_TILE", tile)
+    g = S._gen(21)
+    for transposed, cin, cout, stride in ((False, 8, 16, (2, 2, 2)), (True, 16, 8, (1, 2, 2)), (False, 8, 8, (1, 1, 1))):
+        x = torch.randn(2, 4 if stride[0] == 2 else 3, 6 if transposed else 10, width, cin, generator=g)
+        if transposed:
+            w = torch.randn(cin, cout, 3, 3, 3, generator=g, requires_grad=True)
+            y = F.conv_transpose3d(x.permute(0, 4, 1, 2, 3), w, stride=stride, padding=1, output_padding=tuple(s - 1 for s in stride))
+        else:
+            w = torch.randn(cout, cin, 3, 3, 3, generator=g, requires_grad=True)
+            y = F.conv3d(x.permute(0, 4, 1, 2, 3), w, stride=stride, padding=1)
+        gy = torch.randn(y.shape, generator=g)
+        y.backward(gy)
+        gcl = gy.permute(0, 2, 3, 4, 1).contiguous()
+        dwp = autograd._conv_wgrad(gcl, x, (3, 3, 3, cin, cout), transposed, stride)
+        assert rel_l1(autograd._unpack(dwp, transposed), w.grad) < 1e-5
