@@ -77,6 +77,15 @@ int mvs_cost_volume_aggregate(const float* features, int64_t batch_stride, int64
 int mvs_cost_volume_aggregate_tf32(const float* features, int64_t batch_stride, int64_t view_stride,
                                    const float* relproj, const float* depth, const float* vis_weight,
                                    float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream);
+/* Opt-in single-sampling-pass variant (MVS_CV_STORE=1; stages with C/G >= 2, where the per-view correlation is
+ * smaller than the warped tensor): pass A additionally stores corr [B,N,D,H,W,G] and the aggregation becomes one
+ * streaming pass over it.  Bit-identical volume.  mvs_cost_volume_entropy_store returns 1 (nothing launched)
+ * when the shape is not covered; the caller then uses the two-pass entry points. */
+int mvs_cost_volume_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride,
+                                  const float* relproj, const float* depth, float* entropy, float* sim_sum, float* corr,
+                                  int B, int V, int C, int G, int D, int H, int W, void* stream);
+int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume, int B, int N, int D, int H, int W,
+                       int round_tf32, void* stream);
 /* sim_depth = depth[argmax_d sim_sum] (:151-156).  out [B,H,W]. */
 int mvs_argmax_gather(const float* score, const float* depth, float* out, int B, int D, int H, int W, void* stream);
 

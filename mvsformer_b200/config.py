@@ -9,11 +9,17 @@
 * ``"fp32"``   — FP32 CUDA-core kernels (exact fp32 FMA chains).
 
 Set with ``set_conv_precision()`` or the environment variable ``MVS_CONV_PRECISION``.
+
+``cv_store`` (``MVS_CV_STORE=1``, default off) — cost-volume build with ONE sampling pass at the stages where
+the per-view group correlation is smaller than the warped tensor (C/G >= 2, stages 1-3): pass A stores it, the
+aggregation streams over it (bit-identical volume; +2 x N x G x D x h x w x 4 B of HBM traffic instead of a
+second warp).  Opt-in until it has been timed on the GPU.
 """
 import os
 
 _VALID = ("tf32x3", "tf32", "fp32")
-_state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3")}
+_state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
+          "cv_store": os.environ.get("MVS_CV_STORE", "0") not in ("", "0")}
 if _state["conv_precision"] not in _VALID:
     raise RuntimeError("MVS_CONV_PRECISION must be one of %s" % (_VALID,))
 
@@ -26,3 +32,11 @@ def set_conv_precision(mode):
     if mode not in _VALID:
         raise ValueError("conv precision must be one of %s, got %r" % (_VALID, mode))
     _state["conv_precision"] = mode
+
+
+def cv_store():
+    return _state["cv_store"]
+
+
+def set_cv_store(flag):
+    _state["cv_store"] = bool(flag)

@@ -219,7 +219,50 @@ static int check_cv_args(const char* fn, const float* features, const float* rel
     return MVS_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming aggregation over STORED per-view correlations (opt-in, MVS_CV_STORE=1): the second
+// sampling pass is replaced by one read of corr [B,N,D,H,W,8] written by the STORE variant of
+// pass A.  Same FMA sequence as pass B (acc = fma(corr_v, w_v, acc) in view order, then * 1/(sum w + 1e-6)),
+// so the volume is bit-identical.  One thread per voxel: N x 32 B in, 32 B out — a pure HBM stream.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+corr_aggregate_kernel(const float* __restrict__ corr, const float* __restrict__ vis_weight, float* __restrict__ volume,
+                      int N, int D, int64_t hw, int64_t total, int round_tf32) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;          // (b, k, pixel)
+    if (idx >= total) return;
+    const int64_t pix = idx % hw;
+    const int64_t bk = idx / hw;
+    const int k = (int)(bk % D);
+    const int64_t b = bk / D;
+    float acc[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc[g] = 0.0f;
+    float wsum = 0.0f;
+    for (int v = 0; v < N; ++v) {
+        const float wv = __ldg(vis_weight + (b * N + v) * hw + pix);
+        wsum += wv;
+        const float4* c = reinterpret_cast<const float4*>(corr + ((((b * N + v) * D + k) * hw + pix) << 3));
+        const float4 c0 = __ldg(c), c1 = __ldg(c + 1);
+        acc[0] = fmaf(c0.x, wv, acc[0]); acc[1] = fmaf(c0.y, wv, acc[1]);
+        acc[2] = fmaf(c0.z, wv, acc[2]); acc[3] = fmaf(c0.w, wv, acc[3]);
+        acc[4] = fmaf(c1.x, wv, acc[4]); acc[5] = fmaf(c1.y, wv, acc[5]);
+        acc[6] = fmaf(c1.z, wv, acc[6]); acc[7] = fmaf(c1.w, wv, acc[7]);
+    }
+    const float inv = 1.0f / (wsum + 1e-6f);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        acc[g] *= inv;
+        if (round_tf32) acc[g] = round_to_tf32(acc[g]);
+    }
+    float4* out = reinterpret_cast<float4*>(volume + (idx << 3));
+    out[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 // TMA-staged production kernels (cost_volume_tma.cu); return 1 when the shape is not covered.
+int cost_volume_tma_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
+                                  const float* depth, float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G,
+                                  int D, int H, int W, cudaStream_t st);
 int cost_volume_tma_entropy(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
                             const float* depth, float* entropy, float* sim_sum, int B, int V, int C, int G, int D, int H, int W,
                             cudaStream_t st);
@@ -250,6 +293,29 @@ extern "C" int mvs_cost_volume_entropy(const float* features, int64_t batch_stri
     cudaStream_t st = (cudaStream_t)stream;
     return sim_sum ? mvs::dispatch_entropy<true>(p, entropy, sim_sum, B, st)
                    : mvs::dispatch_entropy<false>(p, entropy, nullptr, B, st);
+}
+
+extern "C" int mvs_cost_volume_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride,
+                                             const float* relproj, const float* depth, float* entropy, float* sim_sum,
+                                             float* corr, int B, int V, int C, int G, int D, int H, int W, void* stream) {
+    int rc = mvs::check_cv_args("mvs_cost_volume_entropy_store", features, relproj, depth, B, V, C, G, D, H, W);
+    if (rc) return rc;
+    MVS_REQUIRE(entropy && corr, "mvs_cost_volume_entropy_store: null output");
+    if (!mvs::use_tma_kernels()) return 1;
+    return mvs::cost_volume_tma_entropy_store(features, batch_stride, view_stride, relproj, depth, entropy, sim_sum, corr, B, V,
+                                              C, G, D, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume, int B, int N, int D, int H,
+                                  int W, int round_tf32, void* stream) {
+    MVS_REQUIRE(corr && vis_weight && volume, "mvs_corr_aggregate: null pointer");
+    MVS_REQUIRE(B >= 1 && N >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_corr_aggregate: empty shape");
+    MVS_REQUIRE((((uintptr_t)corr | (uintptr_t)volume) & 15) == 0, "mvs_corr_aggregate: buffers must be 16-byte aligned");
+    const int64_t hw = (int64_t)H * W, total = hw * D * B;
+    mvs::corr_aggregate_kernel<<<mvs::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(corr, vis_weight, volume, N, D, hw,
+                                                                                         total, round_tf32);
+    MVS_LAUNCH_OK("corr_aggregate_kernel");
+    return MVS_OK;
 }
 
 static int cost_volume_aggregate_impl(const float* features, int64_t batch_stride, int64_t view_stride,

@@ -43,6 +43,7 @@ struct K1Params {
     int N, V, H, W;
     float* entropy;          // pass A out [B, N, H, W]
     float* sim_sum;          // pass A out [B, D, H, W] (SIM)
+    float* corr;             // pass A out [B, N, D, H, W, 8] (STORE): per-view group correlation
     const float* vis_weight; // pass B in  [B, N, H, W]
     float* volume;           // pass B out [B, D, H, W, 8]
     int round_tf32;          // pass B: round the stored volume to TF32
@@ -88,7 +89,11 @@ __device__ __forceinline__ void project(const RelProj& m, const PixelRay& ray, f
 }
 
 // MINB = CTAs per SM the register allocation must allow (co-resident CTAs hide each other's TMA waits).
-template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, int MINB = (CPG == 1 ? (PASS_B ? 3 : 4) : 2)>
+// STORE (pass A only, opt-in, MVS_CV_STORE=1): also write every view's group correlation, so that the
+// aggregation becomes one streaming pass over it (corr_aggregate_kernel, cost_volume.cu) instead of a second
+// sampling pass.  Only instantiated where the correlation is smaller than the warped tensor (C/G >= 2).
+template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, bool STORE = false,
+          int MINB = (CPG == 1 ? (PASS_B ? 3 : 4) : 2)>
 __global__ void __launch_bounds__(256, MINB)
 cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     constexpr int G = 8, C = G * CPG, D = DG * KPT;
@@ -203,8 +208,13 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
             wsum += wv;
         }
         float sview[KPT];
+        float ag[STORE ? G : 1][KPT];                            // STORE: this view's per-group sums, in pass B's FMA order
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) sview[j] = 0.0f;
+        for (int j = 0; j < KPT; ++j) {
+            sview[j] = 0.0f;
+#pragma unroll
+            for (int g = 0; g < (STORE ? G : 1); ++g) ag[g][j] = 0.0f;
+        }
 
         // ---- 3. channel chunks -------------------------------------------------------------------
 #pragma unroll
@@ -248,7 +258,9 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
                                 const float* q = t + (g * CPC + cpl) * PLANE;
                                 float s = q[0] * w00;
                                 s = fmaf(q[1], w01, s); s = fmaf(q[BW], w10, s); s = fmaf(q[BW + 1], w11, s);
-                                a = fmaf(s_ref[(g * CPG + cp0 + cpl) * TP + pix], s, a);
+                                const float r = s_ref[(g * CPG + cp0 + cpl) * TP + pix];
+                                a = fmaf(r, s, a);
+                                if (STORE) ag[STORE ? g : 0][j] = fmaf(r, s, ag[STORE ? g : 0][j]);
                                 if (SIM) wn = fmaf(s, s, wn);
                             }
                             sview[j] += a;
@@ -276,7 +288,13 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
                             for (int g = 0; g < G; ++g) {
                                 const int c = g * CPG + cp0 + cpl;
                                 const float s = sample4(src + (int64_t)c * hw, tp);
-                                a = fmaf(s_ref[c * TP + pix], s, a);
+                                const float r = s_ref[c * TP + pix];
+                                a = fmaf(r, s, a);
+                                if (STORE) {
+#pragma unroll
+                                    for (int gg = 0; gg < G; ++gg)
+                                        if (gg == g) ag[STORE ? gg : 0][j] = fmaf(r, s, ag[STORE ? gg : 0][j]);
+                                }
                                 if (SIM) wn = fmaf(s, s, wn);
                             }
                             sview[j] += a;
@@ -290,6 +308,17 @@ cost_volume_kernel(const __grid_constant__ CUtensorMap tmap, K1Params p) {
                         }
                     }
                 }
+            }
+        }
+
+        if (STORE && live) {
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) {
+                float* out = p.corr + ((((int64_t)b * p.N + v) * D + dg * KPT + j) * hw + pixoff) * G;
+                *reinterpret_cast<float4*>(out) = make_float4(ag[0][j] * inv_cpg, ag[STORE ? 1 : 0][j] * inv_cpg,
+                                                              ag[STORE ? 2 : 0][j] * inv_cpg, ag[STORE ? 3 : 0][j] * inv_cpg);
+                *reinterpret_cast<float4*>(out + 4) = make_float4(ag[STORE ? 4 : 0][j] * inv_cpg, ag[STORE ? 5 : 0][j] * inv_cpg,
+                                                                  ag[STORE ? 6 : 0][j] * inv_cpg, ag[STORE ? 7 : 0][j] * inv_cpg);
             }
         }
 
@@ -369,7 +398,7 @@ static int make_feature_map(CUtensorMap* map, const float* feat, int BV, int G, 
     return MVS_OK;
 }
 
-template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM>
+template <int CPG, int DG, int KPT, int BW, int BH, int NCH, bool PASS_B, bool SIM, bool STORE = false>
 static int launch(const K1Params& p, int B, cudaStream_t st) {
     constexpr int G = 8, C = G * CPG, D = DG * KPT, TP = 256 / DG, TH = 8 / DG, CC = C / NCH;
     constexpr int CPC = PASS_B ? CPG : CPG / NCH, GPC = PASS_B ? G / NCH : G;
@@ -377,7 +406,8 @@ static int launch(const K1Params& p, int B, cudaStream_t st) {
     CUtensorMap map;
     int rc = make_feature_map(&map, p.feat, B * p.V, G, CPG, p.H, p.W, BW, BH, CPC, GPC);
     if (rc) return rc;
-    auto kern = cost_volume_kernel<CPG, DG, KPT, BW, BH, NCH, PASS_B, SIM>;
+    static_assert(!STORE || (!PASS_B && CPG >= 2), "STORE is a pass A variant for C/G >= 2");
+    auto kern = cost_volume_kernel<CPG, DG, KPT, BW, BH, NCH, PASS_B, SIM, STORE>;
     MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(p.W, 32), cdiv(p.H, TH), B);
     kern<<<grid, 256, smem, st>>>(map, p);
@@ -405,6 +435,15 @@ static int dispatch(const K1Params& p, int B, int C, int D, cudaStream_t st) {
     return 1;   // not covered: caller uses the generic kernels
 }
 
+// pass A with the per-view correlation stored (stages with C/G >= 2 only; box sizes as above)
+template <bool SIM>
+static int dispatch_store(const K1Params& p, int B, int C, int D, cudaStream_t st) {
+    if (C == 64 && D == 32) return launch<8, 8, 4, 128, 10, 4, false, SIM, true>(p, B, st);
+    if (C == 32 && D == 16) return launch<4, 4, 4, 64, 8, 2, false, SIM, true>(p, B, st);
+    if (C == 16 && D == 8) return launch<2, 2, 4, 64, 12, 1, false, SIM, true>(p, B, st);
+    return 1;
+}
+
 }  // namespace k1
 
 // Returns 1 when the shape is not covered by the TMA kernels (the generic kernels of
@@ -414,8 +453,18 @@ int cost_volume_tma_entropy(const float* features, int64_t batch_stride, int64_t
                             cudaStream_t st) {
     const int64_t hw = (int64_t)H * W;
     if (G != 8 || (W % 4) != 0 || view_stride != C * hw || batch_stride != V * C * hw || ((uintptr_t)features & 15)) return 1;
-    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, entropy, sim_sum, nullptr, nullptr, 0};
+    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, entropy, sim_sum, nullptr, nullptr, nullptr, 0};
     return sim_sum ? k1::dispatch<false, true>(p, B, C, D, st) : k1::dispatch<false, false>(p, B, C, D, st);
+}
+
+// Pass A that also stores corr [B,N,D,H,W,8]; returns 1 when the shape is not covered.
+int cost_volume_tma_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
+                                  const float* depth, float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G,
+                                  int D, int H, int W, cudaStream_t st) {
+    const int64_t hw = (int64_t)H * W;
+    if (G != 8 || (W % 4) != 0 || view_stride != C * hw || batch_stride != V * C * hw || ((uintptr_t)features & 15)) return 1;
+    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, entropy, sim_sum, corr, nullptr, nullptr, 0};
+    return sim_sum ? k1::dispatch_store<true>(p, B, C, D, st) : k1::dispatch_store<false>(p, B, C, D, st);
 }
 
 int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
@@ -423,7 +472,7 @@ int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64
                               int H, int W, int round_tf32, cudaStream_t st) {
     const int64_t hw = (int64_t)H * W;
     if (G != 8 || (W % 4) != 0 || view_stride != C * hw || batch_stride != V * C * hw || ((uintptr_t)features & 15)) return 1;
-    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, nullptr, nullptr, vis_weight, volume, round_tf32};
+    k1::K1Params p{features, relproj, depth, V - 1, V, H, W, nullptr, nullptr, nullptr, vis_weight, volume, round_tf32};
     return k1::dispatch<true, false>(p, B, C, D, st);
 }
 

@@ -92,6 +92,40 @@ def cost_volume_aggregate(features, relproj, depth_values, vis_weight, groups, r
     return volume
 
 
+def cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim):
+    """Pass A that also stores the per-view correlation (opt-in, config.cv_store()).  Returns
+    (entropy, sim, corr [B,N,D,H,W,G]) or None when the kernels do not cover the shape."""
+    features = _f32(features)
+    features, bs, vs = _feature_strides(features)
+    depth_values = _f32(depth_values).contiguous()
+    require_cuda(relproj, depth_values)
+    if not features.is_cuda:
+        raise RuntimeError("mvsformer_b200 runs on CUDA tensors only; there is no CPU path")
+    b, v, c, h, w = features.shape
+    d = depth_values.shape[1]
+    entropy = torch.empty(b, v - 1, h, w, device=features.device, dtype=torch.float32)
+    sim = torch.empty(b, d, h, w, device=features.device, dtype=torch.float32) if want_sim else None
+    corr = torch.empty(b, v - 1, d, h, w, groups, device=features.device, dtype=torch.float32)
+    rc = _lib.load().mvs_cost_volume_entropy_store(ptr(features), bs, vs, ptr(relproj), ptr(depth_values), ptr(entropy),
+                                                   ptr(sim), ptr(corr), b, v, c, groups, d, h, w, stream())
+    if rc == 1:
+        return None
+    check(rc, "mvs_cost_volume_entropy_store")
+    return entropy, sim, corr
+
+
+def corr_aggregate(corr, vis_weight, round_tf32=False):
+    """corr [B,N,D,H,W,8], vis_weight [B,N,H,W] -> volume channels-last [B,D,H,W,8]."""
+    require_cuda(corr, vis_weight)
+    b, n, d, h, w, g = corr.shape
+    if g != 8:
+        raise RuntimeError("corr_aggregate: only G = 8 groups is built")
+    volume = torch.empty(b, d, h, w, g, device=corr.device, dtype=torch.float32)
+    check(_lib.load().mvs_corr_aggregate(ptr(corr), ptr(vis_weight), ptr(volume), b, n, d, h, w, 1 if round_tf32 else 0,
+                                         stream()), "mvs_corr_aggregate")
+    return volume
+
+
 def argmax_gather(score, depth_values):
     require_cuda(score, depth_values)
     b, d, h, w = score.shape

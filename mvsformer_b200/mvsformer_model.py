@@ -111,10 +111,17 @@ class StageNet(nn.Module):
             raise RuntimeError("shape '[%d, %d, -1, ...]' is invalid for %d feature channels"
                                % (b, groups, features.shape[2]))
         relproj = engine.relative_projections(proj_matrices)
+        round_tf32 = config.conv_precision() == "tf32"
+        if config.cv_store() and features.shape[2] // groups >= 2:
+            # opt-in: one sampling pass, the per-view correlation is stored and streamed back (config.py)
+            stored = engine.cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim=not self.training)
+            if stored is not None:
+                entropy, sim, corr = stored
+                weight = self._vis_weight(entropy)
+                return engine.corr_aggregate(corr, weight, round_tf32), sim, entropy, weight
         entropy, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=not self.training)
         weight = self._vis_weight(entropy)
-        volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups,
-                                              round_tf32=config.conv_precision() == "tf32")
+        volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups, round_tf32=round_tf32)
         return volume, sim, entropy, weight
 
     def _vis_weight_train(self, entropy):
