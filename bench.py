@@ -48,7 +48,9 @@ def conv_mode():
 
 
 def workload_config(n_gpus):
-    return {"workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, "
+    from mvsformer_b200 import config
+    extra = {"cost_volume_build": "one sampling pass at stages 1-3 (MVS_CV_STORE)"} if config.cv_store() else {}
+    return {**extra, "workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, "
                         "feat ch 64/32/16/8, G=8, B=1 ref view per GPU per step" % (HEIGHT, WIDTH, VIEWS),
             "precision": "fp32 features/volume/activations; conv math %s" % conv_mode(), "parallelism": "ref views sharded, %d rank(s), no collective" % n_gpus,
             "l2_policy": "inputs 530 MB/step > 126 MB L2; every intermediate volume is rewritten each step"}
@@ -160,8 +162,15 @@ class KernelProfiler:
             outs = out if isinstance(out, (tuple, list)) else (out,)
             return numel_bytes(*outs) + numel_bytes(*[t for t in a if torch.is_tensor(t)]), 0
 
+        def ent_store_cost(out, features, relproj, depth_values, groups, want_sim):
+            base, _ = cv_cost(out, features, relproj, depth_values)
+            return base + (numel_bytes(*out) if out is not None else 0), 0
+
         self._wrap(engine, "cost_volume_entropy", "cv_entropy(passA)", ent_cost)
         self._wrap(engine, "cost_volume_aggregate", "cv_aggregate(passB)", agg_cost)
+        # opt-in MVS_CV_STORE path: pass A with stored correlation + streaming aggregation
+        self._wrap(engine, "cost_volume_entropy_store", "cv_entropy_store(passA)", ent_store_cost)
+        self._wrap(engine, "corr_aggregate", "cv_corr_aggregate(stream)", io_cost)
         self._wrap(engine, "vis_weight", "vis_net", vis_cost)
         self._wrap(engine, "vis_first_cl", "vis_net(thin layers)", io_cost)
         self._wrap(engine, "vis_last_cl", "vis_net(thin layers)", io_cost)
