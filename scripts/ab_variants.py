@@ -1,0 +1,102 @@
+"""One-process A/B harness for the opt-in variants that were written without GPU time (round 1) — meant to be
+the FIRST gpurun call of the next round: it runs the gated experimental parity tests, then times every variant
+with CUDA events on the bench workload, and writes one JSON.
+
+    python scripts/ab_variants.py gpurun_out/ab            # ~40 s on a B200
+
+Variants
+  cost-volume build   two sampling passes (shipped)  vs  MVS_CV_STORE (pass A stores corr, streaming aggregation)
+  weight gradients    8x8 register tiles (default)   vs  MVS_WGRAD_TILE=4
+Each inference variant reports ms per reference view (cfg 2, inputs resident) and the per-kernel-class CUDA-event
+attribution of bench.py's KernelProfiler; the training variants report ms per cfg-5-shaped training step and the
+per-entry-point breakdown of scripts/train_profile.py.
+"""
+import contextlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+os.chdir(ROOT)
+out_dir = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/ab"
+os.makedirs(out_dir, exist_ok=True)
+os.environ["MVS_TEST_EXPERIMENTAL"] = "1"
+
+import pytest  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from mvsformer_b200 import config, engine  # noqa: E402
+
+
+def time_inference(net, feats, cams, dv, steps=8, warmup=3):
+    tmp = list(bench.S.EVAL_TMP)
+    with torch.no_grad():
+        for _ in range(warmup):
+            net(feats, cams, dv, tmp=tmp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = net(feats, cams, dv, tmp=tmp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        prof = bench.KernelProfiler()
+        prof.install(engine)
+        for _ in range(3):
+            net(feats, cams, dv, tmp=tmp)
+        torch.cuda.synchronize()
+        prof.uninstall(engine)
+        kern = {k: round(v["ms_per_step"], 4) for k, v in prof.summary(3).items()}
+    return ms, kern, out["refined_depth"].clone()
+
+
+def main():
+    result = {}
+    with open(os.path.join(out_dir, "experimental_tests.log"), "w") as f, contextlib.redirect_stdout(f), \
+            contextlib.redirect_stderr(f):
+        rc = pytest.main(["tests/test_gpu_experimental.py", "-q", "-x", "-p", "no:cacheprovider"])
+    result["experimental_tests_rc"] = int(rc)
+    print("experimental tests rc", int(rc), flush=True)
+
+    device = torch.device("cuda", 0)
+    config.set_conv_precision(os.environ.get("MVS_CONV_PRECISION", "tf32"))
+    net = bench.build_engine(device)
+    feats_h, cams_h, dv_h = bench.host_inputs(bench.HEIGHT, bench.WIDTH, bench.VIEWS, 1234, pin=False)
+    feats = {k: v.to(device) for k, v in feats_h.items()}
+    cams = {k: v.to(device) for k, v in cams_h.items()}
+    dv = dv_h.to(device)
+    depths = {}
+    for name, flag in (("two_pass", False), ("cv_store", True)):
+        if flag and rc != 0:
+            result[name] = {"skipped": "experimental parity tests failed"}
+            continue
+        config.set_cv_store(flag)
+        ms, kern, depths[name] = time_inference(net, feats, cams, dv)
+        result[name] = {"ms_per_ref_view": ms, "maps_per_s": 1e3 / ms, "kernels_ms": kern}
+        print(name, round(ms, 3), "ms", flush=True)
+    config.set_cv_store(False)
+    if len(depths) == 2:
+        result["cv_store_refined_depth_bit_identical"] = bool(torch.equal(depths["two_pass"], depths["cv_store"]))
+
+    import train_profile  # noqa: E402
+    for tile in ("8", "4"):
+        os.environ["MVS_WGRAD_TILE"] = tile
+        path = os.path.join(out_dir, "train_profile_tile%s.json" % tile)
+        with open(path, "w") as f, contextlib.redirect_stdout(f):
+            train_profile.main()
+        d = json.load(open(path))
+        result["train_wgrad_tile" + tile] = {"step_ms": d["step_ms_unprofiled"], "kernel_ms_sum": d["kernel_ms_sum"],
+                                             "entry_points_ms": {k: v["ms"] for k, v in d["entry_points"].items()}}
+        print("train tile", tile, round(d["step_ms_unprofiled"], 2), "ms", flush=True)
+    os.environ.pop("MVS_WGRAD_TILE", None)
+    with open(os.path.join(out_dir, "ab_variants.json"), "w") as f:
+        json.dump(result, f, indent=1)
+    print(json.dumps(result)[:3000])
+
+
+if __name__ == "__main__":
+    main()
