@@ -137,6 +137,11 @@ int mvs_conv3d_tcz(const float* x, const float* w, const float* shift, const flo
                    int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
 int mvs_deconv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
                      int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
+/* Opt-in "kz-fused N" variant of mvs_conv3d_tcz for kd = 3 (MVS_TCZ_KZF; conv3d_tcz_kzf.cu): the three depth taps of an
+ * input slab are one tcgen05.mma of N = 3 * n_tile over adjacent TMEM accumulators, so the A tile is read from shared
+ * memory once instead of three times.  Weights (TF32): [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4]. */
+int mvs_conv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                       int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
 /* Row-tiled variant of mvs_conv3d_tcz for wide stride-1 layers (Cin <= 32): R rows x 128 columns x zc
  * slices per CTA, all taps resident.  Weights (TF32): [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4]. */
 int mvs_conv3d_tcr(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,

@@ -14,12 +14,17 @@ Set with ``set_conv_precision()`` or the environment variable ``MVS_CONV_PRECISI
 the per-view group correlation is smaller than the warped tensor (C/G >= 2, stages 1-3): pass A stores it, the
 aggregation streams over it (bit-identical volume; +2 x N x G x D x h x w x 4 B of HBM traffic instead of a
 second warp).  Opt-in until it has been timed on the GPU.
+
+``tcz_kzf`` (``MVS_TCZ_KZF=1``; ``2`` = also prefer it over the row-tiled kernel; default 0) — "kz-fused N" variant
+of the depth-fused tensor-core convolution (mvs_conv3d_tcz_kzf): one MMA of N = 3 x Cout-tile per slab instead of
+three, i.e. a third of the shared-memory A-operand reads.  TF32 mode only.  Opt-in until run on the GPU.
 """
 import os
 
 _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
-          "cv_store": os.environ.get("MVS_CV_STORE", "0") not in ("", "0")}
+          "cv_store": os.environ.get("MVS_CV_STORE", "0") not in ("", "0"),
+          "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "0") or 0)}
 if _state["conv_precision"] not in _VALID:
     raise RuntimeError("MVS_CONV_PRECISION must be one of %s" % (_VALID,))
 
@@ -40,3 +45,11 @@ def cv_store():
 
 def set_cv_store(flag):
     _state["cv_store"] = bool(flag)
+
+
+def tcz_kzf():
+    return _state["tcz_kzf"]
+
+
+def set_tcz_kzf(level):
+    _state["tcz_kzf"] = int(level)

@@ -1,0 +1,341 @@
+// conv3d_tcz_kzf.cu — OPT-IN "kz-fused N" variant of the depth-fused tcgen05 convolution of conv3d_tcz.cu
+// (MVS_TCZ_KZF=1; compiled and reviewed, not yet executed on a B200 — see DESIGN.md §10 item 2).
+//
+// It lives in its own translation unit, as a modified copy of conv3d_tcz_kernel and its launch code, so that
+// the shipped, GPU-verified kernels of conv3d_tcz.cu keep the exact binary they were verified with; once this
+// variant has passed its parity tests on the device the two files merge again.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace mvs {
+namespace tc {
+namespace kzf {
+
+constexpr int TZ_THREADS = 128;
+constexpr int TZ_SLOTS = 132;
+constexpr int TZ_SL = TZ_SLOTS * 16;
+constexpr int TZ_STAGES = 4;
+
+struct TzDims {
+    int B, D, H, W, Ho, Wo, Cin, Cout;
+    int kd;                  // 1 or 3 (depth stride is 1)
+    int s2;                  // conv: stride 2 in y and x
+    int relu;
+    int PW, tiles_per_plane;
+    int zc;                  // output depth slices per CTA
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TAPS = weight taps staged per (kh | dy, channel-slice) group and depth tap: conv 3 (kw), deconv 6.
+template <int CS, int NT, int TAPS, int NPLANES>
+struct TzSmem {
+    static constexpr int CH = CS / 4;
+    static constexpr int A_STAGE = NPLANES * CH * TZ_SL;
+    static constexpr int B_TAP = CH * NT * 16;
+    static __host__ __device__ constexpr int b_group(int kd) { return kd * TAPS * B_TAP; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward convolution, kernel (kd,3,3), stride (1, s, s)
+// ------------------------------------------------------------------------------------------------
+// KZF (opt-in, MVS_TCZ_KZF=1; not yet timed): "kz-fused N".  Every tcgen05.mma re-reads its 4 KB A tile from
+// shared memory, i.e. 4/N bytes per MAC, and N = Cout tile is only 16..64 here — the wide layers sit at that
+// operand-read bound.  The depth taps kz = 0,1,2 of an input slab iz feed the output slices
+// iz+1, iz, iz-1; with the slice accumulators laid out in DEcreasing slice order they form one contiguous
+// window of TMEM columns, so ONE MMA with the B rows [kz][n] (N = 3*NT, weights packed
+// [Cout_tiles][kh][Cin/CS][kw][CS/4][kd][n_tile][4]) replaces three and reads A once.  Only the very first
+// MMA of each slab in the first (kh, channel-slice) group stays per-slice: that is where accumulators are
+// initialised (accumulate = 0) and the slices of a window are in different states.
+template <int CS, int NT, bool S2, bool KZF = false>
+__global__ void __launch_bounds__(TZ_THREADS)
+conv3d_tcz_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                  const float* __restrict__ skip, float* __restrict__ y, TzDims d) {
+    constexpr int NPL = S2 ? 2 : 1;
+    using L = TzSmem<CS, NT, 3, NPL>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int bgroup = L::b_group(d.kd);
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;                 // weight-buffer ring (see header)
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TZ_STAGES * L::A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)br * bgroup);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ncols = d.zc * NT;
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : (ncols <= 256 ? 256 : 512)));
+    if (tid == 0) {
+        for (int s = 0; s < TZ_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int b = blockIdx.z;
+    const int tile = blockIdx.x;
+    const int z0 = blockIdx.y * d.zc;                          // first output slice of this CTA
+    const int nz = min(d.zc, d.D - z0);
+    const int j0 = (tile % d.tiles_per_plane) * 128;
+    const int ct = tile / d.tiles_per_plane;                   // Cout tile
+    const int co0 = ct * NT;
+    const int pd = d.kd / 2;
+    const int nch = d.Cin / CS;
+
+    // input slices that feed this z-chunk
+    const int iz_lo = max(z0 - pd, 0), iz_hi = min(z0 + nz - 1 + pd, d.D - 1);
+    const int niz = iz_hi - iz_lo + 1;
+    const int ngroups = 3 * nch;                               // (kh, channel slice)
+    const int nit = ngroups * niz;
+    const int glen = br == 2 ? niz : 1;                        // iterations sharing one weight buffer
+
+    int sy[2], sa[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int jv = j0 + tid + u * 128;
+        sy[u] = jv / d.PW;
+        sa[u] = jv - sy[u] * d.PW;
+    }
+    const int nslot_iters = (tid + 128 < 130) ? 2 : 1;
+    const float* wt = w + (size_t)ct * ngroups * (bgroup / 4);
+
+    auto issue = [&](int it) {
+        const int g = it / niz, iz = iz_lo + (it - g * niz);
+        const int kh = g / nch, ch = g - kh * nch;
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+            for (int u = 0; u < nslot_iters; ++u) {
+                const int slot = tid + u * 128;
+                const int yy = S2 ? 2 * sy[u] + kh - 1 : sy[u] + kh - 1;
+                const int xx = S2 ? (p == 0 ? 2 * sa[u] : 2 * sa[u] - 1) : sa[u] - 1;
+                const bool ok = yy >= 0 && yy < d.H && xx >= 0 && xx < d.W;
+                const float* src = x + ((((size_t)b * d.D + iz) * d.H + (ok ? yy : 0)) * d.W + (ok ? xx : 0)) * d.Cin + ch * CS;
+                const uint32_t dst = a_base + (uint32_t)p * L::CH * TZ_SL + slot * 16;
+#pragma unroll
+                for (int q = 0; q < L::CH; ++q) cp_async16(dst + q * TZ_SL, src + q * 4, ok ? 16u : 0u);
+            }
+        }
+        // weights: once per group (glen > 1) or with every iteration (glen == 1)
+        if (glen == 1 || it == g * niz) {
+            const int slot_b = glen == 1 ? it % TZ_STAGES : g % 2;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)slot_b * bgroup;
+            const float4* srcb = reinterpret_cast<const float4*>(wt) + (size_t)g * (bgroup / 16);
+            for (int i = tid; i < bgroup / 16; i += TZ_THREADS) cp_async16(b_base + i * 16, srcb + i, 16u);
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < TZ_STAGES - 1; ++i) {
+        if (i < nit) issue(i);
+        cp_async_commit();
+    }
+
+    uint32_t started = 0;                                      // per-slice "accumulator written" bits (thread 0)
+    for (int it = 0; it < nit; ++it) {
+        const int nx = it + TZ_STAGES - 1;
+        if (nx < nit) {
+            // stage of iteration nx was last read by the MMAs of iteration it-1
+            if (it >= 1) mbar_wait(&bars[(it - 1) % TZ_STAGES], ((it - 1) / TZ_STAGES) & 1);
+            issue(nx);
+        }
+        cp_async_commit();
+        cp_async_wait<TZ_STAGES - 1>();                        // this thread's copies of iteration `it` have landed
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const int g = it / niz, iz = iz_lo + (it - g * niz);
+            const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)(glen == 1 ? it % TZ_STAGES : g % 2) * bgroup;
+            if (!KZF) {
+            for (int kz = 0; kz < d.kd; ++kz) {
+                const int oz = iz + pd - kz;                   // output slice fed through depth tap kz
+                if (oz < z0 || oz >= z0 + nz) continue;
+                const uint32_t dcol = tmem + (uint32_t)(oz - z0) * NT;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int p = S2 ? (kw == 1 ? 0 : 1) : 0;
+                    const int sh = S2 ? (kw == 2 ? 1 : 0) : kw;
+                    const uint32_t aoff = (uint32_t)p * L::CH * TZ_SL + (uint32_t)sh * 16;
+#pragma unroll
+                    for (int kk = 0; kk < CS / 8; ++kk) {
+                        const uint32_t acc = (started >> (oz - z0)) & 1u;
+                        started |= 1u << (oz - z0);
+                        const uint64_t ad = make_smem_desc(a_base + aoff + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
+                        const uint64_t bd = make_smem_desc(b_base + (uint32_t)(kz * 3 + kw) * L::B_TAP + (uint32_t)(2 * kk) * NT * 16, NT * 16, 128);
+                        mma_tf32_ss(dcol, ad, bd, idesc, acc);
+                    }
+                }
+            }
+            } else {
+                // depth taps whose output slice lies in this CTA's chunk: one contiguous range
+                const int kz_lo = max(0, iz + pd - (z0 + nz - 1)), kz_hi = min(d.kd - 1, iz + pd - z0);
+                if (kz_lo <= kz_hi) {
+                    const uint32_t plane = (uint32_t)(d.kd * NT) * 16;      // bytes between the K chunks of a tap: rows [kz][n]
+                    const uint32_t btap = (uint32_t)L::CH * plane;          // bytes per kw
+                    const int zi_top = iz + pd - kz_lo - z0;                // slice of tap kz_lo = first column block of the window
+                    const uint32_t dwin = tmem + (uint32_t)(nz - 1 - zi_top) * NT;
+                    const uint32_t idesc_w = make_idesc_tf32(128, (kz_hi - kz_lo + 1) * NT);
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int p = S2 ? (kw == 1 ? 0 : 1) : 0;
+                        const int sh = S2 ? (kw == 2 ? 1 : 0) : kw;
+                        const uint32_t aoff = (uint32_t)p * L::CH * TZ_SL + (uint32_t)sh * 16;
+#pragma unroll
+                        for (int kk = 0; kk < CS / 8; ++kk) {
+                            const uint64_t ad = make_smem_desc(a_base + aoff + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
+                            const uint32_t bk = b_base + (uint32_t)kw * btap + (uint32_t)(2 * kk) * plane;
+                            if (g == 0 && kw == 0 && kk == 0) {
+                                // accumulator initialisation: per slice, each with its own accumulate flag
+                                for (int kz = kz_lo; kz <= kz_hi; ++kz) {
+                                    const int zi = iz + pd - kz - z0;
+                                    const uint32_t acc = (started >> zi) & 1u;
+                                    started |= 1u << zi;
+                                    const uint64_t bd = make_smem_desc(bk + (uint32_t)(kz * NT) * 16, plane, 128);
+                                    mma_tf32_ss(tmem + (uint32_t)(nz - 1 - zi) * NT, ad, bd, idesc, acc);
+                                }
+                            } else {
+                                const uint64_t bd = make_smem_desc(bk + (uint32_t)(kz_lo * NT) * 16, plane, 128);
+                                mma_tf32_ss(dwin, ad, bd, idesc_w, 1u);
+                            }
+                        }
+                    }
+                }
+            }
+            mma_commit(&bars[it % TZ_STAGES]);
+        }
+    }
+
+    const int last = nit - 1;
+    mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
+    tc_fence_after_sync();
+    const int oy = sy[0], ox = sa[0];
+    const bool live = oy < d.Ho && ox < d.Wo;
+    for (int zi = 0; zi < nz; ++zi) {
+        float acc[NT];
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16)
+            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (KZF ? nz - 1 - zi : zi) * NT + c0, acc + c0);
+        if (!live) continue;
+        const size_t o = ((((size_t)b * d.D + z0 + zi) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0;
+#pragma unroll
+        for (int q = 0; q < NT / 4; ++q) {
+            if (co0 + q * 4 >= d.Cout) break;
+            float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            if (shift) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+            if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+            if (skip) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
+                r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+            // consumers read this tensor as a TF32 operand: round once here
+            r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+            reinterpret_cast<float4*>(y + o)[q] = r;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <int CS, int NT, bool S2, bool KZF>
+static int launch_conv_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, const TzDims& d,
+                           cudaStream_t st) {
+    using L = TzSmem<CS, NT, 3, S2 ? 2 : 1>;
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;
+    const size_t smem = (size_t)TZ_STAGES * L::A_STAGE + (size_t)br * L::b_group(d.kd) + 128;
+    MVS_REQUIRE(smem <= 227 * 1024, "mvs_conv3d_tcz_kzf: needs %zu bytes of shared memory", smem);
+    auto kern = conv3d_tcz_kernel<CS, NT, S2, KZF>;
+    MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (d.Cout + NT - 1) / NT;
+    dim3 grid((unsigned)(d.tiles_per_plane * ntiles), (unsigned)((d.D + d.zc - 1) / d.zc), (unsigned)d.B);
+    kern<<<grid, TZ_THREADS, smem, st>>>(x, w, shift, skip, y, d);
+    MVS_LAUNCH_OK("conv3d_tcz_kernel<KZF>");
+    return MVS_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int pick_zc(int D, int cols_per_slice, size_t a_bytes, size_t bgroup, int64_t ctas_per_slice) {
+    const int max_cols = env_int("MVS_TCZ_MAX_COLS", 256);
+    const int min_ctas = env_int("MVS_TCZ_MIN_CTAS", 296);
+    int best_fit = 0, best_cols = 0, best_all = 0;
+    for (int zc = D < 8 ? D : 8; zc >= 1; --zc) {
+        if (D % zc) continue;
+        if (zc * cols_per_slice > 512) continue;
+        const int br = zc >= 3 ? 2 : TZ_STAGES;
+        if (a_bytes + (size_t)br * bgroup + 128 > 227 * 1024) continue;
+        if (!best_fit) best_fit = zc;
+        const bool cols_ok = zc * cols_per_slice <= max_cols;
+        if (cols_ok && !best_cols) best_cols = zc;
+        if (cols_ok && ctas_per_slice * (D / zc) >= min_ctas && !best_all) best_all = zc;
+    }
+    return best_all ? best_all : (best_cols ? best_cols : best_fit);
+}
+
+}  // namespace kzf
+}  // namespace tc
+}  // namespace mvs
+
+static int conv3d_tcz_kzf_impl(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                               int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream) {
+    using namespace mvs;
+    using namespace mvs::tc;
+    using namespace mvs::tc::kzf;
+    MVS_REQUIRE(x && w && y, "mvs_conv3d_tcz_kzf: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && B <= 65535, "mvs_conv3d_tcz_kzf: bad shape");
+    MVS_REQUIRE(kd == 1 || kd == 3, "mvs_conv3d_tcz_kzf: depth kernel size must be 1 or 3 (got %d)", kd);
+    MVS_REQUIRE(shw == 1 || shw == 2, "mvs_conv3d_tcz_kzf: in-plane stride must be 1 or 2");
+    MVS_REQUIRE(Cout % 8 == 0 && Cout >= 8, "mvs_conv3d_tcz_kzf: Cout must be a multiple of 8 (got %d)", Cout);
+    const int cs = Cin >= 32 ? 32 : Cin;
+    MVS_REQUIRE(Cin % cs == 0 && (cs == 8 || cs == 16 || cs == 32), "mvs_conv3d_tcz_kzf: Cin must be 8, 16 or a multiple of 32 (got %d)", Cin);
+    TzDims d;
+    d.B = B; d.D = D; d.H = H; d.W = W;
+    d.Ho = (H - 1) / shw + 1; d.Wo = (W - 1) / shw + 1;
+    d.Cin = Cin; d.Cout = Cout; d.kd = kd; d.s2 = shw == 2; d.relu = relu;
+    d.PW = d.s2 ? d.Wo + 1 : d.Wo + 2;
+    d.tiles_per_plane = (int)(((int64_t)d.Ho * d.PW + 127) / 128);
+    const size_t a_bytes = (size_t)TZ_STAGES * (d.s2 ? 2 : 1) * (cs / 4) * TZ_SL;
+    const size_t bgroup = (size_t)kd * 3 * (cs / 4) * n_tile * 16;
+    d.zc = pick_zc(D, n_tile, a_bytes, bgroup, (int64_t)B * d.tiles_per_plane * ((Cout + n_tile - 1) / n_tile));
+    if (d.zc == 0) MVS_UNSUPPORTED("mvs_conv3d_tcz_kzf: no depth chunking fits D=%d with N tile %d", D, n_tile);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_TZ_CASE(CS_, NT_)                                                                          \
+    if (cs == CS_ && n_tile == NT_)                                                                    \
+        return d.s2 ? launch_conv_tcz<CS_, NT_, true, true>(x, w, shift, skip, y, d, st)               \
+                    : launch_conv_tcz<CS_, NT_, false, true>(x, w, shift, skip, y, d, st);
+    MVS_TZ_CASE(8, 16)
+    MVS_TZ_CASE(16, 16)
+    MVS_TZ_CASE(16, 32)
+    MVS_TZ_CASE(32, 16)
+    MVS_TZ_CASE(32, 32)
+    MVS_TZ_CASE(32, 64)
+#undef MVS_TZ_CASE
+    MVS_UNSUPPORTED("mvs_conv3d_tcz_kzf: no instantiation for Cin=%d, N tile=%d", Cin, n_tile);
+}
+
+// kz-fused variant (see conv3d_tcz_kernel, KZF): weights packed [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4].
+extern "C" int mvs_conv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B,
+                                  int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream) {
+    MVS_REQUIRE(kd == 3, "mvs_conv3d_tcz_kzf: depth kernel size must be 3 (got %d)", kd);
+    return conv3d_tcz_kzf_impl(x, w, shift, skip, y, B, D, H, W, Cin, Cout, n_tile, kd, shw, relu, stream);
+}
+

@@ -450,6 +450,34 @@ def pack_tcz_weights(w_packed, stride2):
     return round_tf32(w), nt
 
 
+def pack_tcz_kzf_weights(w_packed, stride2):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4], TF32-rounded: the B rows of one
+    (kw, K chunk) are [kz][n], so the depth taps of a slab are one operand of N = kd * n_tile rows
+    (mvs_conv3d_tcz_kzf)."""
+    kd, _, _, cin, cout = w_packed.shape
+    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2)
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    #            [kz, kh, kw, ch, q, e, tile, n]  ->  [tile, kh, ch, kw, q, kz, n, e]
+    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt).permute(6, 1, 3, 2, 4, 0, 7, 5).contiguous()
+    return round_tf32(w), nt
+
+
+def conv3d_tcz_kzf(x, w_kzf, n_tile, cout, kd, shift, skip, shw, relu=True):
+    require_cuda(x, w_kzf, shift, skip)
+    b, d, h, w, cin = x.shape
+    ho, wo = (h - 1) // shw + 1, (w - 1) // shw + 1
+    y = torch.empty(b, d, ho, wo, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_tcz_kzf(ptr(x), ptr(w_kzf), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile,
+                                         kd, shw, 1 if relu else 0, stream()), "mvs_conv3d_tcz_kzf")
+    return y
+
+
 def pack_tcz_deconv_weights(w_packed):
     """[kd,3,3,Cin,Cout] -> [Cout_tiles][2 dy][Cin/CS][kd][6 taps][CS/4][n_tile][4], TF32-rounded."""
     kd, _, _, cin, cout = w_packed.shape

@@ -77,6 +77,12 @@ def _tc_eligible(cin, cout, transposed):
 
 def _run_conv(cache, x, w, shift, skip, stride, relu):
     kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    kzf = config.tcz_kzf() if (config.conv_precision() == "tf32" and kd == 3 and stride[0] == 1 and stride[1] == stride[2]
+                               and engine.tcz_supported(cin, cout, x.shape[1], kd, stride[1] == 2)) else 0
+    if kzf == 2 or (kzf == 1 and not (stride == (1, 1, 1) and engine.tcr_supported(cin, cout, x.shape[3]))):
+        # opt-in kz-fused tensor-core kernel (config.py): same shape rules as the tcz kernel
+        wk, nt = cache.get_derived("tcz_kzf_s%d" % stride[1], lambda v: engine.pack_tcz_kzf_weights(v[0], stride[1] == 2))
+        return engine.conv3d_tcz_kzf(x, wk, nt, cout, kd, shift, skip, stride[1], relu)
     if (config.conv_precision() == "tf32" and stride == (1, 1, 1) and engine.tcr_supported(cin, cout, x.shape[3])):
         wr, nt = cache.get_derived("tcr", lambda v: engine.pack_tcr_weights(v[0]))
         return engine.conv3d_tcr(x, wr, nt, cout, kd, shift, skip, relu)

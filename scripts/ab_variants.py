@@ -6,6 +6,7 @@ with CUDA events on the bench workload, and writes one JSON.
 
 Variants
   cost-volume build   two sampling passes (shipped)  vs  MVS_CV_STORE (pass A stores corr, streaming aggregation)
+  3D CNN              depth-fused tcgen05 convs      vs  MVS_TCZ_KZF=1/2 (kz-fused N: one MMA per slab instead of three)
   weight gradients    8x8 register tiles (default)   vs  MVS_WGRAD_TILE=4
 Each inference variant reports ms per reference view (cfg 2, inputs resident) and the per-kernel-class CUDA-event
 attribution of bench.py's KernelProfiler; the training variants report ms per cfg-5-shaped training step and the
@@ -70,17 +71,23 @@ def main():
     cams = {k: v.to(device) for k, v in cams_h.items()}
     dv = dv_h.to(device)
     depths = {}
-    for name, flag in (("two_pass", False), ("cv_store", True)):
-        if flag and rc != 0:
+    for name, store, kzf in (("shipped", False, 0), ("cv_store", True, 0), ("tcz_kzf_1", False, 1), ("tcz_kzf_2", False, 2),
+                             ("cv_store+tcz_kzf_2", True, 2)):
+        if (store or kzf) and rc != 0:
             result[name] = {"skipped": "experimental parity tests failed"}
             continue
-        config.set_cv_store(flag)
+        config.set_cv_store(store)
+        config.set_tcz_kzf(kzf)
         ms, kern, depths[name] = time_inference(net, feats, cams, dv)
         result[name] = {"ms_per_ref_view": ms, "maps_per_s": 1e3 / ms, "kernels_ms": kern}
         print(name, round(ms, 3), "ms", flush=True)
     config.set_cv_store(False)
-    if len(depths) == 2:
-        result["cv_store_refined_depth_bit_identical"] = bool(torch.equal(depths["two_pass"], depths["cv_store"]))
+    config.set_tcz_kzf(0)
+    if "cv_store" in depths:
+        result["cv_store_refined_depth_bit_identical"] = bool(torch.equal(depths["shipped"], depths["cv_store"]))
+    if "tcz_kzf_2" in depths:
+        d0, d2 = depths["shipped"], depths["tcz_kzf_2"]
+        result["tcz_kzf_refined_depth_rel_l1"] = float((d2 - d0).abs().mean() / d0.abs().mean())
 
     import train_profile  # noqa: E402
     for tile in ("8", "4"):

@@ -64,3 +64,63 @@ def test_cv_store_falls_back_at_stage4():
     a = _build(net, feats, cams, hyp, True)[0]
     b = _build(net, feats, cams, hyp, False)[0]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cin,cout,depth,h,w,stride2", [
+    (8, 16, 4, 32, 48, True), (16, 16, 4, 32, 48, False), (16, 32, 8, 32, 48, True), (32, 32, 4, 24, 40, False),
+    (32, 64, 8, 32, 48, True), (64, 64, 4, 16, 24, False), (64, 64, 8, 16, 24, False), (16, 8, 2, 16, 24, False)])
+def test_tcz_kzf_matches_tcz(cin, cout, depth, h, w, stride2):
+    """MVS_TCZ_KZF: the kz-fused tensor-core convolution vs the shipped depth-fused kernel (same TF32 operands,
+    different fp32 accumulation order) and vs an fp64 convolution of the same rounded operands."""
+    import torch.nn.functional as F
+    from mvsformer_b200 import engine
+
+    g = S._gen(cin * 100 + cout)
+    wp = engine.round_tf32(torch.randn(3, 3, 3, cin, cout, generator=g) * 0.1)
+    x = engine.round_tf32(torch.randn(2, depth, h, w, cin, generator=g))
+    shift = torch.randn(cout, generator=g)
+    if not engine.tcz_supported(cin, cout, depth, 3, stride2):
+        pytest.skip("shape not covered by the tcz kernels")
+    wz, nt = engine.pack_tcz_weights(wp, stride2)
+    wk, nt2 = engine.pack_tcz_kzf_weights(wp, stride2)
+    assert nt == nt2
+    shw = 2 if stride2 else 1
+    ref = engine.conv3d_tcz(x.to(DEV), wz.to(DEV), nt, cout, 3, shift.to(DEV), None, shw, True)
+    got = engine.conv3d_tcz_kzf(x.to(DEV), wk.to(DEV), nt, cout, 3, shift.to(DEV), None, shw, True)
+    torch.cuda.synchronize()
+    want = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), wp.permute(4, 3, 0, 1, 2).double(), stride=(1, shw, shw), padding=1)
+    want = torch.relu(want + shift.double().view(1, -1, 1, 1, 1)).permute(0, 2, 3, 4, 1)
+    err_ref = float((ref.cpu().double() - want).abs().mean() / want.abs().mean())
+    err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
+    assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6        # outputs are TF32-rounded by the epilogue
+    assert float((got - ref).abs().max()) < 1e-2
+
+
+def test_tcz_kzf_cascade_matches_default():
+    """Whole TF32 cascade with MVS_TCZ_KZF=2 (kz-fused kernel wherever it applies) vs the shipped kernels."""
+    from mvsformer_b200.mvsformer_model import CascadeMVS
+    from tests.helpers import CASCADE_ARGS
+
+    height, width, batch, views = 128, 192, 1, 3
+    feats = {k: v.to(DEV) for k, v in S.make_features(batch, views, height, width, seed=3).items()}
+    cams = {k: v.to(DEV) for k, v in S.make_cameras(batch, views, height, width).items()}
+    dv = S.make_depth_range(batch).to(DEV)
+    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
+    full = {}
+    for s in range(4):
+        full.update({"fusions.%d.%s" % (s, k): v for k, v in S.fill_state_dict(net.fusions[s].state_dict(), seed=40 + s).items()})
+    net.load_state_dict(full)
+    net = net.to(DEV)
+    old = config.conv_precision()
+    config.set_conv_precision("tf32")
+    try:
+        outs = {}
+        for level in (0, 2):
+            config.set_tcz_kzf(level)
+            with torch.no_grad():
+                outs[level] = net(feats, cams, dv, tmp=list(S.EVAL_TMP))["refined_depth"].clone()
+    finally:
+        config.set_tcz_kzf(0)
+        config.set_conv_precision(old)
+    rel = float((outs[2] - outs[0]).abs().mean() / outs[0].abs().mean())
+    assert rel < 1e-3

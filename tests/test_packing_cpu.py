@@ -105,3 +105,81 @@ def test_feature_cache_lru_and_pinning():
         c.reserve("f", pinned=("c", "d", "e"))
     with pytest.raises(ValueError):
         FeatureCache(1)
+
+
+def _emulate_tcz_kzf(x, w_packed_flat, nt, cin, cout, kd, depth, zc):
+    """Host emulation of the MMA issue loop of conv3d_tcz_kernel<.., KZF=true> (conv3d_tcz_kzf.cu), stride 1:
+    same group / slab order, same window, column, accumulate-flag and B-descriptor arithmetic, with the tensor-core
+    product written as a matrix product.  x [D,H,W,Cin] (numpy), returns y [D,H,W,Cout]."""
+    cs = engine.tc_channel_slice(cin)
+    ch_n, nch, pd = cs // 4, cin // cs, kd // 2
+    d_, h_, w_ = x.shape[:3]
+    ngroups = 3 * nch
+    plane = kd * nt * 16                      # bytes between the K chunks of a tap
+    btap = ch_n * plane                       # bytes per kw
+    bgroup = 3 * btap
+    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    y = np.zeros((d_, h_, w_, cout), np.float64)
+    ntiles = (cout + nt - 1) // nt
+    for ct in range(ntiles):
+        for z0 in range(0, d_, zc):
+            nz = min(zc, d_ - z0)
+            tmem = np.full((h_ * w_, zc * nt), np.nan)          # garbage until an accumulate=0 MMA writes it
+            started = 0
+            iz_lo, iz_hi = max(z0 - pd, 0), min(z0 + nz - 1 + pd, d_ - 1)
+            for g in range(ngroups):
+                kh, ch = g // nch, g % nch
+                group = w_packed_flat[(ct * ngroups + g) * (bgroup // 4):(ct * ngroups + g + 1) * (bgroup // 4)]
+                for iz in range(iz_lo, iz_hi + 1):
+                    kz_lo, kz_hi = max(0, iz + pd - (z0 + nz - 1)), min(kd - 1, iz + pd - z0)
+                    if kz_lo > kz_hi:
+                        continue
+                    zi_top = iz + pd - kz_lo - z0
+                    dwin = (nz - 1 - zi_top) * nt
+                    for kw in range(3):
+                        for kk in range(cs // 8):
+                            a = xp[iz, kh:kh + h_, kw:kw + w_, ch * cs + kk * 8: ch * cs + kk * 8 + 8].reshape(-1, 8)
+
+                            def b_rows(first_row, nrows):
+                                out = np.empty((nrows, 8))
+                                for r in range(nrows):
+                                    for k in range(8):
+                                        byte = kw * btap + (2 * kk + k // 4) * plane + (first_row + r) * 16 + (k % 4) * 4
+                                        out[r, k] = group[byte // 4]
+                                return out
+                            if g == 0 and kw == 0 and kk == 0:
+                                for kz in range(kz_lo, kz_hi + 1):
+                                    zi = iz + pd - kz - z0
+                                    col = (nz - 1 - zi) * nt
+                                    prod = a @ b_rows(kz * nt, nt).T
+                                    tmem[:, col:col + nt] = prod + (tmem[:, col:col + nt] if (started >> zi) & 1 else 0.0)
+                                    started |= 1 << zi
+                            else:
+                                n = (kz_hi - kz_lo + 1) * nt
+                                tmem[:, dwin:dwin + n] += a @ b_rows(kz_lo * nt, n).T
+            for zi in range(nz):
+                col = (nz - 1 - zi) * nt
+                ncout = min(nt, cout - ct * nt)
+                y[z0 + zi, :, :, ct * nt: ct * nt + ncout] = tmem[:, col:col + ncout].reshape(h_, w_, ncout)
+    return y
+
+
+def test_tcz_kzf_issue_loop_and_packing():
+    """The opt-in kz-fused convolution: packed-weight layout + window / column / accumulate logic of the kernel's
+    MMA issue loop, emulated on the host, reproduce conv3d for every depth chunking (no accumulator is read before
+    it is initialised: uninitialised TMEM is NaN here)."""
+    import torch.nn.functional as F
+    for cin, cout, depth in ((16, 16, 4), (64, 32, 4), (8, 8, 8)):
+        kd = 3
+        g = torch.Generator().manual_seed(cin + cout)
+        w = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g))
+        x = engine.round_tf32(torch.randn(depth, 5, 6, cin, generator=g))
+        wk, nt = engine.pack_tcz_kzf_weights(w, stride2=False)
+        cs = engine.tc_channel_slice(cin)
+        assert wk.shape == ((cout + nt - 1) // nt, 3, cin // cs, 3, cs // 4, kd, nt, 4)
+        want = F.conv3d(x.permute(3, 0, 1, 2).unsqueeze(0).double(), w.permute(4, 3, 0, 1, 2).double(), padding=1)[0]
+        want = want.permute(1, 2, 3, 0).numpy()
+        for zc in (1, 2, 4):
+            got = _emulate_tcz_kzf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, depth, zc)
+            assert np.isfinite(got).all(), (cin, cout, zc)
+            assert np.abs(got - want).max() < 1e-9, (cin, cout, zc)
