@@ -142,6 +142,10 @@ int mvs_deconv3d_tcz(const float* x, const float* w, const float* shift, const f
  * memory once instead of three times.  Weights (TF32): [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4]. */
 int mvs_conv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
                        int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
+/* Same for mvs_deconv3d_tcz (kd = 3): accumulators laid out [parity class][slice]; weights (TF32)
+ * [Cout_tiles][2 dy][Cin/CS][6 taps][CS/4][kd][n_tile][4] (tap order as mvs_deconv3d_tc). */
+int mvs_deconv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                         int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
 /* Row-tiled variant of mvs_conv3d_tcz for wide stride-1 layers (Cin <= 32): R rows x 128 columns x zc
  * slices per CTA, all taps resident.  Weights (TF32): [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4]. */
 int mvs_conv3d_tcr(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,

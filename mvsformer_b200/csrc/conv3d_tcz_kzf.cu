@@ -269,6 +269,229 @@ static int launch_conv_tcz(const float* x, const float* w, const float* shift, c
     return MVS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// transposed convolution, kernel (3,3,3), stride (1,2,2), kz-fused: the accumulators of a CTA are laid out
+// [parity class][slice], so for a tap (-> class) the output slices iz-1, iz, iz+1 of the depth taps kz = 0,1,2
+// are one contiguous window (ascending in kz) and one MMA of N = 3*NT feeds them.  Weights packed
+// [Cout_tiles][2 dy][Cin/CS][6 taps][CS/4][kd][n_tile][4].  Modified copy of deconv3d_tcz_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int CS, int NT>
+__global__ void __launch_bounds__(TZ_THREADS)
+deconv3d_tcz_kzf_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                    const float* __restrict__ skip, float* __restrict__ y, TzDims d) {
+    using L = TzSmem<CS, NT, 6, 1>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int bgroup = L::b_group(d.kd);
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TZ_STAGES * L::A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)br * bgroup);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ncols = d.zc * 4 * NT;
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : (ncols <= 256 ? 256 : 512)));
+    if (tid == 0) {
+        for (int s = 0; s < TZ_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int b = blockIdx.z;
+    const int z0 = blockIdx.y * d.zc;
+    const int nz = min(d.zc, d.D - z0);
+    const int j0 = (blockIdx.x % d.tiles_per_plane) * 128;
+    const int ct = blockIdx.x / d.tiles_per_plane;
+    const int co0 = ct * NT;
+    const int pd = d.kd / 2;
+    const int nch = d.Cin / CS;
+    const int iz_lo = max(z0 - pd, 0), iz_hi = min(z0 + nz - 1 + pd, d.D - 1);
+    const int niz = iz_hi - iz_lo + 1;
+    const int ngroups = 2 * nch;                               // (dy, channel slice)
+    const int nit = ngroups * niz;
+    const int glen = br == 2 ? niz : 1;
+
+    int sy[2], sa[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int jv = j0 + tid + u * 128;
+        sy[u] = jv / d.PW;
+        sa[u] = jv - sy[u] * d.PW;
+    }
+    const int nslot_iters = (tid + 128 < 129) ? 2 : 1;
+    const float* wt = w + (size_t)ct * ngroups * (bgroup / 4);
+
+    auto issue = [&](int it) {
+        const int g = it / niz, iz = iz_lo + (it - g * niz);
+        const int dy = g / nch, ch = g - dy * nch;
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+        for (int u = 0; u < nslot_iters; ++u) {
+            const int slot = tid + u * 128;
+            const int yy = sy[u] + dy, xx = sa[u];
+            const bool ok = yy < d.H && xx < d.W;
+            const float* src = x + ((((size_t)b * d.D + iz) * d.H + (ok ? yy : 0)) * d.W + (ok ? xx : 0)) * d.Cin + ch * CS;
+            const uint32_t dst = a_base + slot * 16;
+#pragma unroll
+            for (int q = 0; q < L::CH; ++q) cp_async16(dst + q * TZ_SL, src + q * 4, ok ? 16u : 0u);
+        }
+        if (glen == 1 || it == g * niz) {
+            const int slot_b = glen == 1 ? it % TZ_STAGES : g % 2;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)slot_b * bgroup;
+            const float4* srcb = reinterpret_cast<const float4*>(wt) + (size_t)g * (bgroup / 16);
+            for (int i = tid; i < bgroup / 16; i += TZ_THREADS) cp_async16(b_base + i * 16, srcb + i, 16u);
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < TZ_STAGES - 1; ++i) {
+        if (i < nit) issue(i);
+        cp_async_commit();
+    }
+
+    uint32_t started = 0;                                      // bit (class * nz + slice)
+    for (int it = 0; it < nit; ++it) {
+        const int nx = it + TZ_STAGES - 1;
+        if (nx < nit) {
+            if (it >= 1) mbar_wait(&bars[(it - 1) % TZ_STAGES], ((it - 1) / TZ_STAGES) & 1);
+            issue(nx);
+        }
+        cp_async_commit();
+        cp_async_wait<TZ_STAGES - 1>();
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const int g = it / niz, iz = iz_lo + (it - g * niz);
+            const int dy = g / nch;
+            const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * L::A_STAGE;
+            const uint32_t b_base = smem_u32(sB) + (uint32_t)(glen == 1 ? it % TZ_STAGES : g % 2) * bgroup;
+            const int ntaps = dy == 0 ? 6 : 3;
+            // depth taps whose output slice (oz = iz - pd + kz) lies in this CTA's chunk: one contiguous range
+            const int kz_lo = max(0, z0 - iz + pd), kz_hi = min(d.kd - 1, z0 + nz - 1 - iz + pd);
+            if (kz_lo <= kz_hi) {
+                const uint32_t plane = (uint32_t)(d.kd * NT) * 16;          // bytes between the K chunks of a tap: rows [kz][n]
+                const uint32_t btap = (uint32_t)L::CH * plane;              // bytes per tap
+                const int zi_lo = iz - pd + kz_lo - z0;                     // first slice of the window
+                const uint32_t idesc_w = make_idesc_tf32(128, (kz_hi - kz_lo + 1) * NT);
+                for (int t = 0; t < ntaps; ++t) {
+                    const int kh = dy == 0 ? 1 + t / 3 : 0;
+                    const int kw = t % 3;
+                    const int cls = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);
+                    const int sh = (kw == 0) ? 1 : 0;
+                    // accumulators are laid out [class][slice]: the window of a class is contiguous, ascending in kz
+                    const uint32_t dwin = tmem + (uint32_t)(cls * nz + zi_lo) * NT;
+                    // every class is first touched in group 0 (dy = 0, first channel slice) by these taps
+                    const bool starter = g == 0 && (t == 0 || t == 1 || t == 3 || t == 4);
+#pragma unroll
+                    for (int kk = 0; kk < CS / 8; ++kk) {
+                        const uint64_t ad = make_smem_desc(a_base + (uint32_t)sh * 16 + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
+                        const uint32_t bk = b_base + (uint32_t)t * btap + (uint32_t)(2 * kk) * plane;
+                        if (starter && kk == 0) {
+                            for (int kz = kz_lo; kz <= kz_hi; ++kz) {
+                                const int slot_acc = cls * nz + (iz - pd + kz - z0);
+                                const uint32_t acc = (started >> slot_acc) & 1u;
+                                started |= 1u << slot_acc;
+                                const uint64_t bd = make_smem_desc(bk + (uint32_t)(kz * NT) * 16, plane, 128);
+                                mma_tf32_ss(tmem + (uint32_t)slot_acc * NT, ad, bd, idesc, acc);
+                            }
+                        } else {
+                            const uint64_t bd = make_smem_desc(bk + (uint32_t)(kz_lo * NT) * 16, plane, 128);
+                            mma_tf32_ss(dwin, ad, bd, idesc_w, 1u);
+                        }
+                    }
+                }
+            }
+            mma_commit(&bars[it % TZ_STAGES]);
+        }
+    }
+
+    const int last = nit - 1;
+    mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
+    tc_fence_after_sync();
+    // Epilogue.  The skip tensor does not depend on the MMAs: its loads for the next group of
+    // accumulators are issued before the current group is drained, so their latency is hidden.
+    const int iy = sy[0], ix = sa[0];
+    const bool live = iy < d.H && ix < d.W;
+    constexpr int U = 64 / NT;                                  // accumulators per prefetch group (<= 16 float4)
+    const int nacc = nz * 4;
+    float4 skA[U][NT / 4], skB[U][NT / 4];                      // ping-pong register buffers (static indexing)
+    auto out_index = [&](int a) -> size_t {
+        const int zi = a >> 2, cls = a & 3;
+        return ((((size_t)b * d.D + z0 + zi) * d.Ho + 2 * iy + (cls >> 1)) * d.Wo + 2 * ix + (cls & 1)) * d.Cout + co0;
+    };
+    auto prefetch = [&](int a0, float4 (&buf)[U][NT / 4]) {
+        if (!skip || !live) return;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (a0 + u < nacc) {
+                const float4* sp = reinterpret_cast<const float4*>(skip + out_index(a0 + u));
+#pragma unroll
+                for (int q = 0; q < NT / 4; ++q)
+                    if (co0 + q * 4 < d.Cout) buf[u][q] = __ldg(sp + q);
+            }
+        }
+    };
+    auto drain = [&](int a0, float4 (&buf)[U][NT / 4]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (a0 + u < nacc) {                                 // uniform across the CTA
+                float acc[NT];
+#pragma unroll
+                for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (((a0 + u) & 3) * nz + ((a0 + u) >> 2)) * NT + c0, acc + c0);
+                if (live) {
+                    const size_t o = out_index(a0 + u);
+#pragma unroll
+                    for (int q = 0; q < NT / 4; ++q) {
+                        if (co0 + q * 4 < d.Cout) {
+                            float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+                            if (shift) {
+                                const float4 sft = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                                r.x += sft.x; r.y += sft.y; r.z += sft.z; r.w += sft.w;
+                            }
+                            if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                            if (skip) { r.x += buf[u][q].x; r.y += buf[u][q].y; r.z += buf[u][q].z; r.w += buf[u][q].w; }
+                            r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+                            reinterpret_cast<float4*>(y + o)[q] = r;
+                        }
+                    }
+                }
+            }
+        }
+    };
+    prefetch(0, skA);
+    for (int a0 = 0; a0 < nacc; a0 += 2 * U) {
+        if (a0 + U < nacc) prefetch(a0 + U, skB);
+        drain(a0, skA);
+        if (a0 + 2 * U < nacc) prefetch(a0 + 2 * U, skA);
+        if (a0 + U < nacc) drain(a0 + U, skB);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <int CS, int NT>
+static int launch_deconv_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, const TzDims& d,
+                             cudaStream_t st) {
+    using L = TzSmem<CS, NT, 6, 1>;
+    const int br = d.zc >= 3 ? 2 : TZ_STAGES;
+    const size_t smem = (size_t)TZ_STAGES * L::A_STAGE + (size_t)br * L::b_group(d.kd) + 128;
+    MVS_REQUIRE(smem <= 227 * 1024, "mvs_deconv3d_tcz_kzf: needs %zu bytes of shared memory", smem);
+    auto kern = deconv3d_tcz_kzf_kernel<CS, NT>;
+    MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (d.Cout + NT - 1) / NT;
+    dim3 grid((unsigned)(d.tiles_per_plane * ntiles), (unsigned)((d.D + d.zc - 1) / d.zc), (unsigned)d.B);
+    kern<<<grid, TZ_THREADS, smem, st>>>(x, w, shift, skip, y, d);
+    MVS_LAUNCH_OK("deconv3d_tcz_kzf_kernel");
+    return MVS_OK;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -339,3 +562,34 @@ extern "C" int mvs_conv3d_tcz_kzf(const float* x, const float* w, const float* s
     return conv3d_tcz_kzf_impl(x, w, shift, skip, y, B, D, H, W, Cin, Cout, n_tile, kd, shw, relu, stream);
 }
 
+// kz-fused transposed convolution (see deconv3d_tcz_kzf_kernel).
+extern "C" int mvs_deconv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                                int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream) {
+    using namespace mvs;
+    using namespace mvs::tc;
+    using namespace mvs::tc::kzf;
+    MVS_REQUIRE(x && w && y, "mvs_deconv3d_tcz_kzf: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && B <= 65535, "mvs_deconv3d_tcz_kzf: bad shape");
+    MVS_REQUIRE(kd == 3, "mvs_deconv3d_tcz_kzf: depth kernel size must be 3 (got %d)", kd);
+    MVS_REQUIRE(Cout % 8 == 0 && Cout >= 8, "mvs_deconv3d_tcz_kzf: Cout must be a multiple of 8 (got %d)", Cout);
+    const int cs = Cin >= 32 ? 32 : Cin;
+    MVS_REQUIRE(Cin % cs == 0 && (cs == 16 || cs == 32), "mvs_deconv3d_tcz_kzf: Cin must be 16 or a multiple of 32 (got %d)", Cin);
+    TzDims d;
+    d.B = B; d.D = D; d.H = H; d.W = W;
+    d.Ho = 2 * H; d.Wo = 2 * W;
+    d.Cin = Cin; d.Cout = Cout; d.kd = kd; d.s2 = 1; d.relu = relu;
+    d.PW = W + 1;
+    d.tiles_per_plane = (int)(((int64_t)H * d.PW + 127) / 128);
+    const size_t a_bytes = (size_t)TZ_STAGES * (cs / 4) * TZ_SL;
+    const size_t bgroup = (size_t)kd * 6 * (cs / 4) * n_tile * 16;
+    d.zc = pick_zc(D, 4 * n_tile, a_bytes, bgroup, (int64_t)B * d.tiles_per_plane * ((Cout + n_tile - 1) / n_tile));
+    if (d.zc == 0) MVS_UNSUPPORTED("mvs_deconv3d_tcz_kzf: no depth chunking fits D=%d with N tile %d", D, n_tile);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_TZD_CASE(CS_, NT_) \
+    if (cs == CS_ && n_tile == NT_) return launch_deconv_tcz_kzf<CS_, NT_>(x, w, shift, skip, y, d, st);
+    MVS_TZD_CASE(16, 16)
+    MVS_TZD_CASE(32, 16)
+    MVS_TZD_CASE(32, 32)
+#undef MVS_TZD_CASE
+    MVS_UNSUPPORTED("mvs_deconv3d_tcz_kzf: no instantiation for Cin=%d, N tile=%d", Cin, n_tile);
+}

@@ -495,6 +495,25 @@ def pack_tcz_deconv_weights(w_packed):
     return round_tf32(out.contiguous()), nt
 
 
+def pack_tcz_kzf_deconv_weights(w_packed):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][2 dy][Cin/CS][6 taps][CS/4][kd][n_tile][4], TF32-rounded (mvs_deconv3d_tcz_kzf):
+    the layout of pack_tcz_deconv_weights with the depth tap moved next to the row index."""
+    wz, nt = pack_tcz_deconv_weights(w_packed)               # [tile, dy, ch, kz, t, q, n, e]
+    return wz.permute(0, 1, 2, 4, 5, 3, 6, 7).contiguous(), nt
+
+
+def deconv3d_tcz_kzf(x, w_kzf, n_tile, cout, kd, shift, skip, relu=True):
+    require_cuda(x, w_kzf, shift, skip)
+    b, d, h, w, cin = x.shape
+    y = torch.empty(b, d, h * 2, w * 2, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_deconv3d_tcz_kzf(ptr(x), ptr(w_kzf), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile,
+                                           kd, 1 if relu else 0, stream()), "mvs_deconv3d_tcz_kzf")
+    return y
+
+
 def conv3d_tcz(x, w_tcz, n_tile, cout, kd, shift, skip, shw, relu=True):
     require_cuda(x, w_tcz, shift, skip)
     b, d, h, w, cin = x.shape

@@ -100,6 +100,9 @@ def _run_conv(cache, x, w, shift, skip, stride, relu):
 def _run_deconv(cache, x, w, shift, skip, sd, relu):
     kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
     if config.conv_precision() == "tf32" and sd == 1 and engine.tcz_supported(cin, cout, x.shape[1], kd, transposed=True):
+        if config.tcz_kzf() and kd == 3:                 # opt-in kz-fused kernel (config.py)
+            wk, nt = cache.get_derived("tczd_kzf", lambda v: engine.pack_tcz_kzf_deconv_weights(v[0]))
+            return engine.deconv3d_tcz_kzf(x, wk, nt, cout, kd, shift, skip, relu)
         wz, nt = cache.get_derived("tczd", lambda v: engine.pack_tcz_deconv_weights(v[0]))
         return engine.deconv3d_tcz(x, wz, nt, cout, kd, shift, skip, relu)
     if _tc_eligible(cin, cout, True):

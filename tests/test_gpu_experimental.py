@@ -124,3 +124,32 @@ def test_tcz_kzf_cascade_matches_default():
         config.set_conv_precision(old)
     rel = float((outs[2] - outs[0]).abs().mean() / outs[0].abs().mean())
     assert rel < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,depth,h,w", [(16, 8, 4, 32, 48), (32, 16, 4, 24, 40), (64, 32, 8, 16, 24), (64, 32, 4, 16, 24),
+                                                (16, 8, 2, 16, 24)])
+def test_deconv_tcz_kzf_matches_tcz(cin, cout, depth, h, w):
+    """MVS_TCZ_KZF: kz-fused transposed convolution vs the shipped depth-fused kernel and vs fp64 (with skip add)."""
+    import torch.nn.functional as F
+    from mvsformer_b200 import engine
+
+    if not engine.tcz_supported(cin, cout, depth, 3, transposed=True):
+        pytest.skip("shape not covered by the tcz kernels")
+    g = S._gen(cin * 100 + cout + 1)
+    wp = engine.round_tf32(torch.randn(3, 3, 3, cin, cout, generator=g) * 0.1)
+    x = engine.round_tf32(torch.randn(2, depth, h, w, cin, generator=g))
+    shift = torch.randn(cout, generator=g)
+    skip = torch.randn(2, depth, 2 * h, 2 * w, cout, generator=g)
+    wz, nt = engine.pack_tcz_deconv_weights(wp)
+    wk, nt2 = engine.pack_tcz_kzf_deconv_weights(wp)
+    assert nt == nt2
+    ref = engine.deconv3d_tcz(x.to(DEV), wz.to(DEV), nt, cout, 3, shift.to(DEV), skip.to(DEV), True)
+    got = engine.deconv3d_tcz_kzf(x.to(DEV), wk.to(DEV), nt, cout, 3, shift.to(DEV), skip.to(DEV), True)
+    torch.cuda.synchronize()
+    want = F.conv_transpose3d(x.permute(0, 4, 1, 2, 3).double(), wp.permute(3, 4, 0, 1, 2).double(), stride=(1, 2, 2),
+                              padding=1, output_padding=(0, 1, 1))
+    want = (torch.relu(want + shift.double().view(1, -1, 1, 1, 1))).permute(0, 2, 3, 4, 1) + skip.double()
+    err_ref = float((ref.cpu().double() - want).abs().mean() / want.abs().mean())
+    err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
+    assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6
+    assert float((got - ref).abs().max()) < 1e-2

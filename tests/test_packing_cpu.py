@@ -183,3 +183,84 @@ def test_tcz_kzf_issue_loop_and_packing():
             got = _emulate_tcz_kzf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, depth, zc)
             assert np.isfinite(got).all(), (cin, cout, zc)
             assert np.abs(got - want).max() < 1e-9, (cin, cout, zc)
+
+
+def _emulate_deconv_tcz_kzf(x, flat, nt, cin, cout, kd, zc):
+    """Host emulation of the MMA issue loop of deconv3d_tcz_kzf_kernel (conv3d_tcz_kzf.cu): groups (dy, channel
+    slice), slabs iz, taps -> parity class, accumulators [class][slice], per-slice initialisation in group 0,
+    fused N = 3 * NT windows elsewhere.  x [D,H,W,Cin] -> y [D,2H,2W,Cout] (stride (1,2,2), pad 1, output_padding (0,1,1))."""
+    cs = engine.tc_channel_slice(cin)
+    ch_n, nch, pd = cs // 4, cin // cs, kd // 2
+    d_, h_, w_ = x.shape[:3]
+    ngroups = 2 * nch
+    plane = kd * nt * 16
+    btap = ch_n * plane
+    bgroup = 6 * btap
+    xp = np.pad(x, ((0, 0), (0, 1), (0, 1), (0, 0)))          # zero row / column past the image (dy = 1, sh = 1)
+    y = np.zeros((d_, 2 * h_, 2 * w_, cout))
+    for ct in range((cout + nt - 1) // nt):
+        for z0 in range(0, d_, zc):
+            nz = min(zc, d_ - z0)
+            tmem = np.full((h_ * w_, nz * 4 * nt), np.nan)
+            started = 0
+            iz_lo, iz_hi = max(z0 - pd, 0), min(z0 + nz - 1 + pd, d_ - 1)
+            for g in range(ngroups):
+                dy, ch = g // nch, g % nch
+                group = flat[(ct * ngroups + g) * (bgroup // 4):(ct * ngroups + g + 1) * (bgroup // 4)]
+                for iz in range(iz_lo, iz_hi + 1):
+                    kz_lo, kz_hi = max(0, z0 - iz + pd), min(kd - 1, z0 + nz - 1 - iz + pd)
+                    if kz_lo > kz_hi:
+                        continue
+                    zi_lo = iz - pd + kz_lo - z0
+                    for t in range(6 if dy == 0 else 3):
+                        kh = 1 + t // 3 if dy == 0 else 0
+                        kw = t % 3
+                        cls = (0 if kh == 1 else 2) + (0 if kw == 1 else 1)
+                        sh = 1 if kw == 0 else 0
+                        dwin = (cls * nz + zi_lo) * nt
+                        starter = g == 0 and t in (0, 1, 3, 4)
+                        for kk in range(cs // 8):
+                            a = xp[iz, dy:dy + h_, sh:sh + w_, ch * cs + kk * 8: ch * cs + kk * 8 + 8].reshape(-1, 8)
+
+                            def b_rows(first_row, nrows):
+                                out = np.empty((nrows, 8))
+                                for r in range(nrows):
+                                    for k in range(8):
+                                        byte = t * btap + (2 * kk + k // 4) * plane + (first_row + r) * 16 + (k % 4) * 4
+                                        out[r, k] = group[byte // 4]
+                                return out
+                            if starter and kk == 0:
+                                for kz in range(kz_lo, kz_hi + 1):
+                                    slot = cls * nz + (iz - pd + kz - z0)
+                                    prod = a @ b_rows(kz * nt, nt).T
+                                    col = slot * nt
+                                    tmem[:, col:col + nt] = prod + (tmem[:, col:col + nt] if (started >> slot) & 1 else 0.0)
+                                    started |= 1 << slot
+                            else:
+                                n = (kz_hi - kz_lo + 1) * nt
+                                tmem[:, dwin:dwin + n] += a @ b_rows(kz_lo * nt, n).T
+            ncout = min(nt, cout - ct * nt)
+            for zi in range(nz):
+                for cls in range(4):
+                    col = (cls * nz + zi) * nt
+                    y[z0 + zi, (cls >> 1)::2, (cls & 1)::2, ct * nt: ct * nt + ncout] = \
+                        tmem[:, col:col + ncout].reshape(h_, w_, ncout)
+    return y
+
+
+def test_deconv_tcz_kzf_issue_loop_and_packing():
+    import torch.nn.functional as F
+    for cin, cout, depth in ((16, 8, 4), (32, 16, 4), (64, 32, 8)):
+        kd = 3
+        g = torch.Generator().manual_seed(cin * 7 + cout)
+        w = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g))            # packed [kd,3,3,Cin,Cout]
+        x = engine.round_tf32(torch.randn(depth, 4, 5, cin, generator=g))
+        wk, nt = engine.pack_tcz_kzf_deconv_weights(w)
+        cs = engine.tc_channel_slice(cin)
+        assert wk.shape == ((cout + nt - 1) // nt, 2, cin // cs, 6, cs // 4, kd, nt, 4)
+        want = F.conv_transpose3d(x.permute(3, 0, 1, 2).unsqueeze(0).double(), w.permute(3, 4, 0, 1, 2).double(),
+                                  stride=(1, 2, 2), padding=1, output_padding=(0, 1, 1))[0].permute(1, 2, 3, 0).numpy()
+        for zc in (1, 2, 4):
+            got = _emulate_deconv_tcz_kzf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, zc)
+            assert np.isfinite(got).all(), (cin, cout, zc)
+            assert np.abs(got - want).max() < 1e-9, (cin, cout, zc)
