@@ -197,6 +197,8 @@ class KernelProfiler:
         self._wrap(engine, "deconv3d_tcz", "deconv3d_tcz", deconv_tcz_cost)
         self._wrap(engine, "conv3d_tcz_kzf", "conv3d_tcz_kzf", conv_tcz_cost)          # opt-in MVS_TCZ_KZF
         self._wrap(engine, "deconv3d_tcz_kzf", "deconv3d_tcz_kzf", deconv_tcz_cost)
+        self._wrap(engine, "conv3d_tcr_khf", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcr_khf",
+                   conv_tcr_cost)
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
         self._wrap(engine, "conv3d_tc", "conv3d_tc", conv_tc_cost)

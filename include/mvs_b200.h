@@ -150,6 +150,10 @@ int mvs_deconv3d_tcz_kzf(const float* x, const float* w, const float* shift, con
  * slices per CTA, all taps resident.  Weights (TF32): [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4]. */
 int mvs_conv3d_tcr(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
                    int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
+/* Opt-in kh-fused variant of mvs_conv3d_tcr (MVS_TCZ_KZF; conv3d_tcz_kzf.cu): the three kh taps of an input row are one
+ * MMA of N = 3 * n_tile over adjacent accumulators.  Weights (TF32): [Cout_tiles][kd][3 kw][Cin/4][3 kh][n_tile][4]. */
+int mvs_conv3d_tcr_khf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                       int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
 /* Diagnostic: nk MMAs (M=128, N, K=8) over caller-made shared-memory operand images with explicit
  * descriptor strides; dumps the 128 x N accumulator (used by tests to pin the operand layouts). */
 int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,

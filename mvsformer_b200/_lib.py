@@ -45,6 +45,7 @@ _SIGNATURES = {
     "mvs_conv3d_tcz": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
     "mvs_conv3d_tcz_kzf": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
     "mvs_deconv3d_tcz_kzf": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
+    "mvs_conv3d_tcr_khf": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_conv3d_tcr": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_deconv3d_tcz": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_ncdhw_to_cl_tf32": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),

@@ -492,6 +492,194 @@ static int launch_deconv_tcz_kzf(const float* x, const float* w, const float* sh
     return MVS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// row-tiled convolution, kh-fused (MVS_TCZ_KZF; the two tensor-core layers of the visibility net run here with
+// kd = 1, R = 8 rows per CTA): an input row iy feeds the output rows iy+1, iy, iy-1 through kh = 0,1,2; with a
+// slice's accumulators laid out in DEcreasing row order they are one contiguous window, so one MMA with the B rows
+// [kh][n] (N = 3*NT; weights [Cout_tiles][kd][3 kw][Cin/4][3 kh][n_tile][4]) replaces three.  An MMA is fused
+// whenever every accumulator of its window has been initialised, per-row otherwise.  Modified copy of conv3d_tcr_kernel.
+// ------------------------------------------------------------------------------------------------
+struct TrDims {
+    int B, D, H, W, Cin, Cout;
+    int kd, relu;
+    int nxb;                 // 128-column blocks per row
+    int R, zc;               // rows and depth slices per CTA
+    int nrb, nzc;            // row blocks, z chunks
+};
+
+template <int CS, int NT>
+__global__ void __launch_bounds__(TZ_THREADS)
+conv3d_tcr_khf_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                  const float* __restrict__ skip, float* __restrict__ y, TrDims d) {
+    constexpr int CH = CS / 4;
+    constexpr int A_STAGE = CH * TZ_SL;
+    constexpr int B_TAP = CH * NT * 16;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int b_bytes = d.kd * 9 * B_TAP;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TZ_STAGES * A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TZ_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ncols = d.R * d.zc * NT;
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : (ncols <= 256 ? 256 : 512)));
+    if (tid == 0) {
+        for (int s = 0; s < TZ_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int b = blockIdx.z;
+    const int xb = blockIdx.x % d.nxb, ct = blockIdx.x / d.nxb;
+    const int rb = blockIdx.y % d.nrb, zcix = blockIdx.y / d.nrb;
+    const int x0 = xb * 128, y0 = rb * d.R, z0 = zcix * d.zc;
+    const int nr = min(d.R, d.H - y0), nz = min(d.zc, d.D - z0);
+    const int co0 = ct * NT;
+    const int pd = d.kd / 2;
+
+    const int iz_lo = max(z0 - pd, 0), iz_hi = min(z0 + nz - 1 + pd, d.D - 1);
+    const int iy_lo = max(y0 - 1, 0), iy_hi = min(y0 + nr, d.H - 1);
+    const int niy = iy_hi - iy_lo + 1;
+    const int nit = (iz_hi - iz_lo + 1) * niy;
+    const int nslot_iters = (tid + 128 < 130) ? 2 : 1;
+
+    auto issue = [&](int it) {
+        const int iz = iz_lo + it / niy, iy = iy_lo + it % niy;
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * A_STAGE;
+        for (int u = 0; u < nslot_iters; ++u) {
+            const int slot = tid + u * 128;
+            const int xx = x0 - 1 + slot;
+            const bool ok = xx >= 0 && xx < d.W;
+            const float* src = x + ((((size_t)b * d.D + iz) * d.H + iy) * d.W + (ok ? xx : 0)) * d.Cin;
+            const uint32_t dst = a_base + slot * 16;
+#pragma unroll
+            for (int q = 0; q < CH; ++q) cp_async16(dst + q * TZ_SL, src + q * 4, ok ? 16u : 0u);
+        }
+    };
+
+    // resident weights ride in the first cp.async group
+    {
+        const float4* srcb = reinterpret_cast<const float4*>(w) + (size_t)ct * (b_bytes / 16);
+        const uint32_t b_base = smem_u32(sB);
+        for (int i = tid; i < b_bytes / 16; i += TZ_THREADS) cp_async16(b_base + i * 16, srcb + i, 16u);
+    }
+#pragma unroll
+    for (int i = 0; i < TZ_STAGES - 1; ++i) {
+        if (i < nit) issue(i);
+        cp_async_commit();
+    }
+
+    uint32_t started = 0;
+    for (int it = 0; it < nit; ++it) {
+        const int nx = it + TZ_STAGES - 1;
+        if (nx < nit) {
+            if (it >= 1) mbar_wait(&bars[(it - 1) % TZ_STAGES], ((it - 1) / TZ_STAGES) & 1);
+            issue(nx);
+        }
+        cp_async_commit();
+        cp_async_wait<TZ_STAGES - 1>();
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const int iz = iz_lo + it / niy, iy = iy_lo + it % niy;
+            const uint32_t a_base = smem_u32(sA) + (uint32_t)(it % TZ_STAGES) * A_STAGE;
+            const uint32_t b_base = smem_u32(sB);
+            constexpr uint32_t plane = 3u * NT * 16;                       // bytes between the K chunks of a tap: rows [kh][n]
+            constexpr uint32_t btap = (uint32_t)CH * plane;               // bytes per (kz, kw)
+            // rows fed by this input row: oy = iy + 1 - kh, one contiguous range of kh
+            const int kh_lo = max(0, iy + 1 - (y0 + nr - 1)), kh_hi = min(2, iy + 1 - y0);
+            for (int kz = 0; kz < d.kd; ++kz) {
+                const int oz = iz + pd - kz;
+                if (oz < z0 || oz >= z0 + nz || kh_lo > kh_hi) continue;
+                // accumulators of a slice are laid out in DEcreasing row order: the window ascends with kh
+                const int nk = kh_hi - kh_lo + 1;
+                const int slot0 = (oz - z0) * d.R + (nr - 1 - (iy + 1 - kh_lo - y0));
+                const uint32_t wmask = ((1u << nk) - 1u) << slot0;
+                const uint32_t idesc_w = make_idesc_tf32(128, nk * NT);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                    for (int kk = 0; kk < CS / 8; ++kk) {
+                        const uint64_t ad = make_smem_desc(a_base + (uint32_t)kw * 16 + (uint32_t)(2 * kk) * TZ_SL, TZ_SL, 128);
+                        const uint32_t bk = b_base + (uint32_t)(kz * 3 + kw) * btap + (uint32_t)(2 * kk) * plane;
+                        if ((started & wmask) == wmask) {
+                            // every accumulator of the window is initialised: ONE MMA of N = nk * NT reads A once
+                            const uint64_t bd = make_smem_desc(bk + (uint32_t)(kh_lo * NT) * 16, plane, 128);
+                            mma_tf32_ss(tmem + (uint32_t)slot0 * NT, ad, bd, idesc_w, 1u);
+                        } else {
+                            for (int kh = kh_lo; kh <= kh_hi; ++kh) {
+                                const int slot_acc = slot0 + (kh - kh_lo);
+                                const uint32_t acc = (started >> slot_acc) & 1u;
+                                started |= 1u << slot_acc;
+                                const uint64_t bd = make_smem_desc(bk + (uint32_t)(kh * NT) * 16, plane, 128);
+                                mma_tf32_ss(tmem + (uint32_t)slot_acc * NT, ad, bd, idesc, acc);
+                            }
+                        }
+                    }
+                }
+            }
+            mma_commit(&bars[it % TZ_STAGES]);
+        }
+    }
+
+    const int last = nit - 1;
+    mbar_wait(&bars[last % TZ_STAGES], (last / TZ_STAGES) & 1);
+    tc_fence_after_sync();
+    const int ox = x0 + tid;
+    const bool live = ox < d.W;
+    for (int zi = 0; zi < nz; ++zi) {
+        for (int ri = 0; ri < nr; ++ri) {
+            float acc[NT];
+#pragma unroll
+            for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (zi * d.R + (nr - 1 - ri)) * NT + c0, acc + c0);
+            if (!live) continue;
+            const size_t o = ((((size_t)b * d.D + z0 + zi) * d.H + y0 + ri) * d.W + ox) * d.Cout + co0;
+#pragma unroll
+            for (int q = 0; q < NT / 4; ++q) {
+                if (co0 + q * 4 >= d.Cout) break;
+                float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+                if (shift) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(shift + co0) + q);
+                    r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
+                }
+                if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                if (skip) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
+                    r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
+                }
+                r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+                reinterpret_cast<float4*>(y + o)[q] = r;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <int CS, int NT>
+static int launch_conv_tcr_khf(const float* x, const float* w, const float* shift, const float* skip, float* y, const TrDims& d,
+                           cudaStream_t st) {
+    const size_t smem = (size_t)TZ_STAGES * (CS / 4) * TZ_SL + (size_t)d.kd * 9 * (CS / 4) * NT * 16 + 128;
+    MVS_REQUIRE(smem <= 227 * 1024, "mvs_conv3d_tcr_khf: needs %zu bytes of shared memory", smem);
+    auto kern = conv3d_tcr_khf_kernel<CS, NT>;
+    MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (d.Cout + NT - 1) / NT;
+    dim3 grid((unsigned)(d.nxb * ntiles), (unsigned)(d.nrb * d.nzc), (unsigned)d.B);
+    MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "mvs_conv3d_tcr_khf: grid too large");
+    kern<<<grid, TZ_THREADS, smem, st>>>(x, w, shift, skip, y, d);
+    MVS_LAUNCH_OK("conv3d_tcr_khf_kernel");
+    return MVS_OK;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -592,4 +780,45 @@ extern "C" int mvs_deconv3d_tcz_kzf(const float* x, const float* w, const float*
     MVS_TZD_CASE(32, 32)
 #undef MVS_TZD_CASE
     MVS_UNSUPPORTED("mvs_deconv3d_tcz_kzf: no instantiation for Cin=%d, N tile=%d", Cin, n_tile);
+}
+
+// kh-fused row-tiled convolution (see conv3d_tcr_khf_kernel).
+extern "C" int mvs_conv3d_tcr_khf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
+                              int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream) {
+    using namespace mvs;
+    using namespace mvs::tc;
+    using namespace mvs::tc::kzf;
+    MVS_REQUIRE(x && w && y, "mvs_conv3d_tcr_khf: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && B <= 65535, "mvs_conv3d_tcr_khf: bad shape");
+    MVS_REQUIRE(kd == 1 || kd == 3, "mvs_conv3d_tcr_khf: depth kernel size must be 1 or 3 (got %d)", kd);
+    MVS_REQUIRE(Cout % 8 == 0 && Cout >= 8, "mvs_conv3d_tcr_khf: Cout must be a multiple of 8 (got %d)", Cout);
+    MVS_REQUIRE(Cin == 8 || Cin == 16 || Cin == 32, "mvs_conv3d_tcr_khf: Cin must be 8, 16 or 32 (got %d)", Cin);
+    TrDims d;
+    d.B = B; d.D = D; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.kd = kd; d.relu = relu;
+    d.nxb = (W + 127) / 128;
+    // rows x slices per CTA: accumulators within 256 TMEM columns (two CTAs can co-reside), at most 32 of them
+    int zc = D < 4 ? D : 4;
+    while (D % zc) --zc;
+    int R = 256 / (zc * n_tile);
+    if (R > 2) R = 2;            // measured: 2 rows (more, smaller CTAs) beats 4 on B200
+    if (kd == 1) {               // 2D layers (visibility net): slices share nothing, spend the accumulators on rows
+        zc = 1;
+        R = 128 / n_tile;
+        if (R > 8) R = 8;
+    }
+    if (R < 1) { R = 1; while (zc > 1 && zc * n_tile > 512) --zc; }
+    R = env_int("MVS_TCR_ROWS", R);
+    MVS_REQUIRE(R * zc * n_tile <= 512 && R * zc <= 32, "mvs_conv3d_tcr_khf: accumulators do not fit TMEM (R=%d zc=%d N=%d)", R, zc, n_tile);
+    d.R = R; d.zc = zc;
+    d.nrb = (H + R - 1) / R; d.nzc = (D + zc - 1) / zc;
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_TR_CASE(CS_, NT_) \
+    if (Cin == CS_ && n_tile == NT_) return launch_conv_tcr_khf<CS_, NT_>(x, w, shift, skip, y, d, st);
+    MVS_TR_CASE(8, 16)
+    MVS_TR_CASE(16, 16)
+    MVS_TR_CASE(16, 32)
+    MVS_TR_CASE(32, 16)
+    MVS_TR_CASE(32, 32)
+#undef MVS_TR_CASE
+    MVS_UNSUPPORTED("mvs_conv3d_tcr_khf: no instantiation for Cin=%d, N tile=%d", Cin, n_tile);
 }

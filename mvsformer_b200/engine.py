@@ -562,6 +562,32 @@ def pack_tcr_weights(w_packed):
     return round_tf32(w), nt
 
 
+def pack_tcr_khf_weights(w_packed):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][kd][3 kw][Cin/4][3 kh][n_tile][4], TF32-rounded (mvs_conv3d_tcr_khf): the B rows
+    of one (kz, kw, K chunk) are [kh][n]."""
+    kd, _, _, cin, cout = w_packed.shape
+    nt = 16 if cout <= 16 else 32
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    #            [kz, kh, kw, q, e, tile, n]  ->  [tile, kz, kw, q, kh, n, e]
+    w = w.reshape(kd, 3, 3, cin // 4, 4, ntiles, nt).permute(5, 0, 2, 3, 1, 6, 4).contiguous()
+    return round_tf32(w), nt
+
+
+def conv3d_tcr_khf(x, w_khf, n_tile, cout, kd, shift, skip, relu=True):
+    require_cuda(x, w_khf, shift, skip)
+    b, d, h, w, cin = x.shape
+    y = torch.empty(b, d, h, w, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_tcr_khf(ptr(x), ptr(w_khf), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile,
+                                         kd, 1 if relu else 0, stream()), "mvs_conv3d_tcr_khf")
+    return y
+
+
 def conv3d_tcr(x, w_tcr, n_tile, cout, kd, shift, skip, relu=True):
     require_cuda(x, w_tcr, shift, skip)
     b, d, h, w, cin = x.shape

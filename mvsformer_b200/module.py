@@ -84,6 +84,9 @@ def _run_conv(cache, x, w, shift, skip, stride, relu):
         wk, nt = cache.get_derived("tcz_kzf_s%d" % stride[1], lambda v: engine.pack_tcz_kzf_weights(v[0], stride[1] == 2))
         return engine.conv3d_tcz_kzf(x, wk, nt, cout, kd, shift, skip, stride[1], relu)
     if (config.conv_precision() == "tf32" and stride == (1, 1, 1) and engine.tcr_supported(cin, cout, x.shape[3])):
+        if config.tcz_kzf():                             # opt-in kh-fused row-tiled kernel (config.py)
+            wk, nt = cache.get_derived("tcr_khf", lambda v: engine.pack_tcr_khf_weights(v[0]))
+            return engine.conv3d_tcr_khf(x, wk, nt, cout, kd, shift, skip, relu)
         wr, nt = cache.get_derived("tcr", lambda v: engine.pack_tcr_weights(v[0]))
         return engine.conv3d_tcr(x, wr, nt, cout, kd, shift, skip, relu)
     if (config.conv_precision() == "tf32" and stride[0] == 1 and stride[1] == stride[2]

@@ -79,7 +79,8 @@ class StageNet(nn.Module):
                 w_packed = w.permute(2, 3, 1, 0).unsqueeze(0).contiguous()              # [kd=1,3,3,Ci,Co]
                 wz, nt = engine.pack_tcz_weights(w_packed, False)
                 wr, ntr = engine.pack_tcr_weights(w_packed)
-                mids.append((wz, nt, w.shape[0], shift.contiguous(), wr, ntr))
+                wk, _ = engine.pack_tcr_khf_weights(w_packed)                            # opt-in kh-fused kernel
+                mids.append((wz, nt, w.shape[0], shift.contiguous(), wr, ntr, wk))
             return first, mids, last
         self._vis_params_host()                                   # refreshes the cache key
         return self._vis_cache.get_derived("tc", build)
@@ -91,8 +92,10 @@ class StageNet(nn.Module):
         if config.conv_precision() == "tf32" and engine.tcz_supported(16, 16, b * n, 1):
             first, mids, last = self._vis_params_tc()
             x = engine.vis_first_cl(maps, first).view(1, b * n, h, w, 16)
-            for wz, nt, cout, shift, wr, ntr in mids:
-                if engine.tcr_supported(16, cout, w):
+            for wz, nt, cout, shift, wr, ntr, wk in mids:
+                if engine.tcr_supported(16, cout, w) and config.tcz_kzf():
+                    x = engine.conv3d_tcr_khf(x, wk, ntr, cout, 1, shift, None, True)
+                elif engine.tcr_supported(16, cout, w):
                     x = engine.conv3d_tcr(x, wr, ntr, cout, 1, shift, None, True)
                 else:
                     x = engine.conv3d_tcz(x, wz, nt, cout, 1, shift, None, 1, True)

@@ -153,3 +153,31 @@ def test_deconv_tcz_kzf_matches_tcz(cin, cout, depth, h, w):
     err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
     assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6
     assert float((got - ref).abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout,kd,depth,h,w", [(16, 16, 1, 4, 40, 128), (16, 8, 1, 3, 24, 256), (16, 16, 3, 4, 16, 128),
+                                                   (32, 32, 3, 4, 12, 128), (8, 16, 3, 8, 10, 128), (16, 16, 1, 1, 9, 120)])
+def test_tcr_khf_matches_tcr(cin, cout, kd, depth, h, w):
+    """MVS_TCZ_KZF: kh-fused row-tiled convolution (visibility-net layers with kd = 1, wide 3D layers) vs the shipped
+    row-tiled kernel and vs fp64."""
+    import torch.nn.functional as F
+    from mvsformer_b200 import engine
+
+    if not engine.tcr_supported(cin, cout, w):
+        pytest.skip("width not covered by the row-tiled kernel")
+    g = S._gen(cin * 100 + cout + kd)
+    wp = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g) * 0.1)
+    x = engine.round_tf32(torch.randn(2, depth, h, w, cin, generator=g))
+    shift = torch.randn(cout, generator=g)
+    wr, nt = engine.pack_tcr_weights(wp)
+    wk, nt2 = engine.pack_tcr_khf_weights(wp)
+    assert nt == nt2
+    ref = engine.conv3d_tcr(x.to(DEV), wr.to(DEV), nt, cout, kd, shift.to(DEV), None, True)
+    got = engine.conv3d_tcr_khf(x.to(DEV), wk.to(DEV), nt, cout, kd, shift.to(DEV), None, True)
+    torch.cuda.synchronize()
+    want = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), wp.permute(4, 3, 0, 1, 2).double(), padding=(kd // 2, 1, 1))
+    want = torch.relu(want + shift.double().view(1, -1, 1, 1, 1)).permute(0, 2, 3, 4, 1)
+    err_ref = float((ref.cpu().double() - want).abs().mean() / want.abs().mean())
+    err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
+    assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6
+    assert float((got - ref).abs().max()) < 1e-2

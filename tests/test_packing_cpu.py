@@ -264,3 +264,81 @@ def test_deconv_tcz_kzf_issue_loop_and_packing():
             got = _emulate_deconv_tcz_kzf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, zc)
             assert np.isfinite(got).all(), (cin, cout, zc)
             assert np.abs(got - want).max() < 1e-9, (cin, cout, zc)
+
+
+def _emulate_tcr_khf(x, flat, nt, cin, cout, kd, rows, zc):
+    """Host emulation of the MMA issue loop of conv3d_tcr_khf_kernel (conv3d_tcz_kzf.cu) for one 128-column block:
+    CTAs of `rows` output rows x `zc` slices, iterations over input rows (iz, iy), accumulators [slice][row descending],
+    an MMA fused over kh whenever its whole window is initialised.  x [D,H,W,Cin] with W <= 128."""
+    ch_n, pd = cin // 4, kd // 2
+    d_, h_, w_ = x.shape[:3]
+    plane = 3 * nt * 16
+    btap = ch_n * plane
+    b_bytes = kd * 3 * btap
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (0, 0)))
+    y = np.zeros((d_, h_, w_, cout))
+    fused = unfused = 0
+    for ct in range((cout + nt - 1) // nt):
+        wts = flat[ct * (b_bytes // 4):(ct + 1) * (b_bytes // 4)]
+        for z0 in range(0, d_, zc):
+            nz = min(zc, d_ - z0)
+            for y0 in range(0, h_, rows):
+                nr = min(rows, h_ - y0)
+                tmem = np.full((w_, rows * zc * nt), np.nan)
+                started = 0
+                iz_lo, iz_hi = max(z0 - pd, 0), min(z0 + nz - 1 + pd, d_ - 1)
+                iy_lo, iy_hi = max(y0 - 1, 0), min(y0 + nr, h_ - 1)
+                for iz in range(iz_lo, iz_hi + 1):
+                    for iy in range(iy_lo, iy_hi + 1):
+                        kh_lo, kh_hi = max(0, iy + 1 - (y0 + nr - 1)), min(2, iy + 1 - y0)
+                        for kz in range(kd):
+                            oz = iz + pd - kz
+                            if oz < z0 or oz >= z0 + nz or kh_lo > kh_hi:
+                                continue
+                            nk = kh_hi - kh_lo + 1
+                            slot0 = (oz - z0) * rows + (nr - 1 - (iy + 1 - kh_lo - y0))
+                            wmask = ((1 << nk) - 1) << slot0
+                            for kw in range(3):
+                                for kk in range(cin // 8):
+                                    a = xp[iz, iy, kw:kw + w_, kk * 8:kk * 8 + 8]
+
+                                    def b_rows(first_row, nrows):
+                                        out = np.empty((nrows, 8))
+                                        for r in range(nrows):
+                                            for k in range(8):
+                                                byte = (kz * 3 + kw) * btap + (2 * kk + k // 4) * plane + (first_row + r) * 16 + (k % 4) * 4
+                                                out[r, k] = wts[byte // 4]
+                                        return out
+                                    if (started & wmask) == wmask:
+                                        tmem[:, slot0 * nt:(slot0 + nk) * nt] += a @ b_rows(kh_lo * nt, nk * nt).T
+                                        fused += 1
+                                    else:
+                                        for kh in range(kh_lo, kh_hi + 1):
+                                            slot = slot0 + kh - kh_lo
+                                            prod = a @ b_rows(kh * nt, nt).T
+                                            tmem[:, slot * nt:(slot + 1) * nt] = prod + (tmem[:, slot * nt:(slot + 1) * nt]
+                                                                                         if (started >> slot) & 1 else 0.0)
+                                            started |= 1 << slot
+                                            unfused += 1
+                ncout = min(nt, cout - ct * nt)
+                for zi in range(nz):
+                    for ri in range(nr):
+                        col = (zi * rows + (nr - 1 - ri)) * nt
+                        y[z0 + zi, y0 + ri, :, ct * nt: ct * nt + ncout] = tmem[:, col:col + ncout]
+    return y, fused, unfused
+
+
+def test_tcr_khf_issue_loop_and_packing():
+    import torch.nn.functional as F
+    for cin, cout, kd, depth, height, rows, zc in ((16, 16, 1, 3, 19, 8, 1), (16, 8, 1, 2, 8, 8, 1), (32, 32, 3, 4, 7, 2, 4),
+                                                   (8, 16, 3, 2, 5, 2, 2)):
+        g = torch.Generator().manual_seed(cin * 11 + cout + kd)
+        w = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g))
+        x = engine.round_tf32(torch.randn(depth, height, 9, cin, generator=g))
+        wk, nt = engine.pack_tcr_khf_weights(w)
+        assert wk.shape == ((cout + nt - 1) // nt, kd, 3, cin // 4, 3, nt, 4)
+        want = F.conv3d(x.permute(3, 0, 1, 2).unsqueeze(0).double(), w.permute(4, 3, 0, 1, 2).double(),
+                        padding=(kd // 2, 1, 1))[0].permute(1, 2, 3, 0).numpy()
+        got, fused, unfused = _emulate_tcr_khf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, rows, zc)
+        assert np.isfinite(got).all() and np.abs(got - want).max() < 1e-9, (cin, cout, kd)
+        assert fused > unfused / 2                      # most MMAs take the fused form
