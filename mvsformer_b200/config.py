@@ -15,9 +15,10 @@ the per-view group correlation is smaller than the warped tensor (C/G >= 2, stag
 aggregation streams over it (bit-identical volume; +2 x N x G x D x h x w x 4 B of HBM traffic instead of a
 second warp).  Opt-in until it has been timed on the GPU.
 
-``tcz_kzf`` (``MVS_TCZ_KZF=1``; ``2`` = also prefer it over the row-tiled kernel; default 0) — "kz-fused N" variant
-of the depth-fused tensor-core convolution (mvs_conv3d_tcz_kzf): one MMA of N = 3 x Cout-tile per slab instead of
-three, i.e. a third of the shared-memory A-operand reads.  TF32 mode only.  Opt-in until run on the GPU.
+``tcz_kzf`` (``MVS_TCZ_KZF=1``; ``2`` = also prefer the kz-fused kernel over the row-tiled one; default 0) — "fused N"
+variants of the depth-unstrided tensor-core convolutions (mvs_conv3d_tcz_kzf, mvs_deconv3d_tcz_kzf, mvs_conv3d_tcr_khf):
+one MMA of N = 3 x Cout-tile per slab / input row instead of three, i.e. about a third of the shared-memory
+A-operand reads.  TF32 mode only.  Opt-in until run on the GPU.
 """
 import os
 
