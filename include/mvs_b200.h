@@ -263,6 +263,24 @@ int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, const float* d
 /* p = softmax_d(pre) on [B,D,H,W]: gpre = p * (gp - sum_d gp * p)  (mvsformer_model.py:111). */
 int mvs_softmax_bwd(const float* gp, const float* p, float* gpre, int B, int D, int H, int W, void* stream);
 
+/* ---- depth-map fusion: misc/fusion.py:69-118 as driven by test.py:404-435 -------------
+ * Camera matrices are inverted by the caller in fp64 and passed per (batch, source view) as MVS_FUSION_MAT_FLOATS
+ * floats: ref Kinv (9) Einv (16) E (16) K (9), then src Kinv (9) Einv (16) E (16) K (9).  All maps fp32; masks are
+ * 1.0 / 0.0 like the reference's. */
+#define MVS_FUSION_MAT_FLOATS 100
+/* get_reproj (:79-98): ref_depth [n,h,w], src_depths [n,v,h,w] -> reproj_xyd [n,v,3,h,w], in_range [n,v,h,w]. */
+int mvs_fusion_reproject(const float* ref_depth, const float* src_depths, const float* mats, float* reproj_xyd,
+                         float* in_range, int N, int V, int H, int W, void* stream);
+/* vis_filter (:101-109) + ave_fusion (:112-114): -> masks [n,v,h,w], mask [n,h,w], ave [n,h,w]. */
+int mvs_fusion_filter(const float* ref_depth, const float* reproj_xyd, const float* in_range, float img_dist_thresh,
+                      float depth_thresh, float vthresh, float* masks, float* mask, float* ave, int N, int V, int H, int W,
+                      void* stream);
+/* World points of a depth map (test.py:433-435): depth [n,h,w], mats [n,25] = Kinv (9) Einv (16) -> points [n,3,h,w]. */
+int mvs_fusion_points(const float* depth, const float* mats, float* points, int N, int H, int W, void* stream);
+/* prob_filter (:69-76): prob [n,c,h,w], thresholds [host] (<= 8) -> mask [n,h,w] = AND_i prob[:, i] > thresh[i]. */
+int mvs_fusion_prob_filter(const float* prob, const float* thresh_host, int nthresh, float* mask, int N, int C, int H, int W,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

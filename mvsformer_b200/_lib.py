@@ -80,6 +80,11 @@ _SIGNATURES = {
     "mvs_sigmoid_bwd": (c_i, [c_f, c_f, c_f, c_l, c_f]),
     "mvs_homo_warp_bwd": (c_i, [c_f, c_f, c_f, c_i, c_f] + [c_i] * 5 + [c_f]),
     "mvs_softmax_bwd": (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f]),
+    # depth-map fusion (fusion.cu)
+    "mvs_fusion_reproject": (c_i, [c_f] * 5 + [c_i] * 4 + [c_f]),
+    "mvs_fusion_filter": (c_i, [c_f] * 3 + [c_fl] * 3 + [c_f] * 3 + [c_i] * 4 + [c_f]),
+    "mvs_fusion_points": (c_i, [c_f] * 3 + [c_i] * 3 + [c_f]),
+    "mvs_fusion_prob_filter": (c_i, [c_f, c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
 }
 
 

@@ -159,3 +159,32 @@ def narrow_hypotheses(stage, height, width, batch):
     spacing = itv1 * [1.0, 0.356, 0.1526, 0.1017][stage]
     k = (torch.arange(nd, dtype=torch.float32) - (nd - 1) / 2).view(1, -1, 1, 1)
     return 1.0 / (1.0 / depth.unsqueeze(1) + k * spacing)
+
+
+def make_fusion_case(views, height, width, seed=0, noise=0.3, outlier_frac=0.05):
+    """Consistent depth maps of a tilted plane seen by ``views`` cameras of make_cameras (+ noise, + outlier blocks), in the
+    tensor layout of the reference's fusion code (misc/fusion.py, test.py:413-431):
+    ref_depth [1,1,h,w], src_depths [1,v-1,1,h,w], ref_cam [1,2,4,4], src_cams [1,v-1,2,4,4], ref_conf [1,3,1,h,w]."""
+    g = _gen(seed)
+    cams = make_cameras(1, views, height, width, dtype=torch.float64)["stage4"][0]            # [V,2,4,4]
+    normal = torch.tensor([0.15, -0.1, 1.0], dtype=torch.float64)
+    normal = normal / normal.norm()
+    offset = 660.0                                                                             # plane n . X = offset
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float64) + 0.5, torch.arange(width, dtype=torch.float64) + 0.5,
+                            indexing="ij")
+    pix = torch.stack([xs, ys, torch.ones_like(xs)], dim=-1)                                   # [h,w,3]
+    depths = []
+    for v in range(views):
+        ext, kmat = cams[v, 0], cams[v, 1, :3, :3]
+        rot, trans = ext[:3, :3], ext[:3, 3]
+        rays = pix @ torch.linalg.inv(kmat).T                                                  # z = 1
+        nr = rot @ normal                                                                      # n^T R^T r = (R n) . r
+        depth = (offset + nr @ trans) / (rays @ nr)
+        depth = depth + noise * torch.randn(height, width, generator=g, dtype=torch.float64)
+        bad = torch.rand(height // 4, width // 4, generator=g) < outlier_frac                  # 4x4 blocks of gross errors
+        bad = bad.repeat_interleave(4, 0).repeat_interleave(4, 1)
+        depth = torch.where(bad, depth * 1.2, depth)
+        depths.append(depth.float())
+    conf = torch.rand(1, 3, 1, height, width, generator=g)
+    return {"ref_depth": depths[0].view(1, 1, height, width), "src_depths": torch.stack(depths[1:]).view(1, views - 1, 1, height, width),
+            "ref_cam": cams[0:1].float().contiguous(), "src_cams": cams[1:].float().unsqueeze(0).contiguous(), "ref_conf": conf}

@@ -14,6 +14,7 @@ compared).  Outputs are what the reference functions returned:
 * ``stage2_train.npz``  StageNet.forward (train mode: batch-stat BN, argmax depth)
 * ``stage{2,4}_train_grads.npz``  gradients of a cross-entropy loss on ``prob_volume_pre`` (models/losses.py:340-341)
                         through StageNet.forward in train mode, from torch autograd over the reference
+* ``fusion.npz``         misc/fusion.py:69-118 + test.py:433-435 (prob_filter, get_reproj, vis_filter, ave_fusion, points)
 * ``state_dict_keys.json``  names/shapes of the 302 ``fusions.*`` checkpoint entries
 * ``cascade.npz``       the cascade loop models/mvsformer_model.py:410-449 driven over synthetic features
                         (the loop is re-stated here in 15 lines because the reference only has it
@@ -173,6 +174,29 @@ def gen_train_grads(ns):
                             param_names=np.array(names), **grads)
 
 
+def gen_fusion(ns):
+    """Depth-map fusion: the reference's misc/fusion.py functions on a synthetic consistent scene.  Its
+    get_pixel_grids calls ``.cuda()``; that call is patched to a no-op for the duration (nothing else is touched)."""
+    import importlib
+    sys.path.insert(0, ref_import.REFERENCE_ROOT)
+    fusion = importlib.import_module("misc.fusion")
+    case = S.make_fusion_case(4, 24, 32, seed=21)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        prob_mask = fusion.prob_filter(case["ref_conf"], [0.1, 0.2, 0.3])
+        reproj_xyd, in_range = fusion.get_reproj(case["ref_depth"], case["src_depths"], case["ref_cam"], case["src_cams"])
+        masks, mask = fusion.vis_filter(case["ref_depth"], reproj_xyd, in_range, 1.0, 0.01, 2)
+        ave = fusion.ave_fusion(case["ref_depth"], reproj_xyd, masks)
+        idx_img = fusion.get_pixel_grids(24, 32).unsqueeze(0)
+        points = fusion.idx_cam2world(fusion.idx_img2cam(idx_img, ave, case["ref_cam"]), case["ref_cam"])[..., :3, 0].permute(0, 3, 1, 2)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    np.savez_compressed(os.path.join(OUT, "fusion.npz"), views=4, height=24, width=32, seed=21,
+                        depth_checksum=checksum(case["src_depths"]), prob_mask=np_(prob_mask), reproj_xyd=np_(reproj_xyd),
+                        in_range=np_(in_range), masks=np_(masks), mask=np_(mask), ave=np_(ave), points=np_(points))
+
+
 def reference_cascade(ns, features, cams, depth_values, nets, tmp, ratios):
     """The loop of models/mvsformer_model.py:410-449 (TwinMVSNet.forward after feature extraction),
     calling the reference's own schedulers and StageNets."""
@@ -244,6 +268,7 @@ def main():
     gen_stages(ns)
     gen_cascade(ns)
     gen_train_grads(ns)
+    gen_fusion(ns)
     gen_state_dict_keys(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -89,6 +89,25 @@ def main():
         d0, d2 = depths["shipped"], depths["tcz_kzf_2"]
         result["tcz_kzf_refined_depth_rel_l1"] = float((d2 - d0).abs().mean() / d0.abs().mean())
 
+    # depth-map fusion at DTU size with 10 source views: HBM-bound, (1 + V) maps in, (5 V + 2) out
+    if rc == 0:
+        from mvsformer_b200 import fusion as Fu
+        case = {k: v.to(device) for k, v in bench.S.make_fusion_case(11, bench.HEIGHT, bench.WIDTH, seed=2).items()}
+        for _ in range(3):
+            Fu.filter_view(case["ref_depth"], case["src_depths"], case["ref_cam"], case["src_cams"], 1.0, 0.01, 3)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            Fu.filter_view(case["ref_depth"], case["src_depths"], case["ref_cam"], case["src_cams"], 1.0, 0.01, 3)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        v, hw = 10, bench.HEIGHT * bench.WIDTH
+        alg = 4 * hw * ((1 + v) + (4 * v) + (v + 2) + (1 + 3 * v + v) + 1 + 3)      # reproject in/out, filter in/out, points
+        result["fusion_filter_view"] = {"ms_per_ref_view": ms, "alg_bytes": alg, "gb_per_s": alg / ms / 1e6}
+        print("fusion", round(ms, 3), "ms", flush=True)
+
     import train_profile  # noqa: E402
     for tile in ("8", "4"):
         os.environ["MVS_WGRAD_TILE"] = tile

@@ -11,6 +11,7 @@ LIB = os.path.join(HERE, "libmvs_emu.so")
 def build(force=False):
     deps = [os.path.join(HERE, "emu.cpp"), os.path.join(ROOT, "include", "mvs_b200.h")]
     deps += glob.glob(os.path.join(ROOT, "mvsformer_b200", "csrc", "train_*")) + \
+        glob.glob(os.path.join(ROOT, "mvsformer_b200", "csrc", "fusion_*")) + \
         [os.path.join(ROOT, "mvsformer_b200", "csrc", "geometry.cuh")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > max(os.path.getmtime(d) for d in deps):
         return LIB

@@ -181,3 +181,38 @@ def test_tcr_khf_matches_tcr(cin, cout, kd, depth, h, w):
     err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
     assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6
     assert float((got - ref).abs().max()) < 1e-2
+
+
+def test_fusion_gpu_vs_reference_golden_and_oracle():
+    """Depth-map fusion kernels (csrc/fusion.cu) on the device vs the reference's recorded outputs and the fp64 oracle
+    (the same kernel source passes tests/test_fusion.py on the CPU emulation)."""
+    from mvsformer_b200 import fusion as Fu
+    from oracle import fusion_oracle as FO
+    from tests.helpers import load_golden, rel_l1
+
+    g = load_golden("fusion.npz")
+    c = S.make_fusion_case(int(g["views"]), int(g["height"]), int(g["width"]), seed=int(g["seed"]))
+    d = {k: v.to(DEV) for k, v in c.items()}
+    out = Fu.filter_view(d["ref_depth"], d["src_depths"], d["ref_cam"], d["src_cams"], 1.0, 0.01, 2,
+                         ref_conf=d["ref_conf"], prob_thresh=[0.1, 0.2, 0.3])
+    torch.cuda.synchronize()
+    agree = lambda a, b: float((a.cpu().bool() == torch.as_tensor(b).bool()).float().mean())
+    assert agree(out["in_range"], g["in_range"]) > 0.995
+    assert agree(out["vis_masks"], g["masks"]) > 0.99 and agree(out["vis_mask"], g["mask"]) > 0.99
+    both = (torch.from_numpy(g["in_range"]) > 0.5) & (out["in_range"].cpu() > 0.5)
+    sel = both.expand(-1, -1, 3, -1, -1)
+    assert rel_l1(out["reproj_xyd"].cpu()[sel], torch.from_numpy(g["reproj_xyd"])[sel]) < 1e-4
+    c64 = {k: v.double() for k, v in c.items()}
+    xyd64, _ = FO.get_reproj(c64["ref_depth"], c64["src_depths"], c64["ref_cam"], c64["src_cams"])
+    assert rel_l1(out["reproj_xyd"].cpu()[sel], xyd64[sel]) < 1e-4
+    same = (out["vis_masks"].cpu() == torch.from_numpy(g["masks"])).all(dim=1)
+    assert rel_l1(out["depth_ave"].cpu()[same], torch.from_numpy(g["ave"])[same]) < 1e-5
+    # full DTU size, 10 source views (test.py:405): properties only
+    big = S.make_fusion_case(11, 1152, 1536, seed=2, outlier_frac=0.02)
+    bd = {k: v.to(DEV) for k, v in big.items()}
+    res = Fu.filter_view(bd["ref_depth"], bd["src_depths"], bd["ref_cam"], bd["src_cams"], 1.0, 0.01, 3)
+    torch.cuda.synchronize()
+    frac = float(res["vis_mask"].float().mean())
+    assert 0.5 < frac <= 1.0                                   # a consistent plane: most pixels survive
+    kept = res["vis_mask"]
+    assert float((res["depth_ave"][kept] - bd["ref_depth"][kept]).abs().max()) < 0.02 * float(bd["ref_depth"].max())
