@@ -260,6 +260,12 @@ int mvs_sigmoid_bwd(const float* gy, const float* y, float* gx, int64_t n, void*
  * -> gsrc [B,C,H,W], ZEROED by the caller, fp32 atomics. */
 int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, const float* depth, int depth_is_map, float* gsrc,
                       int B, int C, int D, int H, int W, void* stream);
+/* Backward of mvs_depth_regression w.r.t. p (depth_type 're' in training): gp [B,D,H,W] = gdepth [B,H,W] * depth_values. */
+int mvs_depth_regression_bwd(const float* gdepth, const float* depth_values, int depth_is_map, float* gp, int B, int D,
+                             int H, int W, void* stream);
+/* depth_type 'mixup_ce' head (models/mvsformer_model.py:126-136): prob, depth_values [B,D,H,W] -> depth, confidence [B,H,W]. */
+int mvs_mixup_head(const float* prob, const float* depth_values, float* depth, float* confidence, int B, int D, int H, int W,
+                   void* stream);
 /* p = softmax_d(pre) on [B,D,H,W]: gpre = p * (gp - sum_d gp * p)  (mvsformer_model.py:111). */
 int mvs_softmax_bwd(const float* gp, const float* p, float* gpre, int B, int D, int H, int W, void* stream);
 

@@ -471,3 +471,40 @@ class _Head(torch.autograd.Function):
 
 def train_head(pre, depth_values, tmp):
     return _Head.apply(pre, depth_values, float(tmp))
+
+
+class _DepthRegression(torch.autograd.Function):
+    """depth_regression(p, depth_values) (models/module.py:597-603), differentiable w.r.t. p."""
+
+    @staticmethod
+    def forward(ctx, p, depth_values):
+        ctx.save_for_backward(depth_values)
+        ctx.p_shape = tuple(p.shape)
+        return engine.depth_regression(p, depth_values)
+
+    @staticmethod
+    def backward(ctx, gdepth):
+        (depth_values,) = ctx.saved_tensors
+        gdepth = gdepth.contiguous()
+        dv = depth_values.float().contiguous()
+        _lib.require_cuda(gdepth, dv)
+        b, d, h, w = ctx.p_shape
+        gp = torch.empty(b, d, h, w, device=gdepth.device, dtype=torch.float32)
+        _call("mvs_depth_regression_bwd", _p(gdepth), _p(dv), 1 if dv.dim() == 4 else 0, _p(gp), b, d, h, w)
+        return gp, None
+
+
+def depth_regression(p, depth_values):
+    return _DepthRegression.apply(engine._f32(p).contiguous(), depth_values)
+
+
+def mixup_head(prob, depth_values):
+    """depth_type 'mixup_ce' (models/mvsformer_model.py:126-136) -> (depth, confidence), not differentiable (the
+    reference's losses for this head use prob_volume_pre only, models/losses.py:360-398)."""
+    prob, dv = prob.detach().float().contiguous(), depth_values.float().contiguous()
+    _lib.require_cuda(prob, dv)
+    b, d, h, w = prob.shape
+    depth = torch.empty(b, h, w, device=prob.device, dtype=torch.float32)
+    conf = torch.empty(b, h, w, device=prob.device, dtype=torch.float32)
+    _call("mvs_mixup_head", _p(prob), _p(dv), _p(depth), _p(conf), b, d, h, w)
+    return depth, conf

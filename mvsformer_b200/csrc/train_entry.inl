@@ -223,3 +223,21 @@ extern "C" int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, con
     HomoWarpBwd f{gwarped, relproj, depth, depth_is_map, gsrc, B, C, D, H, W};
     return launch_flat(f, (int64_t)B * D * H * W, stream, "homo_warp_bwd");
 }
+
+extern "C" int mvs_depth_regression_bwd(const float* gdepth, const float* depth_values, int depth_is_map, float* gp, int B,
+                                        int D, int H, int W, void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(gdepth && depth_values && gp, "mvs_depth_regression_bwd: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_depth_regression_bwd: empty shape");
+    DepthRegressionBwd f{gdepth, depth_values, depth_is_map, gp, B, D, (int64_t)H * W};
+    return launch_flat(f, (int64_t)B * D * H * W, stream, "depth_regression_bwd");
+}
+
+extern "C" int mvs_mixup_head(const float* prob, const float* depth_values, float* depth, float* confidence, int B, int D,
+                              int H, int W, void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(prob && depth_values && depth && confidence, "mvs_mixup_head: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 2 && H >= 1 && W >= 1, "mvs_mixup_head: need at least two hypotheses");
+    MixupHead f{prob, depth_values, depth, confidence, B, D, (int64_t)H * W};
+    return launch_flat(f, (int64_t)B * H * W, stream, "mixup_head");
+}

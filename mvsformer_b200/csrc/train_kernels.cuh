@@ -507,6 +507,39 @@ __device__ __forceinline__ void homo_warp_bwd_thread(const float* __restrict__ g
     }
 }
 
+// Backward of depth_regression (models/module.py:597-603): depth = sum_k p[k] * d[k]  ->  gp[k] = gdepth * d[k].
+// d is [B,D,H,W] (depth_is_map) or [B,D]; one thread per (b, k, y, x)
+__device__ __forceinline__ void depth_regression_bwd_thread(const float* __restrict__ gdepth, const float* __restrict__ dv,
+                                                            int depth_is_map, float* __restrict__ gp, int B, int D,
+                                                            int64_t hw, int64_t tid) {
+    if (tid >= (int64_t)B * D * hw) return;
+    const int64_t pix = tid % hw, bk = tid / hw;
+    const int64_t b = bk / D;
+    const float d = depth_is_map ? __ldg(dv + tid) : __ldg(dv + bk);
+    gp[tid] = __ldg(gdepth + b * hw + pix) * d;
+}
+
+// depth_type = 'mixup_ce' head (models/mvsformer_model.py:126-136): adjacent-pair probabilities, first maximal pair,
+// renormalised two-point depth.  prob, dv [B,D,H,W] -> depth, conf [B,H,W]; one thread per (b, y, x)
+__device__ __forceinline__ void mixup_head_thread(const float* __restrict__ prob, const float* __restrict__ dv,
+                                                  float* __restrict__ depth, float* __restrict__ conf, int B, int D,
+                                                  int64_t hw, int64_t tid) {
+    if (tid >= (int64_t)B * hw) return;
+    const int64_t b = tid / hw, pix = tid % hw;
+    const float* p = prob + b * D * hw + pix;
+    const float* d = dv + b * D * hw + pix;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k + 1 < D; ++k) {
+        const float m = __ldg(p + (int64_t)k * hw) + __ldg(p + (int64_t)(k + 1) * hw);
+        if (m > best) { best = m; arg = k; }                      // torch.max: first maximal index
+    }
+    const float pl = __ldg(p + (int64_t)arg * hw), pr = __ldg(p + (int64_t)(arg + 1) * hw);
+    const float s = pl + pr + 1e-7f;
+    conf[tid] = best;
+    depth[tid] = __ldg(d + (int64_t)arg * hw) * (pl / s) + __ldg(d + (int64_t)(arg + 1) * hw) * (pr / s);
+}
+
 // ------------------------------------------------------------------------------------------
 // Functors: one per kernel, called as f(tid, nthreads) by launch_flat (train.cu: a __global__
 // wrapper; tests/emu/emu.cpp: a loop over tid).
@@ -571,6 +604,14 @@ struct SigmoidBwd {
 struct HomoWarpBwd {
     const float *gwarped, *relproj, *depth; int depth_is_map; float* gsrc; int B, C, D, H, W;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { homo_warp_bwd_thread(gwarped, relproj, depth, depth_is_map, gsrc, B, C, D, H, W, tid); }
+};
+struct DepthRegressionBwd {
+    const float *gdepth, *dv; int depth_is_map; float* gp; int B, D; int64_t hw;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { depth_regression_bwd_thread(gdepth, dv, depth_is_map, gp, B, D, hw, tid); }
+};
+struct MixupHead {
+    const float *prob, *dv; float *depth, *conf; int B, D; int64_t hw;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { mixup_head_thread(prob, dv, depth, conf, B, D, hw, tid); }
 };
 struct SoftmaxBwd {
     const float *gp, *p; float* gpre; int B, D; int64_t hw;

@@ -151,15 +151,35 @@ class StageNet(nn.Module):
         weight = torch.stack([self._vis_weight_train(entropy[:, v]) for v in range(entropy.shape[1])], dim=1)
         volume = autograd.aggregate(corr, weight)
         prob_volume_pre = self.cost_reg.forward_cl(volume)
-        prob_volume, depth, conf = autograd.train_head(prob_volume_pre, depth_values, tmp)
+        prob_volume, depth, conf = self._head(prob_volume_pre, depth_values, tmp)
         return {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
                 "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
 
+    def _head(self, prob_volume_pre, depth_values, tmp):
+        """models/mvsformer_model.py:110-146 -> (prob_volume, depth, photometric_confidence) for every depth_type:
+        'ce' / 'was' (argmax depth in training, temperature regression in eval, max-probability confidence),
+        'mixup_ce' (best adjacent pair, :126-136), anything else = regression ('re': expectation depth, windowed
+        confidence by ndepth, :137-146)."""
+        kind = self.args["depth_type"]
+        if kind in ("ce", "was"):
+            if self.training:
+                return autograd.train_head(prob_volume_pre, depth_values, tmp)
+            return engine.regression_head(prob_volume_pre, depth_values, tmp, False)
+        if self.training:                                               # softmax stays differentiable
+            prob_volume, _, max_prob = autograd.train_head(prob_volume_pre, depth_values, 1.0)
+        else:
+            prob_volume, _, max_prob = engine.regression_head(prob_volume_pre, depth_values, 1.0, False)
+        if kind == "mixup_ce":
+            depth, conf = autograd.mixup_head(prob_volume, depth_values)
+            return prob_volume, depth, conf
+        depth = autograd.depth_regression(prob_volume, depth_values) if self.training \
+            else engine.depth_regression(prob_volume, depth_values)
+        window = 4 if self.ndepth >= 32 else (3 if self.ndepth == 16 else (2 if self.ndepth == 8 else 0))
+        conf = engine.conf_regression(prob_volume.detach(), window) if window else max_prob
+        return prob_volume, depth, conf
+
     def forward(self, features, proj_matrices, depth_values, tmp=2.0):
         """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W]."""
-        if self.args["depth_type"] not in ("ce", "was"):
-            raise NotImplementedError("depth_type=%r: only 'ce'/'was' heads are built (the shipped config uses 'ce')"
-                                      % self.args["depth_type"])
         depth_values = depth_values.float().contiguous()
         if self.training:
             if type(tmp) == list or type(tmp) == tuple:
@@ -169,7 +189,7 @@ class StageNet(nn.Module):
         prob_volume_pre = self.cost_reg.forward_cl(volume)
         if type(tmp) == list or type(tmp) == tuple:
             tmp = tmp[self.stage_idx]
-        prob_volume, depth, conf = engine.regression_head(prob_volume_pre, depth_values, tmp, self.training)
+        prob_volume, depth, conf = self._head(prob_volume_pre, depth_values, tmp)
         outputs = {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
                    "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
         if not self.training:

@@ -14,6 +14,7 @@ compared).  Outputs are what the reference functions returned:
 * ``stage2_train.npz``  StageNet.forward (train mode: batch-stat BN, argmax depth)
 * ``stage{2,4}_train_grads.npz``  gradients of a cross-entropy loss on ``prob_volume_pre`` (models/losses.py:340-341)
                         through StageNet.forward in train mode, from torch autograd over the reference
+* ``heads.npz``          StageNet.forward (eval) with depth_type 'mixup_ce' / 're' (models/mvsformer_model.py:126-146)
 * ``fusion.npz``         misc/fusion.py:69-118 + test.py:433-435 (prob_filter, get_reproj, vis_filter, ave_fusion, points)
 * ``state_dict_keys.json``  names/shapes of the 302 ``fusions.*`` checkpoint entries
 * ``cascade.npz``       the cascade loop models/mvsformer_model.py:410-449 driven over synthetic features
@@ -174,6 +175,25 @@ def gen_train_grads(ns):
                             param_names=np.array(names), **grads)
 
 
+def gen_heads(ns):
+    """The non-default heads of StageNet.forward (models/mvsformer_model.py:126-146): depth_type 'mixup_ce' and 're',
+    eval mode, for ndepth 16 (windowed confidence n = 3) and ndepth 4 (max-probability confidence)."""
+    R = ns.mvsformer_model
+    height, width = 64, 96
+    out = {}
+    for kind in ("mixup_ce", "re"):
+        for s in (1, 3):
+            net = R.StageNet(dict(STAGE_ARGS, depth_type=kind), S.NDEPTHS[s], s).eval()
+            net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=70 + s))
+            feats, cams = stage_inputs(s, height, width, batch=1, seed=90 + s)
+            hyp = S.narrow_hypotheses(s, height, width, 1)
+            with torch.no_grad():
+                res = net(feats, cams, hyp, tmp=list(S.EVAL_TMP))
+            for key in ("depth", "photometric_confidence", "prob_volume"):
+                out["%s_s%d_%s" % (kind, s + 1, key)] = np_(res[key])
+    np.savez_compressed(os.path.join(OUT, "heads.npz"), height=height, width=width, **out)
+
+
 def gen_fusion(ns):
     """Depth-map fusion: the reference's misc/fusion.py functions on a synthetic consistent scene.  Its
     get_pixel_grids calls ``.cuda()``; that call is patched to a no-op for the duration (nothing else is touched)."""
@@ -269,6 +289,7 @@ def main():
     gen_cascade(ns)
     gen_train_grads(ns)
     gen_fusion(ns)
+    gen_heads(ns)
     gen_state_dict_keys(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -216,3 +216,23 @@ def test_fusion_gpu_vs_reference_golden_and_oracle():
     assert 0.5 < frac <= 1.0                                   # a consistent plane: most pixels survive
     kept = res["vis_mask"]
     assert float((res["depth_ave"][kept] - bd["ref_depth"][kept]).abs().max()) < 0.02 * float(bd["ref_depth"].max())
+
+
+@pytest.mark.parametrize("kind", ["mixup_ce", "re"])
+@pytest.mark.parametrize("s", [1, 3])
+def test_other_depth_type_heads_gpu(kind, s):
+    """StageNet with depth_type 'mixup_ce' / 're' on the device vs the unmodified reference (tests/golden/heads.npz)."""
+    from tests.helpers import load_golden, rel_l1
+    g = load_golden("heads.npz")
+    height, width = int(g["height"]), int(g["width"])
+    net = StageNet(dict(STAGE_ARGS, depth_type=kind), S.NDEPTHS[s], s).eval()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=70 + s))
+    net = net.to(DEV)
+    feats = S.make_features(1, 3, height, width, seed=90 + s, stages=(s,))["stage%d" % (s + 1)]
+    cams = S.make_cameras(1, 3, height, width)["stage%d" % (s + 1)]
+    hyp = S.narrow_hypotheses(s, height, width, 1)
+    with torch.no_grad():
+        out = net(feats.to(DEV), cams.to(DEV), hyp.to(DEV), tmp=list(S.EVAL_TMP))
+    assert rel_l1(out["prob_volume"].cpu(), g["%s_s%d_prob_volume" % (kind, s + 1)]) < 1e-4
+    assert rel_l1(out["depth"].cpu(), g["%s_s%d_depth" % (kind, s + 1)]) < 1e-4
+    assert rel_l1(out["photometric_confidence"].cpu(), g["%s_s%d_photometric_confidence" % (kind, s + 1)]) < 1e-4

@@ -345,3 +345,37 @@ def test_wgrad_work_split(emu, monkeypatch, rows, xseg, width, tile):
         gcl = gy.permute(0, 2, 3, 4, 1).contiguous()
         dwp = autograd._conv_wgrad(gcl, x, (3, 3, 3, cin, cout), transposed, stride)
         assert rel_l1(autograd._unpack(dwp, transposed), w.grad) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["mixup_ce", "re"])
+@pytest.mark.parametrize("s", [1, 3])
+def test_other_depth_type_heads_vs_reference_golden(emu, kind, s):
+    """depth_type 'mixup_ce' / 're' (models/mvsformer_model.py:126-146): StageNet._head applied to the probability
+    volume the unmodified reference produced (tests/golden/heads.npz) must give the reference's depth and confidence."""
+    from tests.helpers import load_golden
+    g = load_golden("heads.npz")
+    prob = torch.from_numpy(g["%s_s%d_prob_volume" % (kind, s + 1)])
+    hyp = S.narrow_hypotheses(s, int(g["height"]), int(g["width"]), 1)
+    net = StageNet(dict(STAGE_ARGS, depth_type=kind), S.NDEPTHS[s], s).eval()
+    pre = torch.log(prob.clamp_min(1e-30))                                  # softmax(log p) = p
+    got_prob, depth, conf = net._head(pre, hyp, 1.0)
+    assert rel_l1(got_prob, prob) < 1e-5
+    assert rel_l1(depth, g["%s_s%d_depth" % (kind, s + 1)]) < 1e-5
+    assert rel_l1(conf, g["%s_s%d_photometric_confidence" % (kind, s + 1)]) < 1e-5
+
+
+def test_regression_head_training_is_differentiable(emu):
+    """depth_type 're' in training: the expectation depth is differentiable w.r.t. prob_volume_pre
+    (mvs_depth_regression_bwd + mvs_softmax_bwd) exactly as torch autograd over the reference formula."""
+    g = S._gen(31)
+    net = StageNet(dict(STAGE_ARGS, depth_type="re"), 8, 2).train()
+    pre = torch.randn(2, 8, 6, 10, generator=g).requires_grad_(True)
+    dv = (500.0 + 10.0 * torch.arange(8).view(1, 8, 1, 1) + torch.rand(2, 8, 6, 10, generator=g)).contiguous()
+    prob, depth, conf = net._head(pre, dv, 1.0)
+    p2 = pre.detach().clone().requires_grad_(True)
+    want = (torch.softmax(p2, dim=1) * dv).sum(dim=1)
+    assert rel_l1(depth, want) < 1e-6
+    gout = torch.randn(want.shape, generator=g)
+    depth.backward(gout)
+    want.backward(gout)
+    assert rel_l1(pre.grad, p2.grad) < 1e-5
