@@ -281,6 +281,13 @@ int mvs_fusion_reproject(const float* ref_depth, const float* src_depths, const 
 int mvs_fusion_filter(const float* ref_depth, const float* reproj_xyd, const float* in_range, float img_dist_thresh,
                       float depth_thresh, float vthresh, float* masks, float* mask, float* ave, int N, int V, int H, int W,
                       void* stream);
+/* get_reproj_dynamic (:116-152) and vis_filter_dynamic (:155-168) + the vote / averaging of test.py:502-511:
+ * vis_mask [n,v,h,w] (level k = v), geo_mask [n,h,w], ave [n,h,w], level_counts [n,v-1,h,w] or NULL. */
+int mvs_fusion_reproject_dynamic(const float* ref_depth, const float* src_depths, const float* mats, float* reproj_xyd,
+                                 int N, int V, int H, int W, void* stream);
+int mvs_fusion_filter_dynamic(const float* ref_depth, const float* reproj_xyd, float dist_base, float rel_diff_base,
+                              float* vis_mask, float* geo_mask, float* ave, float* level_counts, int N, int V, int H, int W,
+                              void* stream);
 /* World points of a depth map (test.py:433-435): depth [n,h,w], mats [n,25] = Kinv (9) Einv (16) -> points [n,3,h,w]. */
 int mvs_fusion_points(const float* depth, const float* mats, float* points, int N, int H, int W, void* stream);
 /* prob_filter (:69-76): prob [n,c,h,w], thresholds [host] (<= 8) -> mask [n,h,w] = AND_i prob[:, i] > thresh[i]. */

@@ -85,6 +85,8 @@ _SIGNATURES = {
     # depth-map fusion (fusion.cu)
     "mvs_fusion_reproject": (c_i, [c_f] * 5 + [c_i] * 4 + [c_f]),
     "mvs_fusion_filter": (c_i, [c_f] * 3 + [c_fl] * 3 + [c_f] * 3 + [c_i] * 4 + [c_f]),
+    "mvs_fusion_reproject_dynamic": (c_i, [c_f] * 4 + [c_i] * 4 + [c_f]),
+    "mvs_fusion_filter_dynamic": (c_i, [c_f, c_f, c_fl, c_fl] + [c_f] * 4 + [c_i] * 4 + [c_f]),
     "mvs_fusion_points": (c_i, [c_f] * 3 + [c_i] * 3 + [c_f]),
     "mvs_fusion_prob_filter": (c_i, [c_f, c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
 }

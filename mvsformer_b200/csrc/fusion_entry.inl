@@ -42,3 +42,23 @@ extern "C" int mvs_fusion_prob_filter(const float* prob, const float* thresh_hos
     ProbFilter f{prob, th, nthresh, mask, N, C, (int64_t)H * W};
     return launch_flat(f, (int64_t)N * H * W, stream, "fusion_prob_filter");
 }
+
+extern "C" int mvs_fusion_reproject_dynamic(const float* ref_depth, const float* src_depths, const float* mats, float* reproj_xyd,
+                                            int N, int V, int H, int W, void* stream) {
+    using namespace mvs::fusion;
+    MVS_REQUIRE(ref_depth && src_depths && mats && reproj_xyd, "mvs_fusion_reproject_dynamic: null pointer");
+    MVS_REQUIRE(N >= 1 && V >= 1 && H >= 1 && W >= 1, "mvs_fusion_reproject_dynamic: empty shape");
+    ReprojectDynamic f{ref_depth, src_depths, mats, reproj_xyd, N, V, H, W};
+    return launch_flat(f, (int64_t)N * V * H * W, stream, "fusion_reproject_dynamic");
+}
+
+extern "C" int mvs_fusion_filter_dynamic(const float* ref_depth, const float* reproj_xyd, float dist_base, float rel_diff_base,
+                                         float* vis_mask, float* geo_mask, float* ave, float* level_counts, int N, int V, int H,
+                                         int W, void* stream) {
+    using namespace mvs::fusion;
+    MVS_REQUIRE(ref_depth && reproj_xyd && vis_mask && geo_mask && ave, "mvs_fusion_filter_dynamic: null pointer");
+    MVS_REQUIRE(N >= 1 && V >= 1 && V <= MVS_FUSION_MAX_VIEWS && H >= 1 && W >= 1,
+                "mvs_fusion_filter_dynamic: need 1 <= views <= %d", MVS_FUSION_MAX_VIEWS);
+    FilterDynamic f{ref_depth, reproj_xyd, dist_base, rel_diff_base, vis_mask, geo_mask, ave, level_counts, N, V, H, W};
+    return launch_flat(f, (int64_t)N * H * W, stream, "fusion_filter_dynamic");
+}

@@ -168,6 +168,82 @@ __device__ __forceinline__ void prob_filter_thread(const float* __restrict__ pro
     mask[tid] = ok ? 1.0f : 0.0f;
 }
 
+// get_reproj_dynamic (misc/fusion.py:116-152): the reference pixel is projected into the source view, the source
+// DEPTH is bilinearly sampled there (grid normalised with (w-1)/2, i.e. the projected coordinate itself is the sample
+// index), and the sampled surface point is re-expressed in the reference view.  -> reproj_xyd [n,v,3,h,w]
+// one thread per (n, v, y, x)
+__device__ __forceinline__ void reproject_dynamic_thread(const float* __restrict__ ref_depth, const float* __restrict__ src_depths,
+                                                         const float* __restrict__ mats, float* __restrict__ reproj_xyd, int N,
+                                                         int V, int H, int W, int64_t tid) {
+    const int64_t hw = (int64_t)H * W;
+    if (tid >= (int64_t)N * V * hw) return;
+    const int x = (int)(tid % W), y = (int)((tid / W) % H);
+    const int64_t nv = tid / hw;
+    const int64_t n = nv / V;
+    const float* m = mats + nv * MVS_FUSION_MAT_FLOATS;
+    const float *r_kinv = m, *r_einv = m + 9, *r_e = m + 25, *r_k = m + 41;
+    const float *s_kinv = m + 50, *s_einv = m + 59, *s_e = m + 75, *s_k = m + 91;
+    const float dr = __ldg(ref_depth + n * hw + (int64_t)y * W + x);
+    const V3 is = cam2img(s_k, transform_h(s_e, transform_h(r_einv, img2cam(r_kinv, (float)x + 0.5f, (float)y + 0.5f, dr))));
+    // :133-138  normalise with (size-1)/2, grid_sample(align_corners=True) un-normalises with the same factor
+    const float gx = is.x / ((float)(W - 1) / 2.0f) - 1.0f, gy = is.y / ((float)(H - 1) / 2.0f) - 1.0f;
+    const float ix = (gx + 1.0f) * 0.5f * (float)(W - 1), iy = (gy + 1.0f) * 0.5f * (float)(H - 1);
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float wx1 = ix - x0, wx0 = 1.0f - wx1, wy1 = iy - y0, wy0 = 1.0f - wy1;
+    const float* sd = src_depths + nv * hw;
+    float ds = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float fx = x0 + (float)(t & 1), fy = y0 + (float)(t >> 1);
+        if (!(fx >= 0.0f && fx <= (float)(W - 1) && fy >= 0.0f && fy <= (float)(H - 1))) continue;
+        ds += __ldg(sd + (int64_t)fy * W + (int64_t)fx) * (((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0));
+    }
+    // :140-149  lift the projected coordinate with the sampled depth, back into the reference view
+    const V4 cr = transform_h(r_e, transform_h(s_einv, img2cam(s_kinv, is.x, is.y, ds)));
+    const V3 ir = cam2img(r_k, cr);
+    float* out = reproj_xyd + nv * 3 * hw + (int64_t)y * W + x;
+    out[0] = ir.x; out[hw] = ir.y; out[2 * hw] = cr.z;
+}
+
+// vis_filter_dynamic (:155-168) + the consistency vote and averaging of test.py:502-511: a view is consistent at level
+// k (k = 2..v) if its reprojection error is < k / dist_base pixels and its relative depth error < k / rel_diff_base;
+// a pixel is kept if, for some k, at least k views are consistent at level k; the depth is averaged over the views
+// consistent at the loosest level (k = v).
+//   vis_mask [n,v,h,w] (level v), geo_mask [n,h,w], ave [n,h,w], level_counts [n,v-1,h,w] (views consistent at each level)
+// one thread per (n, y, x)
+#define MVS_FUSION_MAX_VIEWS 16
+__device__ __forceinline__ void filter_dynamic_thread(const float* __restrict__ ref_depth, const float* __restrict__ reproj_xyd,
+                                                      float dist_base, float rel_diff_base, float* __restrict__ vis_mask,
+                                                      float* __restrict__ geo_mask, float* __restrict__ ave,
+                                                      float* __restrict__ level_counts, int N, int V, int H, int W, int64_t tid) {
+    const int64_t hw = (int64_t)H * W;
+    if (tid >= (int64_t)N * hw) return;
+    const int64_t n = tid / hw, pix = tid % hw;
+    const float px = (float)(pix % W) + 0.5f, py = (float)(pix / W) + 0.5f;
+    const float dr = __ldg(ref_depth + tid);
+    float cd[MVS_FUSION_MAX_VIEWS], dd[MVS_FUSION_MAX_VIEWS];
+    float dsum = 0.0f, cnt_last = 0.0f;
+    for (int v = 0; v < V; ++v) {
+        const float* r = reproj_xyd + (n * V + v) * 3 * hw + pix;
+        const float ex = __ldg(r) - px, ey = __ldg(r + hw) - py, rd = __ldg(r + 2 * hw);
+        cd[v] = sqrtf(ex * ex + ey * ey);
+        dd[v] = fabsf(dr - rd) / dr;
+        const bool ok = (cd[v] < (float)V / dist_base) && (dd[v] < (float)V / rel_diff_base);     // level k = v
+        vis_mask[(n * V + v) * hw + pix] = ok ? 1.0f : 0.0f;
+        if (ok) { dsum += rd; cnt_last += 1.0f; }
+    }
+    bool keep = false;
+    for (int k = 2; k <= V; ++k) {
+        float cnt = 0.0f;
+        for (int v = 0; v < V; ++v) cnt += ((cd[v] < (float)k / dist_base) && (dd[v] < (float)k / rel_diff_base)) ? 1.0f : 0.0f;
+        if (level_counts) level_counts[(n * (V - 1) + (k - 2)) * hw + pix] = cnt;
+        // test.py:509-511: for i in range(2, dy_range) with dy_range = v + 1
+        keep = keep || (cnt >= (float)k);
+    }
+    geo_mask[tid] = keep ? 1.0f : 0.0f;
+    ave[tid] = (dsum + dr) / (cnt_last + 1.0f);
+}
+
 struct Reproject {
     const float *ref_depth, *src_depths, *mats; float *reproj_xyd, *in_range; int N, V, H, W;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { reproject_thread(ref_depth, src_depths, mats, reproj_xyd, in_range, N, V, H, W, tid); }
@@ -175,6 +251,14 @@ struct Reproject {
 struct Filter {
     const float *ref_depth, *reproj_xyd, *in_range; float img_dist_thresh, depth_thresh, vthresh; float *masks, *mask, *ave; int N, V, H, W;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { filter_thread(ref_depth, reproj_xyd, in_range, img_dist_thresh, depth_thresh, vthresh, masks, mask, ave, N, V, H, W, tid); }
+};
+struct ReprojectDynamic {
+    const float *ref_depth, *src_depths, *mats; float* reproj_xyd; int N, V, H, W;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { reproject_dynamic_thread(ref_depth, src_depths, mats, reproj_xyd, N, V, H, W, tid); }
+};
+struct FilterDynamic {
+    const float *ref_depth, *reproj_xyd; float dist_base, rel_diff_base; float *vis_mask, *geo_mask, *ave, *level_counts; int N, V, H, W;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { filter_dynamic_thread(ref_depth, reproj_xyd, dist_base, rel_diff_base, vis_mask, geo_mask, ave, level_counts, N, V, H, W, tid); }
 };
 struct Points {
     const float *depth, *mats; float* points; int N, H, W;

@@ -6,13 +6,13 @@ as ``test.py:404-435`` (``filter_depth``) drives them:
 * ``vis_filter(ref_depth, reproj_xyd, in_range, img_dist_thresh, depth_thresh, vthresh)``   :101-109
 * ``ave_fusion(ref_depth, reproj_xyd, masks)``                               :112-114
 * ``world_points(depth, cam)`` = ``idx_cam2world(idx_img2cam(get_pixel_grids(h, w), depth, cam), cam)``  test.py:433-435
-* ``filter_view(...)`` — the whole per-reference-view chain in three launches
+* ``get_reproj_dynamic`` / ``vis_filter_dynamic``                           misc/fusion.py:116-168 (``dynamic_filter_depth``, test.py:475-514)
+* ``filter_view(...)`` / ``dynamic_filter_view(...)`` — the whole per-reference-view chain in three launches
 
 Same tensor shapes as the reference (``n1hw`` depths, ``nv1hw`` source depths, ``n244`` cameras).  The per-pixel
 work runs in libmvs_b200.so (``csrc/fusion.cu``): the intermediate per-source-pixel image of ``get_reproj`` is
 evaluated on the fly at the four bilinear taps and never stored.  Camera matrices are inverted once per view pair
-in fp64 on the host side of this module (16-element algebra; plumbing).  The ``*_dynamic`` variants and the
-PLY writer stay the reference's.
+in fp64 on the host side of this module (16-element algebra; plumbing).  The PLY writer stays the reference's.
 """
 import ctypes
 
@@ -109,6 +109,55 @@ def ave_fusion(ref_depth, reproj_xyd, masks):
     n, v, _, h, w = reproj_xyd.shape
     _, _, ave = _filter(ref_depth, reproj_xyd, masks.reshape(n, v, 1, h, w), float("inf"), float("inf"), 0.0)
     return ave
+
+
+def get_reproj_dynamic(ref_depth, srcs_depth, ref_cam, srcs_cam):
+    """misc/fusion.py:116-152 -> reproj_xyd [n,v,3,h,w]."""
+    n, v, _, h, w = srcs_depth.shape
+    rd = ref_depth.float().reshape(n, h, w).contiguous()
+    sd = srcs_depth.float().reshape(n, v, h, w).contiguous()
+    mats = _pair_mats(ref_cam, srcs_cam).to(rd.device)
+    _lib.require_cuda(rd, sd, mats)
+    xyd = torch.empty(n, v, 3, h, w, device=rd.device, dtype=torch.float32)
+    _call("mvs_fusion_reproject_dynamic", _lib.ptr(rd), _lib.ptr(sd), _lib.ptr(mats), _lib.ptr(xyd), n, v, h, w)
+    return xyd
+
+
+def _filter_dynamic(ref_depth, reproj_xyd, dist_base, rel_diff_base, want_levels):
+    n, v, _, h, w = reproj_xyd.shape
+    rd = ref_depth.float().reshape(n, h, w).contiguous()
+    xyd = reproj_xyd.float().contiguous()
+    _lib.require_cuda(rd, xyd)
+    vis = torch.empty(n, v, h, w, device=rd.device, dtype=torch.float32)
+    geo = torch.empty(n, h, w, device=rd.device, dtype=torch.float32)
+    ave = torch.empty(n, h, w, device=rd.device, dtype=torch.float32)
+    levels = torch.empty(n, v - 1, h, w, device=rd.device, dtype=torch.float32) if want_levels and v > 1 else None
+    _call("mvs_fusion_filter_dynamic", _lib.ptr(rd), _lib.ptr(xyd), float(dist_base), float(rel_diff_base), _lib.ptr(vis),
+          _lib.ptr(geo), _lib.ptr(ave), _lib.ptr(levels), n, v, h, w)
+    return vis, geo, ave, levels
+
+
+def vis_filter_dynamic(ref_depth, reproj_xyd, dist_base=4, rel_diff_base=1300):
+    """misc/fusion.py:155-168.  The reference returns (masks [n,v,v-1,h,w], mask [n,v,1,h,w]) and test.py:505-511 only
+    uses ``masks.sum(dim=1)`` and ``mask``; this mirror returns (level_counts [n,v-1,h,w] = masks.sum(dim=1) as float,
+    mask [n,v,1,h,w] bool) and never materialises the v x (v-1) mask stack."""
+    vis, _, _, levels = _filter_dynamic(ref_depth, reproj_xyd, dist_base, rel_diff_base, True)
+    return levels, vis.unsqueeze(2) > 0.5
+
+
+def dynamic_filter_view(ref_depth, srcs_depth, ref_cam, srcs_cam, dist_base=4, rel_diff_base=1300, ref_conf=None,
+                        prob_thresh=None):
+    """The per-reference-view chain of test.py:487-514 (dynamic consistency checking): -> dict(mask, depth_ave, points,
+    geo_mask, vis_mask, reproj_xyd)."""
+    reproj_xyd = get_reproj_dynamic(ref_depth, srcs_depth, ref_cam, srcs_cam)
+    vis, geo, ave, _ = _filter_dynamic(ref_depth, reproj_xyd, dist_base, rel_diff_base, False)
+    geo_mask = geo.unsqueeze(1) > 0.5
+    mask = geo_mask
+    if ref_conf is not None and prob_thresh is not None:
+        mask = bin_op_reduce([prob_filter(ref_conf, prob_thresh), geo_mask], torch.min)
+    ave = ave.unsqueeze(1)
+    return {"mask": mask, "depth_ave": ave, "points": world_points(ave, ref_cam), "geo_mask": geo_mask,
+            "vis_mask": vis.unsqueeze(2) > 0.5, "reproj_xyd": reproj_xyd}
 
 
 def world_points(depth, cam):

@@ -210,11 +210,25 @@ def gen_fusion(ns):
         ave = fusion.ave_fusion(case["ref_depth"], reproj_xyd, masks)
         idx_img = fusion.get_pixel_grids(24, 32).unsqueeze(0)
         points = fusion.idx_cam2world(fusion.idx_img2cam(idx_img, ave, case["ref_cam"]), case["ref_cam"])[..., :3, 0].permute(0, 3, 1, 2)
+        # dynamic consistency checking: misc/fusion.py:116-168 + the vote / averaging of test.py:502-511 (restated verbatim)
+        dyn_xyd = fusion.get_reproj_dynamic(case["ref_depth"], case["src_depths"], case["ref_cam"], case["src_cams"])
+        dyn_masks, dyn_mask = fusion.vis_filter_dynamic(case["ref_depth"], dyn_xyd, dist_base=4, rel_diff_base=1300)
+        dy_range = case["src_depths"].shape[1] + 1
+        reproj_depth = dyn_xyd[:, :, -1].clone()
+        reproj_depth[~dyn_mask.squeeze(2)] = 0
+        geo_mask_sums = dyn_masks.sum(dim=1)
+        geo_mask_sum = dyn_mask.sum(dim=1)
+        dyn_ave = (torch.sum(reproj_depth, dim=1, keepdim=True) + case["ref_depth"]) / (geo_mask_sum + 1)
+        geo_mask = geo_mask_sum >= dy_range
+        for i in range(2, dy_range):
+            geo_mask = torch.logical_or(geo_mask, geo_mask_sums[:, i - 2] >= i)
     finally:
         torch.Tensor.cuda = orig_cuda
     np.savez_compressed(os.path.join(OUT, "fusion.npz"), views=4, height=24, width=32, seed=21,
                         depth_checksum=checksum(case["src_depths"]), prob_mask=np_(prob_mask), reproj_xyd=np_(reproj_xyd),
-                        in_range=np_(in_range), masks=np_(masks), mask=np_(mask), ave=np_(ave), points=np_(points))
+                        in_range=np_(in_range), masks=np_(masks), mask=np_(mask), ave=np_(ave), points=np_(points),
+                        dyn_xyd=np_(dyn_xyd), dyn_level_counts=np_(geo_mask_sums.float()), dyn_mask=np_(dyn_mask),
+                        dyn_ave=np_(dyn_ave), dyn_geo_mask=np_(geo_mask))
 
 
 def reference_cascade(ns, features, cams, depth_values, nets, tmp, ratios):

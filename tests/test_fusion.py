@@ -95,3 +95,22 @@ def test_fusion_edge_cases_emulated(emu):
     assert torch.equal(out["depth_ave"], c["ref_depth"])
     want = FO.vis_filter(c["ref_depth"], *FO.get_reproj(c["ref_depth"], src, c["ref_cam"], cams), 1.0, 0.01, 2)[0]
     assert float(want.sum()) == 0.0
+
+
+def test_dynamic_fusion_emulated_vs_reference(emu):
+    """get_reproj_dynamic / vis_filter_dynamic (misc/fusion.py:116-168) and the vote + averaging of test.py:502-511."""
+    g, c = _case()
+    xyd = Fu.get_reproj_dynamic(c["ref_depth"], c["src_depths"], c["ref_cam"], c["src_cams"])
+    gx = torch.from_numpy(g["dyn_xyd"])
+    assert xyd.shape == gx.shape
+    finite = torch.isfinite(gx) & torch.isfinite(xyd)
+    assert float(finite.float().mean()) > 0.99 and rel_l1(xyd[finite], gx[finite]) < 1e-4
+    # filter on the reference's reprojection: every threshold decision must match
+    levels, mask = Fu.vis_filter_dynamic(c["ref_depth"], gx, dist_base=4, rel_diff_base=1300)
+    assert levels.shape == g["dyn_level_counts"].shape and torch.equal(levels, torch.from_numpy(g["dyn_level_counts"]))
+    assert mask.shape == g["dyn_mask"].shape and _agree(mask, g["dyn_mask"]) == 1.0
+    # whole chain from the depth maps
+    out = Fu.dynamic_filter_view(c["ref_depth"], c["src_depths"], c["ref_cam"], c["src_cams"], 4, 1300)
+    assert _agree(out["vis_mask"], g["dyn_mask"]) > 0.99 and _agree(out["geo_mask"], g["dyn_geo_mask"]) > 0.99
+    same = (out["vis_mask"] == torch.from_numpy(g["dyn_mask"])).all(dim=1)
+    assert rel_l1(out["depth_ave"][same], torch.from_numpy(g["dyn_ave"])[same]) < 1e-5

@@ -236,3 +236,22 @@ def test_other_depth_type_heads_gpu(kind, s):
     assert rel_l1(out["prob_volume"].cpu(), g["%s_s%d_prob_volume" % (kind, s + 1)]) < 1e-4
     assert rel_l1(out["depth"].cpu(), g["%s_s%d_depth" % (kind, s + 1)]) < 1e-4
     assert rel_l1(out["photometric_confidence"].cpu(), g["%s_s%d_photometric_confidence" % (kind, s + 1)]) < 1e-4
+
+
+def test_dynamic_fusion_gpu_vs_reference_golden():
+    from mvsformer_b200 import fusion as Fu
+    from tests.helpers import load_golden, rel_l1
+
+    g = load_golden("fusion.npz")
+    c = S.make_fusion_case(int(g["views"]), int(g["height"]), int(g["width"]), seed=int(g["seed"]))
+    d = {k: v.to(DEV) for k, v in c.items()}
+    out = Fu.dynamic_filter_view(d["ref_depth"], d["src_depths"], d["ref_cam"], d["src_cams"], 4, 1300)
+    torch.cuda.synchronize()
+    gx = torch.from_numpy(g["dyn_xyd"])
+    xyd = out["reproj_xyd"].cpu()
+    finite = torch.isfinite(gx) & torch.isfinite(xyd)
+    assert rel_l1(xyd[finite], gx[finite]) < 1e-4
+    agree = lambda a, b: float((a.cpu().bool() == torch.as_tensor(b).bool()).float().mean())
+    assert agree(out["vis_mask"], g["dyn_mask"]) > 0.99 and agree(out["geo_mask"], g["dyn_geo_mask"]) > 0.99
+    levels, mask = Fu.vis_filter_dynamic(d["ref_depth"], gx.to(DEV), 4, 1300)
+    assert torch.equal(levels.cpu(), torch.from_numpy(g["dyn_level_counts"])) and agree(mask, g["dyn_mask"]) == 1.0
