@@ -54,6 +54,10 @@ def install(setattr_fn):
     setattr_fn(engine, "stream", lambda: None)
     setattr_fn(engine, "relative_projections", _relproj)
     setattr_fn(engine, "regression_head", _head)
+    setattr_fn(engine, "init_range", lambda cur, nd, h, w, inverse: (O.init_inverse_range if inverse else O.init_range)(
+        cur.float(), nd, h, w).contiguous())
+    setattr_fn(engine, "schedule_inverse_range", lambda depth, hypo, nd, split, h, w: O.schedule_inverse_range(
+        depth.float(), hypo.float(), nd, split, h, w).contiguous())
     setattr_fn(engine, "depth_regression", lambda p, dv: O.depth_regression(p.detach(), dv).contiguous())
     setattr_fn(engine, "conf_regression", lambda p, n: O.conf_regression(p.detach(), n).contiguous())
     return lib
