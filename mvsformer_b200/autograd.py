@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import _lib, engine
+from . import _lib, config, engine
 
 
 _PROFILE = None          # {entry point: [(start event, end event), ...]} while profile_kernels() is active
@@ -261,9 +261,38 @@ def _fat(cin, cout):
     return cin % 4 == 0 and cout % 8 == 0
 
 
+_TC_CONV_TILES = {(8, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64)}     # (channel slice, N tile) in conv3d_tc.cu
+_TC_DECONV_TILES = {(16, 16), (32, 16), (32, 32)}
+
+
+def _tensor_core_conv(x, wp, transposed, stride):
+    """Opt-in (config.train_conv): the same convolution through the tcgen05 kernels of the inference path, or None
+    when the layer shape has no instantiation."""
+    mode = config.train_conv()
+    kd, kh, _, cin, cout = wp.shape
+    if mode == "fp32" or kh != 3 or not (cin in (8, 16) or cin % 32 == 0) or cout % 8 or cout > 64:
+        return None
+    x3 = mode == "tf32x3"
+    key = (engine.tc_channel_slice(cin), engine.tc_n_tile(cout, x3, transposed))
+    if transposed:
+        if key not in _TC_DECONV_TILES:
+            return None
+        hi, lo, nt = engine.pack_tc_deconv_weights(wp, x3)
+        with _timed("mvs_deconv3d_tc"):
+            return engine.deconv3d_tc(x, hi, lo, nt, cout, kd, None, None, stride[0], relu=False)
+    if key not in _TC_CONV_TILES or stride[1] != stride[2]:
+        return None
+    hi, lo, nt = engine.pack_tc_weights(wp, x3)
+    with _timed("mvs_conv3d_tc"):
+        return engine.conv3d_tc(x, hi, lo, nt, cout, kd, None, None, stride, relu=False)
+
+
 def _raw_conv(x, wp, transposed, stride):
     """Convolution without bias / BN / activation on channels-last x; wp packed."""
     kd, kh, _, cin, cout = wp.shape
+    y = _tensor_core_conv(x, wp, transposed, stride)
+    if y is not None:
+        return y
     if transposed:
         if not _fat(cin, cout):
             raise NotImplementedError("transposed conv %d->%d channels is not built" % (cin, cout))

@@ -19,13 +19,21 @@ second warp).  Opt-in until it has been timed on the GPU.
 variants of the depth-unstrided tensor-core convolutions (mvs_conv3d_tcz_kzf, mvs_deconv3d_tcz_kzf, mvs_conv3d_tcr_khf):
 one MMA of N = 3 x Cout-tile per slab / input row instead of three, i.e. about a third of the shared-memory
 A-operand reads.  TF32 mode only.  Opt-in until run on the GPU.
+
+``train_conv`` (``MVS_TRAIN_CONV`` = ``fp32`` (default) | ``tf32x3`` | ``tf32``) — arithmetic of the training path's
+forward and data-gradient convolutions: the FP32 CUDA-core kernels, or the tcgen05 kernels of the inference path
+(``tf32x3`` keeps fp32-grade accuracy; the reference itself trains the regulariser under fp16 autocast).  Weight
+gradients stay FP32.  Opt-in until timed on the GPU.
 """
 import os
 
 _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
           "cv_store": os.environ.get("MVS_CV_STORE", "0") not in ("", "0"),
-          "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "0") or 0)}
+          "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "0") or 0),
+          "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
+if _state["train_conv"] not in ("fp32", "tf32x3", "tf32"):
+    raise RuntimeError("MVS_TRAIN_CONV must be fp32, tf32x3 or tf32")
 if _state["conv_precision"] not in _VALID:
     raise RuntimeError("MVS_CONV_PRECISION must be one of %s" % (_VALID,))
 
@@ -54,3 +62,13 @@ def tcz_kzf():
 
 def set_tcz_kzf(level):
     _state["tcz_kzf"] = int(level)
+
+
+def train_conv():
+    return _state["train_conv"]
+
+
+def set_train_conv(mode):
+    if mode not in ("fp32", "tf32x3", "tf32"):
+        raise ValueError("train conv mode must be fp32, tf32x3 or tf32, got %r" % (mode,))
+    _state["train_conv"] = mode

@@ -119,6 +119,19 @@ def main():
                                              "entry_points_ms": {k: v["ms"] for k, v in d["entry_points"].items()}}
         print("train tile", tile, round(d["step_ms_unprofiled"], 2), "ms", flush=True)
     os.environ.pop("MVS_WGRAD_TILE", None)
+    for mode in ("tf32x3", "tf32"):                       # training convs on the tensor cores (config.train_conv)
+        config.set_train_conv(mode)
+        path = os.path.join(out_dir, "train_profile_%s.json" % mode)
+        try:
+            with open(path, "w") as f, contextlib.redirect_stdout(f):
+                train_profile.main()
+            d = json.load(open(path))
+            result["train_conv_" + mode] = {"step_ms": d["step_ms_unprofiled"], "kernel_ms_sum": d["kernel_ms_sum"],
+                                            "entry_points_ms": {k: v["ms"] for k, v in d["entry_points"].items()}}
+        except Exception as exc:
+            result["train_conv_" + mode] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+        print("train conv", mode, result["train_conv_" + mode].get("step_ms"), flush=True)
+    config.set_train_conv("fp32")
     with open(os.path.join(out_dir, "ab_variants.json"), "w") as f:
         json.dump(result, f, indent=1)
     print(json.dumps(result)[:3000])

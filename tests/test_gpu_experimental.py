@@ -255,3 +255,34 @@ def test_dynamic_fusion_gpu_vs_reference_golden():
     assert agree(out["vis_mask"], g["dyn_mask"]) > 0.99 and agree(out["geo_mask"], g["dyn_geo_mask"]) > 0.99
     levels, mask = Fu.vis_filter_dynamic(d["ref_depth"], gx.to(DEV), 4, 1300)
     assert torch.equal(levels.cpu(), torch.from_numpy(g["dyn_level_counts"])) and agree(mask, g["dyn_mask"]) == 1.0
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 5e-3), ("tf32", 5e-2)])
+def test_training_convs_on_tensor_cores(mode, tol):
+    """MVS_TRAIN_CONV: forward / data-gradient convolutions of the training path through the tcgen05 kernels;
+    gradients vs the fp64 oracle (tf32x3 at the fp32 path's tolerance, tf32 loosely)."""
+    import torch.nn.functional as F
+    from tests.helpers import rel_l1
+    from tests.test_gpu_train import _oracle_gradients
+    from tests.test_oracle_golden import _train_grad_case
+
+    s = 1
+    g, feats, cams, hyp, sd, target = _train_grad_case(s)
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).train()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    config.set_train_conv(mode)
+    try:
+        f1 = feats.to(DEV).requires_grad_(True)
+        out = net(f1, cams.to(DEV), hyp.to(DEV))
+        F.cross_entropy(out["prob_volume_pre"], target.to(DEV)).backward()
+        torch.cuda.synchronize()
+    finally:
+        config.set_train_conv("fp32")
+    truth = _oracle_gradients(s, torch.float64)
+    assert rel_l1(out["prob_volume_pre"].cpu(), g["prob_volume_pre"]) < tol
+    assert rel_l1(f1.grad.cpu(), truth["features"]) < 2 * tol
+    for name, p in net.named_parameters():
+        if name == "cost_reg.prob.bias" or name.startswith("vis."):
+            continue
+        assert rel_l1(p.grad.cpu(), truth[name]) < 2 * tol, name
