@@ -260,6 +260,12 @@ int mvs_sigmoid_bwd(const float* gy, const float* y, float* gx, int64_t n, void*
  * -> gsrc [B,C,H,W], ZEROED by the caller, fp32 atomics. */
 int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, const float* depth, int depth_is_map, float* gsrc,
                       int B, int C, int D, int H, int W, void* stream);
+/* Backward of the warp through the sampling grid (diff_homo_warping_3D_with_mask, warping.py:112-152): gdepth [B,D,H,W] or
+ * [B,D], grelproj [B, MVS_WARP_GRAD_REPLICAS, 12] (gradient of the rows of [R|t], spread over replicas: sum over axis 1);
+ * both ZEROED by the caller. */
+#define MVS_WARP_GRAD_REPLICAS 32
+int mvs_homo_warp_bwd_grid(const float* gwarped, const float* src_fea, const float* relproj, const float* depth,
+                           int depth_is_map, float* gdepth, float* grelproj, int B, int C, int D, int H, int W, void* stream);
 /* Backward of mvs_depth_regression w.r.t. p (depth_type 're' in training): gp [B,D,H,W] = gdepth [B,H,W] * depth_values. */
 int mvs_depth_regression_bwd(const float* gdepth, const float* depth_values, int depth_is_map, float* gp, int B, int D,
                              int H, int W, void* stream);

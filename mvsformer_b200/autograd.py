@@ -240,6 +240,49 @@ def homo_warp(src_fea, relproj, depth_values, want_mask):
     return _HomoWarp.apply(engine._f32(src_fea), relproj, depth_values, want_mask)
 
 
+WARP_GRAD_REPLICAS = 32          # MVS_WARP_GRAD_REPLICAS of include/mvs_b200.h
+
+
+class _DiffHomoWarp(torch.autograd.Function):
+    """diff_homo_warping_3D_with_mask (models/warping.py:112-152): the sampling grid is part of the graph, so the
+    relative projection [R|t] (-> cameras, through torch's 4x4 algebra) and the depth hypotheses receive gradients too."""
+
+    @staticmethod
+    def forward(ctx, src_fea, relproj, depth_values):
+        warped, mask = engine.homo_warp(src_fea, relproj, depth_values, True)
+        ctx.save_for_backward(src_fea, relproj, depth_values)
+        ctx.mark_non_differentiable(mask)
+        return warped, mask
+
+    @staticmethod
+    def backward(ctx, gwarped, _gmask):
+        src_fea, relproj, depth_values = ctx.saved_tensors
+        gwarped = gwarped.contiguous()
+        src_fea, dv = src_fea.contiguous(), depth_values.float().contiguous()
+        _lib.require_cuda(gwarped, src_fea, relproj, dv)
+        b, c, h, w = src_fea.shape
+        d = dv.shape[1]
+        is_map = 1 if dv.dim() == 4 else 0
+        gsrc = grel = gdep = None
+        if ctx.needs_input_grad[0]:
+            gsrc = torch.zeros(b, c, h, w, device=gwarped.device, dtype=torch.float32)
+            _call("mvs_homo_warp_bwd", _p(gwarped), _p(relproj), _p(dv), is_map, _p(gsrc), b, c, d, h, w)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gdep = torch.zeros_like(dv)
+            grep = torch.zeros(b, WARP_GRAD_REPLICAS, 12, device=gwarped.device, dtype=torch.float32)
+            _call("mvs_homo_warp_bwd_grid", _p(gwarped), _p(src_fea), _p(relproj), _p(dv), is_map, _p(gdep), _p(grep),
+                  b, c, d, h, w)
+            grel = grep.sum(dim=1)
+        return gsrc, grel if ctx.needs_input_grad[1] else None, gdep if ctx.needs_input_grad[2] else None
+
+
+def diff_homo_warp(src_fea, src_proj, ref_proj, depth_values):
+    """The projection algebra stays torch's (:122-124, differentiable 4x4 matmul / inverse); warp and gradients are ours."""
+    proj = torch.matmul(src_proj.float(), torch.inverse(ref_proj.float()))
+    relproj = torch.cat([proj[:, :3, :3], proj[:, :3, 3:4]], dim=2).reshape(-1, 12).contiguous()
+    return _DiffHomoWarp.apply(engine._f32(src_fea).contiguous(), relproj, depth_values)
+
+
 # ------------------------------------------------------------------------------------------------
 # conv / transposed conv  ->  BatchNorm (batch statistics)  ->  ReLU  (+ skip)
 # ------------------------------------------------------------------------------------------------

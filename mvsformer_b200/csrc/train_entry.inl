@@ -241,3 +241,13 @@ extern "C" int mvs_mixup_head(const float* prob, const float* depth_values, floa
     MixupHead f{prob, depth_values, depth, confidence, B, D, (int64_t)H * W};
     return launch_flat(f, (int64_t)B * H * W, stream, "mixup_head");
 }
+
+extern "C" int mvs_homo_warp_bwd_grid(const float* gwarped, const float* src_fea, const float* relproj, const float* depth,
+                                      int depth_is_map, float* gdepth, float* grelproj, int B, int C, int D, int H, int W,
+                                      void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(gwarped && src_fea && relproj && depth && gdepth && grelproj, "mvs_homo_warp_bwd_grid: null pointer");
+    MVS_REQUIRE(B >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_homo_warp_bwd_grid: empty shape");
+    HomoWarpBwdGrid f{gwarped, src_fea, relproj, depth, depth_is_map, gdepth, grelproj, B, C, D, H, W};
+    return launch_flat(f, (int64_t)B * D * H * W, stream, "homo_warp_bwd_grid");
+}

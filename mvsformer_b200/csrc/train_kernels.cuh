@@ -507,6 +507,59 @@ __device__ __forceinline__ void homo_warp_bwd_thread(const float* __restrict__ g
     }
 }
 
+// Backward of the warp through the SAMPLING GRID (diff_homo_warping_3D_with_mask, models/warping.py:112-152, where the
+// grid is NOT under no_grad): gradients w.r.t. the depth hypotheses and the relative projection [R|t].
+//   d warped / d ix = sum of the bilinear x-differences of the (zero-padded) taps, as ATen's grid_sampler backward;
+//   ix = px, iy = py (the normalise / un-normalise round trip is the identity), p = q.xy / (q.z + 1e-6), q = R (x,y,1) d + t.
+// gdepth [B,D,H,W] (depth_is_map) or [B,D] (atomics); grelproj [B, MVS_WARP_GRAD_REPLICAS, 12] (atomics spread over
+// replicas, summed by the caller); both ZEROED by the caller.  One thread per (b, k, y, x).
+#define MVS_WARP_GRAD_REPLICAS 32
+__device__ __forceinline__ void homo_warp_bwd_grid_thread(const float* __restrict__ gwarped, const float* __restrict__ src,
+                                                          const float* __restrict__ relproj, const float* __restrict__ depth,
+                                                          int depth_is_map, float* __restrict__ gdepth,
+                                                          float* __restrict__ grelproj, int B, int C, int D, int H, int W,
+                                                          int64_t tid) {
+    const int64_t hw = (int64_t)H * W;
+    if (tid >= (int64_t)B * D * hw) return;
+    const int x = (int)(tid % W), y = (int)((tid / W) % H);
+    const int k = (int)((tid / hw) % D), b = (int)(tid / (hw * D));
+    const RelProj m = load_relproj(relproj + (int64_t)b * 12);
+    const PixelRay ray = pixel_ray(m, (float)x, (float)y);
+    const float dep = depth_is_map ? __ldg(depth + ((int64_t)b * D + k) * hw + (int64_t)y * W + x)
+                                   : __ldg(depth + (int64_t)b * D + k);
+    const float qx = ray.x * dep + m.t0, qy = ray.y * dep + m.t1, qz = ray.z * dep + m.t2;
+    const float den = qz + 1e-6f;
+    const float ix = qx / den, iy = qy / den;
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float wx1 = ix - x0, wx0 = 1.0f - wx1, wy1 = iy - y0, wy0 = 1.0f - wy1;
+    const bool vx0 = x0 >= 0.0f && x0 <= (float)(W - 1), vx1 = x0 + 1.0f >= 0.0f && x0 + 1.0f <= (float)(W - 1);
+    const bool vy0 = y0 >= 0.0f && y0 <= (float)(H - 1), vy1 = y0 + 1.0f >= 0.0f && y0 + 1.0f <= (float)(H - 1);
+    if (!((vx0 || vx1) && (vy0 || vy1))) return;                      // every tap is padding (also NaN): zero gradient
+    const int xi0 = vx0 ? (int)x0 : 0, xi1 = vx1 ? (int)x0 + 1 : 0, yi0 = vy0 ? (int)y0 : 0, yi1 = vy1 ? (int)y0 + 1 : 0;
+    const float* sp = src + (int64_t)b * C * hw;
+    const float* gp = gwarped + (((int64_t)b * C) * D + k) * hw + (int64_t)y * W + x;
+    float gix = 0.0f, giy = 0.0f;
+    for (int c = 0; c < C; ++c, sp += hw) {
+        const float g = __ldg(gp + (int64_t)c * D * hw);
+        const float s00 = (vx0 && vy0) ? __ldg(sp + (int64_t)yi0 * W + xi0) : 0.0f;
+        const float s01 = (vx1 && vy0) ? __ldg(sp + (int64_t)yi0 * W + xi1) : 0.0f;
+        const float s10 = (vx0 && vy1) ? __ldg(sp + (int64_t)yi1 * W + xi0) : 0.0f;
+        const float s11 = (vx1 && vy1) ? __ldg(sp + (int64_t)yi1 * W + xi1) : 0.0f;
+        gix += g * ((s01 - s00) * wy0 + (s11 - s10) * wy1);
+        giy += g * ((s10 - s00) * wx0 + (s11 - s01) * wx1);
+    }
+    // p = q.xy / den
+    const float gqx = gix / den, gqy = giy / den, gqz = -(gix * qx + giy * qy) / (den * den);
+    const float gd = gqx * ray.x + gqy * ray.y + gqz * ray.z;
+    if (depth_is_map) gdepth[((int64_t)b * D + k) * hw + (int64_t)y * W + x] = gd;
+    else MVS_ATOMIC_ADD_F(gdepth + (int64_t)b * D + k, gd);
+    float* gr = grelproj + ((int64_t)b * MVS_WARP_GRAD_REPLICAS + (tid % MVS_WARP_GRAD_REPLICAS)) * 12;
+    const float px = (float)x * dep, py = (float)y * dep;              // d q / d R row = depth * (x, y, 1)
+    MVS_ATOMIC_ADD_F(gr + 0, gqx * px); MVS_ATOMIC_ADD_F(gr + 1, gqx * py); MVS_ATOMIC_ADD_F(gr + 2, gqx * dep); MVS_ATOMIC_ADD_F(gr + 3, gqx);
+    MVS_ATOMIC_ADD_F(gr + 4, gqy * px); MVS_ATOMIC_ADD_F(gr + 5, gqy * py); MVS_ATOMIC_ADD_F(gr + 6, gqy * dep); MVS_ATOMIC_ADD_F(gr + 7, gqy);
+    MVS_ATOMIC_ADD_F(gr + 8, gqz * px); MVS_ATOMIC_ADD_F(gr + 9, gqz * py); MVS_ATOMIC_ADD_F(gr + 10, gqz * dep); MVS_ATOMIC_ADD_F(gr + 11, gqz);
+}
+
 // Backward of depth_regression (models/module.py:597-603): depth = sum_k p[k] * d[k]  ->  gp[k] = gdepth * d[k].
 // d is [B,D,H,W] (depth_is_map) or [B,D]; one thread per (b, k, y, x)
 __device__ __forceinline__ void depth_regression_bwd_thread(const float* __restrict__ gdepth, const float* __restrict__ dv,
@@ -604,6 +657,10 @@ struct SigmoidBwd {
 struct HomoWarpBwd {
     const float *gwarped, *relproj, *depth; int depth_is_map; float* gsrc; int B, C, D, H, W;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { homo_warp_bwd_thread(gwarped, relproj, depth, depth_is_map, gsrc, B, C, D, H, W, tid); }
+};
+struct HomoWarpBwdGrid {
+    const float *gwarped, *src, *relproj, *depth; int depth_is_map; float *gdepth, *grelproj; int B, C, D, H, W;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { homo_warp_bwd_grid_thread(gwarped, src, relproj, depth, depth_is_map, gdepth, grelproj, B, C, D, H, W, tid); }
 };
 struct DepthRegressionBwd {
     const float *gdepth, *dv; int depth_is_map; float* gp; int B, D; int64_t hw;

@@ -2,7 +2,7 @@
 
 ``homo_warping_3D_with_mask`` (models/warping.py:69-109), ``homo_warping_3D`` (:155-189) and
 ``diff_homo_warping_3D_with_mask`` (:112-152) keep their signatures and results, and are
-differentiable w.r.t. ``src_fea`` (mvs_homo_warp_bwd).  StageNet does
+differentiable w.r.t. ``src_fea`` (mvs_homo_warp_bwd); the ``diff_`` variant also w.r.t. depth and cameras.  StageNet does
 NOT call them (its cost-volume kernels sample on the fly); they exist for API completeness.
 """
 from . import autograd, engine
@@ -21,10 +21,7 @@ def homo_warping_3D(src_fea, src_proj, ref_proj, depth_values):
 
 
 def diff_homo_warping_3D_with_mask(src_fea, src_proj, ref_proj, depth_values):
-    """The reference variant that lets gradients flow into the sampling grid (:112-152).  Forward
-    values are identical and src_fea is differentiable; the backward through cameras / depth (used by no
-    model in the reference) is not built, so such inputs that require grad are rejected, not silently detached."""
-    for t in (src_proj, ref_proj, depth_values):
-        if t.requires_grad:
-            raise NotImplementedError("diff_homo_warping_3D_with_mask: gradients w.r.t. cameras / depth are not built")
-    return homo_warping_3D_with_mask(src_fea, src_proj, ref_proj, depth_values)
+    """The reference variant whose sampling grid stays in the autograd graph (:112-152): same forward values, and
+    src_fea, depth_values, src_proj and ref_proj all receive gradients (mvs_homo_warp_bwd, mvs_homo_warp_bwd_grid; the
+    4x4 projection algebra and its gradient are torch's).  No model of the reference calls it."""
+    return autograd.diff_homo_warp(src_fea, src_proj, ref_proj, depth_values)

@@ -79,6 +79,30 @@ static int launch_flat(const F& f, int64_t nthreads, void*, const char*) {
 extern "C" const char* mvs_last_error_string(void) { return g_error; }
 extern "C" long long mvs_launch_count(void) { return g_launches; }
 
+// ---- restated semantics of mvs_homo_warp (warp.cu), on the shared geometry helpers ----------------------------
+extern "C" int mvs_homo_warp(const float* src_fea, const float* relproj, const float* depth, int depth_is_map, float* warped,
+                             uint8_t* mask, int B, int C, int D, int H, int W, void*) {
+    using namespace mvs;
+    MVS_REQUIRE(src_fea && relproj && depth && warped, "mvs_homo_warp: null pointer");
+    const int64_t hw = (int64_t)H * W;
+    for (int b = 0; b < B; ++b)
+        for (int d = 0; d < D; ++d)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    const RelProj m = load_relproj(relproj + (int64_t)b * 12);
+                    const PixelRay ray = pixel_ray(m, (float)x, (float)y);
+                    const float dep = depth_is_map ? depth[((int64_t)b * D + d) * hw + (int64_t)y * W + x] : depth[(int64_t)b * D + d];
+                    float gx, gy, qz;
+                    const Taps t = make_taps(m, ray, dep, H, W, (float)((W - 1) / 2.0), (float)((H - 1) / 2.0), &gx, &gy, &qz);
+                    if (mask) mask[((int64_t)b * D + d) * hw + (int64_t)y * W + x] =
+                        ((gx > 1.0f) || (gx < -1.0f) || (gy > 1.0f) || (gy < -1.0f) || (qz <= 0.0f)) ? 1 : 0;
+                    for (int c = 0; c < C; ++c)
+                        warped[(((int64_t)b * C + c) * D + d) * hw + (int64_t)y * W + x] = sample4(src_fea + ((int64_t)b * C + c) * hw, t);
+                }
+    ++g_launches;
+    return MVS_OK;
+}
+
 // ---- restated semantics of the two FP32 convolution entry points (include/mvs_b200.h) --------
 extern "C" int mvs_conv3d_cl(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
                              int H, int W, int Cin, int Cout, int kd, int sd, int sh, int sw, int relu, void*) {

@@ -286,3 +286,36 @@ def test_training_convs_on_tensor_cores(mode, tol):
         if name == "cost_reg.prob.bias" or name.startswith("vis."):
             continue
         assert rel_l1(p.grad.cpu(), truth[name]) < 2 * tol, name
+
+
+def test_diff_homo_warping_gradients_gpu():
+    """diff_homo_warping_3D_with_mask on the device: gradients w.r.t. features, depth and both cameras vs torch autograd
+    through the reference's formula (the kernel source passes the same check on the CPU emulation)."""
+    import torch.nn.functional as F
+    from mvsformer_b200 import warping as Wp
+    from oracle import mvs_oracle as O
+    from tests.helpers import rel_l1
+    from tests.test_train_emulated import _case
+
+    feats, cams, hyp = _case(batch=2, views=2, chans=8, depth=4, height=16, width=24, seed=23)
+    cams = cams.clone()
+    cams[:, 1, 0, 0, 3] += 120.0
+    src_p, ref_p = O.compose_projection(cams[:, 1]), O.compose_projection(cams[:, 0])
+    cpu = [t.clone().requires_grad_(True) for t in (feats[:, 1], src_p, ref_p, hyp)]
+    b, c, h, w = cpu[0].shape
+    nd = hyp.shape[1]
+    proj = torch.matmul(cpu[1], torch.inverse(cpu[2]))
+    y, x = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(h * w))).unsqueeze(0).repeat(b, 1, 1)
+    pxyz = torch.matmul(proj[:, :3, :3], xyz).unsqueeze(2).repeat(1, 1, nd, 1) * cpu[3].reshape(b, 1, nd, -1) + proj[:, :3, 3:4].view(b, 3, 1, 1)
+    pxy = pxyz[:, :2] / (pxyz[:, 2:3] + 1e-6)
+    grid = torch.stack((pxy[:, 0] / ((w - 1) / 2) - 1, pxy[:, 1] / ((h - 1) / 2) - 1), dim=3)
+    want = F.grid_sample(cpu[0], grid.view(b, nd * h, w, 2), mode="bilinear", padding_mode="zeros", align_corners=True).view(b, c, nd, h, w)
+    gout = torch.randn(want.shape, generator=S._gen(3))
+    want.backward(gout)
+    dev = [t.detach().to(DEV).requires_grad_(True) for t in (feats[:, 1].contiguous(), src_p, ref_p, hyp)]
+    got, mask = Wp.diff_homo_warping_3D_with_mask(*dev)
+    got.backward(gout.to(DEV))
+    assert rel_l1(got.cpu(), want) < 1e-5
+    for a, bb, tol in zip(dev, cpu, (1e-4, 2e-3, 2e-3, 2e-3)):
+        assert rel_l1(a.grad.cpu(), bb.grad) < tol

@@ -379,3 +379,53 @@ def test_regression_head_training_is_differentiable(emu):
     depth.backward(gout)
     want.backward(gout)
     assert rel_l1(pre.grad, p2.grad) < 1e-5
+
+
+@pytest.mark.parametrize("depth_is_map", [True, False])
+def test_diff_homo_warping_gradients_vs_reference_formula(emu, depth_is_map):
+    """diff_homo_warping_3D_with_mask (models/warping.py:112-152): gradients w.r.t. features, depth hypotheses and both
+    projection matrices vs torch autograd through the same formula (F.grid_sample with the grid in the graph)."""
+    from mvsformer_b200 import warping as Wp
+
+    feats, cams, hyp = _case(batch=2, views=2, chans=4, depth=3, height=8, width=12, seed=23)
+    cams = cams.clone()
+    cams[:, 1, 0, 0, 3] += 120.0
+    dv = hyp if depth_is_map else hyp[:, :, 0, 0].contiguous()
+    src_p, ref_p = O.compose_projection(cams[:, 1]), O.compose_projection(cams[:, 0])
+
+    def reference(src, sp, rp, d):                      # the reference function's arithmetic (warping.py:112-152)
+        b, c, h, w = src.shape
+        nd = d.shape[1]
+        proj = torch.matmul(sp, torch.inverse(rp))
+        rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
+        y, x = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(h * w))).unsqueeze(0).repeat(b, 1, 1)
+        rot_xyz = torch.matmul(rot, xyz)
+        rot_depth_xyz = rot_xyz.unsqueeze(2).repeat(1, 1, nd, 1) * d.reshape(b, 1, nd, -1)
+        proj_xyz = rot_depth_xyz + trans.view(b, 3, 1, 1)
+        proj_xy = proj_xyz[:, :2] / (proj_xyz[:, 2:3] + 1e-6)
+        grid = torch.stack((proj_xy[:, 0] / ((w - 1) / 2) - 1, proj_xy[:, 1] / ((h - 1) / 2) - 1), dim=3)
+        out = F.grid_sample(src, grid.view(b, nd * h, w, 2), mode="bilinear", padding_mode="zeros", align_corners=True)
+        return out.view(b, c, nd, h, w)
+
+    leaves_r = [t.clone().requires_grad_(True) for t in (feats[:, 1], src_p, ref_p, dv)]
+    want = reference(*leaves_r)
+    gout = torch.randn(want.shape, generator=S._gen(3))
+    want.backward(gout)
+    from oracle import ref_import
+    if ref_import.reference_available():                 # build container: the restatement above IS the reference's function
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            live = [t.clone().requires_grad_(True) for t in (feats[:, 1], src_p, ref_p, dv)]
+            ref_out, _ = ref_import.load_reference().warping.diff_homo_warping_3D_with_mask(*live)
+            ref_out.backward(gout)
+        assert torch.equal(ref_out, want) and all(torch.equal(a.grad, b.grad) for a, b in zip(live, leaves_r))
+    leaves_o = [t.clone().requires_grad_(True) for t in (feats[:, 1], src_p, ref_p, dv)]
+    got, mask = Wp.diff_homo_warping_3D_with_mask(*leaves_o)
+    assert rel_l1(got, want) < 1e-5 and mask.dtype == torch.bool and not mask.requires_grad
+    got.backward(gout)
+    assert rel_l1(leaves_o[0].grad, leaves_r[0].grad) < 1e-5           # features
+    assert rel_l1(leaves_o[3].grad, leaves_r[3].grad) < 1e-3           # depth hypotheses
+    assert rel_l1(leaves_o[1].grad, leaves_r[1].grad) < 1e-3           # src_proj
+    assert rel_l1(leaves_o[2].grad, leaves_r[2].grad) < 1e-3           # ref_proj
