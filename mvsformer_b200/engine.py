@@ -13,6 +13,12 @@ from . import _lib
 from ._lib import check, ptr, require_cuda, stream
 
 
+def require_cuda_device(t):
+    """Device check for tensors whose strides are free (the feature views): CUDA only, there is no CPU path."""
+    if not t.is_cuda:
+        raise RuntimeError("mvsformer_b200 runs on CUDA tensors only; there is no CPU path")
+
+
 def _f32(t):
     return t if t.dtype == torch.float32 else t.float()
 
@@ -67,8 +73,7 @@ def cost_volume_entropy(features, relproj, depth_values, groups, want_sim):
     features, bs, vs = _feature_strides(features)
     depth_values = _f32(depth_values).contiguous()
     require_cuda(relproj, depth_values)
-    if not features.is_cuda:
-        raise RuntimeError("mvsformer_b200 runs on CUDA tensors only; there is no CPU path")
+    require_cuda_device(features)
     b, v, c, h, w = features.shape
     d = depth_values.shape[1]
     entropy = torch.empty(b, v - 1, h, w, device=features.device, dtype=torch.float32)
@@ -99,8 +104,7 @@ def cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim)
     features, bs, vs = _feature_strides(features)
     depth_values = _f32(depth_values).contiguous()
     require_cuda(relproj, depth_values)
-    if not features.is_cuda:
-        raise RuntimeError("mvsformer_b200 runs on CUDA tensors only; there is no CPU path")
+    require_cuda_device(features)
     b, v, c, h, w = features.shape
     d = depth_values.shape[1]
     entropy = torch.empty(b, v - 1, h, w, device=features.device, dtype=torch.float32)

@@ -1,0 +1,122 @@
+"""Dry run of the host code of every forward path on the CPU: the library handle is replaced by a recorder that checks each
+call against the declared ctypes signature (argument count and convertibility) and launches nothing.  Outputs are
+uninitialised memory, so nothing numerical is asserted — the test exists to catch host-side mistakes (wrong argument
+lists, shape logic, missing attributes) in code paths that only run on a GPU: inference in all three precision modes,
+and the opt-in variants (MVS_CV_STORE, MVS_TCZ_KZF, MVS_TRAIN_CONV)."""
+import ctypes
+
+import pytest
+import torch
+
+from mvsformer_b200 import _lib, config, engine
+from mvsformer_b200 import synthetic as S
+from mvsformer_b200.mvsformer_model import CascadeMVS
+from tests.helpers import CASCADE_ARGS
+
+
+class _Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name not in _lib._SIGNATURES:
+            raise AttributeError("%s is not declared in _lib._SIGNATURES" % name)
+        restype, argtypes = _lib._SIGNATURES[name]
+
+        def fn(*args):
+            assert len(args) == len(argtypes), "%s: %d arguments, signature has %d" % (name, len(args), len(argtypes))
+            for a, t in zip(args, argtypes):
+                if t is ctypes.c_void_p:
+                    assert a is None or isinstance(a, (int, ctypes.c_void_p)) or hasattr(a, "_as_parameter_") \
+                        or isinstance(a, ctypes._SimpleCData) or isinstance(a, ctypes.Array), (name, type(a))
+                else:
+                    t(a)                                         # raises TypeError when not convertible
+            self.calls.append(name)
+            return b"dry run" if restype is ctypes.c_char_p else 0
+        return fn
+
+
+@pytest.fixture()
+def dry(monkeypatch):
+    rec = _Recorder()
+    monkeypatch.setattr(_lib, "load", lambda: rec)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(_lib, "stream", lambda: None)
+    monkeypatch.setattr(engine, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(engine, "stream", lambda: None)
+    monkeypatch.setattr(engine, "require_cuda_device", lambda t: None)
+    return rec
+
+
+def _cascade_inputs(height=128, width=256, views=3):
+    feats = S.make_features(1, views, height, width, seed=3)
+    cams = S.make_cameras(1, views, height, width)
+    return feats, cams, S.make_depth_range(1)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "fp32"])
+@pytest.mark.parametrize("cv_store,kzf", [(False, 0), (True, 0), (False, 1), (True, 2)])
+def test_inference_host_path(dry, mode, cv_store, kzf):
+    feats, cams, dv = _cascade_inputs()
+    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
+    old = config.conv_precision()
+    config.set_conv_precision(mode)
+    config.set_cv_store(cv_store)
+    config.set_tcz_kzf(kzf)
+    try:
+        with torch.no_grad():
+            out = net(feats, cams, dv, tmp=list(S.EVAL_TMP))
+    finally:
+        config.set_conv_precision(old)
+        config.set_cv_store(False)
+        config.set_tcz_kzf(0)
+    assert out["refined_depth"].shape == (1, 128, 256) and out["photometric_confidence"].shape == (1, 128, 256)
+    assert set(out["stage1"]) >= {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre", "sim_depth"}
+    called = set(dry.calls)
+    assert "mvs_cost_volume_entropy" in called or "mvs_cost_volume_entropy_store" in called
+    if cv_store:
+        assert "mvs_cost_volume_entropy_store" in called and "mvs_corr_aggregate" in called
+    if kzf and mode == "tf32":
+        assert called & {"mvs_conv3d_tcz_kzf", "mvs_deconv3d_tcz_kzf", "mvs_conv3d_tcr_khf"}
+    if mode == "fp32":
+        assert "mvs_conv3d_cl" in called and not any("_tc" in c for c in called)
+
+
+@pytest.mark.parametrize("train_conv", ["fp32", "tf32x3", "tf32"])
+def test_training_host_path(dry, train_conv):
+    feats, cams, dv = _cascade_inputs(64, 128)
+    feats = {k: v.requires_grad_(True) for k, v in feats.items()}
+    net = CascadeMVS(dict(CASCADE_ARGS)).train()
+    config.set_train_conv(train_conv)
+    try:
+        out = net(feats, cams, dv)
+        loss = sum(out["stage%d" % (s + 1)]["prob_volume_pre"].float().mean() for s in range(4))
+        loss.backward()
+    finally:
+        config.set_train_conv("fp32")
+    called = set(dry.calls)
+    assert {"mvs_group_corr_fwd", "mvs_group_corr_bwd", "mvs_aggregate_bwd", "mvs_conv_wgrad_cl", "mvs_bn_act_bwd_apply"} <= called
+    if train_conv != "fp32":
+        assert "mvs_conv3d_tc" in called and "mvs_deconv3d_tc" in called
+    assert all(p.grad is not None for p in net.parameters())
+
+
+def test_other_module_entry_points_host_path(dry):
+    from mvsformer_b200 import fusion as Fu
+    from mvsformer_b200 import module as M
+    from mvsformer_b200 import warping as Wp
+
+    x = torch.zeros(1, 8, 8, 16, 24)
+    for cls in (M.CostRegNet, M.CostRegNet3D, M.CostRegNet2D):
+        assert cls(8, 8).eval()(x).shape == (1, 1, 8, 16, 24)
+    p, dv = torch.zeros(1, 8, 4, 6), torch.zeros(1, 8)
+    assert M.depth_regression(p, dv).shape == (1, 4, 6) and M.conf_regression(p, 2).shape == (1, 4, 6)
+    assert M.init_inverse_range(torch.ones(1, 192), 32, None, None, 4, 6).shape == (1, 32, 4, 6)
+    eye = torch.eye(4).unsqueeze(0)
+    warped, mask = Wp.homo_warping_3D_with_mask(torch.zeros(1, 8, 4, 6), eye, eye, dv)
+    assert warped.shape == (1, 8, 8, 4, 6) and mask.shape == (1, 8, 4, 6)
+    c = S.make_fusion_case(3, 8, 12)
+    out = Fu.filter_view(c["ref_depth"], c["src_depths"], c["ref_cam"], c["src_cams"], 1.0, 0.01, 2,
+                         ref_conf=c["ref_conf"], prob_thresh=[0.1, 0.2, 0.3])
+    assert out["points"].shape == (1, 3, 8, 12)
+    assert Fu.dynamic_filter_view(c["ref_depth"], c["src_depths"], c["ref_cam"], c["src_cams"])["depth_ave"].shape == (1, 1, 8, 12)
