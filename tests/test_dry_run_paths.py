@@ -120,3 +120,15 @@ def test_other_module_entry_points_host_path(dry):
                          ref_conf=c["ref_conf"], prob_thresh=[0.1, 0.2, 0.3])
     assert out["points"].shape == (1, 3, 8, 12)
     assert Fu.dynamic_filter_view(c["ref_depth"], c["src_depths"], c["ref_cam"], c["src_cams"])["depth_ave"].shape == (1, 1, 8, 12)
+
+
+def test_bench_kernel_profiler_wraps_existing_entry_points():
+    """bench.py's per-kernel attribution wraps engine functions by name: every name must exist (also the opt-in ones)."""
+    import bench
+
+    prof = bench.KernelProfiler()
+    before = {k: getattr(engine, k) for k in dir(engine) if callable(getattr(engine, k))}
+    prof.install(engine)
+    assert {"cost_volume_entropy_store", "corr_aggregate", "conv3d_tcz_kzf", "deconv3d_tcz_kzf", "conv3d_tcr_khf"} <= set(prof._saved)
+    prof.uninstall(engine)
+    assert all(getattr(engine, k) is v for k, v in before.items())
