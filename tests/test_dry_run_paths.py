@@ -132,3 +132,44 @@ def test_bench_kernel_profiler_wraps_existing_entry_points():
     assert {"cost_volume_entropy_store", "corr_aggregate", "conv3d_tcz_kzf", "deconv3d_tcz_kzf", "conv3d_tcr_khf"} <= set(prof._saved)
     prof.uninstall(engine)
     assert all(getattr(engine, k) is v for k, v in before.items())
+
+
+@pytest.mark.parametrize("cv_store,kzf", [(False, 0), (True, 2), (False, 1)])
+def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
+    """The profiler's algorithmic-byte / flop lambdas must accept the argument lists the engine wrappers are called
+    with, for the shipped path and for the opt-in variants (scripts/ab_variants.py depends on it)."""
+    import bench
+
+    class _Event:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    feats, cams, dv = _cascade_inputs()
+    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
+    old = config.conv_precision()
+    config.set_conv_precision("tf32")
+    config.set_cv_store(cv_store)
+    config.set_tcz_kzf(kzf)
+    prof = bench.KernelProfiler()
+    prof.install(engine)
+    try:
+        with torch.no_grad():
+            net(feats, cams, dv, tmp=list(S.EVAL_TMP))
+    finally:
+        prof.uninstall(engine)
+        config.set_conv_precision(old)
+        config.set_cv_store(False)
+        config.set_tcz_kzf(0)
+    summ = prof.summary(1)
+    assert all(v["alg_bytes_per_step"] > 0 for v in summ.values())
+    if cv_store:
+        assert "cv_entropy_store(passA)" in summ and "cv_corr_aggregate(stream)" in summ
+    if kzf:
+        assert any("kzf" in k or "khf" in k for k in summ) or "vis_net(tensor-core layers)" in summ
