@@ -429,3 +429,9 @@ def test_diff_homo_warping_gradients_vs_reference_formula(emu, depth_is_map):
     assert rel_l1(leaves_o[3].grad, leaves_r[3].grad) < 1e-3           # depth hypotheses
     assert rel_l1(leaves_o[1].grad, leaves_r[1].grad) < 1e-3           # src_proj
     assert rel_l1(leaves_o[2].grad, leaves_r[2].grad) < 1e-3           # ref_proj
+
+
+def test_smoke_training_step_logic(emu):
+    """__graft_entry__.smoke()'s training check (run by the driver on the GPU), executed here on the kernel emulation."""
+    import __graft_entry__ as entry
+    entry._smoke_train_step(device="cpu")
