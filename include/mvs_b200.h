@@ -260,6 +260,17 @@ int mvs_sigmoid_bwd(const float* gy, const float* y, float* gx, int64_t n, void*
  * -> gsrc [B,C,H,W], ZEROED by the caller, fp32 atomics. */
 int mvs_homo_warp_bwd(const float* gwarped, const float* relproj, const float* depth, int depth_is_map, float* gsrc,
                       int B, int C, int D, int H, int W, void* stream);
+/* fusion_type 'epipole' / 'epipoleV2' (mvsformer_model.py:92-104): per-hypothesis softmax view weights.
+ * corr [B,N,D,H,W,G] (mvs_group_corr_fwd), mask [B,N,D,H,W] 1/0 from mvs_proj_mask (V2) or NULL, weight
+ * w_v[k] = softmax_k(sum_g corr_v / temperature - 10000 mask)[k] / norm -> volume [B,D,H,W,G], wsum [B,D,H,W],
+ * stats [B,N,H,W,2] (softmax max / normaliser, kept for the backward).  Backward: gcorr [B,N,D,H,W,G] and the gradient
+ * w.r.t. the temperature as 32 partial sums gtemp32 (ZEROED by the caller; NULL to skip). */
+int mvs_proj_mask(const float* relproj, const float* depth, float* mask, int B, int N, int D, int H, int W, void* stream);
+int mvs_epipole_aggregate_fwd(const float* corr, const float* mask, float temperature, float norm, float* stats,
+                              float* volume, float* wsum, int B, int N, int G, int D, int H, int W, void* stream);
+int mvs_epipole_aggregate_bwd(const float* gvol, const float* corr, const float* mask, const float* stats,
+                              const float* volume, const float* wsum, float temperature, float norm, float* gcorr,
+                              float* gtemp32, int B, int N, int G, int D, int H, int W, void* stream);
 /* Backward of the warp through the sampling grid (diff_homo_warping_3D_with_mask, warping.py:112-152): gdepth [B,D,H,W] or
  * [B,D], grelproj [B, MVS_WARP_GRAD_REPLICAS, 12] (gradient of the rows of [R|t], spread over replicas: sum over axis 1);
  * both ZEROED by the caller. */

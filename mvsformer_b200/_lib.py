@@ -79,6 +79,9 @@ _SIGNATURES = {
     "mvs_thin_conv_cl": (c_i, [c_f] * 4 + [c_i] * 9 + [c_f]),
     "mvs_sigmoid_bwd": (c_i, [c_f, c_f, c_f, c_l, c_f]),
     "mvs_homo_warp_bwd": (c_i, [c_f, c_f, c_f, c_i, c_f] + [c_i] * 5 + [c_f]),
+    "mvs_proj_mask": (c_i, [c_f, c_f, c_f] + [c_i] * 5 + [c_f]),
+    "mvs_epipole_aggregate_fwd": (c_i, [c_f, c_f, c_fl, c_fl, c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
+    "mvs_epipole_aggregate_bwd": (c_i, [c_f] * 6 + [c_fl, c_fl, c_f, c_f] + [c_i] * 6 + [c_f]),
     "mvs_homo_warp_bwd_grid": (c_i, [c_f] * 4 + [c_i] + [c_f, c_f] + [c_i] * 5 + [c_f]),
     "mvs_depth_regression_bwd": (c_i, [c_f, c_f, c_i, c_f] + [c_i] * 4 + [c_f]),
     "mvs_mixup_head": (c_i, [c_f] * 4 + [c_i] * 4 + [c_f]),

@@ -580,3 +580,65 @@ def mixup_head(prob, depth_values):
     conf = torch.empty(b, h, w, device=prob.device, dtype=torch.float32)
     _call("mvs_mixup_head", _p(prob), _p(dv), _p(depth), _p(conf), b, d, h, w)
     return depth, conf
+
+
+# ------------------------------------------------------------------------------------------------
+# fusion_type 'epipole' / 'epipoleV2'                                  models/mvsformer_model.py:92-104
+# ------------------------------------------------------------------------------------------------
+
+
+def proj_mask(relproj, depth_values):
+    """[B,N,12], [B,D,H,W] -> float 1/0 [B,N,D,H,W]: sample outside the source image or behind it (warping.py:99-103)."""
+    dv = depth_values.float().contiguous()
+    _lib.require_cuda(relproj, dv)
+    b, n = relproj.shape[:2]
+    d, h, w = dv.shape[1:]
+    mask = torch.empty(b, n, d, h, w, device=dv.device, dtype=torch.float32)
+    _call("mvs_proj_mask", _p(relproj), _p(dv), _p(mask), b, n, d, h, w)
+    return mask
+
+
+class _EpipoleAggregate(torch.autograd.Function):
+    """volume = sum_v corr_v w_v / (sum_v w_v + 1e-6) with per-hypothesis softmax weights; differentiable w.r.t. corr
+    (both through the product and through the weights) and the temperature."""
+
+    @staticmethod
+    def forward(ctx, corr, temperature, mask, norm, clamp):
+        t_eff = float(temperature)
+        if clamp is not None:
+            t_eff = min(max(t_eff, clamp[0]), clamp[1])
+        _lib.require_cuda(corr, mask)
+        b, n, d, h, w, g = corr.shape
+        stats = torch.empty(b, n, h, w, 2, device=corr.device, dtype=torch.float32)
+        volume = torch.empty(b, d, h, w, g, device=corr.device, dtype=torch.float32)
+        wsum = torch.empty(b, d, h, w, device=corr.device, dtype=torch.float32)
+        _call("mvs_epipole_aggregate_fwd", _p(corr), _p(mask), t_eff, float(norm), _p(stats), _p(volume), _p(wsum), b, n, g, d, h, w)
+        ctx.save_for_backward(corr, mask, stats, volume, wsum)
+        inside = clamp is None or (clamp[0] <= float(temperature) <= clamp[1])
+        ctx.cfg = (t_eff, float(norm), inside)
+        return volume
+
+    @staticmethod
+    def backward(ctx, gvol):
+        corr, mask, stats, volume, wsum = ctx.saved_tensors
+        t_eff, norm, inside = ctx.cfg
+        gvol = gvol.contiguous()
+        _lib.require_cuda(gvol)
+        b, n, d, h, w, g = corr.shape
+        gcorr = torch.empty_like(corr)
+        want_t = ctx.needs_input_grad[1]
+        gtemp = torch.zeros(32, device=corr.device, dtype=torch.float32) if want_t else None
+        _call("mvs_epipole_aggregate_bwd", _p(gvol), _p(corr), _p(mask), _p(stats), _p(volume), _p(wsum), t_eff, norm, _p(gcorr),
+              _p(gtemp), b, n, g, d, h, w)
+        gt = None
+        if want_t:
+            gt = gtemp.sum().reshape(()) if inside else torch.zeros((), device=corr.device)      # clamp passes gradient inside its range
+        return gcorr, gt, None, None, None
+
+
+def epipole_aggregate(corr, temperature, mask, norm, clamp=None):
+    """corr [B,N,D,H,W,G]; ``temperature`` a python float ('epipole') or a 0-d tensor / nn.Parameter ('epipoleV2');
+    ``mask`` [B,N,D,H,W] or None; ``clamp`` = (lo, hi) applied to the temperature (V2: 0.1, 10)."""
+    if not torch.is_tensor(temperature):
+        temperature = torch.tensor(float(temperature), device=corr.device)
+    return _EpipoleAggregate.apply(corr.contiguous(), temperature, mask, float(norm), clamp)

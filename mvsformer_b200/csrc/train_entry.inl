@@ -251,3 +251,39 @@ extern "C" int mvs_homo_warp_bwd_grid(const float* gwarped, const float* src_fea
     HomoWarpBwdGrid f{gwarped, src_fea, relproj, depth, depth_is_map, gdepth, grelproj, B, C, D, H, W};
     return launch_flat(f, (int64_t)B * D * H * W, stream, "homo_warp_bwd_grid");
 }
+
+// ---- fusion_type 'epipole' / 'epipoleV2' (models/mvsformer_model.py:92-104) ------------------------------------------
+extern "C" int mvs_proj_mask(const float* relproj, const float* depth, float* mask, int B, int N, int D, int H, int W,
+                             void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(relproj && depth && mask, "mvs_proj_mask: null pointer");
+    MVS_REQUIRE(B >= 1 && N >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_proj_mask: empty shape");
+    ProjMask f{relproj, depth, mask, B, N, D, H, W};
+    return launch_flat(f, (int64_t)B * N * D * H * W, stream, "proj_mask");
+}
+
+extern "C" int mvs_epipole_aggregate_fwd(const float* corr, const float* mask, float temperature, float norm, float* stats,
+                                         float* volume, float* wsum, int B, int N, int G, int D, int H, int W, void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(corr && stats && volume && wsum, "mvs_epipole_aggregate_fwd: null pointer");
+    MVS_REQUIRE(B >= 1 && N >= 1 && G >= 1 && G <= 8 && D >= 1 && H >= 1 && W >= 1, "mvs_epipole_aggregate_fwd: bad shape (G <= 8)");
+    MVS_REQUIRE(temperature > 0.0f && norm > 0.0f, "mvs_epipole_aggregate_fwd: temperature and norm must be positive");
+    const int64_t hw = (int64_t)H * W;
+    EpipoleStats f1{corr, mask, 1.0f / temperature, stats, B * N, G, D, hw};
+    int rc = launch_flat(f1, (int64_t)B * N * hw, stream, "epipole_stats");
+    if (rc) return rc;
+    EpipoleAggregateFwd f2{corr, mask, stats, 1.0f / temperature, 1.0f / norm, volume, wsum, B, N, G, D, hw};
+    return launch_flat(f2, (int64_t)B * D * hw, stream, "epipole_aggregate_fwd");
+}
+
+extern "C" int mvs_epipole_aggregate_bwd(const float* gvol, const float* corr, const float* mask, const float* stats,
+                                         const float* volume, const float* wsum, float temperature, float norm, float* gcorr,
+                                         float* gtemp32, int B, int N, int G, int D, int H, int W, void* stream) {
+    using namespace mvs::train;
+    MVS_REQUIRE(gvol && corr && stats && volume && wsum && gcorr, "mvs_epipole_aggregate_bwd: null pointer");
+    MVS_REQUIRE(B >= 1 && N >= 1 && G >= 1 && G <= 8 && D >= 1 && H >= 1 && W >= 1, "mvs_epipole_aggregate_bwd: bad shape (G <= 8)");
+    MVS_REQUIRE(temperature > 0.0f && norm > 0.0f, "mvs_epipole_aggregate_bwd: temperature and norm must be positive");
+    EpipoleAggregateBwd f{gvol, corr, mask, stats, volume, wsum, 1.0f / temperature, 1.0f / norm, gcorr, gtemp32, B, N, G, D,
+                          (int64_t)H * W};
+    return launch_flat(f, (int64_t)B * N * H * W, stream, "epipole_aggregate_bwd");
+}

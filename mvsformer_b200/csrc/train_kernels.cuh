@@ -507,6 +507,122 @@ __device__ __forceinline__ void homo_warp_bwd_thread(const float* __restrict__ g
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fusion_type 'epipole' / 'epipoleV2' (models/mvsformer_model.py:92-104): the view weight is a softmax over the depth
+// hypotheses of the summed correlation, per pixel AND per hypothesis:
+//   s_v[k] = sum_g corr_v[k,g] / T  (- 10000 * proj_mask_v[k] for V2);  w_v[k] = softmax_k(s_v)[k] / norm;
+//   volume[k,g] = sum_v corr_v[k,g] w_v[k] / (sum_v w_v[k] + 1e-6)
+// corr [B,N,D,H,W,G], mask [B,N,D,H,W] (1/0) or NULL, stats [B,N,H,W,2] = (max_k s, sum_k exp(s - max)).
+// ------------------------------------------------------------------------------------------
+// out-of-bounds / behind-the-camera flag of a sample (models/warping.py:99-103); one thread per (b, v, k, y, x)
+__device__ __forceinline__ void proj_mask_thread(const float* __restrict__ relproj, const float* __restrict__ depth,
+                                                 float* __restrict__ mask, int B, int N, int D, int H, int W, int64_t tid) {
+    const int64_t hw = (int64_t)H * W;
+    if (tid >= (int64_t)B * N * D * hw) return;
+    const int x = (int)(tid % W), y = (int)((tid / W) % H);
+    const int k = (int)((tid / hw) % D);
+    const int64_t bv = tid / (hw * D);
+    const int64_t b = bv / N;
+    const RelProj m = load_relproj(relproj + bv * 12);
+    const PixelRay ray = pixel_ray(m, (float)x, (float)y);
+    const float dep = __ldg(depth + ((b * D + k) * H + y) * W + x);
+    float gx, gy, qz;
+    make_taps(m, ray, dep, H, W, (float)((W - 1) / 2.0), (float)((H - 1) / 2.0), &gx, &gy, &qz);
+    mask[tid] = ((gx > 1.0f) || (gx < -1.0f) || (gy > 1.0f) || (gy < -1.0f) || (qz <= 0.0f)) ? 1.0f : 0.0f;
+}
+
+__device__ __forceinline__ float epipole_score(const float* __restrict__ p, int G, float inv_t, const float* __restrict__ mk) {
+    float s = 0.0f;
+    for (int g = 0; g < G; ++g) s += __ldg(p + g);
+    s *= inv_t;
+    if (mk) s += -10000.0f * __ldg(mk);
+    return s;
+}
+
+// one thread per (b, v, y, x): softmax statistics of the depth column
+__device__ __forceinline__ void epipole_stats_thread(const float* __restrict__ corr, const float* __restrict__ mask, float inv_t,
+                                                     float* __restrict__ stats, int BN, int G, int D, int64_t hw, int64_t tid) {
+    if (tid >= (int64_t)BN * hw) return;
+    const int64_t pix = tid % hw, bv = tid / hw;
+    float mx = -INFINITY;
+    for (int k = 0; k < D; ++k)
+        mx = fmaxf(mx, epipole_score(corr + ((bv * D + k) * hw + pix) * G, G, inv_t, mask ? mask + (bv * D + k) * hw + pix : nullptr));
+    float z = 0.0f;
+    for (int k = 0; k < D; ++k)
+        z += expf(epipole_score(corr + ((bv * D + k) * hw + pix) * G, G, inv_t, mask ? mask + (bv * D + k) * hw + pix : nullptr) - mx);
+    stats[tid * 2] = mx;
+    stats[tid * 2 + 1] = z;
+}
+
+// one thread per (b, k, y, x): volume [B,D,H,W,G] and wsum [B,D,H,W]
+__device__ __forceinline__ void epipole_aggregate_fwd_thread(const float* __restrict__ corr, const float* __restrict__ mask,
+                                                             const float* __restrict__ stats, float inv_t, float inv_norm,
+                                                             float* __restrict__ volume, float* __restrict__ wsum, int B, int N,
+                                                             int G, int D, int64_t hw, int64_t tid) {
+    if (tid >= (int64_t)B * D * hw) return;
+    const int64_t pix = tid % hw;
+    const int k = (int)((tid / hw) % D);
+    const int64_t b = tid / (hw * D);
+    float acc[8];
+    for (int g = 0; g < G; ++g) acc[g] = 0.0f;
+    float ws = 0.0f;
+    for (int v = 0; v < N; ++v) {
+        const int64_t bv = b * N + v;
+        const float* p = corr + ((bv * D + k) * hw + pix) * G;
+        const float s = epipole_score(p, G, inv_t, mask ? mask + (bv * D + k) * hw + pix : nullptr);
+        const float w = expf(s - __ldg(stats + (bv * hw + pix) * 2)) / __ldg(stats + (bv * hw + pix) * 2 + 1) * inv_norm;
+        for (int g = 0; g < G; ++g) acc[g] += __ldg(p + g) * w;
+        ws += w;
+    }
+    const float inv = 1.0f / (ws + 1e-6f);
+    for (int g = 0; g < G; ++g) volume[tid * G + g] = acc[g] * inv;
+    wsum[tid] = ws;
+}
+
+// Backward, one thread per (b, v, y, x) (a whole depth column, because of the softmax):
+//   direct:  gcorr[k,g]  = gvol[k,g] * w[k] / (S[k] + eps)
+//   via w:   gw[k]       = sum_g gvol[k,g] (corr[k,g] - vol[k,g]) / (S[k] + eps)
+//            gs[k]       = w[k] (gw[k] - sum_j gw[j] p[j]),  p = softmax = w * norm      (d w_k / d s_j = (p_k (delta - p_j)) / norm)
+//            gcorr[k,g] += gs[k] / T;    gT -= sum_k gs[k] * (sum_g corr[k,g]) / T^2     (fp32 atomic on gtemp[0])
+__device__ __forceinline__ void epipole_aggregate_bwd_thread(const float* __restrict__ gvol, const float* __restrict__ corr,
+                                                             const float* __restrict__ mask, const float* __restrict__ stats,
+                                                             const float* __restrict__ volume, const float* __restrict__ wsum,
+                                                             float inv_t, float inv_norm, float* __restrict__ gcorr,
+                                                             float* __restrict__ gtemp, int B, int N, int G, int D, int64_t hw,
+                                                             int64_t tid) {
+    if (tid >= (int64_t)B * N * hw) return;
+    const int64_t pix = tid % hw, bv = tid / hw;
+    const int64_t b = bv / N;
+    const float mx = __ldg(stats + tid * 2), z = __ldg(stats + tid * 2 + 1);
+    float dot = 0.0f;                                              // sum_j gw[j] p[j]
+    for (int k = 0; k < D; ++k) {
+        const float* p = corr + ((bv * D + k) * hw + pix) * G;
+        const int64_t o = (b * D + k) * hw + pix;
+        const float prob = expf(epipole_score(p, G, inv_t, mask ? mask + (bv * D + k) * hw + pix : nullptr) - mx) / z;
+        const float inv = 1.0f / (__ldg(wsum + o) + 1e-6f);
+        float gw = 0.0f;
+        for (int g = 0; g < G; ++g) gw += __ldg(gvol + o * G + g) * (__ldg(p + g) - __ldg(volume + o * G + g));
+        dot += gw * inv * prob;
+    }
+    float gt = 0.0f;
+    for (int k = 0; k < D; ++k) {
+        const float* p = corr + ((bv * D + k) * hw + pix) * G;
+        const int64_t o = (b * D + k) * hw + pix;
+        const float prob = expf(epipole_score(p, G, inv_t, mask ? mask + (bv * D + k) * hw + pix : nullptr) - mx) / z;
+        const float w = prob * inv_norm;
+        const float inv = 1.0f / (__ldg(wsum + o) + 1e-6f);
+        float gw = 0.0f, raw = 0.0f;
+        for (int g = 0; g < G; ++g) {
+            gw += __ldg(gvol + o * G + g) * (__ldg(p + g) - __ldg(volume + o * G + g));
+            raw += __ldg(p + g);
+        }
+        const float gs = w * (gw * inv - dot);
+        for (int g = 0; g < G; ++g) gcorr[((bv * D + k) * hw + pix) * G + g] = __ldg(gvol + o * G + g) * w * inv + gs * inv_t;
+        gt -= gs * raw * inv_t * inv_t;
+    }
+    if (gtemp) MVS_ATOMIC_ADD_F(gtemp + (tid % 32), gt);          // 32 replicas, summed by the caller
+}
+
 // Backward of the warp through the SAMPLING GRID (diff_homo_warping_3D_with_mask, models/warping.py:112-152, where the
 // grid is NOT under no_grad): gradients w.r.t. the depth hypotheses and the relative projection [R|t].
 //   d warped / d ix = sum of the bilinear x-differences of the (zero-padded) taps, as ATen's grid_sampler backward;
@@ -657,6 +773,22 @@ struct SigmoidBwd {
 struct HomoWarpBwd {
     const float *gwarped, *relproj, *depth; int depth_is_map; float* gsrc; int B, C, D, H, W;
     __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { homo_warp_bwd_thread(gwarped, relproj, depth, depth_is_map, gsrc, B, C, D, H, W, tid); }
+};
+struct ProjMask {
+    const float *relproj, *depth; float* mask; int B, N, D, H, W;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { proj_mask_thread(relproj, depth, mask, B, N, D, H, W, tid); }
+};
+struct EpipoleStats {
+    const float *corr, *mask; float inv_t; float* stats; int BN, G, D; int64_t hw;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { epipole_stats_thread(corr, mask, inv_t, stats, BN, G, D, hw, tid); }
+};
+struct EpipoleAggregateFwd {
+    const float *corr, *mask, *stats; float inv_t, inv_norm; float *volume, *wsum; int B, N, G, D; int64_t hw;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { epipole_aggregate_fwd_thread(corr, mask, stats, inv_t, inv_norm, volume, wsum, B, N, G, D, hw, tid); }
+};
+struct EpipoleAggregateBwd {
+    const float *gvol, *corr, *mask, *stats, *volume, *wsum; float inv_t, inv_norm; float *gcorr, *gtemp; int B, N, G, D; int64_t hw;
+    __device__ __forceinline__ void operator()(int64_t tid, int64_t) const { epipole_aggregate_bwd_thread(gvol, corr, mask, stats, volume, wsum, inv_t, inv_norm, gcorr, gtemp, B, N, G, D, hw, tid); }
 };
 struct HomoWarpBwdGrid {
     const float *gwarped, *src, *relproj, *depth; int depth_is_map; float *gdepth, *grelproj; int B, C, D, H, W;

@@ -12,6 +12,8 @@
                    which is how ``models/mvsformer_model.py`` uses the engine as a drop-in
                    (see INTEGRATION.md).
 """
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -37,9 +39,13 @@ class StageNet(nn.Module):
                 self.cost_reg = CostRegNet3D(in_channels, args["base_ch"])
             else:
                 self.cost_reg = CostRegNet(in_channels, args["base_ch"])
-        elif self.fusion_type in ("epipole", "epipoleV2"):
-            # present in the reference's code but used by no shipped config
-            raise NotImplementedError("fusion_type=%r is outside the accelerated path (only 'cnn' ships)" % self.fusion_type)
+        elif self.fusion_type == "epipole":
+            # models/mvsformer_model.py:42-44 (in the reference's code, used by no shipped config)
+            self.attn_temp = args.get("attn_temp", 2.0)
+            self.cost_reg = CostRegNet2D(in_channels, args["base_ch"])
+        elif self.fusion_type == "epipoleV2":
+            self.attn_temp = nn.Parameter(torch.tensor(1.0, dtype=torch.float32), requires_grad=True)    # :45-47
+            self.cost_reg = CostRegNet3D(in_channels, args["base_ch"])
         else:
             raise NotImplementedError
         self._vis_cache = _FoldCache()
@@ -155,6 +161,33 @@ class StageNet(nn.Module):
         return {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
                 "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
 
+    def _forward_epipole(self, features, proj_matrices, depth_values, tmp):
+        """fusion_type 'epipole' / 'epipoleV2' (models/mvsformer_model.py:92-104): per-hypothesis softmax view weights.
+        Used by no shipped config, so it runs through the materialised correlation of the training path in eval too."""
+        if features.dim() != 5:
+            raise RuntimeError("features must be [B,V,C,H,W]")
+        assert features.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
+        groups, chans = self.args["base_ch"], features.shape[2]
+        if chans % groups:
+            raise RuntimeError("shape '[%d, %d, -1, ...]' is invalid for %d feature channels" % (features.shape[0], groups, chans))
+        relproj = engine.relative_projections(proj_matrices)
+        corr = autograd.group_correlation(features, relproj, depth_values, groups)
+        if self.fusion_type == "epipoleV2":
+            volume = autograd.epipole_aggregate(corr, self.attn_temp, autograd.proj_mask(relproj, depth_values),
+                                                math.sqrt(groups), clamp=(0.1, 10.0))
+        else:
+            volume = autograd.epipole_aggregate(corr, self.attn_temp, None, math.sqrt(chans))
+        if not self.training and config.conv_precision() == "tf32":
+            volume = engine.round_tf32(volume)                     # operand contract of the TF32 tensor-core convolutions
+        prob_volume_pre = self.cost_reg.forward_cl(volume)
+        prob_volume, depth, conf = self._head(prob_volume_pre, depth_values, tmp)
+        outputs = {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
+                   "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
+        if not self.training:
+            _, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=True)
+            outputs["sim_depth"] = engine.argmax_gather(sim, depth_values)
+        return outputs
+
     def _head(self, prob_volume_pre, depth_values, tmp):
         """models/mvsformer_model.py:110-146 -> (prob_volume, depth, photometric_confidence) for every depth_type:
         'ce' / 'was' (argmax depth in training, temperature regression in eval, max-probability confidence),
@@ -181,6 +214,10 @@ class StageNet(nn.Module):
     def forward(self, features, proj_matrices, depth_values, tmp=2.0):
         """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W]."""
         depth_values = depth_values.float().contiguous()
+        if self.fusion_type != "cnn":
+            if type(tmp) == list or type(tmp) == tuple:
+                tmp = tmp[self.stage_idx]
+            return self._forward_epipole(features, proj_matrices, depth_values, tmp)
         if self.training:
             if type(tmp) == list or type(tmp) == tuple:
                 tmp = tmp[self.stage_idx]

@@ -14,6 +14,7 @@ compared).  Outputs are what the reference functions returned:
 * ``stage2_train.npz``  StageNet.forward (train mode: batch-stat BN, argmax depth)
 * ``stage{2,4}_train_grads.npz``  gradients of a cross-entropy loss on ``prob_volume_pre`` (models/losses.py:340-341)
                         through StageNet.forward in train mode, from torch autograd over the reference
+* ``epipole.npz``        StageNet.forward with fusion_type 'epipole' / 'epipoleV2' (train gradients, eval outputs)
 * ``heads.npz``          StageNet.forward (eval) with depth_type 'mixup_ce' / 're' (models/mvsformer_model.py:126-146)
 * ``fusion.npz``         misc/fusion.py:69-118 + test.py:433-435 (prob_filter, get_reproj, vis_filter, ave_fusion, points)
 * ``state_dict_keys.json``  names/shapes of the 302 ``fusions.*`` checkpoint entries
@@ -194,6 +195,42 @@ def gen_heads(ns):
     np.savez_compressed(os.path.join(OUT, "heads.npz"), height=height, width=width, **out)
 
 
+def gen_epipole(ns):
+    """fusion_type 'epipole' / 'epipoleV2' (models/mvsformer_model.py:92-104; no shipped config uses them): the reference
+    StageNet in training (CE loss, gradients) and in eval."""
+    R = ns.mvsformer_model
+    height, width = 64, 96
+    out = {}
+    for kind in ("epipole", "epipoleV2"):
+        s = 2                                                   # stage 3: C = 16, D = 8, half resolution
+        args = dict(STAGE_ARGS, fusion_type=kind, attn_temp=2.0)
+        feats, cams = stage_inputs(s, height, width, batch=1, seed=60)
+        cams = cams.clone()
+        cams[:, 2, 0, 0, 3] += 90.0                             # part of a view leaves the image: V2's mask matters
+        hyp = S.narrow_hypotheses(s, height, width, 1)
+        target = train_target(s, 1, feats.shape[-2], feats.shape[-1])
+        net = R.StageNet(args, S.NDEPTHS[s], s).train()
+        net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=80))
+        if kind == "epipoleV2":
+            with torch.no_grad():
+                net.attn_temp.fill_(1.7)
+        f = feats.clone().requires_grad_(True)
+        res = net(f, cams, hyp, tmp=list(S.EVAL_TMP))
+        F.cross_entropy(res["prob_volume_pre"], target).backward()
+        out[kind + "_train_pre"] = np_(res["prob_volume_pre"])
+        out[kind + "_train_gfeat"] = np_(f.grad)
+        out[kind + "_train_gconv1"] = np_(net.cost_reg.conv1.conv.weight.grad)
+        if kind == "epipoleV2":
+            out[kind + "_train_gtemp"] = np_(net.attn_temp.grad)
+        net2 = R.StageNet(args, S.NDEPTHS[s], s).eval()
+        net2.load_state_dict(S.fill_state_dict(net2.state_dict(), seed=80))
+        with torch.no_grad():
+            ev = net2(feats, cams, hyp, tmp=list(S.EVAL_TMP))
+        for key in ("prob_volume_pre", "depth", "sim_depth"):
+            out["%s_eval_%s" % (kind, key)] = np_(ev[key])
+    np.savez_compressed(os.path.join(OUT, "epipole.npz"), height=height, width=width, **out)
+
+
 def gen_fusion(ns):
     """Depth-map fusion: the reference's misc/fusion.py functions on a synthetic consistent scene.  Its
     get_pixel_grids calls ``.cuda()``; that call is patched to a no-op for the duration (nothing else is touched)."""
@@ -304,6 +341,7 @@ def main():
     gen_train_grads(ns)
     gen_fusion(ns)
     gen_heads(ns)
+    gen_epipole(ns)
     gen_state_dict_keys(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -16,7 +16,7 @@ EMU_SYMBOLS = [
     "mvs_last_error_string", "mvs_launch_count", "mvs_conv3d_cl", "mvs_deconv3d_cl", "mvs_group_corr_fwd",
     "mvs_group_corr_bwd", "mvs_corr_entropy", "mvs_aggregate_fwd", "mvs_aggregate_bwd", "mvs_bn_stats", "mvs_bn_collapse", "mvs_bn_finalize",
     "mvs_bn_act_fwd", "mvs_bn_act_bwd_reduce", "mvs_bn_act_bwd_apply", "mvs_conv_wgrad_cl", "mvs_thin_conv_cl",
-    "mvs_sigmoid_bwd", "mvs_softmax_bwd", "mvs_homo_warp", "mvs_homo_warp_bwd", "mvs_homo_warp_bwd_grid", "mvs_depth_regression_bwd", "mvs_mixup_head",
+    "mvs_sigmoid_bwd", "mvs_softmax_bwd", "mvs_proj_mask", "mvs_epipole_aggregate_fwd", "mvs_epipole_aggregate_bwd", "mvs_homo_warp", "mvs_homo_warp_bwd", "mvs_homo_warp_bwd_grid", "mvs_depth_regression_bwd", "mvs_mixup_head",
     "mvs_fusion_reproject", "mvs_fusion_reproject_dynamic", "mvs_fusion_filter_dynamic", "mvs_fusion_filter", "mvs_fusion_points", "mvs_fusion_prob_filter"]
 
 

@@ -101,6 +101,27 @@ def test_training_host_path(dry, train_conv):
     assert all(p.grad is not None for p in net.parameters())
 
 
+@pytest.mark.parametrize("kind", ["epipole", "epipoleV2"])
+@pytest.mark.parametrize("training", [False, True])
+def test_epipole_host_path(dry, kind, training):
+    from mvsformer_b200.mvsformer_model import StageNet
+    from tests.helpers import STAGE_ARGS
+
+    feats = S.make_features(1, 3, 64, 96, seed=1, stages=(2,))["stage3"]
+    cams = S.make_cameras(1, 3, 64, 96)["stage3"]
+    hyp = S.narrow_hypotheses(2, 64, 96, 1)
+    net = StageNet(dict(STAGE_ARGS, fusion_type=kind), 8, 2)
+    net = net.train() if training else net.eval()
+    old = config.conv_precision()
+    config.set_conv_precision("tf32")
+    try:
+        out = net(feats, cams, hyp, tmp=[5.0, 5.0, 5.0, 1.0])
+    finally:
+        config.set_conv_precision(old)
+    assert out["prob_volume_pre"].shape == (1, 8, 32, 48) and ("sim_depth" in out) == (not training)
+    assert "mvs_epipole_aggregate_fwd" in dry.calls and (("mvs_proj_mask" in dry.calls) == (kind == "epipoleV2"))
+
+
 def test_other_module_entry_points_host_path(dry):
     from mvsformer_b200 import fusion as Fu
     from mvsformer_b200 import module as M

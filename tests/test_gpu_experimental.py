@@ -319,3 +319,40 @@ def test_diff_homo_warping_gradients_gpu():
     assert rel_l1(got.cpu(), want) < 1e-5
     for a, bb, tol in zip(dev, cpu, (1e-4, 2e-3, 2e-3, 2e-3)):
         assert rel_l1(a.grad.cpu(), bb.grad) < tol
+
+
+@pytest.mark.parametrize("kind", ["epipole", "epipoleV2"])
+def test_epipole_fusion_gpu_vs_reference_golden(kind):
+    """fusion_type 'epipole' / 'epipoleV2' on the device: train-mode forward + gradients and eval outputs vs the unmodified
+    reference (tests/golden/epipole.npz)."""
+    import torch.nn.functional as F
+    from tests.helpers import load_golden, rel_l1
+    g = load_golden("epipole.npz")
+    s, height, width = 2, int(g["height"]), int(g["width"])
+    args = dict(STAGE_ARGS, fusion_type=kind, attn_temp=2.0)
+    feats = S.make_features(1, 3, height, width, seed=60, stages=(s,))["stage%d" % (s + 1)]
+    cams = S.make_cameras(1, 3, height, width)["stage%d" % (s + 1)].clone()
+    cams[:, 2, 0, 0, 3] += 90.0
+    hyp = S.narrow_hypotheses(s, height, width, 1)
+    target = torch.randint(0, S.NDEPTHS[s], (1, feats.shape[-2], feats.shape[-1]), generator=S._gen(700 + s))
+    net = StageNet(args, S.NDEPTHS[s], s).train()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=80))
+    if kind == "epipoleV2":
+        with torch.no_grad():
+            net.attn_temp.fill_(1.7)
+    net = net.to(DEV)
+    f = feats.to(DEV).requires_grad_(True)
+    out = net(f, cams.to(DEV), hyp.to(DEV), tmp=list(S.EVAL_TMP))
+    assert rel_l1(out["prob_volume_pre"].cpu(), g[kind + "_train_pre"]) < 2e-4
+    F.cross_entropy(out["prob_volume_pre"], target.to(DEV)).backward()
+    assert rel_l1(f.grad.cpu(), g[kind + "_train_gfeat"]) < 2e-2
+    if kind == "epipoleV2":
+        assert float(net.attn_temp.grad) == pytest.approx(float(g[kind + "_train_gtemp"]), rel=5e-2)
+    ev = StageNet(args, S.NDEPTHS[s], s).eval()
+    ev.load_state_dict(S.fill_state_dict(ev.state_dict(), seed=80))
+    ev = ev.to(DEV)
+    with torch.no_grad():
+        res = ev(feats.to(DEV), cams.to(DEV), hyp.to(DEV), tmp=list(S.EVAL_TMP))
+    assert rel_l1(res["prob_volume_pre"].cpu(), g[kind + "_eval_prob_volume_pre"]) < 2e-4
+    assert rel_l1(res["depth"].cpu(), g[kind + "_eval_depth"]) < 1e-4
+    assert (res["sim_depth"].cpu() == torch.from_numpy(g[kind + "_eval_sim_depth"])).float().mean() > 0.99

@@ -435,3 +435,80 @@ def test_smoke_training_step_logic(emu):
     """__graft_entry__.smoke()'s training check (run by the driver on the GPU), executed here on the kernel emulation."""
     import __graft_entry__ as entry
     entry._smoke_train_step(device="cpu")
+
+
+@pytest.mark.parametrize("kind", ["epipole", "epipoleV2"])
+def test_epipole_fusion_training_step_vs_reference_golden(emu, kind):
+    """fusion_type 'epipole' / 'epipoleV2' (models/mvsformer_model.py:92-104): train-mode forward and gradients (features,
+    regulariser, the learnable temperature of V2) vs what the unmodified reference produced (tests/golden/epipole.npz)."""
+    from tests.helpers import load_golden
+    g = load_golden("epipole.npz")
+    s, height, width = 2, int(g["height"]), int(g["width"])
+    args = dict(STAGE_ARGS, fusion_type=kind, attn_temp=2.0)
+    feats = S.make_features(1, 3, height, width, seed=60, stages=(s,))["stage%d" % (s + 1)]
+    cams = S.make_cameras(1, 3, height, width)["stage%d" % (s + 1)].clone()
+    cams[:, 2, 0, 0, 3] += 90.0
+    hyp = S.narrow_hypotheses(s, height, width, 1)
+    target = torch.randint(0, S.NDEPTHS[s], (1, feats.shape[-2], feats.shape[-1]), generator=S._gen(700 + s))
+    net = StageNet(args, S.NDEPTHS[s], s).train()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=80))
+    if kind == "epipoleV2":
+        with torch.no_grad():
+            net.attn_temp.fill_(1.7)
+    f = feats.clone().requires_grad_(True)
+    out = net(f, cams, hyp, tmp=list(S.EVAL_TMP))
+    assert set(out) == {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre"}
+    assert rel_l1(out["prob_volume_pre"], g[kind + "_train_pre"]) < 1e-4
+    F.cross_entropy(out["prob_volume_pre"], target).backward()
+    # V2 runs the batch-statistics CostRegNet3D on one 8x32x48 item: its fp32 backward is conditioned like stage 4's
+    # (DESIGN.md §4.4) — the regulariser's own first-layer gradient, which does not involve the fusion code at all, is
+    # 6e-3 from the reference's — so the bar is 1e-2 there and 2e-3 for 'epipole' (CostRegNet2D)
+    tol = 1e-2 if kind == "epipoleV2" else 2e-3
+    assert rel_l1(f.grad, g[kind + "_train_gfeat"]) < tol
+    assert rel_l1(net.cost_reg.conv1.conv.weight.grad, g[kind + "_train_gconv1"]) < tol
+    if kind == "epipoleV2":
+        assert float(net.attn_temp.grad) == pytest.approx(float(g[kind + "_train_gtemp"]), rel=2e-2)
+
+
+def test_epipole_state_dict_contract():
+    """Same parameter names as the reference: 'epipole' has no vis net and a CostRegNet2D, V2 adds the attn_temp parameter."""
+    a = StageNet(dict(STAGE_ARGS, fusion_type="epipole"), 8, 2)
+    b = StageNet(dict(STAGE_ARGS, fusion_type="epipoleV2"), 8, 2)
+    assert not any(k.startswith("vis.") for k in a.state_dict()) and "attn_temp" not in a.state_dict()
+    assert "attn_temp" in b.state_dict() and "cost_reg.conv7.0.weight" in b.state_dict()
+    assert tuple(a.state_dict()["cost_reg.conv1.conv.weight"].shape) == (16, 8, 1, 3, 3)
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_epipole_aggregate_forward_backward(emu, with_mask):
+    """The fusion operator alone vs torch autograd over the reference's formula (mvsformer_model.py:92-104):
+    gradients through the product AND through the softmax weights, and w.r.t. the (clamped) temperature."""
+    import math
+    g = S._gen(41)
+    b, n, d, h, w, grp = 2, 3, 5, 4, 6, 8
+    corr = torch.randn(b, n, d, h, w, grp, generator=g)
+    mask = (torch.rand(b, n, d, h, w, generator=g) < 0.2).float() if with_mask else None
+    temp = torch.tensor(1.7, requires_grad=True)
+    c1 = corr.clone().requires_grad_(True)
+    vol = autograd.epipole_aggregate(c1, temp, mask, math.sqrt(grp), clamp=(0.1, 10.0))
+    c2, t2 = corr.clone().requires_grad_(True), torch.tensor(1.7, requires_grad=True)
+    vsum, wsum = 0.0, 0.0
+    for v in range(n):
+        ipv = c2[:, v].permute(0, 4, 1, 2, 3)                                   # [B,G,D,H,W]
+        score = ipv.sum(1) / torch.clamp(t2, 0.1, 10.0)
+        if with_mask:
+            score = score + (-10000.0 * mask[:, v])
+        wgt = torch.softmax(score, dim=1) / math.sqrt(grp)
+        vsum = vsum + ipv * wgt.unsqueeze(1)
+        wsum = wsum + wgt
+    want = (vsum / (wsum.unsqueeze(1) + 1e-6)).permute(0, 2, 3, 4, 1)
+    assert rel_l1(vol, want) < 1e-5
+    gout = torch.randn(want.shape, generator=g)
+    vol.backward(gout)
+    want.backward(gout)
+    assert rel_l1(c1.grad, c2.grad) < 1e-4
+    assert float(temp.grad) == pytest.approx(float(t2.grad), rel=1e-3)
+    # outside the clamp range the temperature receives no gradient (torch.clamp semantics)
+    t3 = torch.tensor(20.0, requires_grad=True)
+    autograd.epipole_aggregate(corr.clone().requires_grad_(True), t3, mask, math.sqrt(grp), clamp=(0.1, 10.0)).sum().backward()
+    assert float(t3.grad) == 0.0
