@@ -512,3 +512,21 @@ def test_epipole_aggregate_forward_backward(emu, with_mask):
     t3 = torch.tensor(20.0, requires_grad=True)
     autograd.epipole_aggregate(corr.clone().requires_grad_(True), t3, mask, math.sqrt(grp), clamp=(0.1, 10.0)).sum().backward()
     assert float(t3.grad) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,depth,height,width,expect", [(16, 16, 2, 64, 160, "xseg"), (64, 64, 16, 32, 20, "rows")])
+def test_wgrad_automatic_work_split(emu, monkeypatch, cin, cout, depth, height, width, expect):
+    """mvs_conv_wgrad_cl with the work split it chooses by itself at realistic layer shapes: x-segmentation when there are
+    few (row, task) pairs, several rows per thread when there are many."""
+    for var in ("MVS_WGRAD_ROWS", "MVS_WGRAD_XSEG", "MVS_WGRAD_TILE"):
+        monkeypatch.delenv(var, raising=False)
+    ntasks, nrows = 27 * (cin // 8) * (cout // 8), depth * height
+    assert (ntasks * nrows < 512 * 1024) == (expect == "xseg")
+    g = S._gen(51)
+    x = torch.randn(1, depth, height, width, cin, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, requires_grad=True)
+    y = F.conv3d(x.permute(0, 4, 1, 2, 3), w, padding=1)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    dwp = autograd._conv_wgrad(gy.permute(0, 2, 3, 4, 1).contiguous(), x, (3, 3, 3, cin, cout), False, (1, 1, 1))
+    assert rel_l1(autograd._unpack(dwp, False), w.grad) < 1e-4
