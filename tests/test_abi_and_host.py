@@ -89,3 +89,30 @@ def test_algorithmic_bytes_match_survey():
     # cfg 2 = 1009 MB / ref view, 13.27 Mvox
     assert abs(S.cost_volume_algorithmic_bytes(5, 1152, 1536) / 1e6 - 1009) < 2
     assert abs(S.voxels_per_ref_view(1152, 1536) / 1e6 - 13.27) < 0.01
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype of include/mvs_b200.h has a ctypes signature with the same number of parameters and compatible
+    kinds (pointer / integer / floating point), and vice versa — drift here would only show up as a crash on the GPU."""
+    import ctypes
+    import re
+
+    from mvsformer_b200 import _lib
+
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    protos = dict(re.findall(r"\b(mvs_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
+    assert set(protos) == set(_lib._SIGNATURES), (set(protos) ^ set(_lib._SIGNATURES))
+    for name, params in protos.items():
+        plist = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        _, argtypes = _lib._SIGNATURES[name]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for p, t in zip(plist, argtypes):
+            if "*" in p:
+                assert t is ctypes.c_void_p or (isinstance(t, type) and issubclass(t, ctypes._Pointer)), (name, p, t)
+            elif re.match(r"^(const\s+)?(float|double)\b", p):
+                assert t in (ctypes.c_float, ctypes.c_double) and (t is ctypes.c_double) == ("double" in p), (name, p, t)
+            else:
+                assert t in (ctypes.c_int, ctypes.c_int64, ctypes.c_uint, ctypes.c_longlong), (name, p, t)
+                assert (t is ctypes.c_int64) == ("int64_t" in p), (name, p, t)

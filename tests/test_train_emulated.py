@@ -530,3 +530,25 @@ def test_wgrad_automatic_work_split(emu, monkeypatch, cin, cout, depth, height, 
     y.backward(gy)
     dwp = autograd._conv_wgrad(gy.permute(0, 2, 3, 4, 1).contiguous(), x, (3, 3, 3, cin, cout), False, (1, 1, 1))
     assert rel_l1(autograd._unpack(dwp, False), w.grad) < 1e-4
+
+
+def test_training_entry_points_reject_bad_arguments(emu):
+    """Error convention of the C ABI (negative return code + message) on the training / fusion entry points."""
+    from mvsformer_b200 import _lib
+
+    x = torch.zeros(4, 6)
+    sums = torch.zeros(32 * 12, dtype=torch.float64)
+    assert emu.mvs_bn_stats(_lib.ptr(x), _lib.ptr(sums), 4, 6, None) == -1            # C is not a power of two
+    assert b"power of two" in emu.mvs_last_error_string()
+    assert emu.mvs_bn_stats(None, _lib.ptr(sums), 4, 8, None) == -1
+    assert b"null pointer" in emu.mvs_last_error_string()
+    a, b_ = torch.zeros(1, 2, 4, 4, 8), torch.zeros(1, 2, 4, 4, 8)
+    dw = torch.zeros(3, 3, 3, 8, 8)
+    args = [_lib.ptr(a), _lib.ptr(b_), _lib.ptr(dw), 1, 2, 4, 4, 2, 9, 4, 8, 8, 3, 3, 1, 1, 1, None]     # Hb = 9 vs Hs = 4
+    assert emu.mvs_conv_wgrad_cl(*args) == -1 and b"do not match" in emu.mvs_last_error_string()
+    with pytest.raises(RuntimeError, match="kernel sizes must be 1 or 3"):
+        _lib.check(emu.mvs_thin_conv_cl(_lib.ptr(a), _lib.ptr(dw), None, _lib.ptr(b_), 1, 2, 4, 4, 8, 8, 5, 3, 0, None), "mvs_thin_conv_cl")
+    assert emu.mvs_fusion_filter_dynamic(_lib.ptr(a), _lib.ptr(a), 4.0, 1300.0, _lib.ptr(a), _lib.ptr(a), _lib.ptr(a), None,
+                                         1, 17, 4, 4, None) == -1                       # more than 16 views
+    assert emu.mvs_epipole_aggregate_fwd(_lib.ptr(a), None, 0.0, 1.0, _lib.ptr(a), _lib.ptr(a), _lib.ptr(a), 1, 1, 8, 2, 4, 4, None) == -1
+    assert b"positive" in emu.mvs_last_error_string()
