@@ -10,15 +10,17 @@
 
 Set with ``set_conv_precision()`` or the environment variable ``MVS_CONV_PRECISION``.
 
-``cv_store`` (``MVS_CV_STORE=1``, default off) — cost-volume build with ONE sampling pass at the stages where
-the per-view group correlation is smaller than the warped tensor (C/G >= 2, stages 1-3): pass A stores it, the
-aggregation streams over it (bit-identical volume; +2 x N x G x D x h x w x 4 B of HBM traffic instead of a
-second warp).  Opt-in until it has been timed on the GPU.
+``cv_store`` (``MVS_CV_STORE``, default ON since round 2; ``0`` restores two sampling passes) — cost-volume build with
+ONE sampling pass at the stages where the per-view group correlation is smaller than the warped tensor (C/G >= 2,
+stages 1-3): pass A stores it, the aggregation streams over it (bit-identical volume; +2 x N x G x D x h x w x 4 B of
+HBM traffic instead of a second warp).  Measured on B200 (profiles/r02_ab_variants.json): 7.87 -> 7.30 ms per
+reference view at cfg 2, refined depth bit-identical.
 
-``tcz_kzf`` (``MVS_TCZ_KZF=1``; ``2`` = also prefer the kz-fused kernel over the row-tiled one; default 0) — "fused N"
+``tcz_kzf`` (``MVS_TCZ_KZF``: ``0`` off, ``1`` default, ``2`` = also prefer the kz-fused kernel over the row-tiled one) — "fused N"
 variants of the depth-unstrided tensor-core convolutions (mvs_conv3d_tcz_kzf, mvs_deconv3d_tcz_kzf, mvs_conv3d_tcr_khf):
 one MMA of N = 3 x Cout-tile per slab / input row instead of three, i.e. about a third of the shared-memory
-A-operand reads.  TF32 mode only.  Opt-in until run on the GPU.
+A-operand reads.  TF32 mode only.  Default 1 since round 2 (measured 7.87 -> 7.43 ms, refined depth rel-L1 2e-6 vs the unfused kernels;
+level 2 was slower: 8.93 ms).
 
 ``train_conv`` (``MVS_TRAIN_CONV`` = ``fp32`` (default) | ``tf32x3`` | ``tf32``) — arithmetic of the training path's
 forward and data-gradient convolutions: the FP32 CUDA-core kernels, or the tcgen05 kernels of the inference path
@@ -29,8 +31,8 @@ import os
 
 _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
-          "cv_store": os.environ.get("MVS_CV_STORE", "0") not in ("", "0"),
-          "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "0") or 0),
+          "cv_store": os.environ.get("MVS_CV_STORE", "1") not in ("", "0"),
+          "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "1") or 0),
           "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
 if _state["train_conv"] not in ("fp32", "tf32x3", "tf32"):
     raise RuntimeError("MVS_TRAIN_CONV must be fp32, tf32x3 or tf32")

@@ -153,8 +153,9 @@ extern "C" int mvs_conv_wgrad_cl(const float* small, const float* big, float* dw
     // register tile of a thread: 8x8 channels (four 128-bit loads per 64 FMAs) when both channel counts allow,
     // else 4 or 1 per side.  The first version (4x4 tile, scalar loads) was load-instruction bound:
     // 13 of 40 ms of a cfg-5 training step (profiles/r01_train_step_entry_points_final.json).
-    // MVS_WGRAD_TILE=4 caps the tile at 4 per side (64 registers, 4x the threads) for A/B measurements.
-    int tmax = 8;
+    // Measured on B200 (profiles/r02_ab_variants.json): the 8x8 tile is SLOWER (36.2 vs 13.6 ms of weight gradients per
+    // cfg-5 step: a quarter of the threads, 152 registers), so 4 per side is the default; MVS_WGRAD_TILE=8 selects it.
+    int tmax = 4;
     if (const char* env = getenv("MVS_WGRAD_TILE")) tmax = atoi(env);
     const int ts = (Cs % 8 == 0 && tmax >= 8) ? 8 : (Cs % 4 == 0 && tmax >= 4 ? 4 : 1);
     const int tb = (Cb % 8 == 0 && tmax >= 8) ? 8 : (Cb % 4 == 0 && tmax >= 4 ? 4 : 1);

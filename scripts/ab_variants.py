@@ -23,13 +23,14 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 os.chdir(ROOT)
 out_dir = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/ab"
 os.makedirs(out_dir, exist_ok=True)
-os.environ["MVS_TEST_EXPERIMENTAL"] = "1"
 
 import pytest  # noqa: E402
 import torch  # noqa: E402
 
 import bench  # noqa: E402
 from mvsformer_b200 import config, engine  # noqa: E402
+
+_CV_STORE_DEFAULT, _TCZ_KZF_DEFAULT = config.cv_store(), config.tcz_kzf()
 
 
 def time_inference(net, feats, cams, dv, steps=8, warmup=3):
@@ -65,7 +66,7 @@ def main():
             contextlib.redirect_stderr(f):
         for name, expr in groups.items():
             print("==== group %s (-k %r)" % (name, expr), flush=True)
-            ok[name] = int(pytest.main(["tests/test_gpu_experimental.py", "-q", "-k", expr, "-p", "no:cacheprovider"])) == 0
+            ok[name] = int(pytest.main(["tests/test_gpu_variants.py", "-q", "-k", expr, "-p", "no:cacheprovider"])) == 0
     result["experimental_tests_passed"] = ok
     print("experimental tests", ok, flush=True)
 
@@ -87,8 +88,8 @@ def main():
         ms, kern, depths[name] = time_inference(net, feats, cams, dv)
         result[name] = {"ms_per_ref_view": ms, "maps_per_s": 1e3 / ms, "kernels_ms": kern}
         print(name, round(ms, 3), "ms", flush=True)
-    config.set_cv_store(False)
-    config.set_tcz_kzf(0)
+    config.set_cv_store(_CV_STORE_DEFAULT)
+    config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     if "cv_store" in depths:
         result["cv_store_refined_depth_bit_identical"] = bool(torch.equal(depths["shipped"], depths["cv_store"]))
     if "tcz_kzf_2" in depths:

@@ -13,6 +13,8 @@ from mvsformer_b200 import synthetic as S
 from mvsformer_b200.mvsformer_model import CascadeMVS
 from tests.helpers import CASCADE_ARGS
 
+_CV_STORE_DEFAULT, _TCZ_KZF_DEFAULT = config.cv_store(), config.tcz_kzf()
+
 
 class _Recorder:
     def __init__(self):
@@ -68,8 +70,8 @@ def test_inference_host_path(dry, mode, cv_store, kzf):
             out = net(feats, cams, dv, tmp=list(S.EVAL_TMP))
     finally:
         config.set_conv_precision(old)
-        config.set_cv_store(False)
-        config.set_tcz_kzf(0)
+        config.set_cv_store(_CV_STORE_DEFAULT)
+        config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     assert out["refined_depth"].shape == (1, 128, 256) and out["photometric_confidence"].shape == (1, 128, 256)
     assert set(out["stage1"]) >= {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre", "sim_depth"}
     called = set(dry.calls)
@@ -186,8 +188,8 @@ def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
     finally:
         prof.uninstall(engine)
         config.set_conv_precision(old)
-        config.set_cv_store(False)
-        config.set_tcz_kzf(0)
+        config.set_cv_store(_CV_STORE_DEFAULT)
+        config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     summ = prof.summary(1)
     assert all(v["alg_bytes_per_step"] > 0 for v in summ.values())
     if cv_store:

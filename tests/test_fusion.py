@@ -1,7 +1,7 @@
 """Depth-map fusion: the CPU oracle is pinned to what the reference's own misc/fusion.py
 functions returned (tests/golden/fusion.npz), and the kernels of csrc/fusion_kernels.cuh are run on the CPU thread
 emulation (tests/emu) through the package's drop-in mirror mvsformer_b200/fusion.py and compared with both.
-The GPU run of the same kernels is in tests/test_gpu_experimental.py."""
+The GPU run of the same kernels is in tests/test_gpu_variants.py."""
 import pytest
 import torch
 

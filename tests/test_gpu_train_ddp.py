@@ -1,7 +1,6 @@
 """Two-GPU NCCL run of the training path (BASELINE cfg 5: one reference view per rank, SyncBatchNorm,
 DDP gradient all-reduce over NVLink): 2 ranks x 1 item must equal 1 rank x 2 items — the device twin of
-tests/test_train_ddp_gloo.py.  Needs >= 2 GPUs; written without GPU time, so it is also gated behind
-MVS_TEST_EXPERIMENTAL=1 until it has run once."""
+tests/test_train_ddp_gloo.py.  Needs >= 2 GPUs (skipped on a one-GPU box)."""
 import os
 import socket
 
@@ -15,8 +14,6 @@ from mvsformer_b200 import synthetic as S
 from tests.helpers import STAGE_ARGS, rel_l1
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MVS_TEST_EXPERIMENTAL", "0") in ("", "0"),
-                                 reason="not yet run on a GPU box; set MVS_TEST_EXPERIMENTAL=1"),
               pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")]
 
 
