@@ -14,8 +14,12 @@ Printed JSON line (rank 0): value (inputs resident in HBM), e2e (same call with 
 inputs, H2D + D2H inside the timed region), roofline of the dominant kernel (live CUDA-event
 timing per kernel class), cpu_baseline (the CPU oracle port on a bounded sample), clocks.
 
-`--impl reference` times the reference's CPU arithmetic (the oracle port of the reference's own
-torch-CPU path: the reference is Python and cannot travel to the GPU box) on all host threads.
+`--impl reference` times the UNMODIFIED reference's hot path (its own StageNet modules and schedulers, staged
+under oracle/_ref by oracle/build_ref.py; the oracle port only if the staged copy is missing) on the host cores:
+every step is a bounded 256x384 sample of the workload (rate scaled by the pixel ratio, which the line's own
+`config` says), followed by ONE untimed-by-the-driver full-size cfg-2 pass that checks the extrapolation.
+`--impl eager` (and the `gpu_eager_baseline` key of the engine line) runs the same reference modules on cuda:0:
+PyTorch eager + cuDNN on the same B200, the baseline the hand-written kernels have to beat.
 """
 import argparse
 import json
@@ -270,29 +274,92 @@ def best_thread_count():
     return best
 
 
-def cpu_cascade_rate(steps, warmup, threads):
-    """The reference's CPU arithmetic (oracle port) on the bounded sample; returns (maps/s scaled to
-    the full workload by pixel ratio, seconds per sample step)."""
+def bench_state_dicts():
     from mvsformer_b200.mvsformer_model import CascadeMVS
-    from oracle import mvs_oracle as O
-    torch.set_num_threads(threads)
-    feats, cams, dv = host_inputs(SAMPLE_H, SAMPLE_W, VIEWS, 1234, pin=False)
     net = CascadeMVS(dict(CASCADE_ARGS)).eval()
-    sds = [S.fill_state_dict(net.fusions[s].state_dict(), seed=s) for s in range(4)]
-    with torch.no_grad():
-        for _ in range(warmup):
-            O.cascade_forward(feats, cams, dv, sds)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            O.cascade_forward(feats, cams, dv, sds)
-        dt = (time.perf_counter() - t0) / steps
-    frac = (SAMPLE_H * SAMPLE_W) / float(HEIGHT * WIDTH)
+    return [S.fill_state_dict(net.fusions[s].state_dict(), seed=s) for s in range(4)]
+
+
+def cpu_kind():
+    from oracle import ref_cascade
+    return "reference" if ref_cascade.available() else "port"
+
+
+def cpu_cascade_rate(steps, warmup, threads, height=SAMPLE_H, width=SAMPLE_W):
+    """The reference's own hot path on the host (the unmodified modules staged under oracle/_ref; the oracle port
+    when they are missing) on a height x width workload; returns (maps/s scaled to the full workload by the
+    pixel ratio, seconds per step)."""
+    from oracle import mvs_oracle as O
+    from oracle import ref_cascade
+    torch.set_num_threads(threads)
+    feats, cams, dv = host_inputs(height, width, VIEWS, 1234, pin=False)
+    sds = bench_state_dicts()
+    if ref_cascade.available():
+        nets = ref_cascade.build_stage_nets(sds)
+        dt = ref_cascade.time_cpu(nets, feats, cams, dv, steps, warmup)
+    else:
+        with torch.no_grad():
+            for _ in range(warmup):
+                O.cascade_forward(feats, cams, dv, sds)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                O.cascade_forward(feats, cams, dv, sds)
+            dt = (time.perf_counter() - t0) / steps
+    frac = (height * width) / float(HEIGHT * WIDTH)
     return frac / dt, dt
 
 
-def sample_desc():
+def gpu_eager_baseline(device, steps=10, warmup=3):
+    """The reference's own modules on the GPU: PyTorch eager + cuDNN (TF32 convs as torch defaults), cfg 2 full size,
+    inputs resident, CUDA events.  None when oracle/_ref is not staged."""
+    from oracle import ref_cascade
+    if not ref_cascade.available():
+        return None
+    feats, cams, dv = host_inputs(HEIGHT, WIDTH, VIEWS, 1234, pin=False)
+    feats = {k: v.to(device) for k, v in feats.items()}
+    cams = {k: v.to(device) for k, v in cams.items()}
+    nets = ref_cascade.build_stage_nets(bench_state_dicts(), device)
+    t = ref_cascade.time_cuda(nets, feats, cams, dv.to(device), steps, warmup)
+    out = {"value": 1e3 / t["ms_per_step"], "unit": UNIT, "ms_per_step": t["ms_per_step"],
+           "parts_ms": {"cnn(cost_reg x4)": t["cnn_ms"], "cost_volume_build+head": t["cost_volume_and_head_ms"]},
+           "steps": steps, "warmup": warmup,
+           "kind": "unmodified reference StageNet/scheduler modules (oracle/_ref) on the same GPU: PyTorch %s eager + cuDNN, "
+                   "cudnn.allow_tf32=%s, matmul.allow_tf32=%s, inputs resident" % (torch.__version__, torch.backends.cudnn.allow_tf32,
+                                                                                    torch.backends.cuda.matmul.allow_tf32)}
+    del nets, feats
+    torch.cuda.empty_cache()
+    return out
+
+
+def full_size_parity(net, feats_d, cams_d, dv_d, feats_h, cams_h, dv_h, tmp):
+    """Refined depth of the precision mode being timed vs the fp32 CPU oracle on the SAME full-size cfg-2 inputs."""
+    from oracle import mvs_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        got = net(feats_d, cams_d, dv_d, tmp=tmp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        want = O.cascade_forward({k: v.clone() for k, v in feats_h.items()}, cams_h, dv_h, bench_state_dicts())
+        dt = time.perf_counter() - t0
+    d, c = got["refined_depth"].cpu(), got["photometric_confidence"].cpu()
+    rel = float((d - want["refined_depth"]).abs().mean() / want["refined_depth"].abs().mean())
+    relc = float((c - want["photometric_confidence"]).abs().mean() / want["photometric_confidence"].abs().mean())
+    return {"refined_depth_rel_l1": rel, "confidence_rel_l1": relc, "tolerance": 1e-3, "ok": bool(rel < 1e-3),
+            "against": "oracle/mvs_oracle.py (fp32 torch-CPU restatement, pinned to the reference's goldens) on the full cfg-2 inputs of this run",
+            "oracle_seconds": dt}
+
+
+def sample_desc(height=SAMPLE_H, width=SAMPLE_W):
+    if (height, width) == (HEIGHT, WIDTH):
+        return "the full cfg-2 workload (%dx%d, %d views, 4-stage cascade), no extrapolation" % (HEIGHT, WIDTH, VIEWS)
     return ("4-stage cascade, %d views, 192-depth range, image %dx%d = 1/%d of the %dx%d pixels; rate scaled by the "
-            "pixel ratio" % (VIEWS, SAMPLE_H, SAMPLE_W, round(HEIGHT * WIDTH / (SAMPLE_H * SAMPLE_W)), HEIGHT, WIDTH))
+            "pixel ratio" % (VIEWS, height, width, round(HEIGHT * WIDTH / (height * width)), HEIGHT, WIDTH))
+
+
+def cpu_threads():
+    """All host cores for the unmodified reference (what a user of the reference gets); the calibrated best count
+    for the oracle port (many tiny ops: fork/join of every core can cost more than it buys)."""
+    return (os.cpu_count() or 1) if cpu_kind() == "reference" else best_thread_count()
 
 
 def measured_peaks():
@@ -305,20 +372,45 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_config(n_gpus, height, width):
+    return {"workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, feat ch 64/32/16/8, G=8; "
+                        "each timed step = %s" % (HEIGHT, WIDTH, VIEWS, sample_desc(height, width)),
+            "precision": "fp32 torch CPU kernels (the reference's own arithmetic)",
+            "parallelism": "rank 0 only, host cores; %d GPU(s) idle" % n_gpus}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from mvsformer_b200 import config
-    config.set_conv_precision(os.environ.get("MVS_CONV_PRECISION", "tf32"))     # same `config` as the engine arm
-    threads = best_thread_count()
+    kind, threads = cpu_kind(), cpu_threads()
     value, dt = cpu_cascade_rate(args.steps, max(args.warmup, 1), threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port", "sample": sample_desc()},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": reference_config(args.gpus, SAMPLE_H, SAMPLE_W),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": kind, "sample": sample_desc()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_full_size:
+        # one pass over the FULL workload (outside the K timed steps): the extrapolation above against a measurement
+        vf, dtf = cpu_cascade_rate(1, 0, threads, HEIGHT, WIDTH)
+        line["full_size_check"] = {"value": vf, "unit": UNIT, "seconds_per_step": dtf, "steps": 1, "sample": sample_desc(HEIGHT, WIDTH),
+                                   "extrapolated_over_measured": value / vf}
     print(json.dumps(line))
+
+
+def run_eager(args, rank, world, local_rank):
+    """`--impl eager`: the reference's modules on cuda (one line per invocation, rank 0 only)."""
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    g = gpu_eager_baseline(torch.device("cuda", local_rank), args.steps, max(args.warmup, 3))
+    if g is None:
+        print(json.dumps({"impl": "eager", "unavailable": "oracle/_ref is not staged (run python -m oracle.build_ref where /root/reference exists)"}))
+        return
+    print(json.dumps({"impl": "eager", "metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": g["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32 (cuDNN TF32 conv math)", "data": "synthetic",
+                      "config": {"workload": workload_config(1)["workload"], "precision": g["kind"]}, "parts_ms": g["parts_ms"]}))
 
 
 def measure_train_step(device, steps=5, warmup=3):
@@ -369,14 +461,14 @@ def measure_train_step(device, steps=5, warmup=3):
                       "SGD; fp32 CUDA-core kernels; features given (backbone out of scope)"}
 
 
-def profile_traffic(kernel_family):
-    """DRAM bytes per launch of the dominant kernel family from the committed ncu --set full capture
-    (profiles/r01_traffic.json, written by scripts/summarise_ncu.py); None when not captured."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def profile_traffic():
+    """DRAM bytes from the committed ncu --set full capture of this round (profiles/r02_traffic.json, written by
+    scripts/summarise_ncu.py); {} when not captured."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(path):
-        return None
+        return {}
     with open(path) as f:
-        return json.load(f).get(kernel_family)
+        return json.load(f)
 
 
 def run_engine(args, rank, world, local_rank):
@@ -438,7 +530,7 @@ def run_engine(args, rank, world, local_rank):
                 scan_pos[0] += 1
                 yield ScanSample([n + j for j in range(VIEWS)], lambda vid: view_host[vid % VIEWS], cams_h, dv_h)
         checksum = 0.0
-        for depth_h, conf_h in streamer.run_scan(samples(), capacity=16):
+        for depth_h, conf_h in streamer.run_scan(samples(), capacity=16, keep_cache=True):     # warm-up and timed calls continue ONE scan
             checksum += float(depth_h[0, 0, 0])
         return checksum
 
@@ -511,32 +603,38 @@ def run_engine(args, rank, world, local_rank):
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     peaks = measured_peaks()
 
-    # kernel families for the roofline: pass A and pass B are the same templated kernel (cost_volume_kernel)
-    families = {}
-    for name, k in kernels.items():
-        fam = "cost_volume_kernel" if name.startswith("cv_") else name
-        f = families.setdefault(fam, {"ms_per_step": 0.0, "alg_bytes_per_step": 0.0, "alg_flops_per_step": 0.0, "launches_per_step": 0.0})
-        for key in f:
-            f[key] += k[key]
-    for f in families.values():
-        f["avg_launch_ms"] = f["ms_per_step"] / max(f["launches_per_step"], 1)
-    dom = max(families, key=lambda k: families[k]["ms_per_step"])
-    kd = families[dom]
-    if kd["alg_flops_per_step"] > 100 * kd["alg_bytes_per_step"]:
-        achieved = kd["alg_flops_per_step"] / (kd["ms_per_step"] * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": profile_traffic(dom),
-                "note": "conv math %s; peak = %s sustained cuBLAS bf16 (dense TF32 peak is half of it)" % (conv_mode(), peaks["source"])}
-    else:
-        achieved = kd["alg_bytes_per_step"] / (kd["ms_per_step"] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": profile_traffic(dom), "note": "peak = %s copy bandwidth" % peaks["source"]}
-    roof["avg_launch_ms"] = kd["avg_launch_ms"]
-    roof["share_of_step"] = kd["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())
-
-    # cost-volume build (pass A + vis net + pass B) against the HBM roofline — the north-star kernel
-    cv_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith("cv_") or k.startswith("vis_net"))
+    # ---- rooflines ---------------------------------------------------------------------------------
+    # K1 = the cost-volume build's own kernels (warp + correlation sampling passes and the streaming aggregation), all
+    # four stages.  Numerator: §8d's algorithmic bytes ONCE per reference view (features, hypotheses, volume; 1 009 MB at
+    # cfg 2) — not once per pass.  `cost_volume` below adds the visibility net's time, as §8d's Gvox/s definition does.
+    step_ms_sum = sum(k["ms_per_step"] for k in kernels.values())
     cv_bytes = S.cost_volume_algorithmic_bytes(VIEWS, HEIGHT, WIDTH)
+    k1 = [k for n, k in kernels.items() if n.startswith("cv_")]
+    k1_ms = sum(k["ms_per_step"] for k in k1)
+    k1_launches = sum(k["launches_per_step"] for k in k1)
+    traffic = profile_traffic()
+    achieved = cv_bytes / (k1_ms * 1e-3) / 1e9
+    roof = {"kernel": "cost-volume build K1: " + " + ".join(sorted(n for n in kernels if n.startswith("cv_"))), "bound": "hbm",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": traffic.get("k1_dram_bytes_per_launch"), "alg_bytes_per_launch": cv_bytes / max(k1_launches, 1),
+            "alg_bytes_per_step": cv_bytes, "ms_per_step": k1_ms, "launches_per_step": k1_launches,
+            "avg_launch_ms": k1_ms / max(k1_launches, 1), "share_of_step": k1_ms / step_ms_sum,
+            "note": "peak = %s copy bandwidth; numerator = SURVEY §8d bytes counted once per reference view; traffic = ncu dram "
+                    "bytes per launch (profiles/r02_traffic.json)" % peaks["source"]}
+    conv = [k for n, k in kernels.items() if n.startswith("conv3d") or n.startswith("deconv3d")]
+    conv_ms = sum(k["ms_per_step"] for k in conv)
+    conv_flops = sum(k["alg_flops_per_step"] for k in conv)
+    conv_bytes = sum(k["alg_bytes_per_step"] for k in conv)
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    roof_conv = {"kernel": "3D-CNN convolutions (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": conv_flops / (conv_ms * 1e-3) / 1e12,
+                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / tf32_peak,
+                 "hbm": {"alg_bytes_per_step": conv_bytes, "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                         "frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "unit": "GB/s"},
+                 "traffic": traffic.get("conv_dram_bytes_per_step"), "ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms_sum,
+                 "note": "dense TF32 peak taken as half of the %s sustained cuBLAS bf16 figure; layer-wise bytes = in + out + skip per layer" % peaks["source"]}
+
+    # cost-volume build incl. the visibility net against the HBM roofline — §8d's Gvox/s
+    cv_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith("cv_") or k.startswith("vis_net"))
     cost_volume = {"ms_per_step": cv_ms, "gvox_per_s": S.voxels_per_ref_view(HEIGHT, WIDTH) / (cv_ms * 1e-3) / 1e9,
                    "alg_bytes": cv_bytes, "achieved_gbs": cv_bytes / (cv_ms * 1e-3) / 1e9,
                    "frac_of_hbm": cv_bytes / (cv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -552,13 +650,20 @@ def run_engine(args, rank, world, local_rank):
                          "h2d_bytes_per_step": h2d_scan, "d2h_bytes_per_step": d2h,
                          "api": "mvsformer_b200.pipeline.StreamedCascade.run_scan (per-view feature cache: consecutive reference "
                                 "views share 4 of 5 views, only the new view crosses PCIe; not the headline e2e)"},
-            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "cost_volume": cost_volume,
-            "kernels": kernels}
+            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "roofline_conv": roof_conv,
+            "cost_volume": cost_volume, "kernels": kernels}
+    if world == 1 and not args.no_parity:
+        line["parity"] = full_size_parity(net, feats_d, cams_d, dv_d, feats_h, cams_h, dv_h, tmp)
     if world == 1 and not args.no_cpu_baseline:
-        threads = best_thread_count()
+        threads = cpu_threads()
         v, dt = cpu_cascade_rate(3, 1, threads)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": cpu_kind(),
                                 "sample": sample_desc(), "seconds_per_sample_step": dt}
+    if world == 1 and not args.no_eager:
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(device)
+        except Exception as exc:
+            line["gpu_eager_baseline"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     if world == 1 and not args.no_train_step:
         try:                                   # last on purpose: nothing above depends on it
             line["train_step_cfg5"] = measure_train_step(device)
@@ -574,8 +679,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference", "eager"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (reference modules on cuda:0)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity check against the CPU oracle")
+    ap.add_argument("--no-full-size", action="store_true", help="reference arm: skip the one full-size pass")
     ap.add_argument("--no-train-step", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
@@ -584,6 +692,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "eager":
+        run_eager(args, rank, world, local_rank)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")

@@ -133,10 +133,19 @@ def require_cuda(*tensors):
         if not t.is_cuda:
             raise RuntimeError("mvsformer_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path"
                                % t.device.type)
+        check_device(t)
         if t.dtype != torch.float32:
             raise RuntimeError("expected a float32 tensor, got %s" % t.dtype)
         if not t.is_contiguous():
             raise RuntimeError("expected a contiguous tensor (shape %s, strides %s)" % (tuple(t.shape), t.stride()))
+
+
+def check_device(t):
+    """Kernels are enqueued on the CURRENT device's current stream (the C side never calls cudaSetDevice): a tensor
+    on another GPU would be launched against the wrong context, so refuse it."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("tensor on %s but the current CUDA device is cuda:%d; call inside `with torch.cuda.device(%d)`"
+                           % (t.device, torch.cuda.current_device(), t.device.index))
 
 
 def ptr(t):

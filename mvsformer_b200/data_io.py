@@ -84,7 +84,7 @@ class AsyncResultWriter:
             finally:
                 self._q.task_done()
 
-    def submit(self, depth_path, depth, conf_path=None, confidence=None, copy=False):
+    def submit(self, depth_path, depth, conf_path=None, confidence=None, copy=True):
         if self._error is not None:
             raise self._error
         depth = np.asarray(depth, dtype=np.float32)

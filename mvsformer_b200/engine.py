@@ -17,6 +17,7 @@ def require_cuda_device(t):
     """Device check for tensors whose strides are free (the feature views): CUDA only, there is no CPU path."""
     if not t.is_cuda:
         raise RuntimeError("mvsformer_b200 runs on CUDA tensors only; there is no CPU path")
+    _lib.check_device(t)
 
 
 def _f32(t):

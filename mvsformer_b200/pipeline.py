@@ -199,12 +199,25 @@ class StreamedCascade:
         self._gather_done.record(torch.cuda.current_stream(self.device))
         return self._gathered
 
-    def run_scan(self, samples, capacity=64):
+    def run_scan(self, samples, capacity=64, keep_cache=False):
         """Like ``run`` for ``ScanSample``s that share views: each view's features cross PCIe once
-        (while resident).  Yields (depth, confidence) pinned host tensors, one step behind the GPU."""
+        (while resident).  Yields (depth, confidence) pinned host tensors, one step behind the GPU; a yielded pair
+        stays valid until the next-but-one result is requested (``ring + 1`` pinned buffers rotate).
+
+        View ids are the caller's and are only meaningful inside one scan (the reference numbers the views of every
+        scan 0..48), so the cache is EMPTIED at the start of every call; pass ``keep_cache=True`` to continue the same
+        scan across calls (same ids = same features)."""
+        with torch.cuda.device(self.device):
+            yield from self._run_scan(samples, capacity, keep_cache)
+
+    def _run_scan(self, samples, capacity, keep_cache):
         main = torch.cuda.current_stream(self.device)
         if self.cache is None or self.cache.capacity != capacity:
             self.cache, self._pools, self._gathered, self._gather_done = FeatureCache(capacity), None, None, None
+        elif not keep_cache:
+            if self._gather_done is not None:
+                self.copy_stream.wait_event(self._gather_done)      # pools may still be read by the last gather
+            self.cache = FeatureCache(capacity)                      # pools are reused, their contents forgotten
         it = iter(samples)
         nxt = next(it, None)
         if nxt is None:
@@ -222,7 +235,7 @@ class StreamedCascade:
                 staged = self._stage_scan(nxt) if nxt is not None else None  # overlaps with this view's compute
                 out = self.net(f, c, d, tmp=self.tmp)
                 bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
-                hd, hc, done = bufs[i % self.ring]
+                hd, hc, done = bufs[i % len(bufs)]
                 hd.copy_(out["refined_depth"], non_blocking=True)
                 hc.copy_(out["photometric_confidence"], non_blocking=True)
                 done.record(main)
@@ -241,12 +254,17 @@ class StreamedCascade:
         if self._out is None or self._out[0][0].shape != depth.shape:
             self._out = [(torch.empty(depth.shape, dtype=torch.float32).pin_memory(),
                           torch.empty(conf.shape, dtype=torch.float32).pin_memory(), torch.cuda.Event())
-                         for _ in range(self.ring)]
+                         for _ in range(self.ring + 1)]     # +1: a yielded pair survives one more next()
         return self._out
 
     def run(self, samples):
-        """Iterates over host samples; yields (depth, confidence) pinned host tensors, valid until
-        ``ring`` further results have been produced."""
+        """Iterates over host samples; yields (depth, confidence) pinned host tensors.  ``ring + 1`` pinned buffers
+        rotate, so a yielded pair stays valid until the next-but-one result is requested; copy it (or use
+        ``AsyncResultWriter.submit(..., copy=True)``) to keep it longer."""
+        with torch.cuda.device(self.device):
+            yield from self._run(samples)
+
+    def _run(self, samples):
         main = torch.cuda.current_stream(self.device)
         it = iter(samples)
         nxt = next(it, None)
@@ -266,7 +284,7 @@ class StreamedCascade:
                     slot[1] = torch.cuda.Event()
                     slot[1].record(main)
                 bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
-                hd, hc, done = bufs[i % self.ring]
+                hd, hc, done = bufs[i % len(bufs)]
                 hd.copy_(out["refined_depth"], non_blocking=True)
                 hc.copy_(out["photometric_confidence"], non_blocking=True)
                 done.record(main)

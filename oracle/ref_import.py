@@ -6,8 +6,9 @@ The reference is pure Python/PyTorch; its hot-path modules import with torch onl
 those two packages in ``sys.modules`` and import the reference files
 from where they lie.  Nothing is copied into this repository.
 
-``/root/reference`` exists only in the build container, never on the GPU box: callers must use
-``reference_available()`` and skip otherwise.
+``/root/reference`` exists only in the build container, never on the GPU box; there the staged, unmodified
+copy ``oracle/_ref/`` (git-ignored; made by ``oracle/build_ref.py``, travels with the gpurun snapshot) is
+used.  Callers must use ``reference_available()`` and skip otherwise.
 """
 import importlib
 import os
@@ -15,7 +16,20 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("MVS_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("MVS_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(root, "models", "mvsformer_model.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():

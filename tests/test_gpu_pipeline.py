@@ -84,3 +84,51 @@ def test_run_scan_serves_shared_views_from_the_cache():
             assert streamer.cache.hits == 3 * nviews - nviews
         else:
             assert len(loads) > nviews                              # evictions forced re-uploads
+
+
+def test_two_scans_with_the_same_view_ids_on_one_streamer():
+    """View ids are per scan (the reference numbers every scan's views 0..48): a second scan on the same streamer
+    must not be served the first scan's features; ``keep_cache=True`` is the explicit opt-in to continue a scan."""
+    net = _net()
+    cams = {k: v.pin_memory() for k, v in S.make_cameras(1, V, H, W).items()}
+    dv = S.make_depth_range(1).pin_memory()
+    streamer = StreamedCascade(net, DEV, list(S.EVAL_TMP))
+    results = []
+    for scan in range(2):
+        per_view = []
+        for i in range(V):
+            f = S.make_features(1, 1, H, W, seed=900 + 10 * scan + i)
+            per_view.append({k: v[0, 0].contiguous().pin_memory() for k, v in f.items()})
+        dense = {k: torch.stack([per_view[v][k] for v in range(V)]).unsqueeze(0) for k in per_view[0]}
+        want = _direct(net, dense, cams, dv)
+        loads = []
+
+        def load(vid, per_view=per_view, loads=loads):
+            loads.append(vid)
+            return per_view[vid]
+
+        got = [(d.clone(), c.clone()) for d, c in streamer.run_scan(iter([ScanSample(list(range(V)), load, cams, dv)]), capacity=8)]
+        assert sorted(loads) == list(range(V))                      # nothing served from the previous scan
+        assert torch.equal(got[0][0], want[0]) and torch.equal(got[0][1], want[1])
+        results.append(got[0][0])
+    assert not torch.equal(results[0], results[1])
+    # same scan continued: no uploads at all
+    loads.clear()
+    again = [(d.clone(), c.clone()) for d, c in streamer.run_scan(iter([ScanSample(list(range(V)), load, cams, dv)]), capacity=8,
+                                                                    keep_cache=True)]
+    assert loads == [] and torch.equal(again[0][0], results[1])
+
+
+def test_yielded_results_survive_one_more_step():
+    """ring + 1 pinned buffers: a yielded (depth, confidence) pair is still intact after the next result was requested."""
+    net = _net()
+    cams = {k: v.pin_memory() for k, v in S.make_cameras(1, V, H, W).items()}
+    dv = S.make_depth_range(1).pin_memory()
+    samples = [{k: v.pin_memory() for k, v in S.make_features(1, V, H, W, seed=700 + i).items()} for i in range(4)]
+    want = [_direct(net, f, cams, dv) for f in samples]
+    streamer = StreamedCascade(net, DEV, list(S.EVAL_TMP))
+    held = []
+    for i, (d, c) in enumerate(streamer.run((f, cams, dv) for f in samples)):
+        held.append((d, c))
+        if i >= 1:                                                  # the previous pair, one next() later
+            assert torch.equal(held[i - 1][0], want[i - 1][0]) and torch.equal(held[i - 1][1], want[i - 1][1])
