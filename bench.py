@@ -170,6 +170,22 @@ class KernelProfiler:
             base, _ = cv_cost(out, features, relproj, depth_values)
             return base + (numel_bytes(*out) if out is not None else 0), 0
 
+        def cl_ent_cost(out, feat_cl, relproj, depth_values, groups, want_sim):
+            if out is None:
+                return 0, 0
+            return numel_bytes(feat_cl, depth_values, *out), 0
+
+        def cl_agg_cost(out, feat_cl, relproj, depth_values, vis_weight, groups, round_tf32=False):
+            return numel_bytes(feat_cl, depth_values, vis_weight, out), 0
+
+        def to_cl_cost(out, feature_list):
+            return 2 * numel_bytes(*feature_list), 0
+
+        # round-2 channels-last cost-volume kernels (csrc/cost_volume_cl.cu)
+        self._wrap(engine, "features_to_cl", "cv_layout(nchw->channels-last)", to_cl_cost)
+        self._wrap(engine, "cost_volume_cl_entropy", lambda f, r, d, g, want_sim: "cv_cl_passA+store" if f.shape[-1] >= 16 else "cv_cl_passA(stage4)",
+                   cl_ent_cost)
+        self._wrap(engine, "cost_volume_cl_aggregate", "cv_cl_passB(stage4)", cl_agg_cost)
         self._wrap(engine, "cost_volume_entropy", "cv_entropy(passA)", ent_cost)
         self._wrap(engine, "cost_volume_aggregate", "cv_aggregate(passB)", agg_cost)
         # opt-in MVS_CV_STORE path: pass A with stored correlation + streaming aggregation

@@ -86,6 +86,21 @@ int mvs_cost_volume_entropy_store(const float* features, int64_t batch_stride, i
                                   int B, int V, int C, int G, int D, int H, int W, void* stream);
 int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume, int B, int N, int D, int H, int W,
                        int round_tf32, void* stream);
+/* Round-2 production cost-volume build over CHANNELS-LAST features (csrc/cost_volume_cl.cu): same arithmetic and outputs
+ * as the entry points above (models/mvsformer_model.py:61-105, models/warping.py:84-107), features given as
+ * feat_cl [B,V,H,W,C] (dense).  mvs_features_to_cl converts up to four NCHW tensors in ONE launch: segment s is
+ * in[s] = [maps[s]][channels[s]][hw[s]]  ->  out[s] = [maps[s]][hw[s]][channels[s]]  (all five arrays are HOST arrays
+ * of nseg entries; in/out entries are device pointers).
+ * mvs_cost_volume_cl_entropy: pass A; corr != NULL additionally stores the per-view group correlation [B,N,D,H,W,G]
+ * (required where C/G >= 2, i.e. (C,D) = (64,32), (32,16), (16,8); must be NULL for (8,4), which keeps two sampling
+ * passes so that the warped tensor never reaches HBM).  mvs_cost_volume_cl_aggregate: pass B for (C,D) = (8,4).
+ * Both return 1 (nothing launched) for shapes they do not cover; the caller then uses the NCHW entry points. */
+int mvs_features_to_cl(const float* const* in, float* const* out, const int* channels, const int64_t* hw,
+                       const int64_t* maps, int nseg, void* stream);
+int mvs_cost_volume_cl_entropy(const float* feat_cl, const float* relproj, const float* depth, float* entropy,
+                               float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W, void* stream);
+int mvs_cost_volume_cl_aggregate(const float* feat_cl, const float* relproj, const float* depth, const float* vis_weight,
+                                 float* volume, int B, int V, int C, int G, int D, int H, int W, int round_tf32, void* stream);
 /* sim_depth = depth[argmax_d sim_sum] (:151-156).  out [B,H,W]. */
 int mvs_argmax_gather(const float* score, const float* depth, float* out, int B, int D, int H, int W, void* stream);
 

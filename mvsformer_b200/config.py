@@ -16,6 +16,11 @@ stages 1-3): pass A stores it, the aggregation streams over it (bit-identical vo
 HBM traffic instead of a second warp).  Measured on B200 (profiles/r02_ab_variants.json): 7.87 -> 7.30 ms per
 reference view at cfg 2, refined depth bit-identical.
 
+``cv_layout`` (``MVS_CV_LAYOUT`` = ``cl`` (default) | ``nchw``) — which cost-volume kernels sample the features: the
+round-2 channels-last kernels (csrc/cost_volume_cl.cu: one LDS.128 per 4-channel tap, conflict-free lane order, next
+item's TMA tile in flight; features are re-laid out once per call by mvs_features_to_cl) or the round-1 channel-planar
+TMA kernels (csrc/cost_volume_tma.cu), kept for A/B runs.
+
 ``tcz_kzf`` (``MVS_TCZ_KZF``: ``0`` off, ``1`` default, ``2`` = also prefer the kz-fused kernel over the row-tiled one) — "fused N"
 variants of the depth-unstrided tensor-core convolutions (mvs_conv3d_tcz_kzf, mvs_deconv3d_tcz_kzf, mvs_conv3d_tcr_khf):
 one MMA of N = 3 x Cout-tile per slab / input row instead of three, i.e. about a third of the shared-memory
@@ -32,10 +37,13 @@ import os
 _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
           "cv_store": os.environ.get("MVS_CV_STORE", "1") not in ("", "0"),
+          "cv_layout": os.environ.get("MVS_CV_LAYOUT", "cl"),
           "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "1") or 0),
           "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
 if _state["train_conv"] not in ("fp32", "tf32x3", "tf32"):
     raise RuntimeError("MVS_TRAIN_CONV must be fp32, tf32x3 or tf32")
+if _state["cv_layout"] not in ("cl", "nchw"):
+    raise RuntimeError("MVS_CV_LAYOUT must be cl or nchw")
 if _state["conv_precision"] not in _VALID:
     raise RuntimeError("MVS_CONV_PRECISION must be one of %s" % (_VALID,))
 
@@ -56,6 +64,16 @@ def cv_store():
 
 def set_cv_store(flag):
     _state["cv_store"] = bool(flag)
+
+
+def cv_layout():
+    return _state["cv_layout"]
+
+
+def set_cv_layout(mode):
+    if mode not in ("cl", "nchw"):
+        raise ValueError("cv layout must be cl or nchw, got %r" % (mode,))
+    _state["cv_layout"] = mode
 
 
 def tcz_kzf():

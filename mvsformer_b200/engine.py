@@ -119,6 +119,66 @@ def cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim)
     return entropy, sim, corr
 
 
+def features_to_cl(feature_list):
+    """NCHW feature tensors ``[..., C, H, W]`` (up to four, e.g. the four stages of one feature set) -> channels-last
+    ``[..., H, W, C]`` copies, ONE launch (mvs_features_to_cl).  The cost-volume kernels sample channels-last texels."""
+    if not 1 <= len(feature_list) <= 4:
+        raise RuntimeError("features_to_cl converts 1..4 tensors per call")
+    ins, outs = [], []
+    for t in feature_list:
+        t = _f32(t).contiguous()
+        require_cuda(t)
+        ins.append(t)
+        outs.append(torch.empty(t.shape[:-3] + (t.shape[-2], t.shape[-1], t.shape[-3]), device=t.device, dtype=torch.float32))
+    n = len(ins)
+    arr_p = ctypes.c_void_p * n
+    in_p = arr_p(*[t.data_ptr() for t in ins])
+    out_p = arr_p(*[t.data_ptr() for t in outs])
+    chans = (ctypes.c_int * n)(*[t.shape[-3] for t in ins])
+    hw = (ctypes.c_int64 * n)(*[t.shape[-2] * t.shape[-1] for t in ins])
+    maps = (ctypes.c_int64 * n)(*[t.numel() // (t.shape[-3] * t.shape[-2] * t.shape[-1]) for t in ins])
+    check(_lib.load().mvs_features_to_cl(ctypes.cast(in_p, ctypes.c_void_p), ctypes.cast(out_p, ctypes.c_void_p),
+                                         ctypes.cast(chans, ctypes.c_void_p), ctypes.cast(hw, ctypes.c_void_p),
+                                         ctypes.cast(maps, ctypes.c_void_p), n, stream()), "mvs_features_to_cl")
+    return outs
+
+
+def cl_supported(chans, ndepth, groups):
+    """Shapes the channels-last cost-volume kernels are built for (the reference's four stages)."""
+    return groups == 8 and (chans, ndepth) in ((64, 32), (32, 16), (16, 8), (8, 4))
+
+
+def cost_volume_cl_entropy(feat_cl, relproj, depth_values, groups, want_sim):
+    """Pass A over channels-last features [B,V,H,W,C].  Returns (entropy [B,N,H,W], sim or None, corr [B,N,D,H,W,G] or
+    None): the per-view correlation is stored where C/G >= 2 (one sampling pass); None when the shape is not covered."""
+    require_cuda(feat_cl, relproj, depth_values)
+    b, v, h, w, c = feat_cl.shape
+    d = depth_values.shape[1]
+    if not cl_supported(c, d, groups):
+        return None
+    entropy = torch.empty(b, v - 1, h, w, device=feat_cl.device, dtype=torch.float32)
+    sim = torch.empty(b, d, h, w, device=feat_cl.device, dtype=torch.float32) if want_sim else None
+    corr = torch.empty(b, v - 1, d, h, w, groups, device=feat_cl.device, dtype=torch.float32) if c // groups >= 2 else None
+    rc = _lib.load().mvs_cost_volume_cl_entropy(ptr(feat_cl), ptr(relproj), ptr(depth_values), ptr(entropy), ptr(sim), ptr(corr),
+                                                b, v, c, groups, d, h, w, stream())
+    if rc == 1:
+        return None
+    check(rc, "mvs_cost_volume_cl_entropy")
+    return entropy, sim, corr
+
+
+def cost_volume_cl_aggregate(feat_cl, relproj, depth_values, vis_weight, groups, round_tf32=False):
+    """Pass B over channels-last features (the stage whose correlation is as large as the warped tensor: C/G = 1)."""
+    require_cuda(feat_cl, relproj, depth_values, vis_weight)
+    b, v, h, w, c = feat_cl.shape
+    d = depth_values.shape[1]
+    volume = torch.empty(b, d, h, w, groups, device=feat_cl.device, dtype=torch.float32)
+    check(_lib.load().mvs_cost_volume_cl_aggregate(ptr(feat_cl), ptr(relproj), ptr(depth_values), ptr(vis_weight), ptr(volume),
+                                                   b, v, c, groups, d, h, w, 1 if round_tf32 else 0, stream()),
+          "mvs_cost_volume_cl_aggregate")
+    return volume
+
+
 def corr_aggregate(corr, vis_weight, round_tf32=False):
     """corr [B,N,D,H,W,8], vis_weight [B,N,H,W] -> volume channels-last [B,D,H,W,8]."""
     require_cuda(corr, vis_weight)

@@ -108,9 +108,10 @@ class StageNet(nn.Module):
             return engine.vis_last_cl(x.view(b * n, h, w, 8), last).view(b, n, h, w)
         return engine.vis_weight(maps, self._vis_params_host()).view(b, n, h, w)
 
-    def build_cost_volume(self, features, proj_matrices, depth_values):
+    def build_cost_volume(self, features, proj_matrices, depth_values, features_cl=None):
         """models/mvsformer_model.py:52-105 -> (volume channels-last [B,D,H,W,G], sim_sum or None,
-        entropy [B,N,H,W], vis_weight [B,N,H,W])."""
+        entropy [B,N,H,W], vis_weight [B,N,H,W]).  ``features_cl`` [B,V,H,W,C]: the same features already re-laid
+        out channels-last (CascadeMVS converts all stages in one launch); made here when absent."""
         if features.dim() != 5:
             raise RuntimeError("features must be [B,V,C,H,W]")
         b, v = features.shape[:2]
@@ -121,6 +122,17 @@ class StageNet(nn.Module):
                                % (b, groups, features.shape[2]))
         relproj = engine.relative_projections(proj_matrices)
         round_tf32 = config.conv_precision() == "tf32"
+        if config.cv_layout() == "cl" and engine.cl_supported(features.shape[2], depth_values.shape[1], groups):
+            if features_cl is None:
+                features_cl = engine.features_to_cl([features])[0]
+            built = engine.cost_volume_cl_entropy(features_cl, relproj, depth_values, groups, want_sim=not self.training)
+            if built is not None:
+                entropy, sim, corr = built
+                weight = self._vis_weight(entropy)
+                if corr is not None:                       # one sampling pass: the stored correlation is streamed back
+                    return engine.corr_aggregate(corr, weight, round_tf32), sim, entropy, weight
+                volume = engine.cost_volume_cl_aggregate(features_cl, relproj, depth_values, weight, groups, round_tf32)
+                return volume, sim, entropy, weight
         if config.cv_store() and features.shape[2] // groups >= 2:
             # opt-in: one sampling pass, the per-view correlation is stored and streamed back (config.py)
             stored = engine.cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim=not self.training)
@@ -211,8 +223,9 @@ class StageNet(nn.Module):
         conf = engine.conf_regression(prob_volume.detach(), window) if window else max_prob
         return prob_volume, depth, conf
 
-    def forward(self, features, proj_matrices, depth_values, tmp=2.0):
-        """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W]."""
+    def forward(self, features, proj_matrices, depth_values, tmp=2.0, features_cl=None):
+        """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W] (the reference's signature);
+        ``features_cl``: optional channels-last copy of ``features`` (see build_cost_volume)."""
         depth_values = depth_values.float().contiguous()
         if self.fusion_type != "cnn":
             if type(tmp) == list or type(tmp) == tuple:
@@ -222,7 +235,7 @@ class StageNet(nn.Module):
             if type(tmp) == list or type(tmp) == tuple:
                 tmp = tmp[self.stage_idx]
             return self._forward_train(features, proj_matrices, depth_values, tmp)
-        volume, sim, _, _ = self.build_cost_volume(features, proj_matrices, depth_values)
+        volume, sim, _, _ = self.build_cost_volume(features, proj_matrices, depth_values, features_cl)
         prob_volume_pre = self.cost_reg.forward_cl(volume)
         if type(tmp) == list or type(tmp) == tuple:
             tmp = tmp[self.stage_idx]
@@ -246,6 +259,20 @@ class CascadeMVS(nn.Module):
         self.inverse_depth = args.get("inverse_depth", False)
         self.fusions = nn.ModuleList([StageNet(args, self.ndepths[i], i) for i in range(len(self.ndepths))])
 
+    def _features_cl(self, features):
+        """Channels-last copies of all stages' features in ONE launch (eval, 'cnn' fusion, shapes the channels-last
+        kernels cover); None otherwise — every StageNet then decides for itself."""
+        nst = len(self.ndepths)
+        if self.training or nst > 4 or config.cv_layout() != "cl":
+            return None
+        feats = [features["stage%d" % (s + 1)] for s in range(nst)]
+        groups = self.args["base_ch"]
+        for s, f in enumerate(feats):
+            if self.fusions[s].fusion_type != "cnn" or f.dim() != 5 or not f.is_cuda \
+                    or not engine.cl_supported(f.shape[2], self.ndepths[s], groups):
+                return None
+        return engine.features_to_cl(feats)
+
     def forward(self, features, proj_matrices, depth_values, tmp=2.0, full_hw=None):
         """features {"stageK": [B,V,C,h,w]}, proj_matrices {"stageK": [B,V,2,4,4]}, depth_values [B,ND]."""
         nst = len(self.ndepths)
@@ -258,6 +285,7 @@ class CascadeMVS(nn.Module):
         use_conf = self.args["depth_type"] in ("ce", "mixup_ce")
         prob_maps = torch.zeros(b, full_hw[0], full_hw[1], dtype=torch.float32, device=last_feat.device) if use_conf else None
         depth_interval = depth_values[:, 1] - depth_values[:, 0]
+        feats_cl = self._features_cl(features)
         for s in range(nst):
             feats = features["stage%d" % (s + 1)]
             h, w = feats.shape[-2:]
@@ -270,7 +298,11 @@ class CascadeMVS(nn.Module):
             else:
                 depth_samples = schedule_range(outputs_stage["depth"].detach(), self.ndepths[s],
                                                self.depth_interals_ratio[s] * depth_interval, h, w)
-            outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp)
+            if feats_cl is not None:
+                outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
+                                                features_cl=feats_cl[s])
+            else:
+                outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp)
             outputs["stage%d" % (s + 1)] = outputs_stage
             if use_conf:
                 conf = outputs_stage["photometric_confidence"]

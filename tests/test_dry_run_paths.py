@@ -57,12 +57,14 @@ def _cascade_inputs(height=128, width=256, views=3):
 
 
 @pytest.mark.parametrize("mode", ["tf32", "tf32x3", "fp32"])
-@pytest.mark.parametrize("cv_store,kzf", [(False, 0), (True, 0), (False, 1), (True, 2)])
-def test_inference_host_path(dry, mode, cv_store, kzf):
+@pytest.mark.parametrize("layout,cv_store,kzf", [("nchw", False, 0), ("nchw", True, 0), ("nchw", False, 1), ("nchw", True, 2),
+                                                 ("cl", True, 1)])
+def test_inference_host_path(dry, mode, layout, cv_store, kzf):
     feats, cams, dv = _cascade_inputs()
     net = CascadeMVS(dict(CASCADE_ARGS)).eval()
     old = config.conv_precision()
     config.set_conv_precision(mode)
+    config.set_cv_layout(layout)
     config.set_cv_store(cv_store)
     config.set_tcz_kzf(kzf)
     try:
@@ -70,11 +72,17 @@ def test_inference_host_path(dry, mode, cv_store, kzf):
             out = net(feats, cams, dv, tmp=list(S.EVAL_TMP))
     finally:
         config.set_conv_precision(old)
+        config.set_cv_layout("cl")
         config.set_cv_store(_CV_STORE_DEFAULT)
         config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     assert out["refined_depth"].shape == (1, 128, 256) and out["photometric_confidence"].shape == (1, 128, 256)
     assert set(out["stage1"]) >= {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre", "sim_depth"}
     called = set(dry.calls)
+    if layout == "cl":                   # round-2 default: channels-last kernels, one sampling pass at stages 1-3
+        assert {"mvs_features_to_cl", "mvs_cost_volume_cl_entropy", "mvs_cost_volume_cl_aggregate", "mvs_corr_aggregate"} <= called
+        assert dry.calls.count("mvs_cost_volume_cl_entropy") == 4 and dry.calls.count("mvs_cost_volume_cl_aggregate") == 1
+        assert not called & {"mvs_cost_volume_entropy", "mvs_cost_volume_entropy_store", "mvs_cost_volume_aggregate"}
+        return
     assert "mvs_cost_volume_entropy" in called or "mvs_cost_volume_entropy_store" in called
     if cv_store:
         assert "mvs_cost_volume_entropy_store" in called and "mvs_corr_aggregate" in called
@@ -192,7 +200,8 @@ def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
         config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     summ = prof.summary(1)
     assert all(v["alg_bytes_per_step"] > 0 for v in summ.values())
-    if cv_store:
-        assert "cv_entropy_store(passA)" in summ and "cv_corr_aggregate(stream)" in summ
+    # round-2 default layout: the channels-last kernels (one sampling pass at stages 1-3 + streaming aggregation)
+    assert {"cv_layout(nchw->channels-last)", "cv_cl_passA+store", "cv_cl_passA(stage4)", "cv_cl_passB(stage4)",
+            "cv_corr_aggregate(stream)"} <= set(summ)
     if kzf:
         assert any("kzf" in k or "khf" in k for k in summ) or "vis_net(tensor-core layers)" in summ

@@ -357,3 +357,46 @@ def test_epipole_fusion_gpu_vs_reference_golden(kind):
     assert rel_l1(res["prob_volume_pre"].cpu(), g[kind + "_eval_prob_volume_pre"]) < 2e-4
     assert rel_l1(res["depth"].cpu(), g[kind + "_eval_depth"]) < 1e-4
     assert (res["sim_depth"].cpu() == torch.from_numpy(g[kind + "_eval_sim_depth"])).float().mean() > 0.99
+
+
+# ---- round-2 channels-last cost-volume kernels (csrc/cost_volume_cl.cu) ------------------------------------------------
+def test_features_to_cl_is_an_exact_permutation():
+    from mvsformer_b200 import engine
+    ts = [torch.randn(2, 3, c, h, w, device=DEV) for c, h, w in ((64, 16, 24), (32, 32, 48), (16, 37, 50), (8, 5, 7))]
+    outs = engine.features_to_cl(ts)
+    for t, o in zip(ts, outs):
+        assert o.shape == (2, 3) + (t.shape[3], t.shape[4], t.shape[2])
+        assert torch.equal(o, t.permute(0, 1, 3, 4, 2).contiguous())
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+@pytest.mark.parametrize("wild", [False, True])
+@pytest.mark.parametrize("shape", [(128, 192, 2, 4), (64, 104, 1, 3)])
+def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
+    """Same arithmetic, different summation order over the channels of a sample: volume / entropy / similarity of the
+    channels-last kernels vs the round-1 kernels (each separately pinned to the oracle in test_gpu_parity.py), incl.
+    samples outside the staged box / the image (predicated global path) and partial tiles (width 104/8 = 13 px)."""
+    from tests.helpers import rel_l1
+    height, width, batch, views = shape
+    feats = S.make_features(batch, views, height, width, stages=(s,), smooth=not wild)["stage%d" % (s + 1)]
+    cams = S.make_cameras(batch, views, height, width)["stage%d" % (s + 1)].clone()
+    hyp = S.narrow_hypotheses(s, height, width, batch)
+    if wild:
+        cams[:, 1, 0, :3, 3] += torch.tensor([400.0, -250.0, 0.0])
+        hyp = hyp * (1.0 + 0.3 * torch.rand(hyp.shape, generator=S._gen(5)))
+    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=3))
+    net = net.to(DEV)
+    res = {}
+    for layout in ("nchw", "cl"):
+        config.set_cv_layout(layout)
+        try:
+            res[layout] = net.build_cost_volume(feats.to(DEV), cams.to(DEV), hyp.to(DEV))
+        finally:
+            config.set_cv_layout("cl")
+    (v0, s0, e0, w0), (v1, s1, e1, w1) = res["nchw"], res["cl"]
+    assert rel_l1(e1, e0) < 2e-6, rel_l1(e1, e0)
+    assert rel_l1(w1, w0) < 2e-6
+    assert rel_l1(v1, v0) < 5e-6, rel_l1(v1, v0)
+    assert rel_l1(s1, s0) < 5e-6, rel_l1(s1, s0)
+    assert torch.isfinite(v1).all()
