@@ -214,6 +214,11 @@ class KernelProfiler:
 
         self._wrap(engine, "conv3d_tcr", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcr",
                    conv_tcr_cost)
+        def conv_tma_cost(out, x, w_tma, n_tile, cout, kd, shift, skip, relu=True, mode=0):
+            vox = (x.numel() // x.shape[-1]) if mode == 2 else (out.numel() // out.shape[-1])
+            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * vox
+
+        self._wrap(engine, "conv3d_tma", "conv3d_tma", conv_tma_cost)                    # round-2 persistent TMA kernels
         self._wrap(engine, "deconv3d_tcz", "deconv3d_tcz", deconv_tcz_cost)
         self._wrap(engine, "conv3d_tcz_kzf", "conv3d_tcz_kzf", conv_tcz_cost)          # opt-in MVS_TCZ_KZF
         self._wrap(engine, "deconv3d_tcz_kzf", "deconv3d_tcz_kzf", deconv_tcz_cost)

@@ -326,6 +326,18 @@ int mvs_fusion_points(const float* depth, const float* mats, float* points, int 
 int mvs_fusion_prob_filter(const float* prob, const float* thresh_host, int nthresh, float* mask, int N, int C, int H, int W,
                            void* stream);
 
+/* ---- round-2 persistent TMA-fed tcgen05 convolutions (csrc/conv3d_tma.cu) ---------------------------------------------
+ * Depth-unstrided layers of CostRegNet3D (models/module.py:550-594) and the 3x3 tensor-core layers of the visibility net
+ * (models/mvsformer_model.py:37).  x [B,D,H,W,Cin] channels-last with TF32-rounded values, y [B,D,H,W,Cout]
+ * (TF32-rounded), shift [Cout] or NULL (folded BN / bias), skip like y or NULL, relu applied before the skip add.
+ * w is packed by the host (mvsformer_b200.engine.pack_tma_weights): [Cout tiles][kh][kw][Cin/4][kd][n_tile][4].
+ * Kernel (kd,3,3), kd in {1,3}, depth stride 1, padding (kd/2,1,1).  mode 0: stride 1, y [B,D,H,W,Cout]; mode 1: stride
+ * (1,2,2), y [B,D,ceil(H/2),ceil(W/2),Cout]; mode 2: transposed convolution, stride (1,2,2), output_padding (0,1,1),
+ * y [B,D,2H,2W,Cout] (w from torch's ConvTranspose3d weight permuted to [kd,kh,kw,Cin,Cout] before packing).
+ * Accumulators live in tensor memory: (mode 2 ? 4 : 1) * D * n_tile <= 512 columns (double-buffered when twice that fits). */
+int mvs_conv3d_tma(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D, int H,
+                   int W, int Cin, int Cout, int n_tile, int kd, int mode, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "mvs_deconv3d_cl": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_conv3d_tc": (c_i, [c_f] * 6 + [c_i] * 11 + [c_f]),
     "mvs_deconv3d_tc": (c_i, [c_f] * 6 + [c_i] * 10 + [c_f]),
+    "mvs_conv3d_tma": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
     "mvs_conv3d_tcz": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
     "mvs_conv3d_tcz_kzf": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
     "mvs_deconv3d_tcz_kzf": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),

@@ -21,6 +21,9 @@ round-2 channels-last kernels (csrc/cost_volume_cl.cu: one LDS.128 per 4-channel
 item's TMA tile in flight; features are re-laid out once per call by mvs_features_to_cl) or the round-1 channel-planar
 TMA kernels (csrc/cost_volume_tma.cu), kept for A/B runs.
 
+``conv_tma`` (``MVS_CONV_TMA``, default 1; ``0`` = round-1 kernels only) — depth-unstrided 3x3x3 layers (CostRegNet3D) through the
+persistent, warp-specialised, TMA-fed tcgen05 kernels of csrc/conv3d_tma.cu (TF32 mode only).
+
 ``tcz_kzf`` (``MVS_TCZ_KZF``: ``0`` off, ``1`` default, ``2`` = also prefer the kz-fused kernel over the row-tiled one) — "fused N"
 variants of the depth-unstrided tensor-core convolutions (mvs_conv3d_tcz_kzf, mvs_deconv3d_tcz_kzf, mvs_conv3d_tcr_khf):
 one MMA of N = 3 x Cout-tile per slab / input row instead of three, i.e. about a third of the shared-memory
@@ -38,6 +41,7 @@ _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
           "cv_store": os.environ.get("MVS_CV_STORE", "1") not in ("", "0"),
           "cv_layout": os.environ.get("MVS_CV_LAYOUT", "cl"),
+          "conv_tma": os.environ.get("MVS_CONV_TMA", "1") not in ("", "0"),
           "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "1") or 0),
           "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
 if _state["train_conv"] not in ("fp32", "tf32x3", "tf32"):
@@ -74,6 +78,14 @@ def set_cv_layout(mode):
     if mode not in ("cl", "nchw"):
         raise ValueError("cv layout must be cl or nchw, got %r" % (mode,))
     _state["cv_layout"] = mode
+
+
+def conv_tma():
+    return _state["conv_tma"]
+
+
+def set_conv_tma(flag):
+    _state["conv_tma"] = bool(flag)
 
 
 def tcz_kzf():

@@ -515,6 +515,57 @@ def pack_tcz_weights(w_packed, stride2):
     return round_tf32(w), nt
 
 
+# ------------------------------------------------------------------------------------------------
+# round-2 persistent TMA-fed tcgen05 convolutions (conv3d_tma.cu)
+# ------------------------------------------------------------------------------------------------
+TMA_S1, TMA_S2, TMA_DECONV = 0, 1, 2
+_TMA_BUILT = {(0, 16, 16), (0, 32, 32), (0, 64, 16), (1, 8, 16), (1, 16, 32), (1, 32, 16), (2, 64, 16), (2, 32, 16), (2, 16, 16)}
+
+
+def tma_n_tile(cin, cout, mode=TMA_S1):
+    """N tile such that the layer's whole weight tile (27 x Cin x n_tile floats) and the input stages fit shared memory."""
+    if mode == TMA_DECONV or cout <= 16 or cin >= 64 or (mode == TMA_S2 and cin >= 32):
+        return 16
+    return 32
+
+
+def tma_supported(cin, cout, d, kd, stride2=False, transposed=False):
+    """Shapes mvs_conv3d_tma is built for (depth-unstrided layers)."""
+    if kd not in (1, 3) or cout % 4:
+        return False
+    mode = TMA_DECONV if transposed else (TMA_S2 if stride2 else TMA_S1)
+    nt = tma_n_tile(cin, cout, mode)
+    return (mode, cin, nt) in _TMA_BUILT and (4 if transposed else 1) * d * nt <= 512
+
+
+def pack_tma_weights(w_packed, mode=TMA_S1):
+    """[kd,3,3,Cin,Cout] -> [Cout_tiles][kh][kw][Cin/4][kd][n_tile][4], TF32-rounded: per (tap, channel quad) the B rows are
+    [kz][n], so the depth taps of a slab are one operand of N = kd * n_tile rows (mvs_conv3d_tma).  For the transposed mode
+    pass torch's ConvTranspose3d weight permuted to [kd,kh,kw,Cin,Cout]."""
+    kd, _, _, cin, cout = w_packed.shape
+    nt = tma_n_tile(cin, cout, mode)
+    ntiles = (cout + nt - 1) // nt
+    w = w_packed
+    if ntiles * nt != cout:
+        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
+    #            [kz, kh, kw, q, e, tile, n]  ->  [tile, kh, kw, q, kz, n, e]
+    w = w.reshape(kd, 3, 3, cin // 4, 4, ntiles, nt).permute(5, 1, 2, 3, 0, 6, 4).contiguous()
+    return round_tf32(w), nt
+
+
+def conv3d_tma(x, w_tma, n_tile, cout, kd, shift, skip, relu=True, mode=TMA_S1):
+    require_cuda(x, w_tma, shift, skip)
+    b, d, h, w, cin = x.shape
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if mode == TMA_S2 else ((2 * h, 2 * w) if mode == TMA_DECONV else (h, w))
+    y = torch.empty(b, d, ho, wo, cout, device=x.device, dtype=torch.float32)
+    if skip is not None and tuple(skip.shape) != tuple(y.shape):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), tuple(y.shape)))
+    check(_lib.load().mvs_conv3d_tma(ptr(x), ptr(w_tma), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd, mode,
+                                     1 if relu else 0, stream()), "mvs_conv3d_tma")
+    return y
+
+
 def pack_tcz_kzf_weights(w_packed, stride2):
     """[kd,3,3,Cin,Cout] -> [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4], TF32-rounded: the B rows of one
     (kw, K chunk) are [kz][n], so the depth taps of a slab are one operand of N = kd * n_tile rows

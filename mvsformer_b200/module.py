@@ -77,6 +77,12 @@ def _tc_eligible(cin, cout, transposed):
 
 def _run_conv(cache, x, w, shift, skip, stride, relu):
     kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    if (config.conv_precision() == "tf32" and config.conv_tma() and kd == 3 and stride[0] == 1 and stride[1] == stride[2]
+            and engine.tma_supported(cin, cout, x.shape[1], kd, stride[1] == 2)):
+        # round-2 persistent TMA-fed tcgen05 kernels (csrc/conv3d_tma.cu)
+        mode = engine.TMA_S2 if stride[1] == 2 else engine.TMA_S1
+        wt, nt = cache.get_derived("tma_m%d" % mode, lambda v: engine.pack_tma_weights(v[0], mode))
+        return engine.conv3d_tma(x, wt, nt, cout, kd, shift, skip, relu, mode)
     kzf = config.tcz_kzf() if (config.conv_precision() == "tf32" and kd == 3 and stride[0] == 1 and stride[1] == stride[2]
                                and engine.tcz_supported(cin, cout, x.shape[1], kd, stride[1] == 2)) else 0
     if kzf == 2 or (kzf == 1 and not (stride == (1, 1, 1) and engine.tcr_supported(cin, cout, x.shape[3]))):
@@ -102,6 +108,10 @@ def _run_conv(cache, x, w, shift, skip, stride, relu):
 
 def _run_deconv(cache, x, w, shift, skip, sd, relu):
     kd, cin, cout = w.shape[0], w.shape[3], w.shape[4]
+    if (config.conv_precision() == "tf32" and config.conv_tma() and kd == 3 and sd == 1
+            and engine.tma_supported(cin, cout, x.shape[1], kd, transposed=True)):
+        wt, nt = cache.get_derived("tma_m2", lambda v: engine.pack_tma_weights(v[0], engine.TMA_DECONV))
+        return engine.conv3d_tma(x, wt, nt, cout, kd, shift, skip, relu, engine.TMA_DECONV)
     if config.conv_precision() == "tf32" and sd == 1 and engine.tcz_supported(cin, cout, x.shape[1], kd, transposed=True):
         if config.tcz_kzf() and kd == 3:                 # opt-in kz-fused kernel (config.py)
             wk, nt = cache.get_derived("tczd_kzf", lambda v: engine.pack_tcz_kzf_deconv_weights(v[0]))

@@ -280,3 +280,76 @@ def test_tc_probe_a_from_tmem(n, shift):
     if err > 1e-5:
         print("TS probe mismatch", err, got[:3, :4], want[:3, :4].float())
     assert err < 1e-5
+
+
+# ---- round-2 persistent TMA-fed convolutions (csrc/conv3d_tma.cu) --------------------------------------------------------
+TMA_CASES = [
+    # cin, cout, kd, D, H, W, batch
+    (16, 16, 3, 4, 16, 8, 1), (16, 16, 3, 4, 10, 14, 2), (16, 16, 1, 1, 33, 47, 3), (16, 8, 1, 1, 20, 20, 2),
+    (32, 32, 3, 8, 6, 10, 1), (64, 64, 3, 4, 5, 7, 2), (64, 64, 3, 8, 18, 24, 1), (16, 16, 3, 2, 3, 300, 1),
+    (16, 16, 3, 5, 70, 90, 1), (32, 32, 3, 4, 144, 192, 1), (16, 16, 3, 8, 100, 60, 2),
+]
+
+
+@pytest.mark.parametrize("cin,cout,kd,D,H,W,batch", TMA_CASES)
+def test_conv3d_tma(cin, cout, kd, D, H, W, batch):
+    """Persistent warp-specialised kernel vs fp64 F.conv3d: many work items per CTA (ring + TMEM double buffering wrap
+    around), partial tiles, Cout tiles, kd = 1 (visibility-net layers)."""
+    assert engine.tma_supported(cin, cout, D, kd)
+    g = S._gen(cin * 100 + cout + kd + W + D)
+    w = engine.round_tf32(torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = engine.round_tf32(torch.randn(batch, cin, D, H, W, generator=g))
+    want = torch.relu(F.conv3d(x.double(), w.double(), padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    wt, nt = engine.pack_tma_weights(w.permute(2, 3, 4, 1, 0).contiguous().to(DEV))
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.conv3d_tma(x_cl, wt, nt, cout, kd, shift.to(DEV), skip_cl, relu=True).permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got, engine.round_tf32(got))
+    assert rel_l1(got, want + skip.double()) < 5e-4
+    got2 = engine.conv3d_tma(x_cl, wt, nt, cout, kd, None, None, relu=False).permute(0, 4, 1, 2, 3).cpu()
+    want2 = F.conv3d(x.double(), w.double(), padding=(kd // 2, 1, 1))
+    assert rel_l1(got2, want2) < 5e-4
+
+
+TMA_S2_CASES = [(8, 16, 3, 4, 16, 24, 1), (8, 16, 3, 4, 35, 50, 2), (16, 32, 3, 4, 9, 13, 2), (16, 32, 3, 8, 64, 96, 1), (32, 64, 3, 3, 6, 10, 1),
+                (32, 64, 3, 4, 72, 96, 1), (8, 16, 3, 8, 144, 192, 1)]
+
+
+@pytest.mark.parametrize("cin,cout,kd,D,H,W,batch", TMA_S2_CASES)
+def test_conv3d_tma_stride2(cin, cout, kd, D, H, W, batch):
+    assert engine.tma_supported(cin, cout, D, kd, stride2=True)
+    g = S._gen(cin * 100 + cout + kd + W + D)
+    w = engine.round_tf32(torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = engine.round_tf32(torch.randn(batch, cin, D, H, W, generator=g))
+    want = torch.relu(F.conv3d(x.double(), w.double(), stride=(1, 2, 2), padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    wt, nt = engine.pack_tma_weights(w.permute(2, 3, 4, 1, 0).contiguous().to(DEV), engine.TMA_S2)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.conv3d_tma(x_cl, wt, nt, cout, kd, shift.to(DEV), None, True, engine.TMA_S2).permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want) < 5e-4
+
+
+TMA_DECONV_CASES = [(64, 32, 3, 4, 3, 5, 2), (64, 32, 3, 8, 18, 24, 1), (32, 16, 3, 4, 6, 10, 2), (32, 16, 3, 8, 36, 48, 1), (16, 8, 3, 4, 8, 12, 2),
+                    (16, 8, 3, 8, 33, 50, 1), (16, 8, 3, 1, 9, 9, 1), (16, 8, 3, 4, 144, 192, 1)]
+
+
+@pytest.mark.parametrize("cin,cout,kd,D,H,W,batch", TMA_DECONV_CASES)
+def test_conv3d_tma_transposed(cin, cout, kd, D, H, W, batch):
+    assert engine.tma_supported(cin, cout, D, kd, transposed=True)
+    g = S._gen(cin * 7 + cout + kd + W + D)
+    w = engine.round_tf32(torch.randn(cin, cout, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9 / 4)) ** 0.5)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    x = engine.round_tf32(torch.randn(batch, cin, D, H, W, generator=g))
+    want = torch.relu(F.conv_transpose3d(x.double(), w.double(), stride=(1, 2, 2), padding=(kd // 2, 1, 1),
+                                         output_padding=(0, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
+    skip = torch.randn(want.shape, generator=g)
+    wt, nt = engine.pack_tma_weights(w.permute(2, 3, 4, 0, 1).contiguous().to(DEV), engine.TMA_DECONV)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    got = engine.conv3d_tma(x_cl, wt, nt, cout, kd, shift.to(DEV), skip_cl, True, engine.TMA_DECONV).permute(0, 4, 1, 2, 3).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want + skip.double()) < 5e-4
