@@ -94,13 +94,18 @@ int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume
  * mvs_cost_volume_cl_entropy: pass A; corr != NULL additionally stores the per-view group correlation [B,N,D,H,W,G]
  * (required where C/G >= 2, i.e. (C,D) = (64,32), (32,16), (16,8); must be NULL for (8,4), which keeps two sampling
  * passes so that the warped tensor never reaches HBM).  mvs_cost_volume_cl_aggregate: pass B for (C,D) = (8,4).
+ * feat_cl holds nmaps maps [nmaps][H][W][C].  view_slots == NULL: the dense [B,V,H,W,C] tensor (nmaps = B*V).  view_slots !=
+ * NULL (HOST array of V ints, B = 1): the reference view is map view_slots[0] and source view v is map view_slots[v] of a
+ * per-scan feature pool — a reference view's views are addressed in place, nothing is gathered (StreamedCascade.run_scan).
  * Both return 1 (nothing launched) for shapes they do not cover; the caller then uses the NCHW entry points. */
 int mvs_features_to_cl(const float* const* in, float* const* out, const int* channels, const int64_t* hw,
                        const int64_t* maps, int nseg, void* stream);
-int mvs_cost_volume_cl_entropy(const float* feat_cl, const float* relproj, const float* depth, float* entropy,
-                               float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W, void* stream);
-int mvs_cost_volume_cl_aggregate(const float* feat_cl, const float* relproj, const float* depth, const float* vis_weight,
-                                 float* volume, int B, int V, int C, int G, int D, int H, int W, int round_tf32, void* stream);
+int mvs_cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj, const float* depth,
+                               float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W,
+                               void* stream);
+int mvs_cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj,
+                                 const float* depth, const float* vis_weight, float* volume, int B, int V, int C, int G, int D,
+                                 int H, int W, int round_tf32, void* stream);
 /* sim_depth = depth[argmax_d sim_sum] (:151-156).  out [B,H,W]. */
 int mvs_argmax_gather(const float* score, const float* depth, float* out, int B, int D, int H, int W, void* stream);
 

@@ -34,8 +34,8 @@ _SIGNATURES = {
     "mvs_cost_volume_aggregate_tf32": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "mvs_cost_volume_entropy_store": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "mvs_features_to_cl": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_f]),
-    "mvs_cost_volume_cl_entropy": (c_i, [c_f] * 6 + [c_i] * 7 + [c_f]),
-    "mvs_cost_volume_cl_aggregate": (c_i, [c_f] * 5 + [c_i] * 8 + [c_f]),
+    "mvs_cost_volume_cl_entropy": (c_i, [c_f, c_i, c_f] + [c_f] * 5 + [c_i] * 7 + [c_f]),
+    "mvs_cost_volume_cl_aggregate": (c_i, [c_f, c_i, c_f] + [c_f] * 4 + [c_i] * 8 + [c_f]),
     "mvs_corr_aggregate": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
     "mvs_argmax_gather": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "mvs_vis_weight": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),

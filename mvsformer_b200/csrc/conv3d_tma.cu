@@ -270,43 +270,59 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
         for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
             const int buf = d.nbuf == 2 ? (it & 1) : 0, use = d.nbuf == 2 ? (it >> 1) : it;
             const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y, b = item / (d.tiles_x * d.tiles_y);
+            // output element this lane writes in store instruction j of accumulator block cz (class, slice)
+            auto locate = [&](int cz, int j, size_t* o) -> bool {
+                const int cls = cz / d.D, blk = cz - cls * d.D;
+                const int z = MODE == MODE_DECONV ? blk : d.D - 1 - blk;
+                const int row = j * rpi + rsub;                       // accumulator row within the quarter
+                const int ty_v = ty * 16 + q * 4 + (row >> 3), tx_v = tx * 8 + (row & 7);
+                int oy = ty_v, ox = tx_v;
+                bool live = ty_v < d.Ho && tx_v < d.Wo;
+                if (MODE == MODE_DECONV) {                            // tile voxel = input voxel; class = output parity
+                    live = ty_v < d.H && tx_v < d.W;
+                    oy = 2 * ty_v + (cls >> 1); ox = 2 * tx_v + (cls & 1);
+                }
+                *o = ((((size_t)b * d.D + z) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0 + chunk * 4;
+                return live && cvalid && j < cpr;
+            };
+            // The skip tensor does not depend on the MMAs: its loads run one accumulator block ahead (the first block's before
+            // the wait on the accumulators), so their latency never sits between a TMEM drain and its stores.
+            float4 skn[CPR];
+            auto prefetch_skip = [&](int cz) {
+#pragma unroll
+                for (int j = 0; j < CPR; ++j) {
+                    size_t o;
+                    skn[j] = (skip && locate(cz, j, &o)) ? __ldg(reinterpret_cast<const float4*>(skip + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            prefetch_skip(0);
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after_sync();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ncols;
+            const int nblk = NCLS * d.D;
 #pragma unroll 1
-            for (int cz = 0; cz < NCLS * d.D; ++cz) {
-                const int cls = cz / d.D, blk = cz - cls * d.D;
-                const int z = MODE == MODE_DECONV ? blk : d.D - 1 - blk;
+            for (int cz = 0; cz < nblk; ++cz) {
+                float4 skc[CPR];
+#pragma unroll
+                for (int j = 0; j < CPR; ++j) skc[j] = skn[j];
+                if (cz + 1 < nblk) prefetch_skip(cz + 1);
                 float acc[NT];
 #pragma unroll
                 for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tacc + (uint32_t)cz * NT + c0, acc + c0);
-                __syncwarp();                                         // previous slice's reads of the buffer are done
+                __syncwarp();                                         // previous block's reads of the buffer are done
 #pragma unroll
                 for (int c4 = 0; c4 < CPR; ++c4)
                     *reinterpret_cast<float4*>(stg + lane * L::STG_PITCH + c4 * 4) = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
                 __syncwarp();
                 if (d.debug & 2) continue;
-                for (int j = 0; j < cpr; ++j) {
-                    const int row = j * rpi + rsub;                   // accumulator row within the quarter
-                    const int ty_v = ty * 16 + q * 4 + (row >> 3), tx_v = tx * 8 + (row & 7);
-                    int oy, ox;
-                    bool live;
-                    if (MODE == MODE_DECONV) {                        // tile voxel = input voxel; class = output parity
-                        live = ty_v < d.H && tx_v < d.W;
-                        oy = 2 * ty_v + (cls >> 1); ox = 2 * tx_v + (cls & 1);
-                    } else {
-                        live = ty_v < d.Ho && tx_v < d.Wo;
-                        oy = ty_v; ox = tx_v;
-                    }
-                    if (!(live && cvalid)) continue;
-                    float4 r = *reinterpret_cast<const float4*>(stg + row * L::STG_PITCH + chunk * 4);
+#pragma unroll
+                for (int j = 0; j < CPR; ++j) {
+                    size_t o;
+                    if (!locate(cz, j, &o)) continue;
+                    float4 r = *reinterpret_cast<const float4*>(stg + (j * rpi + rsub) * L::STG_PITCH + chunk * 4);
                     r.x += sh.x; r.y += sh.y; r.z += sh.z; r.w += sh.w;
                     if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-                    const size_t o = ((((size_t)b * d.D + z) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0 + chunk * 4;
-                    if (skip) {
-                        const float4 sk = __ldg(reinterpret_cast<const float4*>(skip + o));
-                        r.x += sk.x; r.y += sk.y; r.z += sk.z; r.w += sk.w;
-                    }
+                    r.x += skc[j].x; r.y += skc[j].y; r.z += skc[j].z; r.w += skc[j].w;
                     // consumers read this tensor as a TF32 operand: round once here
                     r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
                     *reinterpret_cast<float4*>(y + o) = r;

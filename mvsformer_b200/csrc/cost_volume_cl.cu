@@ -47,6 +47,8 @@ struct Params {
     const float* vis_weight;  // pass B in  [B, N, H, W]
     float* volume;            // pass B out [B, D, H, W, 8]
     int round_tf32;
+    int use_slots;            // the views of the (single) batch item are maps slot[0] (reference), slot[1..N] of `feat`
+    int slot[17];
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -197,7 +199,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
         for (int i = tid; i < TP * C4; i += 256) {
             const int q = i / C4, cq = i - q * C4;
             const int qx = blockIdx.x * TW + (q % TW), qy = blockIdx.y * CFG::TH + (q / TW);
-            s_ref4[i] = (qx < p.W && qy < p.H) ? __ldg(feat4 + ((int64_t)b * p.V * hw + (int64_t)qy * p.W + qx) * C4 + cq)
+            s_ref4[i] = (qx < p.W && qy < p.H) ? __ldg(feat4 + ((int64_t)(p.use_slots ? p.slot[0] : b * p.V) * hw + (int64_t)qy * p.W + qx) * C4 + cq)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -211,14 +213,14 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
         s_box[slot * 2] = INT_MAX; s_box[slot * 2 + 1] = INT_MAX;        // re-armed for item it+2: ordered before the other
         s_cnt[slot] = 0;                                                  // warps' next atomics by the release of this arrive
         mbar_expect_tx(&full[slot], CFG::TILE_F * 4);                    // and the acquire of their wait on full[slot]
-        tma_load_4d(tile0 + slot * CFG::TILE_F, &tmap, &full[slot], ch * CFG::CC, bx0, by0, b * p.V + v + 1);
+        tma_load_4d(tile0 + slot * CFG::TILE_F, &tmap, &full[slot], ch * CFG::CC, bx0, by0, p.use_slots ? p.slot[v + 1] : b * p.V + v + 1);
     };
 
     const int pix = tid / HB, kk = tid - pix * HB;
     const int x = blockIdx.x * TW + (pix % TW), y = blockIdx.y * CFG::TH + (pix / TW);
     const bool live = x < p.W && y < p.H;
     const int pixoff = live ? y * p.W + x : 0;
-    const float4* ref4 = feat4 + ((int64_t)b * p.V * hw + pixoff) * C4;
+    const float4* ref4 = feat4 + ((int64_t)(p.use_slots ? p.slot[0] : b * p.V) * hw + pixoff) * C4;
     // chunk order of this lane: q = j ^ xq (see the header).  NQ = 8: the 8 lanes of an LDS.128 phase get 8 different
     // bank groups whatever they sample; NQ = 4 / 2: lanes that share a chunk are hypotheses of one pixel (neighbouring
     // texels along the epipolar line) or, with every hypothesis of a pixel in one thread, four neighbouring pixels.
@@ -383,7 +385,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
                 const RelProj m = load_relproj_smem(s_rel + v * 12);
                 const PixelRay sray = pixel_ray(m, (float)x, (float)y);
                 const Taps tp = make_taps(m, sray, s_dep[pix * SD + k], p.H, p.W, geo.half_w, geo.half_h);
-                const float4* src = feat4 + ((int64_t)(b * p.V + v + 1) * hw) * C4 + ch * NQ;
+                const float4* src = feat4 + ((int64_t)(p.use_slots ? p.slot[v + 1] : b * p.V + v + 1) * hw) * C4 + ch * NQ;
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
                     const int q = j ^ xq;
@@ -600,10 +602,10 @@ static int make_feature_map(CUtensorMap* map, const float* feat, int BV, int C, 
 }
 
 template <class CFG, int MODE, bool SIM>
-static int launch(const Params& p, int B, cudaStream_t st) {
+static int launch(const Params& p, int B, int nmaps, cudaStream_t st) {
     constexpr size_t smem = smem_bytes<CFG, MODE, SIM>();
     CUtensorMap map;
-    int rc = make_feature_map(&map, p.feat, B * p.V, CFG::C, p.H, p.W, CFG::CC, CFG::BW, CFG::BH);
+    int rc = make_feature_map(&map, p.feat, nmaps, CFG::C, p.H, p.W, CFG::CC, CFG::BW, CFG::BH);
     if (rc) return rc;
     auto kern = cost_volume_cl_kernel<CFG, MODE, SIM>;
     MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -633,37 +635,46 @@ static int variant(const char* name) {
 
 // Pass A over channels-last features; corr != nullptr also stores the per-view group correlation (C/G >= 2 only).
 // Returns 1 when the shape is not covered (the caller falls back to the NCHW kernels), 0 on success, negative on error.
-int cost_volume_cl_entropy(const float* feat_cl, const float* relproj, const float* depth, float* entropy, float* sim_sum,
-                           float* corr, int B, int V, int C, int G, int D, int H, int W, cudaStream_t st) {
+static void set_slots(k1cl::Params& p, const int* view_slots, int V) {
+    p.use_slots = view_slots != nullptr;
+    for (int i = 0; i < 17; ++i) p.slot[i] = (view_slots && i < V) ? view_slots[i] : 0;
+}
+
+int cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj, const float* depth,
+                           float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W,
+                           cudaStream_t st) {
     using namespace k1cl;
     if (G != 8 || ((uintptr_t)feat_cl & 15) || V - 1 > MAXN) return 1;
     Params p{feat_cl, relproj, depth, V - 1, V, H, W, entropy, sim_sum, corr, nullptr, nullptr, 0};
+    set_slots(p, view_slots, V);
     const bool sim = sim_sum != nullptr;
-    if (C == 64 && D == 32 && corr) return sim ? launch<Stage1, 1, true>(p, B, st) : launch<Stage1, 1, false>(p, B, st);
-    if (C == 32 && D == 16 && corr) return sim ? launch<Stage2, 1, true>(p, B, st) : launch<Stage2, 1, false>(p, B, st);
+    if (C == 64 && D == 32 && corr) return sim ? launch<Stage1, 1, true>(p, B, nmaps, st) : launch<Stage1, 1, false>(p, B, nmaps, st);
+    if (C == 32 && D == 16 && corr) return sim ? launch<Stage2, 1, true>(p, B, nmaps, st) : launch<Stage2, 1, false>(p, B, nmaps, st);
     if (C == 16 && D == 8 && corr) {
-        if (variant("MVS_K1_S3") == 1) return sim ? launch<Stage3b, 1, true>(p, B, st) : launch<Stage3b, 1, false>(p, B, st);
-        return sim ? launch<Stage3, 1, true>(p, B, st) : launch<Stage3, 1, false>(p, B, st);
+        if (variant("MVS_K1_S3") == 1) return sim ? launch<Stage3b, 1, true>(p, B, nmaps, st) : launch<Stage3b, 1, false>(p, B, nmaps, st);
+        return sim ? launch<Stage3, 1, true>(p, B, nmaps, st) : launch<Stage3, 1, false>(p, B, nmaps, st);
     }
     if (C == 8 && D == 4 && !corr) {
         const int var = variant("MVS_K1_S4");
-        if (var == 1) return sim ? launch<Stage4b, 0, true>(p, B, st) : launch<Stage4b, 0, false>(p, B, st);
-        if (var == 2) return sim ? launch<Stage4c, 0, true>(p, B, st) : launch<Stage4c, 0, false>(p, B, st);
-        return sim ? launch<Stage4, 0, true>(p, B, st) : launch<Stage4, 0, false>(p, B, st);
+        if (var == 1) return sim ? launch<Stage4b, 0, true>(p, B, nmaps, st) : launch<Stage4b, 0, false>(p, B, nmaps, st);
+        if (var == 2) return sim ? launch<Stage4c, 0, true>(p, B, nmaps, st) : launch<Stage4c, 0, false>(p, B, nmaps, st);
+        return sim ? launch<Stage4, 0, true>(p, B, nmaps, st) : launch<Stage4, 0, false>(p, B, nmaps, st);
     }
     return 1;
 }
 
-int cost_volume_cl_aggregate(const float* feat_cl, const float* relproj, const float* depth, const float* vis_weight,
-                             float* volume, int B, int V, int C, int G, int D, int H, int W, int round_tf32, cudaStream_t st) {
+int cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj, const float* depth,
+                             const float* vis_weight, float* volume, int B, int V, int C, int G, int D, int H, int W,
+                             int round_tf32, cudaStream_t st) {
     using namespace k1cl;
     if (G != 8 || ((uintptr_t)feat_cl & 15) || V - 1 > MAXN) return 1;
     Params p{feat_cl, relproj, depth, V - 1, V, H, W, nullptr, nullptr, nullptr, vis_weight, volume, round_tf32};
+    set_slots(p, view_slots, V);
     if (C == 8 && D == 4) {
         const int var = variant("MVS_K1_S4");
-        if (var == 1) return launch<Stage4b, 2, false>(p, B, st);
-        if (var == 2) return launch<Stage4c, 2, false>(p, B, st);
-        return launch<Stage4, 2, false>(p, B, st);
+        if (var == 1) return launch<Stage4b, 2, false>(p, B, nmaps, st);
+        if (var == 2) return launch<Stage4c, 2, false>(p, B, nmaps, st);
+        return launch<Stage4, 2, false>(p, B, nmaps, st);
     }
     return 1;
 }
@@ -702,21 +713,36 @@ extern "C" int mvs_features_to_cl(const float* const* in, float* const* out, con
     return mvs::features_to_cl(in, out, channels, hw, maps, nseg, (cudaStream_t)stream);
 }
 
-extern "C" int mvs_cost_volume_cl_entropy(const float* feat_cl, const float* relproj, const float* depth, float* entropy,
-                                          float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W,
-                                          void* stream) {
-    MVS_REQUIRE(feat_cl && relproj && depth && entropy, "mvs_cost_volume_cl_entropy: null pointer");
-    MVS_REQUIRE(B >= 1 && V >= 2 && C >= 1 && G >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_cost_volume_cl_entropy: empty shape");
-    MVS_REQUIRE(C % G == 0, "mvs_cost_volume_cl_entropy: %d channels do not split into %d groups", C, G);
-    return mvs::cost_volume_cl_entropy(feat_cl, relproj, depth, entropy, sim_sum, corr, B, V, C, G, D, H, W, (cudaStream_t)stream);
+static int check_slots(const char* fn, int nmaps, const int* view_slots, int B, int V) {
+    if (!view_slots) {
+        MVS_REQUIRE(nmaps == B * V, "%s: without view_slots the feature tensor must hold B*V = %d maps (got %d)", fn, B * V, nmaps);
+        return MVS_OK;
+    }
+    MVS_REQUIRE(B == 1, "%s: view_slots address the views of ONE batch item (got B = %d)", fn, B);
+    MVS_REQUIRE(V <= 17, "%s: at most 17 views with view_slots (got %d)", fn, V);
+    for (int i = 0; i < V; ++i)
+        MVS_REQUIRE(view_slots[i] >= 0 && view_slots[i] < nmaps, "%s: view_slots[%d] = %d is outside the %d maps", fn, i, view_slots[i], nmaps);
+    return MVS_OK;
 }
 
-extern "C" int mvs_cost_volume_cl_aggregate(const float* feat_cl, const float* relproj, const float* depth,
-                                            const float* vis_weight, float* volume, int B, int V, int C, int G, int D, int H,
-                                            int W, int round_tf32, void* stream) {
+extern "C" int mvs_cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj,
+                                          const float* depth, float* entropy, float* sim_sum, float* corr, int B, int V, int C,
+                                          int G, int D, int H, int W, void* stream) {
+    MVS_REQUIRE(feat_cl && relproj && depth && entropy, "mvs_cost_volume_cl_entropy: null pointer");
+    if (int rc = check_slots("mvs_cost_volume_cl_entropy", nmaps, view_slots, B, V)) return rc;
+    MVS_REQUIRE(B >= 1 && V >= 2 && C >= 1 && G >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_cost_volume_cl_entropy: empty shape");
+    MVS_REQUIRE(C % G == 0, "mvs_cost_volume_cl_entropy: %d channels do not split into %d groups", C, G);
+    return mvs::cost_volume_cl_entropy(feat_cl, nmaps, view_slots, relproj, depth, entropy, sim_sum, corr, B, V, C, G, D, H, W,
+                                       (cudaStream_t)stream);
+}
+
+extern "C" int mvs_cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj,
+                                            const float* depth, const float* vis_weight, float* volume, int B, int V, int C,
+                                            int G, int D, int H, int W, int round_tf32, void* stream) {
     MVS_REQUIRE(feat_cl && relproj && depth && vis_weight && volume, "mvs_cost_volume_cl_aggregate: null pointer");
+    if (int rc = check_slots("mvs_cost_volume_cl_aggregate", nmaps, view_slots, B, V)) return rc;
     MVS_REQUIRE(B >= 1 && V >= 2 && C >= 1 && G >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_cost_volume_cl_aggregate: empty shape");
     MVS_REQUIRE(C % G == 0, "mvs_cost_volume_cl_aggregate: %d channels do not split into %d groups", C, G);
-    return mvs::cost_volume_cl_aggregate(feat_cl, relproj, depth, vis_weight, volume, B, V, C, G, D, H, W, round_tf32,
-                                         (cudaStream_t)stream);
+    return mvs::cost_volume_cl_aggregate(feat_cl, nmaps, view_slots, relproj, depth, vis_weight, volume, B, V, C, G, D, H, W,
+                                         round_tf32, (cudaStream_t)stream);
 }

@@ -119,17 +119,24 @@ def cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim)
     return entropy, sim, corr
 
 
-def features_to_cl(feature_list):
+def features_to_cl(feature_list, outs=None):
     """NCHW feature tensors ``[..., C, H, W]`` (up to four, e.g. the four stages of one feature set) -> channels-last
-    ``[..., H, W, C]`` copies, ONE launch (mvs_features_to_cl).  The cost-volume kernels sample channels-last texels."""
+    ``[..., H, W, C]`` copies, ONE launch (mvs_features_to_cl).  The cost-volume kernels sample channels-last texels.
+    ``outs``: optional preallocated contiguous destinations of the same sizes (e.g. slots of a feature pool)."""
     if not 1 <= len(feature_list) <= 4:
         raise RuntimeError("features_to_cl converts 1..4 tensors per call")
-    ins, outs = [], []
+    ins = []
     for t in feature_list:
         t = _f32(t).contiguous()
         require_cuda(t)
         ins.append(t)
-        outs.append(torch.empty(t.shape[:-3] + (t.shape[-2], t.shape[-1], t.shape[-3]), device=t.device, dtype=torch.float32))
+    if outs is None:
+        outs = [torch.empty(t.shape[:-3] + (t.shape[-2], t.shape[-1], t.shape[-3]), device=t.device, dtype=torch.float32) for t in ins]
+    else:
+        require_cuda(*outs)
+        for t, o in zip(ins, outs):
+            if o.numel() != t.numel():
+                raise RuntimeError("features_to_cl: destination of %d elements for a source of %d" % (o.numel(), t.numel()))
     n = len(ins)
     arr_p = ctypes.c_void_p * n
     in_p = arr_p(*[t.data_ptr() for t in ins])
@@ -148,18 +155,32 @@ def cl_supported(chans, ndepth, groups):
     return groups == 8 and (chans, ndepth) in ((64, 32), (32, 16), (16, 8), (8, 4))
 
 
-def cost_volume_cl_entropy(feat_cl, relproj, depth_values, groups, want_sim):
-    """Pass A over channels-last features [B,V,H,W,C].  Returns (entropy [B,N,H,W], sim or None, corr [B,N,D,H,W,G] or
-    None): the per-view correlation is stored where C/G >= 2 (one sampling pass); None when the shape is not covered."""
+def _cl_views(feat_cl, view_slots):
+    """(B, V, H, W, C, nmaps, slot array or None) of a dense [B,V,H,W,C] tensor or a pool [S,H,W,C] + view slots."""
+    if view_slots is None:
+        b, v, h, w, c = feat_cl.shape
+        return b, v, h, w, c, b * v, None
+    if feat_cl.dim() != 4:
+        raise RuntimeError("with view_slots the features must be a pool [slots,H,W,C]")
+    nmaps, h, w, c = feat_cl.shape
+    slots = (ctypes.c_int * len(view_slots))(*[int(x) for x in view_slots])
+    return 1, len(view_slots), h, w, c, nmaps, slots
+
+
+def cost_volume_cl_entropy(feat_cl, relproj, depth_values, groups, want_sim, view_slots=None):
+    """Pass A over channels-last features [B,V,H,W,C] (or a pool [S,H,W,C] whose maps ``view_slots`` are the views of one
+    batch item).  Returns (entropy [B,N,H,W], sim or None, corr [B,N,D,H,W,G] or None): the per-view correlation is
+    stored where C/G >= 2 (one sampling pass); None when the shape is not covered."""
     require_cuda(feat_cl, relproj, depth_values)
-    b, v, h, w, c = feat_cl.shape
+    b, v, h, w, c, nmaps, slots = _cl_views(feat_cl, view_slots)
     d = depth_values.shape[1]
     if not cl_supported(c, d, groups):
         return None
     entropy = torch.empty(b, v - 1, h, w, device=feat_cl.device, dtype=torch.float32)
     sim = torch.empty(b, d, h, w, device=feat_cl.device, dtype=torch.float32) if want_sim else None
     corr = torch.empty(b, v - 1, d, h, w, groups, device=feat_cl.device, dtype=torch.float32) if c // groups >= 2 else None
-    rc = _lib.load().mvs_cost_volume_cl_entropy(ptr(feat_cl), ptr(relproj), ptr(depth_values), ptr(entropy), ptr(sim), ptr(corr),
+    rc = _lib.load().mvs_cost_volume_cl_entropy(ptr(feat_cl), nmaps, None if slots is None else ctypes.cast(slots, ctypes.c_void_p),
+                                                ptr(relproj), ptr(depth_values), ptr(entropy), ptr(sim), ptr(corr),
                                                 b, v, c, groups, d, h, w, stream())
     if rc == 1:
         return None
@@ -167,13 +188,14 @@ def cost_volume_cl_entropy(feat_cl, relproj, depth_values, groups, want_sim):
     return entropy, sim, corr
 
 
-def cost_volume_cl_aggregate(feat_cl, relproj, depth_values, vis_weight, groups, round_tf32=False):
+def cost_volume_cl_aggregate(feat_cl, relproj, depth_values, vis_weight, groups, round_tf32=False, view_slots=None):
     """Pass B over channels-last features (the stage whose correlation is as large as the warped tensor: C/G = 1)."""
     require_cuda(feat_cl, relproj, depth_values, vis_weight)
-    b, v, h, w, c = feat_cl.shape
+    b, v, h, w, c, nmaps, slots = _cl_views(feat_cl, view_slots)
     d = depth_values.shape[1]
     volume = torch.empty(b, d, h, w, groups, device=feat_cl.device, dtype=torch.float32)
-    check(_lib.load().mvs_cost_volume_cl_aggregate(ptr(feat_cl), ptr(relproj), ptr(depth_values), ptr(vis_weight), ptr(volume),
+    check(_lib.load().mvs_cost_volume_cl_aggregate(ptr(feat_cl), nmaps, None if slots is None else ctypes.cast(slots, ctypes.c_void_p),
+                                                   ptr(relproj), ptr(depth_values), ptr(vis_weight), ptr(volume),
                                                    b, v, c, groups, d, h, w, 1 if round_tf32 else 0, stream()),
           "mvs_cost_volume_cl_aggregate")
     return volume

@@ -108,20 +108,37 @@ class StageNet(nn.Module):
             return engine.vis_last_cl(x.view(b * n, h, w, 8), last).view(b, n, h, w)
         return engine.vis_weight(maps, self._vis_params_host()).view(b, n, h, w)
 
-    def build_cost_volume(self, features, proj_matrices, depth_values, features_cl=None):
+    def build_cost_volume(self, features, proj_matrices, depth_values, features_cl=None, view_slots=None):
         """models/mvsformer_model.py:52-105 -> (volume channels-last [B,D,H,W,G], sim_sum or None,
         entropy [B,N,H,W], vis_weight [B,N,H,W]).  ``features_cl`` [B,V,H,W,C]: the same features already re-laid
-        out channels-last (CascadeMVS converts all stages in one launch); made here when absent."""
+        out channels-last (CascadeMVS converts all stages in one launch); made here when absent.  With ``view_slots``
+        (scan mode, B = 1) ``features`` may be None and ``features_cl`` is a per-scan pool [slots,H,W,C] whose maps
+        ``view_slots`` = [reference, sources...] are this sample's views — nothing is gathered."""
+        groups = self.args["base_ch"]
+        round_tf32 = config.conv_precision() == "tf32"
+        if view_slots is not None:
+            if features_cl is None or features_cl.dim() != 4:
+                raise RuntimeError("view_slots need a channels-last feature pool [slots,H,W,C]")
+            assert len(view_slots) == proj_matrices.shape[1], "Different number of images and projection matrices"
+            relproj = engine.relative_projections(proj_matrices)
+            built = engine.cost_volume_cl_entropy(features_cl, relproj, depth_values, groups, not self.training, view_slots)
+            if built is None:
+                raise RuntimeError("no channels-last cost-volume kernel for %d channels x %d hypotheses"
+                                   % (features_cl.shape[-1], depth_values.shape[1]))
+            entropy, sim, corr = built
+            weight = self._vis_weight(entropy)
+            if corr is not None:
+                return engine.corr_aggregate(corr, weight, round_tf32), sim, entropy, weight
+            volume = engine.cost_volume_cl_aggregate(features_cl, relproj, depth_values, weight, groups, round_tf32, view_slots)
+            return volume, sim, entropy, weight
         if features.dim() != 5:
             raise RuntimeError("features must be [B,V,C,H,W]")
         b, v = features.shape[:2]
         assert v == proj_matrices.shape[1], "Different number of images and projection matrices"
-        groups = self.args["base_ch"]
         if features.shape[2] % groups:
             raise RuntimeError("shape '[%d, %d, -1, ...]' is invalid for %d feature channels"
                                % (b, groups, features.shape[2]))
         relproj = engine.relative_projections(proj_matrices)
-        round_tf32 = config.conv_precision() == "tf32"
         if config.cv_layout() == "cl" and engine.cl_supported(features.shape[2], depth_values.shape[1], groups):
             if features_cl is None:
                 features_cl = engine.features_to_cl([features])[0]
@@ -223,9 +240,9 @@ class StageNet(nn.Module):
         conf = engine.conf_regression(prob_volume.detach(), window) if window else max_prob
         return prob_volume, depth, conf
 
-    def forward(self, features, proj_matrices, depth_values, tmp=2.0, features_cl=None):
+    def forward(self, features, proj_matrices, depth_values, tmp=2.0, features_cl=None, view_slots=None):
         """features [B,V,C,H,W], proj_matrices [B,V,2,4,4], depth_values [B,D,H,W] (the reference's signature);
-        ``features_cl``: optional channels-last copy of ``features`` (see build_cost_volume)."""
+        ``features_cl`` / ``view_slots``: optional channels-last copy of ``features`` / feature pool (see build_cost_volume)."""
         depth_values = depth_values.float().contiguous()
         if self.fusion_type != "cnn":
             if type(tmp) == list or type(tmp) == tuple:
@@ -235,7 +252,7 @@ class StageNet(nn.Module):
             if type(tmp) == list or type(tmp) == tuple:
                 tmp = tmp[self.stage_idx]
             return self._forward_train(features, proj_matrices, depth_values, tmp)
-        volume, sim, _, _ = self.build_cost_volume(features, proj_matrices, depth_values, features_cl)
+        volume, sim, _, _ = self.build_cost_volume(features, proj_matrices, depth_values, features_cl, view_slots)
         prob_volume_pre = self.cost_reg.forward_cl(volume)
         if type(tmp) == list or type(tmp) == tuple:
             tmp = tmp[self.stage_idx]
@@ -273,32 +290,47 @@ class CascadeMVS(nn.Module):
                 return None
         return engine.features_to_cl(feats)
 
-    def forward(self, features, proj_matrices, depth_values, tmp=2.0, full_hw=None):
-        """features {"stageK": [B,V,C,h,w]}, proj_matrices {"stageK": [B,V,2,4,4]}, depth_values [B,ND]."""
+    def forward(self, features, proj_matrices, depth_values, tmp=2.0, full_hw=None, pools_cl=None, view_slots=None):
+        """features {"stageK": [B,V,C,h,w]}, proj_matrices {"stageK": [B,V,2,4,4]}, depth_values [B,ND].
+        Scan mode (eval, B = 1): ``features=None``, ``pools_cl`` {"stageK": channels-last pool [slots,h,w,C]} and
+        ``view_slots`` = the pool maps of [reference view, source views...] (StreamedCascade.run_scan)."""
         nst = len(self.ndepths)
-        last_feat = features["stage%d" % nst]
-        b = last_feat.shape[0]
-        if full_hw is None:
-            full_hw = tuple(last_feat.shape[-2:])
+        if pools_cl is not None:
+            if self.training or view_slots is None:
+                raise RuntimeError("feature pools are an eval-mode input and need view_slots")
+            last_pool = pools_cl["stage%d" % nst]
+            b = 1
+            if full_hw is None:
+                full_hw = tuple(last_pool.shape[1:3])
+            device = last_pool.device
+        else:
+            last_feat = features["stage%d" % nst]
+            b = last_feat.shape[0]
+            if full_hw is None:
+                full_hw = tuple(last_feat.shape[-2:])
+            device = last_feat.device
         outputs = {}
         outputs_stage = None
         use_conf = self.args["depth_type"] in ("ce", "mixup_ce")
-        prob_maps = torch.zeros(b, full_hw[0], full_hw[1], dtype=torch.float32, device=last_feat.device) if use_conf else None
+        prob_maps = torch.zeros(b, full_hw[0], full_hw[1], dtype=torch.float32, device=device) if use_conf else None
         depth_interval = depth_values[:, 1] - depth_values[:, 0]
-        feats_cl = self._features_cl(features)
+        feats_cl = None if pools_cl is not None else self._features_cl(features)
         for s in range(nst):
-            feats = features["stage%d" % (s + 1)]
-            h, w = feats.shape[-2:]
+            feats = None if pools_cl is not None else features["stage%d" % (s + 1)]
+            h, w = pools_cl["stage%d" % (s + 1)].shape[1:3] if pools_cl is not None else feats.shape[-2:]
             if s == 0:
                 rng = init_inverse_range if self.inverse_depth else init_range
-                depth_samples = rng(depth_values, self.ndepths[s], feats.device, torch.float32, h, w)
+                depth_samples = rng(depth_values, self.ndepths[s], device, torch.float32, h, w)
             elif self.inverse_depth:
                 depth_samples = schedule_inverse_range(outputs_stage["depth"].detach(), outputs_stage["depth_values"],
                                                        self.ndepths[s], self.depth_interals_ratio[s], h, w)
             else:
                 depth_samples = schedule_range(outputs_stage["depth"].detach(), self.ndepths[s],
                                                self.depth_interals_ratio[s] * depth_interval, h, w)
-            if feats_cl is not None:
+            if pools_cl is not None:
+                outputs_stage = self.fusions[s](None, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
+                                                features_cl=pools_cl["stage%d" % (s + 1)], view_slots=view_slots)
+            elif feats_cl is not None:
                 outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
                                                 features_cl=feats_cl[s])
             else:

@@ -16,8 +16,9 @@ probability volumes the reference's ``tensor2numpy(outputs)`` drags along (test.
 scan every image is the reference view once and a source view of ~4 neighbours
 (datasets/general_eval.py:71), so the reference re-extracts (and this engine would re-upload) each
 view's feature maps ~5 times.  The cache keeps per-view feature maps resident in HBM (49 DTU views
-x 106 MB = 5.2 GB of the 180 GB), uploads a view the first time a sample names it, and assembles
-the dense ``[1,V,C,h,w]`` operand of the cost-volume kernels by a device-side gather.
+x 106 MB = 5.2 GB of the 180 GB) in the CHANNELS-LAST layout the cost-volume kernels sample (a view is re-laid
+out once, when it is uploaded), and a sample's views are addressed in place through their pool slots
+(``view_slots`` of mvs_cost_volume_cl_*): nothing is gathered or copied on the device.
 """
 from collections import OrderedDict
 
@@ -119,9 +120,9 @@ class StreamedCascade:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.cache = None                # FeatureCache bookkeeping (run_scan)
-        self._pools = None               # {"stageK": [capacity, C, h, w]} device pools
-        self._gathered = None            # {"stageK": [1, V, C, h, w]} dense operand of the current sample
-        self._gather_done = None         # event: last gather has read the pools
+        self._pools = None               # {"stageK": [capacity, h, w, C]} channels-last device pools
+        self._staging = None             # {"stageK": [C, h, w]} landing buffers of an upload (re-laid out into the pool)
+        self._compute_done = None        # event: the last enqueued cascade has read the pools
 
     def _upload(self, sample):
         """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
@@ -157,8 +158,10 @@ class StreamedCascade:
 
     # -- scan mode: per-view feature cache ----------------------------------------------------------
     def _stage_scan(self, sample):
-        """Upload the views of ``sample`` that are not resident (copy stream) and return what the
-        gather needs.  Slots of views this sample uses are pinned against eviction."""
+        """Upload the views of ``sample`` that are not resident (copy stream: H2D into a staging buffer, then one
+        re-layout launch into the view's pool slot) and return the slots.  Slots of views this sample uses are pinned
+        against eviction."""
+        from . import engine
         cache = self.cache
         slots, uploaded = [], 0
         with torch.cuda.stream(self.copy_stream):
@@ -167,14 +170,19 @@ class StreamedCascade:
                 if slot is None:
                     slot, evicted = cache.reserve(vid, pinned=sample.view_ids)
                     feats = sample.load(vid)
+                    keys = sorted(feats)
                     if self._pools is None:
-                        self._pools = {k: torch.empty((cache.capacity,) + tuple(v.shape), dtype=torch.float32, device=self.device)
-                                       for k, v in feats.items()}
-                    if evicted is not None and self._gather_done is not None:
-                        self.copy_stream.wait_event(self._gather_done)   # the evicted view may still be read by a gather
-                    for k, v in feats.items():
-                        self._pools[k][slot].copy_(v, non_blocking=True)
-                        uploaded += 4 * v.numel()
+                        self._pools = {k: torch.empty((cache.capacity,) + tuple(feats[k].shape[1:]) + (feats[k].shape[0],),
+                                                      dtype=torch.float32, device=self.device) for k in keys}
+                        self._staging = {k: torch.empty(tuple(feats[k].shape), dtype=torch.float32, device=self.device) for k in keys}
+                    if evicted is not None and self._compute_done is not None:
+                        self.copy_stream.wait_event(self._compute_done)     # the evicted view may still be read by a cascade
+                    for k in keys:
+                        self._staging[k].copy_(feats[k], non_blocking=True)
+                        uploaded += 4 * feats[k].numel()
+                    for k0 in range(0, len(keys), 4):                        # NCHW -> channels-last, straight into the slot
+                        engine.features_to_cl([self._staging[k] for k in keys[k0:k0 + 4]],
+                                              outs=[self._pools[k][slot] for k in keys[k0:k0 + 4]])
                 slots.append(slot)
             cams = {k: v.to(self.device, non_blocking=True) for k, v in sample.proj_matrices.items()}
             dv = sample.depth_values.to(self.device, non_blocking=True)
@@ -185,19 +193,6 @@ class StreamedCascade:
         for t in list(cams.values()) + [dv]:
             t.record_stream(main)
         return slots, cams, dv, ready, uploaded
-
-    def _gather(self, slots):
-        """Dense [1,V,C,h,w] operand from the pools (device-side copy on the compute stream)."""
-        if self._gathered is None or next(iter(self._gathered.values())).shape[1] != len(slots):
-            self._gathered = {k: torch.empty((1, len(slots)) + tuple(p.shape[1:]), dtype=torch.float32, device=self.device)
-                              for k, p in self._pools.items()}
-        for k, p in self._pools.items():
-            dst = self._gathered[k][0]
-            for j, slot in enumerate(slots):
-                dst[j].copy_(p[slot], non_blocking=True)                     # device-to-device, stream ordered
-        self._gather_done = torch.cuda.Event()
-        self._gather_done.record(torch.cuda.current_stream(self.device))
-        return self._gathered
 
     def run_scan(self, samples, capacity=64, keep_cache=False):
         """Like ``run`` for ``ScanSample``s that share views: each view's features cross PCIe once
@@ -213,10 +208,10 @@ class StreamedCascade:
     def _run_scan(self, samples, capacity, keep_cache):
         main = torch.cuda.current_stream(self.device)
         if self.cache is None or self.cache.capacity != capacity:
-            self.cache, self._pools, self._gathered, self._gather_done = FeatureCache(capacity), None, None, None
+            self.cache, self._pools, self._staging, self._compute_done = FeatureCache(capacity), None, None, None
         elif not keep_cache:
-            if self._gather_done is not None:
-                self.copy_stream.wait_event(self._gather_done)      # pools may still be read by the last gather
+            if self._compute_done is not None:
+                self.copy_stream.wait_event(self._compute_done)     # pools may still be read by the last cascade
             self.cache = FeatureCache(capacity)                      # pools are reused, their contents forgotten
         it = iter(samples)
         nxt = next(it, None)
@@ -229,11 +224,13 @@ class StreamedCascade:
             while staged is not None:
                 slots, c, d, ready, uploaded = staged
                 main.wait_event(ready)
-                f = self._gather(slots)                                      # reads the pools before the next upload may evict
                 self.h2d_bytes = uploaded
+                out = self.net(None, c, d, tmp=self.tmp, pools_cl=self._pools, view_slots=slots)
+                self._compute_done = torch.cuda.Event()
+                self._compute_done.record(main)
+                # staged only now: an upload that evicts a slot waits for the cascade enqueued above, which may read it
                 nxt = next(it, None)
                 staged = self._stage_scan(nxt) if nxt is not None else None  # overlaps with this view's compute
-                out = self.net(f, c, d, tmp=self.tmp)
                 bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
                 hd, hc, done = bufs[i % len(bufs)]
                 hd.copy_(out["refined_depth"], non_blocking=True)

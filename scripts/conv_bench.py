@@ -47,15 +47,17 @@ def strided_cases(out):
             shift = torch.zeros(cout, device=DEV)
             wn, nt = engine.pack_tma_weights(wt, mode)
             y_new = engine.conv3d_tma(x, wn, nt, cout, 3, shift, None, True, mode)
-            res = {"tma_us": timed(lambda: engine.conv3d_tma(x, wn, nt, cout, 3, shift, None, True, mode))}
+            skip = torch.randn_like(y_new) if mode == engine.TMA_DECONV else None       # the up path adds a skip tensor
+            y_new = engine.conv3d_tma(x, wn, nt, cout, 3, shift, skip, True, mode)
+            res = {"tma_us": timed(lambda: engine.conv3d_tma(x, wn, nt, cout, 3, shift, skip, True, mode))}
             if mode == engine.TMA_S2:
                 wk, ntk = engine.pack_tcz_kzf_weights(wt, True)
                 y_old = engine.conv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, None, 2, True)
                 res["old_us"] = timed(lambda: engine.conv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, None, 2, True))
             else:
                 wk, ntk = engine.pack_tcz_kzf_deconv_weights(wt)
-                y_old = engine.deconv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, None, True)
-                res["old_us"] = timed(lambda: engine.deconv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, None, True))
+                y_old = engine.deconv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, skip, True)
+                res["old_us"] = timed(lambda: engine.deconv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, skip, True))
             res["max_abs_diff"] = float((y_new.reshape(-1) - y_old.reshape(-1)).abs().max())
             res["tma_gbs"] = 4.0 * (x.numel() + y_new.numel()) / res["tma_us"] / 1e3
             out[name] = res
