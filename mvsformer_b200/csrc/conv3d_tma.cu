@@ -33,7 +33,7 @@ namespace mvs {
 namespace tc {
 namespace tma3 {
 
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int MODE_S1 = 0, MODE_S2 = 1, MODE_DECONV = 2;
 
 struct Dims {
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t s
 // Shared-memory plan.  A stage holds NPL planes (stride 2: input rows / columns split by parity, so that the taps of a
 // parity are again unit shifts) of NSUB sub-slabs (voxel rows are at most 128 B: 64 channels = two halves), each a dense
 // [PY rows][PX columns][CH floats] TMA box.
-template <int MODE, int CIN, int NT, int STAGES>
+template <int MODE, int CIN, int NT, int STAGES, int NEPI = 8>
 struct Smem {
     static constexpr int CQ = CIN / 4;
     static constexpr int CH = CIN >= 32 ? 32 : CIN;          // channels per sub-slab: voxel rows of 32 / 64 / 128 bytes
@@ -115,17 +115,18 @@ struct Smem {
     static constexpr int SLAB = NPL * PLANE;                 // bytes per stage
     static constexpr uint64_t LAYOUT = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);   // UMMA layout type: SWIZZLE_128B / 64B / 32B
     static constexpr int STG_PITCH = NT + 4;                 // floats per staged accumulator row (epilogue transpose)
-    static constexpr int STG = 4 * 32 * STG_PITCH * 4;       // bytes: one [32][NT+4] buffer per epilogue warp
+    static constexpr int STG = NEPI * 32 * STG_PITCH * 4;    // bytes: one [32][NT+4] buffer per epilogue warp
     static __host__ __device__ constexpr int wbytes(int kd) { return 9 * CQ * kd * NT * 16; }
     static __host__ __device__ constexpr size_t total(int kd) { return (size_t)STAGES * SLAB + wbytes(kd) + STG + 256 + 1024; }
 };
 
 // x channels-last [B,D,H,W,CIN]; y [B,D,Ho,Wo,Cout]; w packed [Cout tiles][kh][kw][CIN/4][kd][NT][4] (TF32-rounded, BN folded)
-template <int MODE, int CIN, int NT, int STAGES, int KD>
+// NEPI = epilogue warps (8, or 4 where the stages leave no room for eight staging buffers)
+template <int MODE, int CIN, int NT, int STAGES, int KD, int NEPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restrict__ w, const float* __restrict__ shift,
                   const float* __restrict__ skip, float* __restrict__ y, Dims d) {
-    using L = Smem<MODE, CIN, NT, STAGES>;
+    using L = Smem<MODE, CIN, NT, STAGES, NEPI>;
     constexpr int NCLS = MODE == MODE_DECONV ? 4 : 1;                 // output parity classes per input voxel
     constexpr int pd = KD / 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -152,7 +153,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(wbar, 1);
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-        mbar_init(&acc_empty[0], 128); mbar_init(&acc_empty[1], 128);
+        mbar_init(&acc_empty[0], NEPI * 32); mbar_init(&acc_empty[1], NEPI * 32);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -251,8 +252,9 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
             }
             mma_commit_elect(&acc_full[buf]);                         // accumulators of this item complete
         }
-    } else {
-        // ===================================================== epilogue (warps 2-5) ===================================
+    } else if (warp < 2 + NEPI) {
+        // ===================================================== epilogue (warps 2-9) ===================================
+        // Two warps per TMEM lane quarter: they take the even / odd accumulator blocks (class, slice) of an item.
         // A warp owns the TMEM lane quarter q = 32 accumulator rows = 4 tile rows x 8 voxels.  tcgen05.ld hands every lane
         // one whole row; stored like that, a warp instruction would touch 32 half-filled sectors 64-128 B apart (measured
         // store-bound at n_tile 32).  The rows go through a per-warp shared-memory buffer instead, so that a store
@@ -262,7 +264,8 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
         // over the real chunks only, so that no store slot is wasted on padding
         const int cpr = min(NT, d.Cout - co0) / 4, rpi = 32 / cpr;    // cpr in {1, 2, 4, 8}; rows per store instruction
         const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-        float* stg = sStage + q * 32 * L::STG_PITCH;
+        const int half = (warp - 2) >> 2;                             // which blocks of the item this warp drains
+        float* stg = sStage + (half * 4 + q) * 32 * L::STG_PITCH;
         const int chunk = lane % cpr, rsub = lane / cpr;
         const bool cvalid = co0 + chunk * 4 < d.Cout;
         const float4 sh = (shift && cvalid) ? __ldg(reinterpret_cast<const float4*>(shift + co0) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -295,17 +298,17 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                     skn[j] = (skip && locate(cz, j, &o)) ? __ldg(reinterpret_cast<const float4*>(skip + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            prefetch_skip(0);
+            const int nblk = NCLS * d.D;
+            if (half < nblk) prefetch_skip(half);
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after_sync();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ncols;
-            const int nblk = NCLS * d.D;
 #pragma unroll 1
-            for (int cz = 0; cz < nblk; ++cz) {
+            for (int cz = half; cz < nblk; cz += NEPI / 4) {
                 float4 skc[CPR];
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) skc[j] = skn[j];
-                if (cz + 1 < nblk) prefetch_skip(cz + 1);
+                if (cz + NEPI / 4 < nblk) prefetch_skip(cz + NEPI / 4);
                 float acc[NT];
 #pragma unroll
                 for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tacc + (uint32_t)cz * NT + c0, acc + c0);
@@ -329,7 +332,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(&acc_empty[buf]);                             // 128 arrivals: buffer may be overwritten
+            mbar_arrive(&acc_empty[buf]);                             // 256 arrivals: buffer may be overwritten
         }
     }
     tc_fence_before_sync();
@@ -383,10 +386,10 @@ static int sm_count() {
     return n;
 }
 
-template <int MODE, int CIN, int NT, int STAGES, int KD>
+template <int MODE, int CIN, int NT, int STAGES, int KD, int NEPI>
 static int launch_k(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D, int H, int W,
                     int Cout, int relu, cudaStream_t st) {
-    using L = Smem<MODE, CIN, NT, STAGES>;
+    using L = Smem<MODE, CIN, NT, STAGES, NEPI>;
     const size_t smem = L::total(KD);
     MVS_REQUIRE(smem <= 227 * 1024, "mvs_conv3d_tma: needs %zu bytes of shared memory", smem);
     CUtensorMap map;
@@ -404,7 +407,7 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     d.nbuf = 2 * ncols <= 512 ? 2 : 1;
     if (const char* e = getenv("MVS_TMA_DEBUG")) d.debug = atoi(e);
     const int ntiles = cdiv(Cout, NT);
-    auto kern = conv3d_tma_kernel<MODE, CIN, NT, STAGES, KD>;
+    auto kern = conv3d_tma_kernel<MODE, CIN, NT, STAGES, KD, NEPI>;
     MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int gx = sm_count() / ntiles;
     if (gx < 1) gx = 1;
@@ -414,11 +417,11 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     return MVS_OK;
 }
 
-template <int MODE, int CIN, int NT, int STAGES>
+template <int MODE, int CIN, int NT, int STAGES, int NEPI>
 static int launch(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D, int H, int W,
                   int Cout, int kd, int relu, cudaStream_t st) {
-    return kd == 1 ? launch_k<MODE, CIN, NT, STAGES, 1>(x, w, shift, skip, y, B, D, H, W, Cout, relu, st)
-                   : launch_k<MODE, CIN, NT, STAGES, 3>(x, w, shift, skip, y, B, D, H, W, Cout, relu, st);
+    return kd == 1 ? launch_k<MODE, CIN, NT, STAGES, 1, NEPI>(x, w, shift, skip, y, B, D, H, W, Cout, relu, st)
+                   : launch_k<MODE, CIN, NT, STAGES, 3, NEPI>(x, w, shift, skip, y, B, D, H, W, Cout, relu, st);
 }
 
 }  // namespace tma3
@@ -441,16 +444,17 @@ extern "C" int mvs_conv3d_tma(const float* x, const float* w, const float* shift
     if ((mode == 2 ? 4 : 1) * D * n_tile > 512)
         MVS_UNSUPPORTED("mvs_conv3d_tma: %d depth slices x n_tile %d exceed the tensor memory", D, n_tile);
     cudaStream_t st = (cudaStream_t)stream;
-#define MVS_TMA_CASE(M, C, N, S) if (mode == M && Cin == C && n_tile == N) return launch<M, C, N, S>(x, w, shift, skip, y, B, D, H, W, Cout, kd, relu, st)
-    MVS_TMA_CASE(MODE_S1, 16, 16, 6);
-    MVS_TMA_CASE(MODE_S1, 32, 32, 4);
-    MVS_TMA_CASE(MODE_S1, 64, 16, 2);
-    MVS_TMA_CASE(MODE_S2, 8, 16, 6);
-    MVS_TMA_CASE(MODE_S2, 16, 32, 3);
-    MVS_TMA_CASE(MODE_S2, 32, 16, 2);
-    MVS_TMA_CASE(MODE_DECONV, 64, 16, 2);
-    MVS_TMA_CASE(MODE_DECONV, 32, 16, 4);
-    MVS_TMA_CASE(MODE_DECONV, 16, 16, 6);
+#define MVS_TMA_CASE(M, C, N, S, E) if (mode == M && Cin == C && n_tile == N) return launch<M, C, N, S, E>(x, w, shift, skip, y, B, D, H, W, Cout, kd, relu, st)
+    //           mode         Cin  NT stages epilogue warps
+    MVS_TMA_CASE(MODE_S1,     16, 16, 6, 8);
+    MVS_TMA_CASE(MODE_S1,     32, 32, 3, 8);
+    MVS_TMA_CASE(MODE_S1,     64, 16, 2, 8);
+    MVS_TMA_CASE(MODE_S2,      8, 16, 6, 8);
+    MVS_TMA_CASE(MODE_S2,     16, 32, 3, 8);
+    MVS_TMA_CASE(MODE_S2,     32, 16, 2, 4);
+    MVS_TMA_CASE(MODE_DECONV, 64, 16, 2, 8);
+    MVS_TMA_CASE(MODE_DECONV, 32, 16, 4, 8);
+    MVS_TMA_CASE(MODE_DECONV, 16, 16, 6, 8);
 #undef MVS_TMA_CASE
     MVS_UNSUPPORTED("mvs_conv3d_tma: no instantiation for mode %d, Cin=%d, n_tile=%d", mode, Cin, n_tile);
 }
