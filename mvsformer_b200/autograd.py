@@ -375,9 +375,17 @@ def _conv_wgrad(g, x, wp_shape, transposed, stride):
     return conv_wgrad(g, x, kd, khw, stride[0], stride[1], small_is_cout=True)
 
 
+def _group(bn):
+    """Process group of a SyncBatchNorm layer (``convert_sync_batchnorm(module, process_group)``; None = default group)."""
+    return getattr(bn, "process_group", None)
+
+
 def _world(bn):
+    """Ranks that share this layer's batch statistics.  Every rank must contribute the same number of elements
+    (one reference view of the same crop size per rank, as the reference's DDP training does: train.py:46,138-139);
+    the statistics are normalised by m * world."""
     if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
-        return dist.get_world_size()
+        return dist.get_world_size(_group(bn))
     return 1
 
 
@@ -400,7 +408,7 @@ class _ConvBnAct(torch.autograd.Function):
             if world > 1:                      # SyncBatchNorm: same spatial size on every rank (DDP)
                 _call("mvs_bn_collapse", _p(sums), c)
                 sums, replicas = sums[:2 * c], 1
-                dist.all_reduce(sums)
+                dist.all_reduce(sums, group=_group(bn))
             mean_invstd = torch.empty(2 * c, device=x.device, dtype=torch.float32)
             track = bn.track_running_stats and bn.running_mean is not None
             _call("mvs_bn_finalize", _p(sums), replicas, float(m * world), float(bn.eps), float(bn.momentum), _p(mean_invstd),
@@ -418,6 +426,7 @@ class _ConvBnAct(torch.autograd.Function):
         _call("mvs_bn_act_fwd", _p(conv), _p(mean_invstd), _p(gamma), _p(beta), _p(skip), _p(y), m, c, 1 if relu else 0)
         ctx.save_for_backward(x, wp, conv, mean_invstd, gamma, beta)
         ctx.cfg = (transposed, tuple(stride), relu, bool(bn.training), world, skip is not None)
+        ctx.group = _group(bn) if world > 1 else None
         return y
 
     @staticmethod
@@ -437,7 +446,7 @@ class _ConvBnAct(torch.autograd.Function):
         if batch_stats:
             if world > 1:
                 sums = sums.clone()
-                dist.all_reduce(sums)
+                dist.all_reduce(sums, group=ctx.group)
             mean_terms = sums
         else:
             mean_terms = torch.zeros_like(sums)                      # statistics were constants

@@ -42,7 +42,7 @@ struct Dims {
     int relu;
     int tiles_x, tiles_y, nitems;
     int nbuf;                // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
-    int debug;               // profiling only (env MVS_TMA_DEBUG): bit 0 = no tap MMAs, bit 1 = no global stores
+    int debug;               // profiling only (env MVS_TMA_DEBUG): bit 0 = no tap MMAs, bit 1 = no global stores, bit 2 = no TMEM drain at all
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -304,7 +304,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
             tc_fence_after_sync();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ncols;
 #pragma unroll 1
-            for (int cz = half; cz < nblk; cz += NEPI / 4) {
+            for (int cz = half; cz < ((d.debug & 4) ? 0 : nblk); cz += NEPI / 4) {
                 float4 skc[CPR];
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) skc[j] = skn[j];

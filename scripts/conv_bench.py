@@ -75,7 +75,10 @@ def main():
 
 
 def unstrided_cases(out):
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     for name, cin, cout, kd, b, d, h, w in CASES:
+        if only and name not in only:
+            continue
         g = torch.Generator().manual_seed(1)
         wt = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g) * 0.05).to(DEV)
         x = engine.round_tf32(torch.randn(b, d, h, w, cin, generator=g)).to(DEV)
