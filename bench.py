@@ -192,6 +192,10 @@ class KernelProfiler:
         # opt-in MVS_CV_STORE path: pass A with stored correlation + streaming aggregation
         self._wrap(engine, "cost_volume_entropy_store", "cv_entropy_store(passA)", ent_store_cost)
         self._wrap(engine, "corr_aggregate", "cv_corr_aggregate(stream)", io_cost)
+        def vis_fused_cost(out, ent, params, w2, w3):
+            return numel_bytes(ent, out), 2 * 3608 * ent.numel()
+
+        self._wrap(engine, "vis_fused", "vis_net(fused)", vis_fused_cost)
         self._wrap(engine, "vis_weight", "vis_net", vis_cost)
         self._wrap(engine, "vis_first_cl", "vis_net(thin layers)", io_cost)
         self._wrap(engine, "vis_last_cl", "vis_net(thin layers)", io_cost)

@@ -331,6 +331,14 @@ int mvs_fusion_points(const float* depth, const float* mats, float* points, int 
 int mvs_fusion_prob_filter(const float* prob, const float* thresh_host, int nthresh, float* mask, int N, int C, int H, int W,
                            void* stream);
 
+/* ---- fused visibility net (csrc/vis_fused.cu): models/mvsformer_model.py:37,91 in ONE kernel --------------------------
+ * entropy [M,H,W] -> weight [M,H,W]; only those two maps touch HBM.  params [host]: w1[16][9] b1[16] shift2[16] shift3[8]
+ * w4[8] b4 (BN folded into w1 / the packed weights; shifts = folded BN biases), MVS_VIS_FUSED_PARAM_FLOATS floats.
+ * w2 (16->16) and w3 (16->8, padded to 16 outputs): device, packed like mvs_conv3d_tma weights with kd = 1, n_tile = 16. */
+#define MVS_VIS_FUSED_PARAM_FLOATS (16 * 9 + 16 + 16 + 8 + 8 + 1)
+int mvs_vis_fused(const float* entropy, const float* params, const float* w2, const float* w3, float* weight, int M, int H,
+                  int W, void* stream);
+
 /* ---- round-2 persistent TMA-fed tcgen05 convolutions (csrc/conv3d_tma.cu) ---------------------------------------------
  * Depth-unstrided layers of CostRegNet3D (models/module.py:550-594) and the 3x3 tensor-core layers of the visibility net
  * (models/mvsformer_model.py:37).  x [B,D,H,W,Cin] channels-last with TF32-rounded values, y [B,D,H,W,Cout]

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "mvs_corr_aggregate": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
     "mvs_argmax_gather": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "mvs_vis_weight": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "mvs_vis_fused": (c_i, [c_f] * 5 + [c_i] * 3 + [c_f]),
     "mvs_vis_first_cl": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "mvs_vis_last_cl": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "mvs_conv3d_cl": (c_i, [c_f] * 5 + [c_i] * 11 + [c_f]),

@@ -21,6 +21,9 @@ round-2 channels-last kernels (csrc/cost_volume_cl.cu: one LDS.128 per 4-channel
 item's TMA tile in flight; features are re-laid out once per call by mvs_features_to_cl) or the round-1 channel-planar
 TMA kernels (csrc/cost_volume_tma.cu), kept for A/B runs.
 
+``vis_fused`` (``MVS_VIS_FUSED``, default 1) — the visibility net as one persistent kernel (csrc/vis_fused.cu, TF32 mode):
+only the entropy map and the weight map touch HBM; ``0`` = the four round-1 kernels.
+
 ``conv_tma`` (``MVS_CONV_TMA``, default 1; ``0`` = round-1 kernels only) — depth-unstrided 3x3x3 layers (CostRegNet3D) through the
 persistent, warp-specialised, TMA-fed tcgen05 kernels of csrc/conv3d_tma.cu (TF32 mode only).
 
@@ -41,6 +44,7 @@ _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
           "cv_store": os.environ.get("MVS_CV_STORE", "1") not in ("", "0"),
           "cv_layout": os.environ.get("MVS_CV_LAYOUT", "cl"),
+          "vis_fused": os.environ.get("MVS_VIS_FUSED", "1") not in ("", "0"),
           "conv_tma": os.environ.get("MVS_CONV_TMA", "1") not in ("", "0"),
           "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "1") or 0),
           "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
@@ -78,6 +82,14 @@ def set_cv_layout(mode):
     if mode not in ("cl", "nchw"):
         raise ValueError("cv layout must be cl or nchw, got %r" % (mode,))
     _state["cv_layout"] = mode
+
+
+def vis_fused():
+    return _state["vis_fused"]
+
+
+def set_vis_fused(flag):
+    _state["vis_fused"] = bool(flag)
 
 
 def conv_tma():

@@ -232,6 +232,17 @@ def vis_weight(entropy_maps, params_host):
     return out
 
 
+def vis_fused(entropy_maps, params_host, w2_packed, w3_packed):
+    """[M,H,W] entropy -> [M,H,W] visibility weight, the whole net in one persistent kernel (mvs_vis_fused)."""
+    require_cuda(entropy_maps, w2_packed, w3_packed)
+    m, h, w = entropy_maps.shape
+    assert params_host.dtype == np.float32 and params_host.flags["C_CONTIGUOUS"] and params_host.size == 193
+    out = torch.empty_like(entropy_maps)
+    check(_lib.load().mvs_vis_fused(ptr(entropy_maps), params_host.ctypes.data_as(ctypes.c_void_p), ptr(w2_packed), ptr(w3_packed),
+                                    ptr(out), m, h, w, stream()), "mvs_vis_fused")
+    return out
+
+
 def vis_first_cl(entropy_maps, params_host):
     """[M,H,W] -> channels-last TF32 [M,H,W,16] (first vis layer)."""
     require_cuda(entropy_maps)

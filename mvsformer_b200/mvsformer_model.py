@@ -91,10 +91,34 @@ class StageNet(nn.Module):
         self._vis_params_host()                                   # refreshes the cache key
         return self._vis_cache.get_derived("tc", build)
 
+    def _vis_params_fused(self):
+        """Operands of the fused kernel: host params (layer 1, the two BN shifts, the 1x1 conv) and the packed TF32 weights
+        of the 16->16 and 16->8 layers."""
+        def build(_):
+            host = self._vis_params_host()
+            first = host[:16 * 9 + 16]
+            last = host[-9:]
+            packed, shifts = [], []
+            for i in (1, 2):
+                blk = self.vis[i]
+                scale, shift = _bn_scale_shift(blk.bn)
+                w = blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)          # [Co,Ci,3,3]
+                wt, nt = engine.pack_tma_weights(w.permute(2, 3, 1, 0).unsqueeze(0).contiguous())
+                assert nt == 16 and wt.numel() == 9 * 16 * 16
+                packed.append(wt)
+                shifts.append(shift.detach().float().cpu().numpy().astype(np.float32))
+            params = np.ascontiguousarray(np.concatenate([first, shifts[0], shifts[1], last]).astype(np.float32))
+            return params, packed[0], packed[1]
+        self._vis_params_host()                                   # refreshes the cache key
+        return self._vis_cache.get_derived("fused", build)
+
     def _vis_weight(self, entropy):
         """entropy [B,N,H,W] -> visibility weight [B,N,H,W] (models/mvsformer_model.py:91)."""
         b, n, h, w = entropy.shape
         maps = entropy.view(b * n, h, w)
+        if config.conv_precision() == "tf32" and config.vis_fused():
+            params, w2p, w3p = self._vis_params_fused()
+            return engine.vis_fused(maps, params, w2p, w3p).view(b, n, h, w)
         if config.conv_precision() == "tf32" and engine.tcz_supported(16, 16, b * n, 1):
             first, mids, last = self._vis_params_tc()
             x = engine.vis_first_cl(maps, first).view(1, b * n, h, w, 16)

@@ -65,6 +65,8 @@ def test_inference_host_path(dry, mode, layout, cv_store, kzf):
     old = config.conv_precision()
     config.set_conv_precision(mode)
     config.set_cv_layout(layout)
+    config.set_conv_tma(layout == "cl")           # the round-1 variants are checked with the round-2 kernels switched off
+    config.set_vis_fused(layout == "cl")
     config.set_cv_store(cv_store)
     config.set_tcz_kzf(kzf)
     try:
@@ -73,6 +75,8 @@ def test_inference_host_path(dry, mode, layout, cv_store, kzf):
     finally:
         config.set_conv_precision(old)
         config.set_cv_layout("cl")
+        config.set_conv_tma(True)
+        config.set_vis_fused(True)
         config.set_cv_store(_CV_STORE_DEFAULT)
         config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     assert out["refined_depth"].shape == (1, 128, 256) and out["photometric_confidence"].shape == (1, 128, 256)
@@ -82,6 +86,11 @@ def test_inference_host_path(dry, mode, layout, cv_store, kzf):
         assert {"mvs_features_to_cl", "mvs_cost_volume_cl_entropy", "mvs_cost_volume_cl_aggregate", "mvs_corr_aggregate"} <= called
         assert dry.calls.count("mvs_cost_volume_cl_entropy") == 4 and dry.calls.count("mvs_cost_volume_cl_aggregate") == 1
         assert not called & {"mvs_cost_volume_entropy", "mvs_cost_volume_entropy_store", "mvs_cost_volume_aggregate"}
+        if mode == "tf32":               # depth-unstrided layers on the persistent TMA kernels, visibility net fused
+            assert dry.calls.count("mvs_conv3d_tma") == 24 and dry.calls.count("mvs_vis_fused") == 4
+            assert not called & {"mvs_vis_first_cl", "mvs_vis_last_cl", "mvs_conv3d_tcr_khf", "mvs_conv3d_tcz_kzf", "mvs_deconv3d_tcz_kzf"}
+        else:
+            assert "mvs_conv3d_tma" not in called and "mvs_vis_fused" not in called
         return
     assert "mvs_cost_volume_entropy" in called or "mvs_cost_volume_entropy_store" in called
     if cv_store:
@@ -203,5 +212,4 @@ def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
     # round-2 default layout: the channels-last kernels (one sampling pass at stages 1-3 + streaming aggregation)
     assert {"cv_layout(nchw->channels-last)", "cv_cl_passA+store", "cv_cl_passA(stage4)", "cv_cl_passB(stage4)",
             "cv_corr_aggregate(stream)"} <= set(summ)
-    if kzf:
-        assert any("kzf" in k or "khf" in k for k in summ) or "vis_net(tensor-core layers)" in summ
+    assert "conv3d_tma" in summ and "vis_net(fused)" in summ

@@ -400,3 +400,30 @@ def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
     assert rel_l1(v1, v0) < 5e-6, rel_l1(v1, v0)
     assert rel_l1(s1, s0) < 5e-6, rel_l1(s1, s0)
     assert torch.isfinite(v1).all()
+
+
+# ---- fused visibility net (csrc/vis_fused.cu) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4, 144, 192), (3, 37, 50), (2, 30, 14), (1, 31, 15), (5, 200, 333)])
+def test_fused_vis_net_is_bit_identical_to_the_four_kernel_route(shape):
+    """Same TF32 operands, same FMA order, same rounding points: the fused kernel must reproduce the unfused tensor-core
+    route bit for bit (which tests/test_gpu_parity.py holds to the oracle), incl. partial tiles and maps smaller than a tile."""
+    from tests.helpers import rel_l1
+    m, h, w = shape
+    net = StageNet(dict(STAGE_ARGS), 8, 2).eval()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=21))
+    net = net.to(DEV)
+    ent = (2.0 * torch.rand(1, m, h, w, generator=S._gen(h + w))).to(DEV)
+    old = config.conv_precision()
+    config.set_conv_precision("tf32")
+    try:
+        config.set_vis_fused(False)
+        want = net._vis_weight(ent)
+        config.set_vis_fused(True)
+        got = net._vis_weight(ent)
+    finally:
+        config.set_vis_fused(True)
+        config.set_conv_precision(old)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert rel_l1(got, want) < 1e-6, rel_l1(got, want)
+    assert torch.equal(got, want)
