@@ -91,7 +91,9 @@ int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume
  * feat_cl [B,V,H,W,C] (dense).  mvs_features_to_cl converts up to four NCHW tensors in ONE launch: segment s is
  * in[s] = [maps[s]][channels[s]][hw[s]]  ->  out[s] = [maps[s]][hw[s]][channels[s]]  (all five arrays are HOST arrays
  * of nseg entries; in/out entries are device pointers).
- * mvs_cost_volume_cl_entropy: pass A; corr != NULL additionally stores the per-view group correlation [B,N,D,H,W,G]
+ * mvs_cost_volume_cl_entropy: pass A; sim_depth [B,H,W] (eval, may be NULL) receives depth[argmax_d of the cosine similarity
+ * summed over views] directly (models/mvsformer_model.py:81-85,151-156) — the similarity volume never reaches HBM;
+ * corr != NULL additionally stores the per-view group correlation [B,N,D,H,W,G]
  * (required where C/G >= 2, i.e. (C,D) = (64,32), (32,16), (16,8); must be NULL for (8,4), which keeps two sampling
  * passes so that the warped tensor never reaches HBM).  mvs_cost_volume_cl_aggregate: pass B for (C,D) = (8,4).
  * feat_cl holds nmaps maps [nmaps][H][W][C].  view_slots == NULL: the dense [B,V,H,W,C] tensor (nmaps = B*V).  view_slots !=
@@ -101,7 +103,7 @@ int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume
 int mvs_features_to_cl(const float* const* in, float* const* out, const int* channels, const int64_t* hw,
                        const int64_t* maps, int nseg, void* stream);
 int mvs_cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj, const float* depth,
-                               float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W,
+                               float* entropy, float* sim_depth, float* corr, int B, int V, int C, int G, int D, int H, int W,
                                void* stream);
 int mvs_cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj,
                                  const float* depth, const float* vis_weight, float* volume, int B, int V, int C, int G, int D,

@@ -143,7 +143,9 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index broadcast from lane 0: the compiler then knows it is warp-uniform, keeps the role branches and everything
+    // derived inside them (descriptors, TMEM addresses) on the uniform datapath — the MMA issue loop is the pipeline's pace-maker
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int ct = blockIdx.y, co0 = ct * NT;
     const int ncols = NCLS * d.D * NT;                                // accumulator columns of one buffer
     const int alloc = d.nbuf * ncols;
@@ -160,7 +162,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ===================================================== producer ==============================================

@@ -42,7 +42,7 @@ struct Params {
     const float* depth;       // [B, D, H, W]
     int N, V, H, W;
     float* entropy;           // pass A out [B, N, H, W]
-    float* sim_sum;           // pass A out [B, D, H, W] (SIM)
+    float* sim_depth;         // pass A out [B, H, W] (SIM): hypothesis with the largest cosine similarity summed over views
     float* corr;              // pass A out [B, N, D, H, W, 8] (STORE)
     const float* vis_weight;  // pass B in  [B, N, H, W]
     float* volume;            // pass B out [B, D, H, W, 8]
@@ -463,8 +463,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
         for (int j = 0; j < KPT; ++j) { ix[j] = n1x[j]; iy[j] = n1y[j]; n1x[j] = n2x[j]; n1y[j] = n2y[j]; }
     }
 
-    if (!live) return;
-    if (PASS_B) {
+    if (PASS_B && live) {
         const float inv = 1.0f / (wsum + 1e-6f);
 #pragma unroll
         for (int jh = 0; jh < (PASS_B ? KPT : 1); ++jh) {
@@ -482,12 +481,25 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
             *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
-    } else if (SIM) {
+    }
+    if (!PASS_B && SIM) {
+        // sim_depth = depth[argmax_k sum_v cos_v[k]] (models/mvsformer_model.py:151-156; first maximum, like torch.argmax).
+        // The pixel's HB threads are lanes of one warp; every lane of the warp takes part in the shuffles.
+        float best = -FLT_MAX;
+        int bk = 0;
 #pragma unroll
         for (int h = 0; h < NHB * KPT; ++h) {
             const int k = (h / KPT) * HPI + kk * KPT + (h % KPT);
-            p.sim_sum[((int64_t)b * D + k) * hw + pixoff] = s_cos[pix * SD + k] * inv_cpg;
+            const float c = s_cos[pix * SD + k];
+            if (c > best || (c == best && k < bk)) { best = c; bk = k; }
         }
+#pragma unroll
+        for (int o = HB / 2; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+        }
+        if (kk == 0 && live) p.sim_depth[(int64_t)b * hw + pixoff] = s_dep[pix * SD + bk];
     }
 }
 
@@ -641,13 +653,13 @@ static void set_slots(k1cl::Params& p, const int* view_slots, int V) {
 }
 
 int cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj, const float* depth,
-                           float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G, int D, int H, int W,
+                           float* entropy, float* sim_depth, float* corr, int B, int V, int C, int G, int D, int H, int W,
                            cudaStream_t st) {
     using namespace k1cl;
     if (G != 8 || ((uintptr_t)feat_cl & 15) || V - 1 > MAXN) return 1;
-    Params p{feat_cl, relproj, depth, V - 1, V, H, W, entropy, sim_sum, corr, nullptr, nullptr, 0};
+    Params p{feat_cl, relproj, depth, V - 1, V, H, W, entropy, sim_depth, corr, nullptr, nullptr, 0};
     set_slots(p, view_slots, V);
-    const bool sim = sim_sum != nullptr;
+    const bool sim = sim_depth != nullptr;
     if (C == 64 && D == 32 && corr) return sim ? launch<Stage1, 1, true>(p, B, nmaps, st) : launch<Stage1, 1, false>(p, B, nmaps, st);
     if (C == 32 && D == 16 && corr) return sim ? launch<Stage2, 1, true>(p, B, nmaps, st) : launch<Stage2, 1, false>(p, B, nmaps, st);
     if (C == 16 && D == 8 && corr) {
@@ -726,13 +738,13 @@ static int check_slots(const char* fn, int nmaps, const int* view_slots, int B, 
 }
 
 extern "C" int mvs_cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slots, const float* relproj,
-                                          const float* depth, float* entropy, float* sim_sum, float* corr, int B, int V, int C,
+                                          const float* depth, float* entropy, float* sim_depth, float* corr, int B, int V, int C,
                                           int G, int D, int H, int W, void* stream) {
     MVS_REQUIRE(feat_cl && relproj && depth && entropy, "mvs_cost_volume_cl_entropy: null pointer");
     if (int rc = check_slots("mvs_cost_volume_cl_entropy", nmaps, view_slots, B, V)) return rc;
     MVS_REQUIRE(B >= 1 && V >= 2 && C >= 1 && G >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_cost_volume_cl_entropy: empty shape");
     MVS_REQUIRE(C % G == 0, "mvs_cost_volume_cl_entropy: %d channels do not split into %d groups", C, G);
-    return mvs::cost_volume_cl_entropy(feat_cl, nmaps, view_slots, relproj, depth, entropy, sim_sum, corr, B, V, C, G, D, H, W,
+    return mvs::cost_volume_cl_entropy(feat_cl, nmaps, view_slots, relproj, depth, entropy, sim_depth, corr, B, V, C, G, D, H, W,
                                        (cudaStream_t)stream);
 }
 

@@ -94,7 +94,9 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
     uint64_t *full2 = bars + 8, *free2 = bars + 9, *acc3_full = bars + 10, *acc3_free = bars + 11;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index broadcast from lane 0: the compiler then knows it is warp-uniform, keeps the role branches and everything
+    // derived inside them (descriptors, TMEM addresses) on the uniform datapath — the MMA issue loop is the pipeline's pace-maker
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full1[i], NPROD); mbar_init(&free1[i], 1);
@@ -112,7 +114,7 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ================================================= MMA issuer (whole warp, convergent) =========================

@@ -169,15 +169,16 @@ def _cl_views(feat_cl, view_slots):
 
 def cost_volume_cl_entropy(feat_cl, relproj, depth_values, groups, want_sim, view_slots=None):
     """Pass A over channels-last features [B,V,H,W,C] (or a pool [S,H,W,C] whose maps ``view_slots`` are the views of one
-    batch item).  Returns (entropy [B,N,H,W], sim or None, corr [B,N,D,H,W,G] or None): the per-view correlation is
-    stored where C/G >= 2 (one sampling pass); None when the shape is not covered."""
+    batch item).  Returns (entropy [B,N,H,W], sim_depth [B,H,W] or None, corr [B,N,D,H,W,G] or None): the per-view
+    correlation is stored where C/G >= 2 (one sampling pass); sim_depth is the hypothesis with the largest summed cosine
+    similarity (the argmax is taken inside the kernel).  None when the shape is not covered."""
     require_cuda(feat_cl, relproj, depth_values)
     b, v, h, w, c, nmaps, slots = _cl_views(feat_cl, view_slots)
     d = depth_values.shape[1]
     if not cl_supported(c, d, groups):
         return None
     entropy = torch.empty(b, v - 1, h, w, device=feat_cl.device, dtype=torch.float32)
-    sim = torch.empty(b, d, h, w, device=feat_cl.device, dtype=torch.float32) if want_sim else None
+    sim = torch.empty(b, h, w, device=feat_cl.device, dtype=torch.float32) if want_sim else None
     corr = torch.empty(b, v - 1, d, h, w, groups, device=feat_cl.device, dtype=torch.float32) if c // groups >= 2 else None
     rc = _lib.load().mvs_cost_volume_cl_entropy(ptr(feat_cl), nmaps, None if slots is None else ctypes.cast(slots, ctypes.c_void_p),
                                                 ptr(relproj), ptr(depth_values), ptr(entropy), ptr(sim), ptr(corr),

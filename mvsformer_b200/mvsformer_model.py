@@ -133,8 +133,9 @@ class StageNet(nn.Module):
         return engine.vis_weight(maps, self._vis_params_host()).view(b, n, h, w)
 
     def build_cost_volume(self, features, proj_matrices, depth_values, features_cl=None, view_slots=None):
-        """models/mvsformer_model.py:52-105 -> (volume channels-last [B,D,H,W,G], sim_sum or None,
-        entropy [B,N,H,W], vis_weight [B,N,H,W]).  ``features_cl`` [B,V,H,W,C]: the same features already re-laid
+        """models/mvsformer_model.py:52-105 -> (volume channels-last [B,D,H,W,G], sim, entropy [B,N,H,W], vis_weight
+        [B,N,H,W]); sim = sim_depth [B,H,W] from the channels-last kernels, the summed similarity volume [B,D,H,W] from the
+        NCHW kernels, None in training.  ``features_cl`` [B,V,H,W,C]: the same features already re-laid
         out channels-last (CascadeMVS converts all stages in one launch); made here when absent.  With ``view_slots``
         (scan mode, B = 1) ``features`` may be None and ``features_cl`` is a per-scan pool [slots,H,W,C] whose maps
         ``view_slots`` = [reference, sources...] are this sample's views — nothing is gathered."""
@@ -284,7 +285,8 @@ class StageNet(nn.Module):
         outputs = {"depth": depth, "prob_volume": prob_volume, "photometric_confidence": conf,
                    "depth_values": depth_values, "prob_volume_pre": prob_volume_pre}
         if not self.training:
-            outputs["sim_depth"] = engine.argmax_gather(sim, depth_values)
+            # the channels-last kernels take the argmax themselves ([B,H,W]); the NCHW kernels return the volume
+            outputs["sim_depth"] = sim if sim.dim() == 3 else engine.argmax_gather(sim, depth_values)
         return outputs
 
 
@@ -299,6 +301,7 @@ class CascadeMVS(nn.Module):
         self.depth_interals_ratio = args["depth_interals_ratio"]
         self.inverse_depth = args.get("inverse_depth", False)
         self.fusions = nn.ModuleList([StageNet(args, self.ndepths[i], i) for i in range(len(self.ndepths))])
+        self._side, self._cl_ready = None, None
 
     def _features_cl(self, features):
         """Channels-last copies of all stages' features in ONE launch (eval, 'cnn' fusion, shapes the channels-last
@@ -312,7 +315,23 @@ class CascadeMVS(nn.Module):
             if self.fusions[s].fusion_type != "cnn" or f.dim() != 5 or not f.is_cuda \
                     or not engine.cl_supported(f.shape[2], self.ndepths[s], groups):
                 return None
-        return engine.features_to_cl(feats)
+        # stage 1 on the compute stream; stages 2-4 (HBM-bound copies) on a side stream, under the latency-bound kernels
+        # of stage 1 — each stage waits for its own features only
+        main = torch.cuda.current_stream(feats[0].device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=feats[0].device)
+        out = engine.features_to_cl(feats[:1])
+        if nst > 1:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                rest = engine.features_to_cl(feats[1:])
+                done = torch.cuda.Event()
+                done.record(self._side)
+            for t in rest:
+                t.record_stream(main)
+            out += rest
+            self._cl_ready = done
+        return out
 
     def forward(self, features, proj_matrices, depth_values, tmp=2.0, full_hw=None, pools_cl=None, view_slots=None):
         """features {"stageK": [B,V,C,h,w]}, proj_matrices {"stageK": [B,V,2,4,4]}, depth_values [B,ND].
@@ -355,6 +374,9 @@ class CascadeMVS(nn.Module):
                 outputs_stage = self.fusions[s](None, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
                                                 features_cl=pools_cl["stage%d" % (s + 1)], view_slots=view_slots)
             elif feats_cl is not None:
+                if s == 1 and self._cl_ready is not None:
+                    torch.cuda.current_stream(device).wait_event(self._cl_ready)      # stages 2-4 were re-laid out on the side stream
+                    self._cl_ready = None
                 outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
                                                 features_cl=feats_cl[s])
             else:

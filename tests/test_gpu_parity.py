@@ -67,6 +67,21 @@ def test_warp_vs_golden_and_oracle():
             assert (mask.cpu() != gm).float().mean() < 2e-3
 
 
+def _check_similarity(net, sim, sim_o, feats, cams, hyp, tol, agree):
+    """The channels-last kernels return sim_depth [B,H,W] (argmax taken inside the kernel): compare the chosen hypotheses with
+    the oracle's argmax, and hold the similarity VOLUME of the NCHW kernels (same arithmetic) to the oracle's."""
+    from mvsformer_b200 import config
+    if sim.dim() == 3:
+        want = torch.gather(hyp, 1, sim_o.argmax(dim=1, keepdim=True)).squeeze(1)
+        assert (sim.cpu() == want).float().mean() > agree
+        config.set_cv_layout("nchw")
+        try:
+            sim = net.build_cost_volume(cu(feats), cu(cams), cu(hyp))[1]
+        finally:
+            config.set_cv_layout("cl")
+    assert rel_l1(sim.cpu(), sim_o) < tol
+
+
 @pytest.mark.parametrize("s", [0, 1, 2, 3])
 @pytest.mark.parametrize("smooth", [True, False])
 def test_cost_volume_parts(s, smooth):
@@ -86,7 +101,7 @@ def test_cost_volume_parts(s, smooth):
     wgt_o = torch.cat(parts["weight"], dim=1)
     assert rel_l1(entropy.cpu(), ent_o) < tol
     assert rel_l1(weight.cpu(), wgt_o) < tol
-    assert rel_l1(sim.cpu(), sim_o) < tol
+    _check_similarity(net, sim, sim_o, feats, cams, hyp, tol, 0.99 if smooth else 0.97)
     assert rel_l1(volume.cpu().permute(0, 4, 1, 2, 3), vol_o) < tol
     # the vis net alone, on the oracle's entropy (isolates the fused 2D CNN)
     b, n, h, w = ent_o.shape
@@ -120,7 +135,7 @@ def test_cost_volume_wild_geometry(s):
     vol_o, sim_o, parts = O.build_cost_volume(feats, cams, hyp, sd, want_parts=True)
     volume, sim, entropy, weight = net.build_cost_volume(cu(feats), cu(cams), cu(hyp))
     assert rel_l1(entropy.cpu(), torch.cat(parts["entropy"], dim=1)) < 1e-4
-    assert rel_l1(sim.cpu(), sim_o) < 1e-4
+    _check_similarity(net, sim, sim_o, feats, cams, hyp, 1e-4, 0.97)
     assert rel_l1(volume.cpu().permute(0, 4, 1, 2, 3), vol_o) < 1e-4
 
 
@@ -274,7 +289,7 @@ def test_stagenet_vs_golden(s):
     assert rel_l1(out["photometric_confidence"].cpu(), g["photometric_confidence"]) < 2e-5
     # argmax over a similarity volume with exact ties in fp32 (the stage-1 case has top-1 == top-2 pixels): a different,
     # equally valid summation order over the channels flips a handful of them (cosine sums agree to 1.2e-7 absolute,
-    # scripts/debug_sim.py: 3 of 768 pixels differ for the round-1 kernels, 4 for the channels-last ones)
+    # measured on B200: 3 of 768 pixels differ for the round-1 kernels, 4 for the channels-last ones)
     assert (out["sim_depth"].cpu() == torch.from_numpy(g["sim_depth"])).float().mean() > 0.99
 
 

@@ -398,7 +398,11 @@ def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
     assert rel_l1(e1, e0) < 2e-6, rel_l1(e1, e0)
     assert rel_l1(w1, w0) < 2e-6
     assert rel_l1(v1, v0) < 5e-6, rel_l1(v1, v0)
-    assert rel_l1(s1, s0) < 5e-6, rel_l1(s1, s0)
+    # the channels-last kernels take the argmax of the similarity inside the kernel: compare the chosen hypotheses
+    from mvsformer_b200 import engine
+    sd0 = engine.argmax_gather(s0, hyp.to(DEV))
+    assert s1.shape == sd0.shape
+    assert (s1 == sd0).float().mean() > (0.97 if wild else 0.99)          # exact ties flip under another summation order
     assert torch.isfinite(v1).all()
 
 
