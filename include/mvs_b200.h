@@ -336,7 +336,9 @@ int mvs_fusion_prob_filter(const float* prob, const float* thresh_host, int nthr
 /* ---- fused visibility net (csrc/vis_fused.cu): models/mvsformer_model.py:37,91 in ONE kernel --------------------------
  * entropy [M,H,W] -> weight [M,H,W]; only those two maps touch HBM.  params [host]: w1[16][9] b1[16] shift2[16] shift3[8]
  * w4[8] b4 (BN folded into w1 / the packed weights; shifts = folded BN biases), MVS_VIS_FUSED_PARAM_FLOATS floats.
- * w2 (16->16) and w3 (16->8, padded to 16 outputs): device, packed like mvs_conv3d_tma weights with kd = 1, n_tile = 16. */
+ * w2 (16->16) and w3 (16->8): device, TF32, packed [kw][4 input-channel quads][rows][4] where the rows of a (kw, quad) are
+ * [kh][cout] — 48 rows for w2, 24 + 8 rows of zeros for w3 (mvsformer_b200.engine.pack_vis_fused_weights): the three kernel
+ * rows are ONE tcgen05.mma operand. */
 #define MVS_VIS_FUSED_PARAM_FLOATS (16 * 9 + 16 + 16 + 8 + 8 + 1)
 int mvs_vis_fused(const float* entropy, const float* params, const float* w2, const float* w3, float* weight, int M, int H,
                   int W, void* stream);

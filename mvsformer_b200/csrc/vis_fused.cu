@@ -4,18 +4,23 @@
 // Why (profiles/r02c_launches.csv): as four kernels the net moved its [maps,H,W,16] activations through HBM three times —
 // 2.7 GB per reference view at stage 4, more than the whole cost-volume build's byte budget — for 1.13 ms of the 5.3 ms step.
 //
-// A CTA lives for the whole launch and takes tiles of 30 x 14 output pixels of one map.  Per tile:
-//   producer warps   layer 1 (1->16, 3x3) on CUDA cores for the 34 x 18 pixels layer 2 needs, written straight into shared memory
+// A CTA lives for the whole launch and takes tiles of 28 x 14 output pixels of one map.  Per tile:
+//   producer warps   layer 1 (1->16, 3x3) on CUDA cores for the 32 x 18 pixels layer 2 reads, written straight into shared memory
 //                    as layer 2's tensor-core operand: channels-last 64-byte pixels in the 64-byte-swizzled K-major layout
 //                    (the same layout TMA produces in conv3d_tma.cu; here the threads apply the address swizzle themselves);
-//   MMA warp         layer 2 (16->16) as 4 M-tiles x 9 taps x 2 tcgen05.mma (kind::tf32, M = 128 = 16 rows x 8 pixels, N = 16),
-//                    a tap being a pixel shift of the descriptor start address — accumulators in TMEM;
-//   epilogue warps   drain layer 2 (+ folded-BN shift, ReLU, TF32 round, zero outside the image = layer 3's padding) back into
-//                    shared memory as layer 3's operand; after layer 3's MMAs (16->8, N padded to 16) drain again and finish
-//                    in registers: ReLU, the 1x1 conv 8->1, sigmoid, one float per pixel to HBM.
+//   MMA warp         layers 2 (16->16) and 3 (16->8) as tcgen05.mma kind::tf32 with the three kh taps FUSED INTO N: an M-tile is
+//                    16 INPUT rows x 8 pixels, the B operand of a (kw, K chunk) is [W(kh=0) | W(kh=1) | W(kh=2)], so one MMA
+//                    yields the partial sums T[kh](input row) of all three kernel rows: 6 MMAs per M-tile and layer instead
+//                    of 18.  (Measured, scripts/mma_rate_probe.cu: a tf32 M = 128 MMA costs ~75 clk for ANY N <= 128, so
+//                    N = 48 is as cheap as N = 16 — the first version of this kernel, 18 MMAs of N = 16, sat at exactly that
+//                    issue floor: 0.75 ms.)
+//   epilogue warps   drain the accumulators, exchange T[1], T[2] through shared memory and form
+//                    out(y) = T[0](y) + T[1](y+1) + T[2](y+2); layer 2: + folded-BN shift, ReLU, TF32 round, zero outside the
+//                    image (= layer 3's padding), written back to shared memory as layer 3's operand; layer 3: ReLU, the 1x1
+//                    conv 8->1, sigmoid, one float per pixel to HBM.
 // Layer 2 of tile i+1 is issued before layer 3 of tile i (double-buffered layer-1 operand and layer-2 accumulators), so the
-// tensor core, the CUDA-core producers and the epilogue warps overlap.  Arithmetic matches the unfused kernels operation by
-// operation (same FMA order in layers 1 and 4, same TF32 operands and rounding points), so the result is bit-identical.
+// tensor core, the CUDA-core producers and the epilogue warps overlap.  Operands and rounding points are those of the
+// unfused kernels; only the order of the three per-kh partial sums differs (fp32, ~1e-7 relative).
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,15 +31,17 @@ namespace mvs {
 namespace tc {
 namespace visf {
 
-constexpr int OUT_Y = 30, OUT_X = 14;            // output pixels per tile
-constexpr int RY = 32, RX = 16;                  // layer-2 region = 2 x 2 M-tiles of 16 rows x 8 pixels
-constexpr int AY = 34, AX = 18;                  // operand arrays: region + 1-pixel halo
+constexpr int OUT_Y = 28, OUT_X = 14;            // output pixels per tile
+constexpr int AY = 32, AX = 18;                  // operand arrays: 2 x 2 M-tiles of 16 input rows x 8 pixels (+2 columns of kw halo)
 constexpr int PIXB = 64;                         // bytes per pixel (16 channels)
-constexpr int ABYTES = (AY * AX * PIXB + 1023) / 1024 * 1024;
-constexpr int WBYTES = 9 * 4 * 16 * 16;          // one packed 3x3 16->16 weight tile
-constexpr int NPROD = 4, NEPI = 8;               // producer / epilogue warps
+constexpr int ABYTES = AY * AX * PIXB;           // 36 KB, a multiple of 1024
+constexpr int N2 = 48, N3 = 32;                  // MMA N: [3 kh][16] and [3 kh][8] padded to 32
+constexpr int W2BYTES = 3 * 4 * N2 * 16, W3BYTES = 3 * 4 * N3 * 16;      // packed [kw][quad][kh][n][4]
+constexpr int XBYTES = 2 * AY * 16 * PIXB;       // exchange buffers for T[1], T[2]: [2][32 rows][16 pixels][64 B]
+constexpr int NPROD = 7, NEPI = 8;               // producer / epilogue warps
 constexpr int THREADS = 32 * (1 + NPROD + NEPI);
-constexpr size_t SMEM = 3 * ABYTES + 2 * WBYTES + 256 + 1024;
+constexpr size_t SMEM = 3 * ABYTES + W2BYTES + W3BYTES + XBYTES + 256 + 1024;
+static_assert(ABYTES % 1024 == 0, "operand arrays keep the swizzle phase");
 
 struct Params {
     float w1[16][9]; float b1[16];               // layer 1, BN folded
@@ -65,6 +72,7 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
         "}" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory"); }   // epilogue warps only
 // K-major operand with the 64-byte swizzle: rows (pixels) 64 B apart, 8-row groups `sbo` bytes apart
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -75,7 +83,7 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_
     d |= (uint64_t)4 << 61;
     return d;
 }
-// byte offset of 16-byte chunk c of pixel `pix` inside a 1024-byte-aligned operand array: Swizzle<2,4,3> on the address
+// byte offset of 16-byte chunk c of pixel `pix` inside a 1024-byte-aligned array of 64-byte pixels: Swizzle<2,4,3> on the address
 __device__ __forceinline__ uint32_t sw64_offset(int pix, int c) {
     const uint32_t off = (uint32_t)pix * PIXB;
     return off + (uint32_t)((c ^ ((off >> 7) & 3)) << 4);
@@ -87,11 +95,13 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA1 = smem;                                   // [2][AY][AX][64 B]  layer-1 output = layer-2 operand
-    uint8_t* sA2 = smem + 2 * ABYTES;                      // [AY][AX][64 B]     layer-2 output = layer-3 operand (border stays zero)
-    uint8_t* sW = sA2 + ABYTES;                            // W2, W3 packed [tap][quad][16 n][4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 2 * WBYTES);
-    uint64_t *full1 = bars, *free1 = bars + 2, *acc2_full = bars + 4, *acc2_free = bars + 6;
-    uint64_t *full2 = bars + 8, *free2 = bars + 9, *acc3_full = bars + 10, *acc3_free = bars + 11;
+    uint8_t* sA2 = smem + 2 * ABYTES;                      // [AY][AX][64 B]     layer-2 output = layer-3 operand (rest stays zero)
+    uint8_t* sX = sA2 + ABYTES;                            // [2][AY][16][64 B]  T[1], T[2] exchange
+    uint8_t* sW2 = sX + XBYTES;                            // [kw][quad][3 kh x 16 n][4]
+    uint8_t* sW3 = sW2 + W2BYTES;                          // [kw][quad][3 kh x 8 n + 8 pad][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW3 + W3BYTES);
+    uint64_t *full1 = bars, *free1 = bars + 2, *acc2_full = bars + 4, *acc2_free = bars + 5;
+    uint64_t *full2 = bars + 6, *free2 = bars + 7, *acc3_full = bars + 8, *acc3_free = bars + 10;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     // warp index broadcast from lane 0: the compiler then knows it is warp-uniform, keeps the role branches and everything
@@ -100,60 +110,64 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full1[i], NPROD); mbar_init(&free1[i], 1);
-            mbar_init(&acc2_full[i], 1); mbar_init(&acc2_free[i], NEPI * 32);
+            mbar_init(&acc3_full[i], 1); mbar_init(&acc3_free[i], NEPI * 32);
         }
-        mbar_init(full2, NEPI * 32); mbar_init(free2, 1); mbar_init(acc3_full, 1); mbar_init(acc3_free, NEPI * 32);
+        mbar_init(full2, NEPI * 32); mbar_init(free2, 1); mbar_init(acc2_full, 1); mbar_init(acc2_free, NEPI * 32);
         mbar_fence_init();
     }
     // weights -> shared memory (plain copies; made visible to the tensor core by the proxy fence below), A2 zeroed once
-    for (int i = tid; i < 2 * WBYTES / 16; i += THREADS)
-        reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(i < WBYTES / 16 ? w2 : w3) + (i < WBYTES / 16 ? i : i - WBYTES / 16));
+    for (int i = tid; i < W2BYTES / 16; i += THREADS) reinterpret_cast<float4*>(sW2)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
+    for (int i = tid; i < W3BYTES / 16; i += THREADS) reinterpret_cast<float4*>(sW3)[i] = __ldg(reinterpret_cast<const float4*>(w3) + i);
     for (int i = tid; i < ABYTES / 16; i += THREADS) reinterpret_cast<float4*>(sA2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // TMEM columns: layer-2 accumulators [4 M-tiles][48] (drained right away, so one buffer), layer-3 accumulators
+    // [2 buffers][4 M-tiles][32]: the epilogue finishes tile i-1 (layer 3) AFTER it has handed tile i's layer-2 output to
+    // the tensor core, so layer 3 of tile i runs while tile i-1's result is still being drained
+    constexpr uint32_t ACC3 = 4 * N2;
 
     if (warp == 0) {
         // ================================================= MMA issuer (whole warp, convergent) =========================
-        constexpr uint32_t idesc = make_idesc_tf32(128, 16);
         const uint64_t a1d = make_desc_sw64(smem_u32(sA1), AX * PIXB), a2d = make_desc_sw64(smem_u32(sA2), AX * PIXB);
-        const uint64_t b2d = make_smem_desc(smem_u32(sW), 256, 128), b3d = make_smem_desc(smem_u32(sW) + WBYTES, 256, 128);
-        // one layer over the four M-tiles of a region: 9 taps x 2 K chunks each, a tap = a pixel shift of the start address
-        auto layer = [&](uint64_t ad, uint64_t bd, uint32_t acc0) {
+        const uint64_t b2d = make_smem_desc(smem_u32(sW2), N2 * 16, 128), b3d = make_smem_desc(smem_u32(sW3), N3 * 16, 128);
+        // one layer over the four M-tiles: 3 kw x 2 K chunks, N = the three kh taps; a kw tap = a pixel shift of the start address
+        auto layer = [&](uint64_t ad, uint64_t bd, uint32_t acc0, uint32_t n, uint32_t idesc) {
 #pragma unroll 1
             for (int t = 0; t < 4; ++t) {
                 const uint64_t at = ad + (uint64_t)((((t >> 1) * 16 * AX + (t & 1) * 8) * PIXB) >> 4);
-                const uint32_t dcol = acc0 + (uint32_t)t * 16;
+                const uint32_t dcol = acc0 + (uint32_t)t * n;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap)
+                for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk)
-                        mma_tf32_ss_elect(dcol, at + (uint64_t)((((tap / 3) * AX + (tap % 3)) * PIXB + kk * 32) >> 4),
-                                          bd + (uint64_t)((tap * 4 + 2 * kk) * 16), idesc, (tap | kk) ? 1u : 0u);
+                        mma_tf32_ss_elect(dcol, at + (uint64_t)((kw * PIXB + kk * 32) >> 4), bd + (uint64_t)((kw * 4 + 2 * kk) * n), idesc,
+                                          (kw | kk) ? 1u : 0u);
             }
         };
         auto layer2 = [&](int j) {
             const int b = j & 1;
             mbar_wait(&full1[b], (j >> 1) & 1);
-            if (j >= 2) mbar_wait(&acc2_free[b], ((j >> 1) - 1) & 1);
+            if (j >= 1) mbar_wait(acc2_free, (j - 1) & 1);
             tc_fence_after_sync();
-            layer(a1d + (uint64_t)(b * (ABYTES >> 4)), b2d, tmem + (uint32_t)b * 64);
+            layer(a1d + (uint64_t)(b * (ABYTES >> 4)), b2d, tmem, N2, make_idesc_tf32(128, N2));
             mma_commit_elect(&free1[b]);
-            mma_commit_elect(&acc2_full[b]);
+            mma_commit_elect(acc2_full);
         };
         int it = 0;
         if ((int)blockIdx.x < d.nitems) layer2(0);
         for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
             if (item + (int)gridDim.x < d.nitems) layer2(it + 1);
+            const int b3 = it & 1;
             mbar_wait(full2, it & 1);
-            if (it >= 1) mbar_wait(acc3_free, (it - 1) & 1);
+            if (it >= 2) mbar_wait(&acc3_free[b3], ((it >> 1) - 1) & 1);
             tc_fence_after_sync();
-            layer(a2d, b3d, tmem + 128);
+            layer(a2d, b3d, tmem + ACC3 + (uint32_t)b3 * 4 * N3, N3, make_idesc_tf32(128, N3));
             mma_commit_elect(free2);
-            mma_commit_elect(acc3_full);
+            mma_commit_elect(&acc3_full[b3]);
         }
     } else if (warp <= NPROD) {
         // ================================================= layer-1 producers (CUDA cores) ==============================
@@ -166,7 +180,7 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
             if (it >= 2) mbar_wait(&free1[b], ((it >> 1) - 1) & 1);
             uint8_t* a1 = sA1 + b * ABYTES;
             for (int pix = pt; pix < AY * AX; pix += NPROD * 32) {
-                const int y = ty * OUT_Y - 2 + pix / AX, x = tx * OUT_X - 2 + pix % AX;
+                const int y = ty * OUT_Y - 2 + pix / AX, x = tx * OUT_X - 2 + pix % AX;      // A1 origin = tile origin - 2
                 float r[16];
                 if (y >= 0 && y < d.H && x >= 0 && x < d.W) {
                     float in[9];
@@ -198,63 +212,115 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
         // ================================================= epilogue warps ==============================================
         const int q = warp & 3;                            // TMEM lane quarter this warp may read
         const int half = (warp - 1 - NPROD) >> 2;          // M-tiles t = half, half + 2
-        const int mrow = q * 32 + lane;                    // accumulator row = pixel of the M-tile
+        const int mrow = q * 32 + lane;                    // accumulator row = (input row, pixel) of the M-tile
         const int tyl = mrow >> 3, txl = mrow & 7;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        int it = 0;
-        for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
-            const int b = it & 1;
-            const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y, m = item / (d.tiles_x * d.tiles_y);
-            // ---- layer 2 -> operand of layer 3
-            mbar_wait(&acc2_full[b], (it >> 1) & 1);
-            if (it >= 1) mbar_wait(free2, (it - 1) & 1);   // layer 3 of the previous tile has read A2
+        uint8_t* sX1 = sX;                                 // T[1] by input row
+        uint8_t* sX2 = sX + XBYTES / 2;                    // T[2] by input row
+        // layer 3 of tile `jt` (item index `jitem`): out3(oy, ox) = T0(oy) + T1(oy + 1) + T2(oy + 2) -> ReLU -> 1x1 conv -> sigmoid
+        auto finish = [&](int jt, int jitem) {
+            const int b3 = jt & 1;
+            const int tx = jitem % d.tiles_x, ty = (jitem / d.tiles_x) % d.tiles_y, m = jitem / (d.tiles_x * d.tiles_y);
+            mbar_wait(&acc3_full[b3], (jt >> 1) & 1);
             tc_fence_after_sync();
+            float u0[2][8];
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 const int t = half + 2 * tt;
-                float acc[16];
-                tmem_ld16(tlane + (uint32_t)b * 64 + (uint32_t)t * 16, acc);
-                const int ry = (t >> 1) * 16 + tyl, rx = (t & 1) * 8 + txl;           // position in the layer-2 region
-                const int y = ty * OUT_Y - 1 + ry, x = tx * OUT_X - 1 + rx;
-                const bool inside = y >= 0 && y < d.H && x >= 0 && x < d.W;
+                const int r = (t >> 1) * 16 + tyl, ox = (t & 1) * 8 + txl;
+                float u[32];
+                tmem_ld16(tlane + ACC3 + (uint32_t)b3 * 4 * N3 + (uint32_t)t * N3, u);
+                tmem_ld16(tlane + ACC3 + (uint32_t)b3 * 4 * N3 + (uint32_t)t * N3 + 16, u + 16);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float4 v;
-                    v.x = inside ? round_to_tf32(fmaxf(acc[4 * c] + P.shift2[4 * c], 0.f)) : 0.f;
-                    v.y = inside ? round_to_tf32(fmaxf(acc[4 * c + 1] + P.shift2[4 * c + 1], 0.f)) : 0.f;
-                    v.z = inside ? round_to_tf32(fmaxf(acc[4 * c + 2] + P.shift2[4 * c + 2], 0.f)) : 0.f;
-                    v.w = inside ? round_to_tf32(fmaxf(acc[4 * c + 3] + P.shift2[4 * c + 3], 0.f)) : 0.f;
-                    *reinterpret_cast<float4*>(sA2 + sw64_offset(ry * AX + rx, c)) = v;
+                for (int i = 0; i < 8; ++i) u0[tt][i] = u[i];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    *reinterpret_cast<float4*>(sX1 + sw64_offset(r * 16 + ox, c)) = make_float4(u[8 + 4 * c], u[9 + 4 * c], u[10 + 4 * c], u[11 + 4 * c]);
+                    *reinterpret_cast<float4*>(sX2 + sw64_offset(r * 16 + ox, c)) = make_float4(u[16 + 4 * c], u[17 + 4 * c], u[18 + 4 * c], u[19 + 4 * c]);
                 }
             }
-            fence_proxy_async_smem();
             tc_fence_before_sync();
-            mbar_arrive(&acc2_free[b]);
-            mbar_arrive(full2);
-            // ---- layer 3 -> ReLU -> 1x1 conv -> sigmoid
-            mbar_wait(acc3_full, it & 1);
-            tc_fence_after_sync();
+            mbar_arrive(&acc3_free[b3]);
+            epi_sync();
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 const int t = half + 2 * tt;
-                float acc[16];
-                tmem_ld16(tlane + 128 + (uint32_t)t * 16, acc);
-                const int oy_l = (t >> 1) * 16 + tyl, ox_l = (t & 1) * 8 + txl;       // output pixel of the tile
-                const int y = ty * OUT_Y + oy_l, x = tx * OUT_X + ox_l;
-                if (oy_l < OUT_Y && ox_l < OUT_X && y < d.H && x < d.W) {
+                const int oy = (t >> 1) * 16 + tyl, ox = (t & 1) * 8 + txl;
+                const int y = ty * OUT_Y + oy, x = tx * OUT_X + ox;
+                if (oy < OUT_Y && ox < OUT_X && y < d.H && x < d.W) {
                     float z = P.b4;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) z = fmaf(round_to_tf32(fmaxf(acc[i] + P.shift3[i], 0.f)), P.w4[i], z);
+                    for (int c = 0; c < 2; ++c) {
+                        const float4 a1 = *reinterpret_cast<const float4*>(sX1 + sw64_offset((oy + 1) * 16 + ox, c));
+                        const float4 a2 = *reinterpret_cast<const float4*>(sX2 + sw64_offset((oy + 2) * 16 + ox, c));
+                        const float e1[4] = {a1.x, a1.y, a1.z, a1.w}, e2[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float act = round_to_tf32(fmaxf((u0[tt][4 * c + i] + e1[i]) + e2[i] + P.shift3[4 * c + i], 0.f));
+                            z = fmaf(act, P.w4[4 * c + i], z);
+                        }
+                    }
                     weight[((int64_t)m * d.H + y) * d.W + x] = 1.0f / (1.0f + expf(-z));
                 }
             }
+            epi_sync();                                    // exchange buffers free again
+        };
+        int it = 0, prev_item = -1;
+        for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
+            const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y;
+            // ---- layer 2: out2(y2, x2) = T0(y2) + T1(y2 + 1) + T2(y2 + 2) -> operand of layer 3
+            mbar_wait(acc2_full, it & 1);
+            tc_fence_after_sync();
+            float t0[2][16];
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                const int t = half + 2 * tt;
+                const int r = (t >> 1) * 16 + tyl, x2 = (t & 1) * 8 + txl;             // input row / pixel column of this lane
+                const uint32_t ta = tlane + (uint32_t)t * N2;
+                float t1[16], t2[16];
+                tmem_ld16(ta, t0[tt]);
+                tmem_ld16(ta + 16, t1);
+                tmem_ld16(ta + 32, t2);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<float4*>(sX1 + sw64_offset(r * 16 + x2, c)) = make_float4(t1[4 * c], t1[4 * c + 1], t1[4 * c + 2], t1[4 * c + 3]);
+                    *reinterpret_cast<float4*>(sX2 + sw64_offset(r * 16 + x2, c)) = make_float4(t2[4 * c], t2[4 * c + 1], t2[4 * c + 2], t2[4 * c + 3]);
+                }
+            }
             tc_fence_before_sync();
-            mbar_arrive(acc3_free);
+            mbar_arrive(acc2_free);                        // accumulators drained: layer 2 of the next tile may run
+            if (it >= 1) mbar_wait(free2, (it - 1) & 1);   // layer 3 of the previous tile has read A2
+            epi_sync();                                    // T[1], T[2] of every input row are in shared memory
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                const int t = half + 2 * tt;
+                const int y2 = (t >> 1) * 16 + tyl, x2 = (t & 1) * 8 + txl;
+                if (y2 >= AY - 2) continue;                // rows 30, 31 are no layer-2 outputs
+                const int y = ty * OUT_Y - 1 + y2, x = tx * OUT_X - 1 + x2;             // A2 origin = tile origin - 1
+                const bool inside = y >= 0 && y < d.H && x >= 0 && x < d.W;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 a1 = *reinterpret_cast<const float4*>(sX1 + sw64_offset((y2 + 1) * 16 + x2, c));
+                    const float4 a2 = *reinterpret_cast<const float4*>(sX2 + sw64_offset((y2 + 2) * 16 + x2, c));
+                    float4 v;
+                    v.x = inside ? round_to_tf32(fmaxf((t0[tt][4 * c] + a1.x) + a2.x + P.shift2[4 * c], 0.f)) : 0.f;
+                    v.y = inside ? round_to_tf32(fmaxf((t0[tt][4 * c + 1] + a1.y) + a2.y + P.shift2[4 * c + 1], 0.f)) : 0.f;
+                    v.z = inside ? round_to_tf32(fmaxf((t0[tt][4 * c + 2] + a1.z) + a2.z + P.shift2[4 * c + 2], 0.f)) : 0.f;
+                    v.w = inside ? round_to_tf32(fmaxf((t0[tt][4 * c + 3] + a1.w) + a2.w + P.shift2[4 * c + 3], 0.f)) : 0.f;
+                    *reinterpret_cast<float4*>(sA2 + sw64_offset(y2 * AX + x2, c)) = v;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(full2);                            // -> the tensor core starts layer 3 of this tile ...
+            epi_sync();                                    // exchange buffers free again
+            if (prev_item >= 0) finish(it - 1, prev_item); // ... while the previous tile's layer-3 result is finished here
+            prev_item = item;
         }
+        if (prev_item >= 0) finish(it - 1, prev_item);
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace visf
@@ -262,7 +328,8 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
 }  // namespace mvs
 
 // entropy [M,H,W] -> visibility weight [M,H,W].  params_host: w1[16][9] b1[16] shift2[16] shift3[8] w4[8] b4 (BN folded);
-// w2 / w3: device, packed like mvs_conv3d_tma weights for kd = 1, Cin = 16, n_tile = 16 ([kh][kw][4 quads][16 n][4], TF32).
+// w2 / w3: device, TF32, packed [kw][Cin/4][kh][n][4] with n = 16 (w2) and n = 8 + 8 rows of zero padding after the three
+// kh blocks (w3: 32 rows per (kw, quad)) — mvsformer_b200.engine.pack_vis_fused_weights.
 extern "C" int mvs_vis_fused(const float* entropy, const float* params_host, const float* w2, const float* w3, float* weight,
                              int M, int H, int W, void* stream) {
     using namespace mvs::tc::visf;

@@ -233,6 +233,16 @@ def vis_weight(entropy_maps, params_host):
     return out
 
 
+def pack_vis_fused_weights(w, rows):
+    """[Cout, 16, 3, 3] (BN folded) -> [kw][4 quads][rows][4] TF32: per (kw, input-channel quad) the B rows are [kh][cout]
+    (3 * Cout of them, zero-padded to ``rows``): the three kernel rows are one MMA operand (mvs_vis_fused)."""
+    cout, cin = w.shape[:2]
+    t = w.permute(3, 1, 2, 0).reshape(3, cin // 4, 4, 3, cout).permute(0, 1, 3, 4, 2).reshape(3, cin // 4, 3 * cout, 4)
+    if rows > 3 * cout:
+        t = torch.nn.functional.pad(t, (0, 0, 0, rows - 3 * cout))
+    return round_tf32(t.contiguous())
+
+
 def vis_fused(entropy_maps, params_host, w2_packed, w3_packed):
     """[M,H,W] entropy -> [M,H,W] visibility weight, the whole net in one persistent kernel (mvs_vis_fused)."""
     require_cuda(entropy_maps, w2_packed, w3_packed)

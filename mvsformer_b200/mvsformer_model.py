@@ -103,9 +103,7 @@ class StageNet(nn.Module):
                 blk = self.vis[i]
                 scale, shift = _bn_scale_shift(blk.bn)
                 w = blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)          # [Co,Ci,3,3]
-                wt, nt = engine.pack_tma_weights(w.permute(2, 3, 1, 0).unsqueeze(0).contiguous())
-                assert nt == 16 and wt.numel() == 9 * 16 * 16
-                packed.append(wt)
+                packed.append(engine.pack_vis_fused_weights(w, 48 if i == 1 else 32))
                 shifts.append(shift.detach().float().cpu().numpy().astype(np.float32))
             params = np.ascontiguousarray(np.concatenate([first, shifts[0], shifts[1], last]).astype(np.float32))
             return params, packed[0], packed[1]

@@ -408,9 +408,10 @@ def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
 
 # ---- fused visibility net (csrc/vis_fused.cu) ----------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(4, 144, 192), (3, 37, 50), (2, 30, 14), (1, 31, 15), (5, 200, 333)])
-def test_fused_vis_net_is_bit_identical_to_the_four_kernel_route(shape):
-    """Same TF32 operands, same FMA order, same rounding points: the fused kernel must reproduce the unfused tensor-core
-    route bit for bit (which tests/test_gpu_parity.py holds to the oracle), incl. partial tiles and maps smaller than a tile."""
+def test_fused_vis_net_matches_the_four_kernel_route(shape):
+    """Same TF32 operands and rounding points as the unfused tensor-core route (which tests/test_gpu_parity.py holds to the
+    oracle); only the order in which the three kernel rows' partial sums are added differs (fp32).  Incl. partial tiles and
+    maps smaller than a tile."""
     from tests.helpers import rel_l1
     m, h, w = shape
     net = StageNet(dict(STAGE_ARGS), 8, 2).eval()
@@ -429,5 +430,6 @@ def test_fused_vis_net_is_bit_identical_to_the_four_kernel_route(shape):
         config.set_conv_precision(old)
     torch.cuda.synchronize()
     assert got.shape == want.shape
-    assert rel_l1(got, want) < 1e-6, rel_l1(got, want)
-    assert torch.equal(got, want)
+    # a 1e-7 difference in a partial sum can flip the TF32 rounding of an activation (2^-11 relative), hence the margins
+    assert rel_l1(got, want) < 2e-5, rel_l1(got, want)
+    assert float((got - want).abs().max()) < 2e-3
