@@ -179,7 +179,7 @@ class KernelProfiler:
         def cl_agg_cost(out, feat_cl, relproj, depth_values, vis_weight, groups, round_tf32=False):
             return numel_bytes(feat_cl, depth_values, vis_weight, out), 0
 
-        def to_cl_cost(out, feature_list):
+        def to_cl_cost(out, feature_list, outs=None):
             return 2 * numel_bytes(*feature_list), 0
 
         # round-2 channels-last cost-volume kernels (csrc/cost_volume_cl.cu)

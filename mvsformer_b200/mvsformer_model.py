@@ -320,13 +320,15 @@ class CascadeMVS(nn.Module):
             self._side = torch.cuda.Stream(device=feats[0].device)
         out = engine.features_to_cl(feats[:1])
         if nst > 1:
+            # destinations are allocated on the compute stream (its allocator pool; no cross-stream frees), only the copies
+            # run on the side stream; the compute stream waits for them before stage 2, i.e. before anything is released
+            rest = [torch.empty(f.shape[:2] + (f.shape[3], f.shape[4], f.shape[2]), device=f.device, dtype=torch.float32)
+                    for f in feats[1:]]
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                rest = engine.features_to_cl(feats[1:])
+                engine.features_to_cl(feats[1:], outs=rest)
                 done = torch.cuda.Event()
                 done.record(self._side)
-            for t in rest:
-                t.record_stream(main)
             out += rest
             self._cl_ready = done
         return out

@@ -123,6 +123,7 @@ class StreamedCascade:
         self._pools = None               # {"stageK": [capacity, h, w, C]} channels-last device pools
         self._staging = None             # {"stageK": [C, h, w]} landing buffers of an upload (re-laid out into the pool)
         self._compute_done = None        # event: the last enqueued cascade has read the pools
+        self._slot_used = {}             # slot -> event of the last cascade that read it
 
     def _upload(self, sample):
         """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
@@ -175,8 +176,9 @@ class StreamedCascade:
                         self._pools = {k: torch.empty((cache.capacity,) + tuple(feats[k].shape[1:]) + (feats[k].shape[0],),
                                                       dtype=torch.float32, device=self.device) for k in keys}
                         self._staging = {k: torch.empty(tuple(feats[k].shape), dtype=torch.float32, device=self.device) for k in keys}
-                    if evicted is not None and self._compute_done is not None:
-                        self.copy_stream.wait_event(self._compute_done)     # the evicted view may still be read by a cascade
+                    if evicted is not None and self._slot_used.get(slot) is not None:
+                        # only the cascades that read this slot matter (LRU: usually finished long ago), not the one in flight
+                        self.copy_stream.wait_event(self._slot_used.pop(slot))
                     for k in keys:
                         self._staging[k].copy_(feats[k], non_blocking=True)
                         uploaded += 4 * feats[k].numel()
@@ -209,10 +211,12 @@ class StreamedCascade:
         main = torch.cuda.current_stream(self.device)
         if self.cache is None or self.cache.capacity != capacity:
             self.cache, self._pools, self._staging, self._compute_done = FeatureCache(capacity), None, None, None
+            self._slot_used = {}
         elif not keep_cache:
             if self._compute_done is not None:
                 self.copy_stream.wait_event(self._compute_done)     # pools may still be read by the last cascade
             self.cache = FeatureCache(capacity)                      # pools are reused, their contents forgotten
+            self._slot_used = {}
         it = iter(samples)
         nxt = next(it, None)
         if nxt is None:
@@ -228,6 +232,8 @@ class StreamedCascade:
                 out = self.net(None, c, d, tmp=self.tmp, pools_cl=self._pools, view_slots=slots)
                 self._compute_done = torch.cuda.Event()
                 self._compute_done.record(main)
+                for sl in slots:
+                    self._slot_used[sl] = self._compute_done
                 # staged only now: an upload that evicts a slot waits for the cascade enqueued above, which may read it
                 nxt = next(it, None)
                 staged = self._stage_scan(nxt) if nxt is not None else None  # overlaps with this view's compute
