@@ -40,6 +40,9 @@ prob_conv_kernel(const float* __restrict__ x, float* __restrict__ pre, int D, in
         acc = fmaf(a.x, P.w[0][0], acc); acc = fmaf(a.y, P.w[0][1], acc); acc = fmaf(a.z, P.w[0][2], acc); acc = fmaf(a.w, P.w[0][3], acc);
         acc = fmaf(c.x, P.w[0][4], acc); acc = fmaf(c.y, P.w[0][5], acc); acc = fmaf(c.z, P.w[0][6], acc); acc = fmaf(c.w, P.w[0][7], acc);
     } else {
+        // eight independent accumulators (one per input channel): a single 216-deep FMA chain made this kernel
+        // latency-bound (54 + 99 us at stages 1-2 for 85 MB, profiles/r02_launches_step.csv)
+        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kz = 0; kz < 3; ++kz) {
             const int iz = oz - 1 + kz;
@@ -53,11 +56,14 @@ prob_conv_kernel(const float* __restrict__ x, float* __restrict__ pre, int D, in
                     const float4* p = reinterpret_cast<const float4*>(x + (((b * D + iz) * H + iy) * (int64_t)W + ix) * 8);
                     const float4 a = __ldg(p), c = __ldg(p + 1);
                     const int t = (kz * 3 + ky) * 3 + kx;
-                    acc = fmaf(a.x, P.w[t][0], acc); acc = fmaf(a.y, P.w[t][1], acc); acc = fmaf(a.z, P.w[t][2], acc); acc = fmaf(a.w, P.w[t][3], acc);
-                    acc = fmaf(c.x, P.w[t][4], acc); acc = fmaf(c.y, P.w[t][5], acc); acc = fmaf(c.z, P.w[t][6], acc); acc = fmaf(c.w, P.w[t][7], acc);
+                    a8[0] = fmaf(a.x, P.w[t][0], a8[0]); a8[1] = fmaf(a.y, P.w[t][1], a8[1]);
+                    a8[2] = fmaf(a.z, P.w[t][2], a8[2]); a8[3] = fmaf(a.w, P.w[t][3], a8[3]);
+                    a8[4] = fmaf(c.x, P.w[t][4], a8[4]); a8[5] = fmaf(c.y, P.w[t][5], a8[5]);
+                    a8[6] = fmaf(c.z, P.w[t][6], a8[6]); a8[7] = fmaf(c.w, P.w[t][7], a8[7]);
                 }
             }
         }
+        acc += ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
     }
     pre[out_idx] = acc;
 }

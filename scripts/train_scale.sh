@@ -2,7 +2,7 @@
 # for each arithmetic of the forward / data-gradient convolutions.  usage: bash scripts/train_scale.sh <out dir> <max gpus>
 OUT=${1:-gpurun_out/train}; MAXN=${2:-1}
 mkdir -p $OUT
-for MODE in fp32 tf32; do
+for MODE in ${MODES:-fp32 tf32}; do
   for N in 1 2 4 8; do
     [ $N -gt $MAXN ] && continue
     MVS_TRAIN_CONV=$MODE timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N \
