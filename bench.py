@@ -54,8 +54,8 @@ def conv_mode():
 
 def workload_config(n_gpus):
     from mvsformer_b200 import config
-    extra = {"cost_volume_build": "one sampling pass at stages 1-3 (MVS_CV_STORE)"} if config.cv_store() else {}
-    return {**extra, "workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, "
+    return {"cost_volume_build": "channels-last kernels, one sampling pass at stages 1-3" if config.cv_layout() == "cl"
+            else "generic NCHW kernels, two sampling passes", "workload": "DTU test (cfg 2): %dx%d, %d views, 192-depth range, 4-stage cascade ndepths 32/16/8/4, "
                         "feat ch 64/32/16/8, G=8, B=1 ref view per GPU per step" % (HEIGHT, WIDTH, VIEWS),
             "precision": "fp32 features/volume/activations; conv math %s" % conv_mode(), "parallelism": "ref views sharded, %d rank(s), no collective" % n_gpus,
             "l2_policy": "inputs 530 MB/step > 126 MB L2; every intermediate volume is rewritten each step"}
@@ -167,10 +167,6 @@ class KernelProfiler:
             outs = out if isinstance(out, (tuple, list)) else (out,)
             return numel_bytes(*outs) + numel_bytes(*[t for t in a if torch.is_tensor(t)]), 0
 
-        def ent_store_cost(out, features, relproj, depth_values, groups, want_sim):
-            base, _ = cv_cost(out, features, relproj, depth_values)
-            return base + (numel_bytes(*out) if out is not None else 0), 0
-
         def cl_ent_cost(out, feat_cl, relproj, depth_values, groups, want_sim):
             if out is None:
                 return 0, 0
@@ -182,53 +178,30 @@ class KernelProfiler:
         def to_cl_cost(out, feature_list, outs=None):
             return 2 * numel_bytes(*feature_list), 0
 
-        # round-2 channels-last cost-volume kernels (csrc/cost_volume_cl.cu)
+        # channels-last cost-volume kernels (csrc/cost_volume_cl.cu)
         self._wrap(engine, "features_to_cl", "cv_layout(nchw->channels-last)", to_cl_cost)
         self._wrap(engine, "cost_volume_cl_entropy", lambda f, r, d, g, want_sim: "cv_cl_passA+store" if f.shape[-1] >= 16 else "cv_cl_passA(stage4)",
                    cl_ent_cost)
         self._wrap(engine, "cost_volume_cl_aggregate", "cv_cl_passB(stage4)", cl_agg_cost)
         self._wrap(engine, "cost_volume_entropy", "cv_entropy(passA)", ent_cost)
         self._wrap(engine, "cost_volume_aggregate", "cv_aggregate(passB)", agg_cost)
-        # opt-in MVS_CV_STORE path: pass A with stored correlation + streaming aggregation
-        self._wrap(engine, "cost_volume_entropy_store", "cv_entropy_store(passA)", ent_store_cost)
         self._wrap(engine, "corr_aggregate", "cv_corr_aggregate(stream)", io_cost)
         def vis_fused_cost(out, ent, params, w2, w3):
             return numel_bytes(ent, out), 2 * 3608 * ent.numel()
 
         self._wrap(engine, "vis_fused", "vis_net(fused)", vis_fused_cost)
         self._wrap(engine, "vis_weight", "vis_net", vis_cost)
-        self._wrap(engine, "vis_first_cl", "vis_net(thin layers)", io_cost)
-        self._wrap(engine, "vis_last_cl", "vis_net(thin layers)", io_cost)
         def conv_tc_cost(out, x, w_hi, w_lo, n_tile, cout, kd, shift, skip, stride, relu=True):
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
 
         def deconv_tc_cost(out, x, w_hi, w_lo, n_tile, cout, kd, shift, skip, sd, relu=True):
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (x.numel() // x.shape[-1])
 
-        def conv_tcz_cost(out, x, w_tcz, n_tile, cout, kd, shift, skip, shw, relu=True):
-            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
-
-        def deconv_tcz_cost(out, x, w_tcz, n_tile, cout, kd, shift, skip, relu=True):
-            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (x.numel() // x.shape[-1])
-
-        # kd = 1 calls are the two middle layers of the visibility net
-        self._wrap(engine, "conv3d_tcz", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcz",
-                   conv_tcz_cost)
-        def conv_tcr_cost(out, x, w_tcr, n_tile, cout, kd, shift, skip, relu=True):
-            return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * (out.numel() // out.shape[-1])
-
-        self._wrap(engine, "conv3d_tcr", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcr",
-                   conv_tcr_cost)
         def conv_tma_cost(out, x, w_tma, n_tile, cout, kd, shift, skip, relu=True, mode=0):
             vox = (x.numel() // x.shape[-1]) if mode == 2 else (out.numel() // out.shape[-1])
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * vox
 
-        self._wrap(engine, "conv3d_tma", "conv3d_tma", conv_tma_cost)                    # round-2 persistent TMA kernels
-        self._wrap(engine, "deconv3d_tcz", "deconv3d_tcz", deconv_tcz_cost)
-        self._wrap(engine, "conv3d_tcz_kzf", "conv3d_tcz_kzf", conv_tcz_cost)          # opt-in MVS_TCZ_KZF
-        self._wrap(engine, "deconv3d_tcz_kzf", "deconv3d_tcz_kzf", deconv_tcz_cost)
-        self._wrap(engine, "conv3d_tcr_khf", lambda x, w, nt, cout, kd, *a, **k: "vis_net(tensor-core layers)" if kd == 1 else "conv3d_tcr_khf",
-                   conv_tcr_cost)
+        self._wrap(engine, "conv3d_tma", "conv3d_tma", conv_tma_cost)                    # persistent TMA-fed kernels
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
         self._wrap(engine, "conv3d_tc", "conv3d_tc", conv_tc_cost)

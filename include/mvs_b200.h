@@ -77,16 +77,11 @@ int mvs_cost_volume_aggregate(const float* features, int64_t batch_stride, int64
 int mvs_cost_volume_aggregate_tf32(const float* features, int64_t batch_stride, int64_t view_stride,
                                    const float* relproj, const float* depth, const float* vis_weight,
                                    float* volume, int B, int V, int C, int G, int D, int H, int W, void* stream);
-/* Opt-in single-sampling-pass variant (MVS_CV_STORE=1; stages with C/G >= 2, where the per-view correlation is
- * smaller than the warped tensor): pass A additionally stores corr [B,N,D,H,W,G] and the aggregation becomes one
- * streaming pass over it.  Bit-identical volume.  mvs_cost_volume_entropy_store returns 1 (nothing launched)
- * when the shape is not covered; the caller then uses the two-pass entry points. */
-int mvs_cost_volume_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride,
-                                  const float* relproj, const float* depth, float* entropy, float* sim_sum, float* corr,
-                                  int B, int V, int C, int G, int D, int H, int W, void* stream);
+/* volume = sum_v w_v corr_v / (sum_v w_v + 1e-6) streamed over a stored per-view correlation corr [B,N,D,H,W,G]
+ * (written by mvs_cost_volume_cl_entropy); models/mvsformer_model.py:97-105. */
 int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume, int B, int N, int D, int H, int W,
                        int round_tf32, void* stream);
-/* Round-2 production cost-volume build over CHANNELS-LAST features (csrc/cost_volume_cl.cu): same arithmetic and outputs
+/* Production cost-volume build over CHANNELS-LAST features (csrc/cost_volume_cl.cu): same arithmetic and outputs
  * as the entry points above (models/mvsformer_model.py:61-105, models/warping.py:84-107), features given as
  * feat_cl [B,V,H,W,C] (dense).  mvs_features_to_cl converts up to four NCHW tensors in ONE launch: segment s is
  * in[s] = [maps[s]][channels[s]][hw[s]]  ->  out[s] = [maps[s]][hw[s]][channels[s]]  (all five arrays are HOST arrays
@@ -117,11 +112,6 @@ int mvs_argmax_gather(const float* score, const float* depth, float* out, int B,
  *   w1[16][9] b1[16] w2[16][16][9] b2[16] w3[8][16][9] b3[8] w4[8] b4[1]   (3641 floats). */
 #define MVS_VIS_PARAM_FLOATS (16 * 9 + 16 + 16 * 16 * 9 + 16 + 8 * 16 * 9 + 8 + 8 + 1)
 int mvs_vis_weight(const float* entropy, const float* params_host, float* weight, int M, int H, int W, void* stream);
-/* Tensor-core route of the same net (TF32 conv mode): first layer (1->16, params [host] w1[16][9] b1[16])
- * to channels-last TF32 [M,H,W,16]; the 16->16 and 16->8 layers run through mvs_conv3d_tcz (kd = 1,
- * D = M); last layer (params [host] w4[8] b4) + sigmoid from channels-last [M,H,W,8]. */
-int mvs_vis_first_cl(const float* entropy, const float* params_host, float* out, int M, int H, int W, void* stream);
-int mvs_vis_last_cl(const float* act, const float* params_host, float* weight, int M, int H, int W, void* stream);
 
 /* ---- A7. 3D-CNN layers: models/module.py:83-159 (Conv3d / Deconv3d blocks), :469-594 --------
  * Channels-last activations.  y = act(conv(x) + shift) (+ skip);  BN (eval) is folded by the
@@ -150,32 +140,6 @@ int mvs_conv3d_tc(const float* x, const float* w_hi, const float* w_lo, const fl
 int mvs_deconv3d_tc(const float* x, const float* w_hi, const float* w_lo, const float* shift, const float* skip,
                     float* y, int B, int D, int H, int W, int Cin, int Cout, int n_tile, int kd, int sd,
                     int relu, void* stream);
-/* Depth-fused, cp.async-pipelined TF32 kernels for depth-unstrided layers (sd = 1; conv3d_tcz.cu).
- * Inputs must already be TF32-rounded (outputs of these kernels, of mvs_cost_volume_aggregate with
- * round_tf32 = 1, or of mvs_ncdhw_to_cl_tf32); outputs are TF32-rounded.  Weights (TF32-rounded):
- *   conv   [Cout_tiles][3 kh][Cin/CS][kd][3 kw][CS/4][n_tile][4]
- *   deconv [Cout_tiles][2 dy][Cin/CS][kd][6 taps][CS/4][n_tile][4]   (tap order as mvs_deconv3d_tc) */
-int mvs_conv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
-                   int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
-int mvs_deconv3d_tcz(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
-                     int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
-/* Opt-in "kz-fused N" variant of mvs_conv3d_tcz for kd = 3 (MVS_TCZ_KZF; conv3d_tcz_kzf.cu): the three depth taps of an
- * input slab are one tcgen05.mma of N = 3 * n_tile over adjacent TMEM accumulators, so the A tile is read from shared
- * memory once instead of three times.  Weights (TF32): [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4]. */
-int mvs_conv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
-                       int H, int W, int Cin, int Cout, int n_tile, int kd, int shw, int relu, void* stream);
-/* Same for mvs_deconv3d_tcz (kd = 3): accumulators laid out [parity class][slice]; weights (TF32)
- * [Cout_tiles][2 dy][Cin/CS][6 taps][CS/4][kd][n_tile][4] (tap order as mvs_deconv3d_tc). */
-int mvs_deconv3d_tcz_kzf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
-                         int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
-/* Row-tiled variant of mvs_conv3d_tcz for wide stride-1 layers (Cin <= 32): R rows x 128 columns x zc
- * slices per CTA, all taps resident.  Weights (TF32): [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4]. */
-int mvs_conv3d_tcr(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
-                   int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
-/* Opt-in kh-fused variant of mvs_conv3d_tcr (MVS_TCZ_KZF; conv3d_tcz_kzf.cu): the three kh taps of an input row are one
- * MMA of N = 3 * n_tile over adjacent accumulators.  Weights (TF32): [Cout_tiles][kd][3 kw][Cin/4][3 kh][n_tile][4]. */
-int mvs_conv3d_tcr_khf(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D,
-                       int H, int W, int Cin, int Cout, int n_tile, int kd, int relu, void* stream);
 /* Diagnostic: nk MMAs (M=128, N, K=8) over caller-made shared-memory operand images with explicit
  * descriptor strides; dumps the 128 x N accumulator (used by tests to pin the operand layouts). */
 int mvs_tc_probe(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo,

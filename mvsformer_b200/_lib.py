@@ -32,7 +32,6 @@ _SIGNATURES = {
     "mvs_cost_volume_entropy": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "mvs_cost_volume_aggregate": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "mvs_cost_volume_aggregate_tf32": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
-    "mvs_cost_volume_entropy_store": (c_i, [c_f, c_l, c_l, c_f, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "mvs_features_to_cl": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_f]),
     "mvs_cost_volume_cl_entropy": (c_i, [c_f, c_i, c_f] + [c_f] * 5 + [c_i] * 7 + [c_f]),
     "mvs_cost_volume_cl_aggregate": (c_i, [c_f, c_i, c_f] + [c_f] * 4 + [c_i] * 8 + [c_f]),
@@ -40,19 +39,11 @@ _SIGNATURES = {
     "mvs_argmax_gather": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
     "mvs_vis_weight": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "mvs_vis_fused": (c_i, [c_f] * 5 + [c_i] * 3 + [c_f]),
-    "mvs_vis_first_cl": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
-    "mvs_vis_last_cl": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "mvs_conv3d_cl": (c_i, [c_f] * 5 + [c_i] * 11 + [c_f]),
     "mvs_deconv3d_cl": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_conv3d_tc": (c_i, [c_f] * 6 + [c_i] * 11 + [c_f]),
     "mvs_deconv3d_tc": (c_i, [c_f] * 6 + [c_i] * 10 + [c_f]),
     "mvs_conv3d_tma": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
-    "mvs_conv3d_tcz": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
-    "mvs_conv3d_tcz_kzf": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
-    "mvs_deconv3d_tcz_kzf": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
-    "mvs_conv3d_tcr_khf": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
-    "mvs_conv3d_tcr": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
-    "mvs_deconv3d_tcz": (c_i, [c_f] * 5 + [c_i] * 9 + [c_f]),
     "mvs_ncdhw_to_cl_tf32": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "mvs_tc_probe": (c_i, [c_f, c_i, c_f, c_i] + [ctypes.c_uint] * 4 + [c_i, c_i, ctypes.c_uint, ctypes.c_uint, c_f, c_f]),
     "mvs_tc_probe_ts": (c_i, [c_f, c_i, c_f, c_i] + [ctypes.c_uint] * 4 + [c_i, c_i, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, c_f, c_f]),

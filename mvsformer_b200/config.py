@@ -10,43 +10,34 @@
 
 Set with ``set_conv_precision()`` or the environment variable ``MVS_CONV_PRECISION``.
 
-``cv_store`` (``MVS_CV_STORE``, default ON since round 2; ``0`` restores two sampling passes) — cost-volume build with
-ONE sampling pass at the stages where the per-view group correlation is smaller than the warped tensor (C/G >= 2,
-stages 1-3): pass A stores it, the aggregation streams over it (bit-identical volume; +2 x N x G x D x h x w x 4 B of
-HBM traffic instead of a second warp).  Measured on B200 (profiles/r02_ab_variants.json): 7.87 -> 7.30 ms per
-reference view at cfg 2, refined depth bit-identical.
-
 ``cv_layout`` (``MVS_CV_LAYOUT`` = ``cl`` (default) | ``nchw``) — which cost-volume kernels sample the features: the
-round-2 channels-last kernels (csrc/cost_volume_cl.cu: one LDS.128 per 4-channel tap, conflict-free lane order, next
-item's TMA tile in flight; features are re-laid out once per call by mvs_features_to_cl) or the round-1 channel-planar
-TMA kernels (csrc/cost_volume_tma.cu), kept for A/B runs.
+channels-last kernels (csrc/cost_volume_cl.cu: one LDS.128 per 4-channel tap, conflict-free lane order, next item's TMA
+tile in flight, one sampling pass at stages 1-3; features are re-laid out once per call by mvs_features_to_cl) or the
+generic any-shape kernels (csrc/cost_volume.cu) that read the reference's NCHW layout directly — they are also the
+fall-back for shapes the channels-last kernels are not built for, and the second implementation the parity tests
+cross-check against.
 
 ``vis_fused`` (``MVS_VIS_FUSED``, default 1) — the visibility net as one persistent kernel (csrc/vis_fused.cu, TF32 mode):
-only the entropy map and the weight map touch HBM; ``0`` = the four round-1 kernels.
+only the entropy map and the weight map touch HBM; ``0`` = the FP32 CUDA-core kernel of csrc/vis_net.cu (also what the
+``tf32x3`` and ``fp32`` modes use).
 
-``conv_tma`` (``MVS_CONV_TMA``, default 1; ``0`` = round-1 kernels only) — depth-unstrided 3x3x3 layers (CostRegNet3D) through the
-persistent, warp-specialised, TMA-fed tcgen05 kernels of csrc/conv3d_tma.cu (TF32 mode only).
-
-``tcz_kzf`` (``MVS_TCZ_KZF``: ``0`` off, ``1`` default, ``2`` = also prefer the kz-fused kernel over the row-tiled one) — "fused N"
-variants of the depth-unstrided tensor-core convolutions (mvs_conv3d_tcz_kzf, mvs_deconv3d_tcz_kzf, mvs_conv3d_tcr_khf):
-one MMA of N = 3 x Cout-tile per slab / input row instead of three, i.e. about a third of the shared-memory
-A-operand reads.  TF32 mode only.  Default 1 since round 2 (measured 7.87 -> 7.43 ms, refined depth rel-L1 2e-6 vs the unfused kernels;
-level 2 was slower: 8.93 ms).
+``conv_tma`` (``MVS_CONV_TMA``, default 1; ``0`` = the generic tcgen05 kernels of csrc/conv3d_tc.cu only) — depth-unstrided
+3x3x3 layers (CostRegNet3D) through the persistent, warp-specialised, TMA-fed tcgen05 kernels of csrc/conv3d_tma.cu
+(TF32 mode only).
 
 ``train_conv`` (``MVS_TRAIN_CONV`` = ``fp32`` (default) | ``tf32x3`` | ``tf32``) — arithmetic of the training path's
 forward and data-gradient convolutions: the FP32 CUDA-core kernels, or the tcgen05 kernels of the inference path
 (``tf32x3`` keeps fp32-grade accuracy; the reference itself trains the regulariser under fp16 autocast).  Weight
-gradients stay FP32.  Opt-in until timed on the GPU.
+gradients stay FP32.  Measured on B200 at the cfg-5 shape (profiles/r02_train_scale.json): fp32 34.96 ms per step, tf32
+43.8 ms (the per-layer operand repacking costs more than the tensor cores save at these sizes), so fp32 stays the default.
 """
 import os
 
 _VALID = ("tf32x3", "tf32", "fp32")
 _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
-          "cv_store": os.environ.get("MVS_CV_STORE", "1") not in ("", "0"),
           "cv_layout": os.environ.get("MVS_CV_LAYOUT", "cl"),
           "vis_fused": os.environ.get("MVS_VIS_FUSED", "1") not in ("", "0"),
           "conv_tma": os.environ.get("MVS_CONV_TMA", "1") not in ("", "0"),
-          "tcz_kzf": int(os.environ.get("MVS_TCZ_KZF", "1") or 0),
           "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
 if _state["train_conv"] not in ("fp32", "tf32x3", "tf32"):
     raise RuntimeError("MVS_TRAIN_CONV must be fp32, tf32x3 or tf32")
@@ -64,14 +55,6 @@ def set_conv_precision(mode):
     if mode not in _VALID:
         raise ValueError("conv precision must be one of %s, got %r" % (_VALID, mode))
     _state["conv_precision"] = mode
-
-
-def cv_store():
-    return _state["cv_store"]
-
-
-def set_cv_store(flag):
-    _state["cv_store"] = bool(flag)
 
 
 def cv_layout():
@@ -98,14 +81,6 @@ def conv_tma():
 
 def set_conv_tma(flag):
     _state["conv_tma"] = bool(flag)
-
-
-def tcz_kzf():
-    return _state["tcz_kzf"]
-
-
-def set_tcz_kzf(level):
-    _state["tcz_kzf"] = int(level)
 
 
 def train_conv():

@@ -42,7 +42,6 @@ struct Dims {
     int relu;
     int tiles_x, tiles_y, nitems;
     int nbuf;                // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
-    int debug;               // profiling only (env MVS_TMA_DEBUG): bit 0 = no tap MMAs, bit 1 = no global stores, bit 2 = no TMEM drain at all
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -245,7 +244,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                                 started |= 1u << bit;
                                 mma_tf32_ss_elect(cbase + (uint32_t)blk * NT, ad, bd + (uint64_t)((kz - kz_lo) * NT), idesc1, acc);
                             }
-                        } else if (!(d.debug & 1)) {
+                        } else {
                             mma_tf32_ss_elect(cbase + (uint32_t)blk_lo * NT, ad, bd, idw, 1u);
                         }
                     }
@@ -306,7 +305,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
             tc_fence_after_sync();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ncols;
 #pragma unroll 1
-            for (int cz = half; cz < ((d.debug & 4) ? 0 : nblk); cz += NEPI / 4) {
+            for (int cz = half; cz < nblk; cz += NEPI / 4) {
                 float4 skc[CPR];
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) skc[j] = skn[j];
@@ -319,7 +318,6 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                 for (int c4 = 0; c4 < CPR; ++c4)
                     *reinterpret_cast<float4*>(stg + lane * L::STG_PITCH + c4 * 4) = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
                 __syncwarp();
-                if (d.debug & 2) continue;
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) {
                     size_t o;
@@ -398,7 +396,7 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     int rc = make_act_map(&map, x, B * D, H, W, CIN, L::CH, L::PX, L::PY, MODE == MODE_S2 ? 2 : 1);
     if (rc) return rc;
     Dims d;
-    d.B = B; d.D = D; d.H = H; d.W = W; d.Cout = Cout; d.relu = relu; d.debug = 0;
+    d.B = B; d.D = D; d.H = H; d.W = W; d.Cout = Cout; d.relu = relu;
     d.Ho = MODE == MODE_S2 ? (H + 1) / 2 : (MODE == MODE_DECONV ? 2 * H : H);
     d.Wo = MODE == MODE_S2 ? (W + 1) / 2 : (MODE == MODE_DECONV ? 2 * W : W);
     const int th = MODE == MODE_DECONV ? H : d.Ho, tw = MODE == MODE_DECONV ? W : d.Wo;      // the tiled plane
@@ -407,7 +405,6 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     const int ncols = (MODE == MODE_DECONV ? 4 : 1) * D * NT;
     MVS_REQUIRE(ncols <= 512, "mvs_conv3d_tma: %d accumulator columns exceed the tensor memory", ncols);
     d.nbuf = 2 * ncols <= 512 ? 2 : 1;
-    if (const char* e = getenv("MVS_TMA_DEBUG")) d.debug = atoi(e);
     const int ntiles = cdiv(Cout, NT);
     auto kern = conv3d_tma_kernel<MODE, CIN, NT, STAGES, KD, NEPI>;
     MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

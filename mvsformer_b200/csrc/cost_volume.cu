@@ -259,23 +259,6 @@ corr_aggregate_kernel(const float* __restrict__ corr, const float* __restrict__ 
     out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
-// TMA-staged production kernels (cost_volume_tma.cu); return 1 when the shape is not covered.
-int cost_volume_tma_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
-                                  const float* depth, float* entropy, float* sim_sum, float* corr, int B, int V, int C, int G,
-                                  int D, int H, int W, cudaStream_t st);
-int cost_volume_tma_entropy(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
-                            const float* depth, float* entropy, float* sim_sum, int B, int V, int C, int G, int D, int H, int W,
-                            cudaStream_t st);
-int cost_volume_tma_aggregate(const float* features, int64_t batch_stride, int64_t view_stride, const float* relproj,
-                              const float* depth, const float* vis_weight, float* volume, int B, int V, int C, int G, int D,
-                              int H, int W, int round_tf32, cudaStream_t st);
-
-// MVS_K1_IMPL=generic forces the generic (non-TMA) kernels, for A/B parity runs.
-static bool use_tma_kernels() {
-    const char* e = getenv("MVS_K1_IMPL");
-    return !(e && strcmp(e, "generic") == 0);
-}
-
 }  // namespace mvs
 
 extern "C" int mvs_cost_volume_entropy(const float* features, int64_t batch_stride, int64_t view_stride,
@@ -284,26 +267,10 @@ extern "C" int mvs_cost_volume_entropy(const float* features, int64_t batch_stri
     int rc = mvs::check_cv_args("mvs_cost_volume_entropy", features, relproj, depth, B, V, C, G, D, H, W);
     if (rc) return rc;
     MVS_REQUIRE(entropy, "mvs_cost_volume_entropy: null entropy output");
-    if (mvs::use_tma_kernels()) {
-        rc = mvs::cost_volume_tma_entropy(features, batch_stride, view_stride, relproj, depth, entropy, sim_sum, B, V, C, G, D, H,
-                                          W, (cudaStream_t)stream);
-        if (rc <= 0) return rc;
-    }
     mvs::CvParams p{features, batch_stride, view_stride, relproj, depth, V - 1, C, G, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     return sim_sum ? mvs::dispatch_entropy<true>(p, entropy, sim_sum, B, st)
                    : mvs::dispatch_entropy<false>(p, entropy, nullptr, B, st);
-}
-
-extern "C" int mvs_cost_volume_entropy_store(const float* features, int64_t batch_stride, int64_t view_stride,
-                                             const float* relproj, const float* depth, float* entropy, float* sim_sum,
-                                             float* corr, int B, int V, int C, int G, int D, int H, int W, void* stream) {
-    int rc = mvs::check_cv_args("mvs_cost_volume_entropy_store", features, relproj, depth, B, V, C, G, D, H, W);
-    if (rc) return rc;
-    MVS_REQUIRE(entropy && corr, "mvs_cost_volume_entropy_store: null output");
-    if (!mvs::use_tma_kernels()) return 1;
-    return mvs::cost_volume_tma_entropy_store(features, batch_stride, view_stride, relproj, depth, entropy, sim_sum, corr, B, V,
-                                              C, G, D, H, W, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_corr_aggregate(const float* corr, const float* vis_weight, float* volume, int B, int N, int D, int H,
@@ -325,11 +292,6 @@ static int cost_volume_aggregate_impl(const float* features, int64_t batch_strid
     if (rc) return rc;
     MVS_REQUIRE(vis_weight && volume, "mvs_cost_volume_aggregate: null pointer");
     if (G != 8) MVS_UNSUPPORTED("mvs_cost_volume_aggregate: only G = 8 groups is built (got %d)", G);
-    if (mvs::use_tma_kernels()) {
-        rc = mvs::cost_volume_tma_aggregate(features, batch_stride, view_stride, relproj, depth, vis_weight, volume, B, V, C, G, D,
-                                            H, W, round_tf32, (cudaStream_t)stream);
-        if (rc <= 0) return rc;
-    }
     mvs::CvParams p{features, batch_stride, view_stride, relproj, depth, V - 1, C, G, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     dim3 block(32, 8);

@@ -628,20 +628,13 @@ static int launch(const Params& p, int B, int nmaps, cudaStream_t st) {
 }
 
 // Tilings (pixel tile, hypotheses per item, box) chosen from measured coverage of the bench workload's noisy depth maps
-// (scripts/box_coverage_cl.py): >= 99.9 % of the samples of every view take the shared-memory path.
+// (scripts/box_coverage.py): >= 99.9 % of the samples of every view take the shared-memory path.  Hypotheses per thread
+// (KPT) from an A/B on the B200 (profiles/r02b_k1_tiling_ab.json): KPT = 1 costs +6 % at stage 3 and +25 % at stage 4.
 //             C   D  TW TH HB KPT BW  BH NCH MINB
 using Stage1 = Cfg<64, 32, 32, 1, 8, 1, 56, 5, 2, 2>;
 using Stage2 = Cfg<32, 16, 32, 1, 8, 1, 56, 5, 1, 2>;
 using Stage3 = Cfg<16, 8, 32, 2, 4, 2, 80, 6, 1, 3>;       // 2 hypotheses per thread
-using Stage3b = Cfg<16, 8, 32, 1, 8, 1, 80, 5, 1, 3>;      // 1 hypothesis per thread (A/B: MVS_K1_S3=1)
 using Stage4 = Cfg<8, 4, 32, 8, 1, 4, 80, 14, 1, 2>;       // all 4 hypotheses of a pixel in one thread
-using Stage4b = Cfg<8, 4, 32, 4, 2, 2, 80, 10, 1, 3>;      // 2 per thread (A/B: MVS_K1_S4=1)
-using Stage4c = Cfg<8, 4, 32, 2, 4, 1, 80, 8, 1, 3>;       // 1 per thread (A/B: MVS_K1_S4=2)
-
-static int variant(const char* name) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : 0;
-}
 
 }  // namespace k1cl
 
@@ -662,16 +655,8 @@ int cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slot
     const bool sim = sim_depth != nullptr;
     if (C == 64 && D == 32 && corr) return sim ? launch<Stage1, 1, true>(p, B, nmaps, st) : launch<Stage1, 1, false>(p, B, nmaps, st);
     if (C == 32 && D == 16 && corr) return sim ? launch<Stage2, 1, true>(p, B, nmaps, st) : launch<Stage2, 1, false>(p, B, nmaps, st);
-    if (C == 16 && D == 8 && corr) {
-        if (variant("MVS_K1_S3") == 1) return sim ? launch<Stage3b, 1, true>(p, B, nmaps, st) : launch<Stage3b, 1, false>(p, B, nmaps, st);
-        return sim ? launch<Stage3, 1, true>(p, B, nmaps, st) : launch<Stage3, 1, false>(p, B, nmaps, st);
-    }
-    if (C == 8 && D == 4 && !corr) {
-        const int var = variant("MVS_K1_S4");
-        if (var == 1) return sim ? launch<Stage4b, 0, true>(p, B, nmaps, st) : launch<Stage4b, 0, false>(p, B, nmaps, st);
-        if (var == 2) return sim ? launch<Stage4c, 0, true>(p, B, nmaps, st) : launch<Stage4c, 0, false>(p, B, nmaps, st);
-        return sim ? launch<Stage4, 0, true>(p, B, nmaps, st) : launch<Stage4, 0, false>(p, B, nmaps, st);
-    }
+    if (C == 16 && D == 8 && corr) return sim ? launch<Stage3, 1, true>(p, B, nmaps, st) : launch<Stage3, 1, false>(p, B, nmaps, st);
+    if (C == 8 && D == 4 && !corr) return sim ? launch<Stage4, 0, true>(p, B, nmaps, st) : launch<Stage4, 0, false>(p, B, nmaps, st);
     return 1;
 }
 
@@ -682,12 +667,7 @@ int cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_sl
     if (G != 8 || ((uintptr_t)feat_cl & 15) || V - 1 > MAXN) return 1;
     Params p{feat_cl, relproj, depth, V - 1, V, H, W, nullptr, nullptr, nullptr, vis_weight, volume, round_tf32};
     set_slots(p, view_slots, V);
-    if (C == 8 && D == 4) {
-        const int var = variant("MVS_K1_S4");
-        if (var == 1) return launch<Stage4b, 2, false>(p, B, nmaps, st);
-        if (var == 2) return launch<Stage4c, 2, false>(p, B, nmaps, st);
-        return launch<Stage4, 2, false>(p, B, nmaps, st);
-    }
+    if (C == 8 && D == 4) return launch<Stage4, 2, false>(p, B, nmaps, st);
     return 1;
 }
 

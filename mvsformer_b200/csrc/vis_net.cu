@@ -112,76 +112,7 @@ vis_net_kernel(const float* __restrict__ entropy, float* __restrict__ weight, in
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Tensor-core route (TF32 conv mode): the two heavy layers (16->16, 16->8; 96 % of the MACs) run
-// as kd = 1 implicit GEMMs in conv3d_tcz.cu with the N source-view maps as its "depth" axis; the
-// thin ends stay here as streaming kernels:
-//   vis_first_kernel  entropy [M,H,W] -> relu(conv3x3 1->16 + b1), channels-last [M,H,W,16], TF32
-//   vis_last_kernel   act3 [M,H,W,8]  -> sigmoid(w4 . act3 + b4)  [M,H,W]
-// ------------------------------------------------------------------------------------------------
-struct VisFirstParams { float w1[16][9]; float b1[16]; };
-struct VisLastParams { float w4[8]; float b4; };
-
-__global__ void __launch_bounds__(256)
-vis_first_kernel(const float* __restrict__ entropy, float* __restrict__ out, int H, int W, const __grid_constant__ VisFirstParams P) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
-    const int64_t plane = (int64_t)blockIdx.z * H * W;
-    float in[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int yy = y - 1 + t / 3, xx = x - 1 + t % 3;
-        in[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(entropy + plane + (int64_t)yy * W + xx) : 0.0f;
-    }
-    float4* o = reinterpret_cast<float4*>(out + (plane + (int64_t)y * W + x) * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float r[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float a = P.b1[q * 4 + e];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) a = fmaf(in[t], P.w1[q * 4 + e][t], a);
-            r[e] = round_to_tf32(fmaxf(a, 0.0f));
-        }
-        o[q] = make_float4(r[0], r[1], r[2], r[3]);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-vis_last_kernel(const float* __restrict__ act, float* __restrict__ weight, int64_t total, const __grid_constant__ VisLastParams P) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(act + i * 8)), c = __ldg(reinterpret_cast<const float4*>(act + i * 8) + 1);
-    float z = P.b4;
-    z = fmaf(a.x, P.w4[0], z); z = fmaf(a.y, P.w4[1], z); z = fmaf(a.z, P.w4[2], z); z = fmaf(a.w, P.w4[3], z);
-    z = fmaf(c.x, P.w4[4], z); z = fmaf(c.y, P.w4[5], z); z = fmaf(c.z, P.w4[6], z); z = fmaf(c.w, P.w4[7], z);
-    weight[i] = 1.0f / (1.0f + expf(-z));
-}
-
 }  // namespace mvs
-
-extern "C" int mvs_vis_first_cl(const float* entropy, const float* params_host, float* out, int M, int H, int W, void* stream) {
-    MVS_REQUIRE(entropy && params_host && out, "mvs_vis_first_cl: null pointer");
-    MVS_REQUIRE(M >= 1 && H >= 1 && W >= 1 && M <= 65535, "mvs_vis_first_cl: bad shape M=%d H=%d W=%d", M, H, W);
-    mvs::VisFirstParams P;
-    memcpy(&P, params_host, sizeof(P));
-    dim3 grid(mvs::cdiv(W, 32), mvs::cdiv(H, 8), M);
-    mvs::vis_first_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(entropy, out, H, W, P);
-    MVS_LAUNCH_OK("vis_first_kernel");
-    return MVS_OK;
-}
-
-extern "C" int mvs_vis_last_cl(const float* act, const float* params_host, float* weight, int M, int H, int W, void* stream) {
-    MVS_REQUIRE(act && params_host && weight, "mvs_vis_last_cl: null pointer");
-    MVS_REQUIRE(M >= 1 && H >= 1 && W >= 1, "mvs_vis_last_cl: bad shape");
-    mvs::VisLastParams P;
-    memcpy(&P, params_host, sizeof(P));
-    const int64_t total = (int64_t)M * H * W;
-    mvs::vis_last_kernel<<<mvs::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(act, weight, total, P);
-    MVS_LAUNCH_OK("vis_last_kernel");
-    return MVS_OK;
-}
 
 extern "C" int mvs_vis_weight(const float* entropy, const float* params_host, float* weight, int M, int H, int W,
                               void* stream) {

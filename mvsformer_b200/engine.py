@@ -98,27 +98,6 @@ def cost_volume_aggregate(features, relproj, depth_values, vis_weight, groups, r
     return volume
 
 
-def cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim):
-    """Pass A that also stores the per-view correlation (opt-in, config.cv_store()).  Returns
-    (entropy, sim, corr [B,N,D,H,W,G]) or None when the kernels do not cover the shape."""
-    features = _f32(features)
-    features, bs, vs = _feature_strides(features)
-    depth_values = _f32(depth_values).contiguous()
-    require_cuda(relproj, depth_values)
-    require_cuda_device(features)
-    b, v, c, h, w = features.shape
-    d = depth_values.shape[1]
-    entropy = torch.empty(b, v - 1, h, w, device=features.device, dtype=torch.float32)
-    sim = torch.empty(b, d, h, w, device=features.device, dtype=torch.float32) if want_sim else None
-    corr = torch.empty(b, v - 1, d, h, w, groups, device=features.device, dtype=torch.float32)
-    rc = _lib.load().mvs_cost_volume_entropy_store(ptr(features), bs, vs, ptr(relproj), ptr(depth_values), ptr(entropy),
-                                                   ptr(sim), ptr(corr), b, v, c, groups, d, h, w, stream())
-    if rc == 1:
-        return None
-    check(rc, "mvs_cost_volume_entropy_store")
-    return entropy, sim, corr
-
-
 def features_to_cl(feature_list, outs=None):
     """NCHW feature tensors ``[..., C, H, W]`` (up to four, e.g. the four stages of one feature set) -> channels-last
     ``[..., H, W, C]`` copies, ONE launch (mvs_features_to_cl).  The cost-volume kernels sample channels-last texels.
@@ -251,26 +230,6 @@ def vis_fused(entropy_maps, params_host, w2_packed, w3_packed):
     out = torch.empty_like(entropy_maps)
     check(_lib.load().mvs_vis_fused(ptr(entropy_maps), params_host.ctypes.data_as(ctypes.c_void_p), ptr(w2_packed), ptr(w3_packed),
                                     ptr(out), m, h, w, stream()), "mvs_vis_fused")
-    return out
-
-
-def vis_first_cl(entropy_maps, params_host):
-    """[M,H,W] -> channels-last TF32 [M,H,W,16] (first vis layer)."""
-    require_cuda(entropy_maps)
-    m, h, w = entropy_maps.shape
-    out = torch.empty(m, h, w, 16, device=entropy_maps.device, dtype=torch.float32)
-    check(_lib.load().mvs_vis_first_cl(ptr(entropy_maps), params_host.ctypes.data_as(ctypes.c_void_p), ptr(out), m, h, w,
-                                       stream()), "mvs_vis_first_cl")
-    return out
-
-
-def vis_last_cl(act, params_host):
-    """channels-last [M,H,W,8] -> sigmoid(1x1 conv) [M,H,W] (last vis layer)."""
-    require_cuda(act)
-    m, h, w, _ = act.shape
-    out = torch.empty(m, h, w, device=act.device, dtype=torch.float32)
-    check(_lib.load().mvs_vis_last_cl(ptr(act), params_host.ctypes.data_as(ctypes.c_void_p), ptr(out), m, h, w, stream()),
-          "mvs_vis_last_cl")
     return out
 
 
@@ -510,56 +469,6 @@ def tc_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, n, nk, a_kstep, b_kstep):
 
 
 # ------------------------------------------------------------------------------------------------
-# depth-fused, cp.async-pipelined TF32 kernels (conv3d_tcz.cu) for depth-unstrided layers
-# ------------------------------------------------------------------------------------------------
-def tcz_n_tile(cout, stride2=False, transposed=False):
-    if cout <= 16:
-        return 16
-    if cout == 32 or stride2 or transposed:
-        return 32
-    return 64
-
-
-def _tcz_pick_zc(d, cols_per_slice, a_bytes, bgroup):
-    """Mirror of pick_zc() in conv3d_tcz.cu: depth slices per CTA (0 = does not fit)."""
-    for zc in range(min(d, 8), 0, -1):
-        if d % zc or zc * cols_per_slice > 512:
-            continue
-        ring = 2 if zc >= 3 else 4
-        if a_bytes + ring * bgroup + 128 <= 227 * 1024:
-            return zc
-    return 0
-
-
-def tcz_supported(cin, cout, d, kd, stride2=False, transposed=False):
-    """Mirror of the shape rules of mvs_conv3d_tcz / mvs_deconv3d_tcz (depth stride 1)."""
-    if not (cin in (8, 16) or cin % 32 == 0) or cout % 8 or cout > 64:
-        return False
-    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2, transposed)
-    if transposed:
-        if (cs, nt) not in ((16, 16), (32, 16), (32, 32)):
-            return False
-        a_bytes, bgroup, cols = 4 * (cs // 4) * 2112, kd * 6 * (cs // 4) * nt * 16, 4 * nt
-    else:
-        if (cs, nt) not in ((8, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64)):
-            return False
-        a_bytes, bgroup, cols = 4 * (2 if stride2 else 1) * (cs // 4) * 2112, kd * 3 * (cs // 4) * nt * 16, nt
-    return _tcz_pick_zc(d, cols, a_bytes, bgroup) > 0
-
-
-def pack_tcz_weights(w_packed, stride2):
-    """[kd,3,3,Cin,Cout] -> [Cout_tiles][3 kh][Cin/CS][kd][3 kw][CS/4][n_tile][4], TF32-rounded."""
-    kd, _, _, cin, cout = w_packed.shape
-    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2)
-    ntiles = (cout + nt - 1) // nt
-    w = w_packed
-    if ntiles * nt != cout:
-        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
-    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt).permute(6, 1, 3, 0, 2, 4, 7, 5).contiguous()
-    return round_tf32(w), nt
-
-
-# ------------------------------------------------------------------------------------------------
 # round-2 persistent TMA-fed tcgen05 convolutions (conv3d_tma.cu)
 # ------------------------------------------------------------------------------------------------
 TMA_S1, TMA_S2, TMA_DECONV = 0, 1, 2
@@ -607,156 +516,6 @@ def conv3d_tma(x, w_tma, n_tile, cout, kd, shift, skip, relu=True, mode=TMA_S1):
                            % (tuple(skip.shape), tuple(y.shape)))
     check(_lib.load().mvs_conv3d_tma(ptr(x), ptr(w_tma), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd, mode,
                                      1 if relu else 0, stream()), "mvs_conv3d_tma")
-    return y
-
-
-def pack_tcz_kzf_weights(w_packed, stride2):
-    """[kd,3,3,Cin,Cout] -> [Cout_tiles][3 kh][Cin/CS][3 kw][CS/4][kd][n_tile][4], TF32-rounded: the B rows of one
-    (kw, K chunk) are [kz][n], so the depth taps of a slab are one operand of N = kd * n_tile rows
-    (mvs_conv3d_tcz_kzf)."""
-    kd, _, _, cin, cout = w_packed.shape
-    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, stride2)
-    ntiles = (cout + nt - 1) // nt
-    w = w_packed
-    if ntiles * nt != cout:
-        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
-    #            [kz, kh, kw, ch, q, e, tile, n]  ->  [tile, kh, ch, kw, q, kz, n, e]
-    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt).permute(6, 1, 3, 2, 4, 0, 7, 5).contiguous()
-    return round_tf32(w), nt
-
-
-def conv3d_tcz_kzf(x, w_kzf, n_tile, cout, kd, shift, skip, shw, relu=True):
-    require_cuda(x, w_kzf, shift, skip)
-    b, d, h, w, cin = x.shape
-    ho, wo = (h - 1) // shw + 1, (w - 1) // shw + 1
-    y = torch.empty(b, d, ho, wo, cout, device=x.device, dtype=torch.float32)
-    if skip is not None and tuple(skip.shape) != tuple(y.shape):
-        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
-                           % (tuple(skip.shape), tuple(y.shape)))
-    check(_lib.load().mvs_conv3d_tcz_kzf(ptr(x), ptr(w_kzf), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile,
-                                         kd, shw, 1 if relu else 0, stream()), "mvs_conv3d_tcz_kzf")
-    return y
-
-
-def pack_tcz_deconv_weights(w_packed):
-    """[kd,3,3,Cin,Cout] -> [Cout_tiles][2 dy][Cin/CS][kd][6 taps][CS/4][n_tile][4], TF32-rounded."""
-    kd, _, _, cin, cout = w_packed.shape
-    cs, nt = tc_channel_slice(cin), tcz_n_tile(cout, transposed=True)
-    ntiles = (cout + nt - 1) // nt
-    w = w_packed
-    if ntiles * nt != cout:
-        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
-    w = w.reshape(kd, 3, 3, cin // cs, cs // 4, 4, ntiles, nt)               # [kz, kh, kw, ch, q, e, tile, n]
-    out = torch.zeros(ntiles, 2, cin // cs, kd, 6, cs // 4, nt, 4, device=w.device, dtype=w.dtype)
-    taps = {0: [(1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2)], 1: [(0, 0), (0, 1), (0, 2)]}
-    for dy, lst in taps.items():
-        for t, (kh, kw) in enumerate(lst):
-            out[:, dy, :, :, t] = w[:, kh, kw].permute(4, 1, 0, 2, 5, 3)      # [tile, ch, kz, q, n, e]
-    return round_tf32(out.contiguous()), nt
-
-
-def pack_tcz_kzf_deconv_weights(w_packed):
-    """[kd,3,3,Cin,Cout] -> [Cout_tiles][2 dy][Cin/CS][6 taps][CS/4][kd][n_tile][4], TF32-rounded (mvs_deconv3d_tcz_kzf):
-    the layout of pack_tcz_deconv_weights with the depth tap moved next to the row index."""
-    wz, nt = pack_tcz_deconv_weights(w_packed)               # [tile, dy, ch, kz, t, q, n, e]
-    return wz.permute(0, 1, 2, 4, 5, 3, 6, 7).contiguous(), nt
-
-
-def deconv3d_tcz_kzf(x, w_kzf, n_tile, cout, kd, shift, skip, relu=True):
-    require_cuda(x, w_kzf, shift, skip)
-    b, d, h, w, cin = x.shape
-    y = torch.empty(b, d, h * 2, w * 2, cout, device=x.device, dtype=torch.float32)
-    if skip is not None and tuple(skip.shape) != tuple(y.shape):
-        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
-                           % (tuple(skip.shape), tuple(y.shape)))
-    check(_lib.load().mvs_deconv3d_tcz_kzf(ptr(x), ptr(w_kzf), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile,
-                                           kd, 1 if relu else 0, stream()), "mvs_deconv3d_tcz_kzf")
-    return y
-
-
-def conv3d_tcz(x, w_tcz, n_tile, cout, kd, shift, skip, shw, relu=True):
-    require_cuda(x, w_tcz, shift, skip)
-    b, d, h, w, cin = x.shape
-    ho, wo = (h - 1) // shw + 1, (w - 1) // shw + 1
-    y = torch.empty(b, d, ho, wo, cout, device=x.device, dtype=torch.float32)
-    if skip is not None and tuple(skip.shape) != tuple(y.shape):
-        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
-                           % (tuple(skip.shape), tuple(y.shape)))
-    check(_lib.load().mvs_conv3d_tcz(ptr(x), ptr(w_tcz), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
-                                     shw, 1 if relu else 0, stream()), "mvs_conv3d_tcz")
-    return y
-
-
-def deconv3d_tcz(x, w_tcz, n_tile, cout, kd, shift, skip, relu=True):
-    require_cuda(x, w_tcz, shift, skip)
-    b, d, h, w, cin = x.shape
-    y = torch.empty(b, d, h * 2, w * 2, cout, device=x.device, dtype=torch.float32)
-    if skip is not None and tuple(skip.shape) != tuple(y.shape):
-        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
-                           % (tuple(skip.shape), tuple(y.shape)))
-    check(_lib.load().mvs_deconv3d_tcz(ptr(x), ptr(w_tcz), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
-                                       1 if relu else 0, stream()), "mvs_deconv3d_tcz")
-    return y
-
-
-# ------------------------------------------------------------------------------------------------
-# row-tiled TF32 kernel (conv3d_tcr) for wide stride-1 layers
-# ------------------------------------------------------------------------------------------------
-def tcr_supported(cin, cout, w, stride2=False):
-    """Stride-1 layers with Cin <= 32 whose width wastes <= 15 % in 128-column blocks."""
-    if stride2 or cin not in (8, 16, 32) or cout % 8 or cout > 32:
-        return False
-    blocks = (w + 127) // 128
-    return (blocks * 128 - w) <= 0.15 * w
-
-
-def pack_tcr_weights(w_packed):
-    """[kd,3,3,Cin,Cout] -> [Cout_tiles][kd][3 kh][3 kw][Cin/4][n_tile][4], TF32-rounded."""
-    kd, _, _, cin, cout = w_packed.shape
-    nt = 16 if cout <= 16 else 32
-    ntiles = (cout + nt - 1) // nt
-    w = w_packed
-    if ntiles * nt != cout:
-        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
-    w = w.reshape(kd, 3, 3, cin // 4, 4, ntiles, nt).permute(5, 0, 1, 2, 3, 6, 4).contiguous()
-    return round_tf32(w), nt
-
-
-def pack_tcr_khf_weights(w_packed):
-    """[kd,3,3,Cin,Cout] -> [Cout_tiles][kd][3 kw][Cin/4][3 kh][n_tile][4], TF32-rounded (mvs_conv3d_tcr_khf): the B rows
-    of one (kz, kw, K chunk) are [kh][n]."""
-    kd, _, _, cin, cout = w_packed.shape
-    nt = 16 if cout <= 16 else 32
-    ntiles = (cout + nt - 1) // nt
-    w = w_packed
-    if ntiles * nt != cout:
-        w = torch.nn.functional.pad(w, (0, ntiles * nt - cout))
-    #            [kz, kh, kw, q, e, tile, n]  ->  [tile, kz, kw, q, kh, n, e]
-    w = w.reshape(kd, 3, 3, cin // 4, 4, ntiles, nt).permute(5, 0, 2, 3, 1, 6, 4).contiguous()
-    return round_tf32(w), nt
-
-
-def conv3d_tcr_khf(x, w_khf, n_tile, cout, kd, shift, skip, relu=True):
-    require_cuda(x, w_khf, shift, skip)
-    b, d, h, w, cin = x.shape
-    y = torch.empty(b, d, h, w, cout, device=x.device, dtype=torch.float32)
-    if skip is not None and tuple(skip.shape) != tuple(y.shape):
-        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
-                           % (tuple(skip.shape), tuple(y.shape)))
-    check(_lib.load().mvs_conv3d_tcr_khf(ptr(x), ptr(w_khf), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile,
-                                         kd, 1 if relu else 0, stream()), "mvs_conv3d_tcr_khf")
-    return y
-
-
-def conv3d_tcr(x, w_tcr, n_tile, cout, kd, shift, skip, relu=True):
-    require_cuda(x, w_tcr, shift, skip)
-    b, d, h, w, cin = x.shape
-    y = torch.empty(b, d, h, w, cout, device=x.device, dtype=torch.float32)
-    if skip is not None and tuple(skip.shape) != tuple(y.shape):
-        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
-                           % (tuple(skip.shape), tuple(y.shape)))
-    check(_lib.load().mvs_conv3d_tcr(ptr(x), ptr(w_tcr), ptr(shift), ptr(skip), ptr(y), b, d, h, w, cin, cout, n_tile, kd,
-                                     1 if relu else 0, stream()), "mvs_conv3d_tcr")
     return y
 
 

@@ -83,22 +83,6 @@ def _run_conv(cache, x, w, shift, skip, stride, relu):
         mode = engine.TMA_S2 if stride[1] == 2 else engine.TMA_S1
         wt, nt = cache.get_derived("tma_m%d" % mode, lambda v: engine.pack_tma_weights(v[0], mode))
         return engine.conv3d_tma(x, wt, nt, cout, kd, shift, skip, relu, mode)
-    kzf = config.tcz_kzf() if (config.conv_precision() == "tf32" and kd == 3 and stride[0] == 1 and stride[1] == stride[2]
-                               and engine.tcz_supported(cin, cout, x.shape[1], kd, stride[1] == 2)) else 0
-    if kzf == 2 or (kzf == 1 and not (stride == (1, 1, 1) and engine.tcr_supported(cin, cout, x.shape[3]))):
-        # opt-in kz-fused tensor-core kernel (config.py): same shape rules as the tcz kernel
-        wk, nt = cache.get_derived("tcz_kzf_s%d" % stride[1], lambda v: engine.pack_tcz_kzf_weights(v[0], stride[1] == 2))
-        return engine.conv3d_tcz_kzf(x, wk, nt, cout, kd, shift, skip, stride[1], relu)
-    if (config.conv_precision() == "tf32" and stride == (1, 1, 1) and engine.tcr_supported(cin, cout, x.shape[3])):
-        if config.tcz_kzf():                             # opt-in kh-fused row-tiled kernel (config.py)
-            wk, nt = cache.get_derived("tcr_khf", lambda v: engine.pack_tcr_khf_weights(v[0]))
-            return engine.conv3d_tcr_khf(x, wk, nt, cout, kd, shift, skip, relu)
-        wr, nt = cache.get_derived("tcr", lambda v: engine.pack_tcr_weights(v[0]))
-        return engine.conv3d_tcr(x, wr, nt, cout, kd, shift, skip, relu)
-    if (config.conv_precision() == "tf32" and stride[0] == 1 and stride[1] == stride[2]
-            and engine.tcz_supported(cin, cout, x.shape[1], kd, stride[1] == 2)):
-        wz, nt = cache.get_derived("tcz_s%d" % stride[1], lambda v: engine.pack_tcz_weights(v[0], stride[1] == 2))
-        return engine.conv3d_tcz(x, wz, nt, cout, kd, shift, skip, stride[1], relu)
     if stride[1] == stride[2] and _tc_eligible(cin, cout, False):
         x3 = config.conv_precision() == "tf32x3"
         hi, lo, nt = cache.get_derived("tc_x3" if x3 else "tc", lambda v: engine.pack_tc_weights(v[0], x3))
@@ -112,12 +96,6 @@ def _run_deconv(cache, x, w, shift, skip, sd, relu):
             and engine.tma_supported(cin, cout, x.shape[1], kd, transposed=True)):
         wt, nt = cache.get_derived("tma_m2", lambda v: engine.pack_tma_weights(v[0], engine.TMA_DECONV))
         return engine.conv3d_tma(x, wt, nt, cout, kd, shift, skip, relu, engine.TMA_DECONV)
-    if config.conv_precision() == "tf32" and sd == 1 and engine.tcz_supported(cin, cout, x.shape[1], kd, transposed=True):
-        if config.tcz_kzf() and kd == 3:                 # opt-in kz-fused kernel (config.py)
-            wk, nt = cache.get_derived("tczd_kzf", lambda v: engine.pack_tcz_kzf_deconv_weights(v[0]))
-            return engine.deconv3d_tcz_kzf(x, wk, nt, cout, kd, shift, skip, relu)
-        wz, nt = cache.get_derived("tczd", lambda v: engine.pack_tcz_deconv_weights(v[0]))
-        return engine.deconv3d_tcz(x, wz, nt, cout, kd, shift, skip, relu)
     if _tc_eligible(cin, cout, True):
         x3 = config.conv_precision() == "tf32x3"
         hi, lo, nt = cache.get_derived("tcd_x3" if x3 else "tcd", lambda v: engine.pack_tc_deconv_weights(v[0], x3))

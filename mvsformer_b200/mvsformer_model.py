@@ -70,27 +70,6 @@ class StageNet(nn.Module):
         tensors += [self.vis[3].weight, self.vis[3].bias]
         return self._vis_cache.get(tensors, build)
 
-    def _vis_params_tc(self):
-        """Operands of the tensor-core route: host params of the thin first / last layers and the
-        TF32 operand-order weights of the 16->16 and 16->8 layers (BN folded)."""
-        def build(_):
-            host = self._vis_params_host()
-            first = np.ascontiguousarray(host[:16 * 9 + 16])
-            last = np.ascontiguousarray(host[-9:])
-            mids = []
-            for i in (1, 2):
-                blk = self.vis[i]
-                scale, shift = _bn_scale_shift(blk.bn)
-                w = blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)          # [Co,Ci,3,3]
-                w_packed = w.permute(2, 3, 1, 0).unsqueeze(0).contiguous()              # [kd=1,3,3,Ci,Co]
-                wz, nt = engine.pack_tcz_weights(w_packed, False)
-                wr, ntr = engine.pack_tcr_weights(w_packed)
-                wk, _ = engine.pack_tcr_khf_weights(w_packed)                            # opt-in kh-fused kernel
-                mids.append((wz, nt, w.shape[0], shift.contiguous(), wr, ntr, wk))
-            return first, mids, last
-        self._vis_params_host()                                   # refreshes the cache key
-        return self._vis_cache.get_derived("tc", build)
-
     def _vis_params_fused(self):
         """Operands of the fused kernel: host params (layer 1, the two BN shifts, the 1x1 conv) and the packed TF32 weights
         of the 16->16 and 16->8 layers."""
@@ -117,17 +96,6 @@ class StageNet(nn.Module):
         if config.conv_precision() == "tf32" and config.vis_fused():
             params, w2p, w3p = self._vis_params_fused()
             return engine.vis_fused(maps, params, w2p, w3p).view(b, n, h, w)
-        if config.conv_precision() == "tf32" and engine.tcz_supported(16, 16, b * n, 1):
-            first, mids, last = self._vis_params_tc()
-            x = engine.vis_first_cl(maps, first).view(1, b * n, h, w, 16)
-            for wz, nt, cout, shift, wr, ntr, wk in mids:
-                if engine.tcr_supported(16, cout, w) and config.tcz_kzf():
-                    x = engine.conv3d_tcr_khf(x, wk, ntr, cout, 1, shift, None, True)
-                elif engine.tcr_supported(16, cout, w):
-                    x = engine.conv3d_tcr(x, wr, ntr, cout, 1, shift, None, True)
-                else:
-                    x = engine.conv3d_tcz(x, wz, nt, cout, 1, shift, None, 1, True)
-            return engine.vis_last_cl(x.view(b * n, h, w, 8), last).view(b, n, h, w)
         return engine.vis_weight(maps, self._vis_params_host()).view(b, n, h, w)
 
     def build_cost_volume(self, features, proj_matrices, depth_values, features_cl=None, view_slots=None):
@@ -173,13 +141,6 @@ class StageNet(nn.Module):
                     return engine.corr_aggregate(corr, weight, round_tf32), sim, entropy, weight
                 volume = engine.cost_volume_cl_aggregate(features_cl, relproj, depth_values, weight, groups, round_tf32)
                 return volume, sim, entropy, weight
-        if config.cv_store() and features.shape[2] // groups >= 2:
-            # opt-in: one sampling pass, the per-view correlation is stored and streamed back (config.py)
-            stored = engine.cost_volume_entropy_store(features, relproj, depth_values, groups, want_sim=not self.training)
-            if stored is not None:
-                entropy, sim, corr = stored
-                weight = self._vis_weight(entropy)
-                return engine.corr_aggregate(corr, weight, round_tf32), sim, entropy, weight
         entropy, sim = engine.cost_volume_entropy(features, relproj, depth_values, groups, want_sim=not self.training)
         weight = self._vis_weight(entropy)
         volume = engine.cost_volume_aggregate(features, relproj, depth_values, weight, groups, round_tf32=round_tf32)

@@ -3,7 +3,7 @@
 For every stage of one cascade pass at the bench configuration, recompute the sample positions of
 all (view, hypothesis, pixel) triples and report, for candidate box sizes BW x BH, the fraction whose
 2x2 footprint lies inside the CTA's box (origin = tile minimum, x rounded down to a multiple of 4,
-exactly as cost_volume_tma.cu does).  Samples outside take the predicated global path."""
+as the cost-volume kernels do).  Samples outside take the predicated global path."""
 import os
 import sys
 

@@ -1,4 +1,4 @@
-"""Per-layer timing of the depth-unstrided convolutions at the cfg-2 shapes: round-1 kernels vs the persistent TMA kernels.
+"""Per-layer timing of the depth-unstrided convolutions at the cfg-2 shapes: the generic tcgen05 kernels (conv3d_tc.cu) vs the persistent TMA-fed kernels (conv3d_tma.cu).
 
     python scripts/conv_bench.py [out.json]
 """
@@ -51,13 +51,13 @@ def strided_cases(out):
             y_new = engine.conv3d_tma(x, wn, nt, cout, 3, shift, skip, True, mode)
             res = {"tma_us": timed(lambda: engine.conv3d_tma(x, wn, nt, cout, 3, shift, skip, True, mode))}
             if mode == engine.TMA_S2:
-                wk, ntk = engine.pack_tcz_kzf_weights(wt, True)
-                y_old = engine.conv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, None, 2, True)
-                res["old_us"] = timed(lambda: engine.conv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, None, 2, True))
+                hi, _, ntk = engine.pack_tc_weights(wt, False)
+                old = lambda: engine.conv3d_tc(x, hi, None, ntk, cout, 3, shift, None, (1, 2, 2), True)
             else:
-                wk, ntk = engine.pack_tcz_kzf_deconv_weights(wt)
-                y_old = engine.deconv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, skip, True)
-                res["old_us"] = timed(lambda: engine.deconv3d_tcz_kzf(x, wk, ntk, cout, 3, shift, skip, True))
+                hi, _, ntk = engine.pack_tc_deconv_weights(wt, False)
+                old = lambda: engine.deconv3d_tc(x, hi, None, ntk, cout, 3, shift, skip, 1, True)
+            y_old = old()
+            res["old_us"] = timed(old)
             res["max_abs_diff"] = float((y_new.reshape(-1) - y_old.reshape(-1)).abs().max())
             res["tma_gbs"] = 4.0 * (x.numel() + y_new.numel()) / res["tma_us"] / 1e3
             out[name] = res
@@ -87,17 +87,10 @@ def unstrided_cases(out):
         wn, nt = engine.pack_tma_weights(wt)
         y_new = engine.conv3d_tma(x, wn, nt, cout, kd, shift, None, True)
         res["tma_us"] = timed(lambda: engine.conv3d_tma(x, wn, nt, cout, kd, shift, None, True))
-        xo = x if kd == 3 else x.view(1, b * d, h, w, cin)          # round-1 path of the vis net: maps as depth slices
-        if engine.tcr_supported(cin, cout, w):
-            wk, ntk = engine.pack_tcr_khf_weights(wt)
-            y_old = engine.conv3d_tcr_khf(xo, wk, ntk, cout, kd, shift, None, True)
-            res["old_us"] = timed(lambda: engine.conv3d_tcr_khf(xo, wk, ntk, cout, kd, shift, None, True))
-            res["old"] = "tcr_khf"
-        else:
-            wk, ntk = engine.pack_tcz_kzf_weights(wt, False)
-            y_old = engine.conv3d_tcz_kzf(xo, wk, ntk, cout, kd, shift, None, 1, True)
-            res["old_us"] = timed(lambda: engine.conv3d_tcz_kzf(xo, wk, ntk, cout, kd, shift, None, 1, True))
-            res["old"] = "tcz_kzf"
+        hi, _, ntk = engine.pack_tc_weights(wt, False)
+        old = lambda: engine.conv3d_tc(x, hi, None, ntk, cout, kd, shift, None, (1, 1, 1), True)
+        y_old = old()
+        res["old_us"] = timed(old)
         res["max_abs_diff"] = float((y_new.reshape(-1) - y_old.reshape(-1)).abs().max())
         flops = 2.0 * 9 * kd * cin * cout * b * d * h * w
         nbytes = 4.0 * b * d * h * w * (cin + cout)

@@ -7,7 +7,7 @@ timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/check/p
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/check/smoke.log 2>&1
 timeout 400 python bench.py > gpurun_out/check/bench.json 2> gpurun_out/check/bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/check/bench_reference.json 2> gpurun_out/check/bench_reference.err
-KERN='mvs|kzf|tc::|k1cl|conv3d|vis_|corr_|cost_|tma3|prob_|regression|schedule|init_|confidence|relproj|argmax|nchw'
+KERN='mvs|tc::|k1cl|conv3d|vis_|corr_|cost_|tma3|prob_|regression|schedule|init_|confidence|relproj|argmax|nchw'
 timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active \
   --clock-control none -k regex:"$KERN" -s 216 -c 170 --csv --log-file gpurun_out/check/launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train-step --no-eager --no-parity > gpurun_out/check/ncu_bench.log 2>&1

@@ -2,7 +2,7 @@
 call against the declared ctypes signature (argument count and convertibility) and launches nothing.  Outputs are
 uninitialised memory, so nothing numerical is asserted — the test exists to catch host-side mistakes (wrong argument
 lists, shape logic, missing attributes) in code paths that only run on a GPU: inference in all three precision modes,
-and the opt-in variants (MVS_CV_STORE, MVS_TCZ_KZF, MVS_TRAIN_CONV)."""
+with every knob of config.py (MVS_CV_LAYOUT, MVS_CONV_TMA, MVS_VIS_FUSED, MVS_TRAIN_CONV)."""
 import ctypes
 
 import pytest
@@ -12,8 +12,6 @@ from mvsformer_b200 import _lib, config, engine
 from mvsformer_b200 import synthetic as S
 from mvsformer_b200.mvsformer_model import CascadeMVS
 from tests.helpers import CASCADE_ARGS
-
-_CV_STORE_DEFAULT, _TCZ_KZF_DEFAULT = config.cv_store(), config.tcz_kzf()
 
 
 class _Recorder:
@@ -57,18 +55,15 @@ def _cascade_inputs(height=128, width=256, views=3):
 
 
 @pytest.mark.parametrize("mode", ["tf32", "tf32x3", "fp32"])
-@pytest.mark.parametrize("layout,cv_store,kzf", [("nchw", False, 0), ("nchw", True, 0), ("nchw", False, 1), ("nchw", True, 2),
-                                                 ("cl", True, 1)])
-def test_inference_host_path(dry, mode, layout, cv_store, kzf):
+@pytest.mark.parametrize("layout,tma,fused", [("cl", True, True), ("cl", False, False), ("nchw", True, True), ("nchw", False, False)])
+def test_inference_host_path(dry, mode, layout, tma, fused):
     feats, cams, dv = _cascade_inputs()
     net = CascadeMVS(dict(CASCADE_ARGS)).eval()
     old = config.conv_precision()
     config.set_conv_precision(mode)
     config.set_cv_layout(layout)
-    config.set_conv_tma(layout == "cl")           # the round-1 variants are checked with the round-2 kernels switched off
-    config.set_vis_fused(layout == "cl")
-    config.set_cv_store(cv_store)
-    config.set_tcz_kzf(kzf)
+    config.set_conv_tma(tma)
+    config.set_vis_fused(fused)
     try:
         with torch.no_grad():
             out = net(feats, cams, dv, tmp=list(S.EVAL_TMP))
@@ -77,28 +72,30 @@ def test_inference_host_path(dry, mode, layout, cv_store, kzf):
         config.set_cv_layout("cl")
         config.set_conv_tma(True)
         config.set_vis_fused(True)
-        config.set_cv_store(_CV_STORE_DEFAULT)
-        config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
     assert out["refined_depth"].shape == (1, 128, 256) and out["photometric_confidence"].shape == (1, 128, 256)
     assert set(out["stage1"]) >= {"depth", "prob_volume", "photometric_confidence", "depth_values", "prob_volume_pre", "sim_depth"}
     called = set(dry.calls)
-    if layout == "cl":                   # round-2 default: channels-last kernels, one sampling pass at stages 1-3
+    if layout == "cl":                   # default: channels-last kernels, one sampling pass at stages 1-3
         assert {"mvs_features_to_cl", "mvs_cost_volume_cl_entropy", "mvs_cost_volume_cl_aggregate", "mvs_corr_aggregate"} <= called
         assert dry.calls.count("mvs_cost_volume_cl_entropy") == 4 and dry.calls.count("mvs_cost_volume_cl_aggregate") == 1
-        assert not called & {"mvs_cost_volume_entropy", "mvs_cost_volume_entropy_store", "mvs_cost_volume_aggregate"}
-        if mode == "tf32":               # depth-unstrided layers on the persistent TMA kernels, visibility net fused
-            assert dry.calls.count("mvs_conv3d_tma") == 24 and dry.calls.count("mvs_vis_fused") == 4
-            assert not called & {"mvs_vis_first_cl", "mvs_vis_last_cl", "mvs_conv3d_tcr_khf", "mvs_conv3d_tcz_kzf", "mvs_deconv3d_tcz_kzf"}
-        else:
-            assert "mvs_conv3d_tma" not in called and "mvs_vis_fused" not in called
-        return
-    assert "mvs_cost_volume_entropy" in called or "mvs_cost_volume_entropy_store" in called
-    if cv_store:
-        assert "mvs_cost_volume_entropy_store" in called and "mvs_corr_aggregate" in called
-    if kzf and mode == "tf32":
-        assert called & {"mvs_conv3d_tcz_kzf", "mvs_deconv3d_tcz_kzf", "mvs_conv3d_tcr_khf"}
+        assert not called & {"mvs_cost_volume_entropy", "mvs_cost_volume_aggregate", "mvs_cost_volume_aggregate_tf32"}
+    else:                                # generic kernels on the reference's NCHW layout, two sampling passes
+        assert dry.calls.count("mvs_cost_volume_entropy") == 4 and "mvs_features_to_cl" not in called
+        assert dry.calls.count("mvs_cost_volume_aggregate" + ("_tf32" if mode == "tf32" else "")) == 4
+        assert dry.calls.count("mvs_argmax_gather") == 4
+    if mode == "tf32" and tma:           # depth-unstrided layers on the persistent TMA kernels, the rest on the generic tcgen05 ones
+        assert dry.calls.count("mvs_conv3d_tma") == 24
+        assert dry.calls.count("mvs_conv3d_tc") + dry.calls.count("mvs_deconv3d_tc") == 12
+    else:
+        assert "mvs_conv3d_tma" not in called
+    if mode == "tf32" and fused:
+        assert dry.calls.count("mvs_vis_fused") == 4 and "mvs_vis_weight" not in called
+    else:
+        assert dry.calls.count("mvs_vis_weight") == 4 and "mvs_vis_fused" not in called
     if mode == "fp32":
-        assert "mvs_conv3d_cl" in called and not any("_tc" in c for c in called)
+        assert "mvs_conv3d_cl" in called and not any("_tc" in c or "_tma" in c for c in called)
+    elif not (mode == "tf32" and tma):
+        assert dry.calls.count("mvs_conv3d_tc") + dry.calls.count("mvs_deconv3d_tc") == 36
 
 
 @pytest.mark.parametrize("train_conv", ["fp32", "tf32x3", "tf32"])
@@ -163,21 +160,22 @@ def test_other_module_entry_points_host_path(dry):
 
 
 def test_bench_kernel_profiler_wraps_existing_entry_points():
-    """bench.py's per-kernel attribution wraps engine functions by name: every name must exist (also the opt-in ones)."""
+    """bench.py's per-kernel attribution wraps engine functions by name: every name must exist."""
     import bench
 
     prof = bench.KernelProfiler()
     before = {k: getattr(engine, k) for k in dir(engine) if callable(getattr(engine, k))}
     prof.install(engine)
-    assert {"cost_volume_entropy_store", "corr_aggregate", "conv3d_tcz_kzf", "deconv3d_tcz_kzf", "conv3d_tcr_khf"} <= set(prof._saved)
+    assert {"features_to_cl", "cost_volume_cl_entropy", "cost_volume_cl_aggregate", "corr_aggregate", "conv3d_tma", "vis_fused",
+            "conv3d_tc", "deconv3d_tc", "cost_volume_entropy", "cost_volume_aggregate", "vis_weight"} <= set(prof._saved)
     prof.uninstall(engine)
     assert all(getattr(engine, k) is v for k, v in before.items())
 
 
-@pytest.mark.parametrize("cv_store,kzf", [(False, 0), (True, 2), (False, 1)])
-def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
+@pytest.mark.parametrize("layout", ["cl", "nchw"])
+def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, layout):
     """The profiler's algorithmic-byte / flop lambdas must accept the argument lists the engine wrappers are called
-    with, for the shipped path and for the opt-in variants (scripts/ab_variants.py depends on it)."""
+    with, for the shipped path and for the generic kernels."""
     import bench
 
     class _Event:
@@ -195,8 +193,7 @@ def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
     net = CascadeMVS(dict(CASCADE_ARGS)).eval()
     old = config.conv_precision()
     config.set_conv_precision("tf32")
-    config.set_cv_store(cv_store)
-    config.set_tcz_kzf(kzf)
+    config.set_cv_layout(layout)
     prof = bench.KernelProfiler()
     prof.install(engine)
     try:
@@ -205,11 +202,12 @@ def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, cv_store, kzf):
     finally:
         prof.uninstall(engine)
         config.set_conv_precision(old)
-        config.set_cv_store(_CV_STORE_DEFAULT)
-        config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
+        config.set_cv_layout("cl")
     summ = prof.summary(1)
     assert all(v["alg_bytes_per_step"] > 0 for v in summ.values())
-    # round-2 default layout: the channels-last kernels (one sampling pass at stages 1-3 + streaming aggregation)
-    assert {"cv_layout(nchw->channels-last)", "cv_cl_passA+store", "cv_cl_passA(stage4)", "cv_cl_passB(stage4)",
-            "cv_corr_aggregate(stream)"} <= set(summ)
+    if layout == "cl":       # the channels-last kernels (one sampling pass at stages 1-3 + streaming aggregation)
+        assert {"cv_layout(nchw->channels-last)", "cv_cl_passA+store", "cv_cl_passA(stage4)", "cv_cl_passB(stage4)",
+                "cv_corr_aggregate(stream)"} <= set(summ)
+    else:
+        assert {"cv_entropy(passA)", "cv_aggregate(passB)"} <= set(summ)
     assert "conv3d_tma" in summ and "vis_net(fused)" in summ

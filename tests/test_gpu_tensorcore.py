@@ -132,54 +132,6 @@ def test_cost_reg_precision_modes(kind, mode, tol):
     assert rel_l1(got, want) < tol
 
 
-TCZ_CASES = [
-    # cin, cout, kd, shw, D, H, W
-    (8, 16, 3, 2, 4, 16, 24), (16, 16, 3, 1, 4, 10, 14), (16, 16, 1, 1, 1, 33, 47), (16, 8, 1, 1, 1, 20, 20),
-    (16, 32, 3, 2, 4, 9, 13), (32, 32, 3, 1, 8, 6, 10), (32, 64, 3, 2, 3, 6, 10), (64, 64, 3, 1, 4, 5, 7),
-    (64, 64, 3, 1, 8, 5, 7), (16, 16, 3, 1, 2, 3, 300), (16, 16, 3, 1, 5, 7, 9),
-]
-
-
-@pytest.mark.parametrize("cin,cout,kd,shw,D,H,W", TCZ_CASES)
-def test_conv3d_tcz(cin, cout, kd, shw, D, H, W):
-    assert engine.tcz_supported(cin, cout, D, kd, shw == 2)
-    g = S._gen(cin * 100 + cout + kd + W + D)
-    w = engine.round_tf32(torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5)
-    shift = 0.1 * torch.randn(cout, generator=g)
-    x = engine.round_tf32(torch.randn(2, cin, D, H, W, generator=g))          # producer-rounded operand
-    want = torch.relu(F.conv3d(x.double(), w.double(), stride=(1, shw, shw), padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
-    skip = torch.randn(want.shape, generator=g)
-    wz, nt = engine.pack_tcz_weights(w.permute(2, 3, 4, 1, 0).contiguous().to(DEV), shw == 2)
-    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
-    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
-    got = engine.conv3d_tcz(x_cl, wz, nt, cout, kd, shift.to(DEV), skip_cl, shw, relu=True).permute(0, 4, 1, 2, 3).cpu()
-    assert got.shape == want.shape
-    assert torch.equal(got, engine.round_tf32(got))                            # output is TF32-rounded
-    assert rel_l1(got, want + skip.double()) < 5e-4                            # exact products; only the output rounding (2^-11)
-
-
-TCZD_CASES = [(64, 32, 3, 4, 3, 5), (64, 32, 3, 8, 3, 5), (32, 16, 3, 4, 6, 10), (16, 8, 3, 4, 8, 12), (16, 8, 1, 3, 8, 12),
-              (32, 16, 3, 8, 5, 200), (16, 8, 3, 8, 4, 6), (16, 8, 3, 1, 9, 9)]
-
-
-@pytest.mark.parametrize("cin,cout,kd,D,H,W", TCZD_CASES)
-def test_deconv3d_tcz(cin, cout, kd, D, H, W):
-    assert engine.tcz_supported(cin, cout, D, kd, transposed=True)
-    g = S._gen(cin * 7 + cout + kd + W + D)
-    w = engine.round_tf32(torch.randn(cin, cout, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9 / 4)) ** 0.5)
-    shift = 0.1 * torch.randn(cout, generator=g)
-    x = engine.round_tf32(torch.randn(2, cin, D, H, W, generator=g))
-    want = torch.relu(F.conv_transpose3d(x.double(), w.double(), stride=(1, 2, 2), padding=(kd // 2, 1, 1),
-                                         output_padding=(0, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
-    skip = torch.randn(want.shape, generator=g)
-    wz, nt = engine.pack_tcz_deconv_weights(w.permute(2, 3, 4, 0, 1).contiguous().to(DEV))
-    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
-    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
-    got = engine.deconv3d_tcz(x_cl, wz, nt, cout, kd, shift.to(DEV), skip_cl, relu=True).permute(0, 4, 1, 2, 3).cpu()
-    assert got.shape == want.shape
-    assert rel_l1(got, want + skip.double()) < 5e-4
-
-
 def test_cascade_tf32_meets_north_star_tolerance():
     """TF32 tensor-core convolutions (the bench default): refined depth within 1e-3 relative L1 of the
     reference's golden output (BASELINE.json north_star tolerance)."""
@@ -210,16 +162,9 @@ def test_cascade_tf32_meets_north_star_tolerance():
     assert err < 1e-3
 
 
-def test_tcz_shape_rules_fall_back():
-    """Shapes the depth-fused kernels cannot hold (tiny D with wide channels) are routed to the
-    generic tensor-core kernel, not rejected."""
-    assert not engine.tcz_supported(64, 64, 2, 3)
-    assert engine.tcz_supported(64, 64, 4, 3) and engine.tcz_supported(16, 16, 1, 1)
-
-
 def test_vis_net_tensor_core_route():
-    """StageNet.vis through the TF32 tensor-core route (first / last layers streaming, middle layers as
-    kd = 1 implicit GEMMs with the views as depth axis) vs the oracle's fp32 visibility net."""
+    """StageNet.vis through the fused tcgen05 kernel (csrc/vis_fused.cu: layer 1 on CUDA cores, the 16->16 and 16->8 layers
+    as TF32 MMAs, 1x1 conv + sigmoid in registers) and through the FP32 kernel vs the oracle's fp32 visibility net."""
     from mvsformer_b200 import config
     from mvsformer_b200.mvsformer_model import StageNet
     from oracle import mvs_oracle as O
@@ -244,26 +189,6 @@ def test_vis_net_tensor_core_route():
         assert rel_l1(got, want) < 2e-3
 
 
-TCR_CASES = [(16, 16, 3, 4, 6, 128), (16, 16, 1, 4, 9, 256), (16, 8, 1, 5, 7, 130), (32, 32, 3, 4, 5, 128), (8, 16, 3, 3, 4, 140),
-             (16, 32, 3, 8, 3, 128), (16, 16, 3, 1, 2, 384)]
-
-
-@pytest.mark.parametrize("cin,cout,kd,D,H,W", TCR_CASES)
-def test_conv3d_tcr(cin, cout, kd, D, H, W):
-    g = S._gen(cin * 100 + cout + kd + W + D + 1)     # includes partial 128-column blocks (W = 130, 140)
-    w = engine.round_tf32(torch.randn(cout, cin, kd, 3, 3, generator=g) * (2.0 / (cin * kd * 9)) ** 0.5)
-    shift = 0.1 * torch.randn(cout, generator=g)
-    x = engine.round_tf32(torch.randn(2, cin, D, H, W, generator=g))
-    want = torch.relu(F.conv3d(x.double(), w.double(), padding=(kd // 2, 1, 1)) + shift.double().view(1, -1, 1, 1, 1))
-    skip = torch.randn(want.shape, generator=g)
-    wr, nt = engine.pack_tcr_weights(w.permute(2, 3, 4, 1, 0).contiguous().to(DEV))
-    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
-    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
-    got = engine.conv3d_tcr(x_cl, wr, nt, cout, kd, shift.to(DEV), skip_cl, relu=True).permute(0, 4, 1, 2, 3).cpu()
-    assert got.shape == want.shape
-    assert rel_l1(got, want + skip.double()) < 5e-4
-
-
 @pytest.mark.parametrize("n,shift", [(16, 0), (16, 2), (32, 1), (64, 0)])
 def test_tc_probe_a_from_tmem(n, shift):
     """A operand copied smem -> TMEM (tcgen05.cp.128x256b, row-shifted descriptor) and read from TMEM by
@@ -282,7 +207,7 @@ def test_tc_probe_a_from_tmem(n, shift):
     assert err < 1e-5
 
 
-# ---- round-2 persistent TMA-fed convolutions (csrc/conv3d_tma.cu) --------------------------------------------------------
+# ---- persistent TMA-fed convolutions (csrc/conv3d_tma.cu) --------------------------------------------------------
 TMA_CASES = [
     # cin, cout, kd, D, H, W, batch
     (16, 16, 3, 4, 16, 8, 1), (16, 16, 3, 4, 10, 14, 2), (16, 16, 1, 1, 33, 47, 3), (16, 8, 1, 1, 20, 20, 2),

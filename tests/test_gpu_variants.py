@@ -1,10 +1,8 @@
-"""GPU tests of the kernel variants behind ``mvsformer_b200.config`` switches and of the paths next to the hot path
-(depth-map fusion, the heads / fusion types no shipped config uses, diff-warp gradients, tensor-core training
-convolutions).  All of them first ran on a B200 at the start of round 2 (profiles/r02_gated_tests_first_run.log);
-the variants that won the A/B (profiles/r02_ab_variants.json) are now the package defaults.
-
-* cv_store: cost-volume build with one sampling pass (pass A stores the per-view correlation, the
-  aggregation streams over it) — must be BIT-identical to the two-pass build (same FMA sequence).
+"""GPU tests of the two implementations behind each ``mvsformer_b200.config`` switch (channels-last vs generic cost-volume
+kernels, fused vs CUDA-core visibility net) and of the paths next to the hot path (depth-map fusion, the heads / fusion types
+no shipped config uses, diff-warp gradients, tensor-core training convolutions).  The round-1 "opt-in variants" that lost
+the A/B on the B200 (profiles/r02_ab_variants.json, profiles/r02_gated_tests_first_run.log) or were superseded by the
+round-2 kernels have been deleted together with their tests.
 """
 import os
 
@@ -17,169 +15,6 @@ from tests.helpers import STAGE_ARGS
 
 pytestmark = [pytest.mark.gpu]
 DEV = "cuda"
-_CV_STORE_DEFAULT, _TCZ_KZF_DEFAULT = config.cv_store(), config.tcz_kzf()
-
-
-def _build(net, feats, cams, hyp, store):
-    config.set_cv_store(store)
-    try:
-        return net.build_cost_volume(feats.to(DEV), cams.to(DEV), hyp.to(DEV))
-    finally:
-        config.set_cv_store(_CV_STORE_DEFAULT)
-
-
-@pytest.mark.parametrize("s", [0, 1, 2])
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
-@pytest.mark.parametrize("wild", [False, True])
-def test_cv_store_is_bit_identical_to_two_pass(s, mode, wild):
-    height, width, batch, views = 128, 192, 2, 4
-    feats = S.make_features(batch, views, height, width, stages=(s,), smooth=not wild)["stage%d" % (s + 1)]
-    cams = S.make_cameras(batch, views, height, width)["stage%d" % (s + 1)].clone()
-    hyp = S.narrow_hypotheses(s, height, width, batch)
-    if wild:                                    # samples outside the staged box / the image: predicated global path
-        cams[:, 2, 0, 0, 3] += 500.0
-        cams[:, 3, 0, 2, 3] -= 900.0
-    net = StageNet(dict(STAGE_ARGS), S.NDEPTHS[s], s).eval()
-    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=s))
-    net = net.to(DEV)
-    old = config.conv_precision()
-    config.set_conv_precision(mode)
-    try:
-        vol2, sim2, ent2, w2 = _build(net, feats, cams, hyp, False)
-        vol1, sim1, ent1, w1 = _build(net, feats, cams, hyp, True)
-    finally:
-        config.set_conv_precision(old)
-    assert torch.equal(ent1, ent2) and torch.equal(sim1, sim2) and torch.equal(w1, w2)
-    assert torch.equal(vol1, vol2)
-
-
-def test_cv_store_falls_back_at_stage4():
-    """C/G = 1 (stage 4): the correlation would be as large as the warped tensor, so the two-pass build runs."""
-    s, height, width = 3, 64, 96
-    feats = S.make_features(1, 3, height, width, stages=(s,))["stage4"]
-    cams = S.make_cameras(1, 3, height, width)["stage4"]
-    hyp = S.narrow_hypotheses(s, height, width, 1)
-    net = StageNet(dict(STAGE_ARGS), 4, s).eval().to(DEV)
-    a = _build(net, feats, cams, hyp, True)[0]
-    b = _build(net, feats, cams, hyp, False)[0]
-    assert torch.equal(a, b)
-
-
-@pytest.mark.parametrize("cin,cout,depth,h,w,stride2", [
-    (8, 16, 4, 32, 48, True), (16, 16, 4, 32, 48, False), (16, 32, 8, 32, 48, True), (32, 32, 4, 24, 40, False),
-    (32, 64, 8, 32, 48, True), (64, 64, 4, 16, 24, False), (64, 64, 8, 16, 24, False), (16, 8, 2, 16, 24, False)])
-def test_tcz_kzf_matches_tcz(cin, cout, depth, h, w, stride2):
-    """MVS_TCZ_KZF: the kz-fused tensor-core convolution vs the shipped depth-fused kernel (same TF32 operands,
-    different fp32 accumulation order) and vs an fp64 convolution of the same rounded operands."""
-    import torch.nn.functional as F
-    from mvsformer_b200 import engine
-
-    g = S._gen(cin * 100 + cout)
-    wp = engine.round_tf32(torch.randn(3, 3, 3, cin, cout, generator=g) * 0.1)
-    x = engine.round_tf32(torch.randn(2, depth, h, w, cin, generator=g))
-    shift = torch.randn(cout, generator=g)
-    if not engine.tcz_supported(cin, cout, depth, 3, stride2):
-        pytest.skip("shape not covered by the tcz kernels")
-    wz, nt = engine.pack_tcz_weights(wp, stride2)
-    wk, nt2 = engine.pack_tcz_kzf_weights(wp, stride2)
-    assert nt == nt2
-    shw = 2 if stride2 else 1
-    ref = engine.conv3d_tcz(x.to(DEV), wz.to(DEV), nt, cout, 3, shift.to(DEV), None, shw, True)
-    got = engine.conv3d_tcz_kzf(x.to(DEV), wk.to(DEV), nt, cout, 3, shift.to(DEV), None, shw, True)
-    torch.cuda.synchronize()
-    want = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), wp.permute(4, 3, 0, 1, 2).double(), stride=(1, shw, shw), padding=1)
-    want = torch.relu(want + shift.double().view(1, -1, 1, 1, 1)).permute(0, 2, 3, 4, 1)
-    err_ref = float((ref.cpu().double() - want).abs().mean() / want.abs().mean())
-    err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
-    assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6        # outputs are TF32-rounded by the epilogue
-    assert float((got - ref).abs().max()) < 1e-2
-
-
-def test_tcz_kzf_cascade_matches_default():
-    """Whole TF32 cascade with MVS_TCZ_KZF=2 (kz-fused kernel wherever it applies) vs the shipped kernels."""
-    from mvsformer_b200.mvsformer_model import CascadeMVS
-    from tests.helpers import CASCADE_ARGS
-
-    height, width, batch, views = 128, 192, 1, 3
-    feats = {k: v.to(DEV) for k, v in S.make_features(batch, views, height, width, seed=3).items()}
-    cams = {k: v.to(DEV) for k, v in S.make_cameras(batch, views, height, width).items()}
-    dv = S.make_depth_range(batch).to(DEV)
-    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
-    full = {}
-    for s in range(4):
-        full.update({"fusions.%d.%s" % (s, k): v for k, v in S.fill_state_dict(net.fusions[s].state_dict(), seed=40 + s).items()})
-    net.load_state_dict(full)
-    net = net.to(DEV)
-    old = config.conv_precision()
-    config.set_conv_precision("tf32")
-    try:
-        outs = {}
-        for level in (0, 2):
-            config.set_tcz_kzf(level)
-            with torch.no_grad():
-                outs[level] = net(feats, cams, dv, tmp=list(S.EVAL_TMP))["refined_depth"].clone()
-    finally:
-        config.set_tcz_kzf(_TCZ_KZF_DEFAULT)
-        config.set_conv_precision(old)
-    rel = float((outs[2] - outs[0]).abs().mean() / outs[0].abs().mean())
-    assert rel < 1e-3
-
-
-@pytest.mark.parametrize("cin,cout,depth,h,w", [(16, 8, 4, 32, 48), (32, 16, 4, 24, 40), (64, 32, 8, 16, 24), (64, 32, 4, 16, 24),
-                                                (16, 8, 2, 16, 24)])
-def test_deconv_tcz_kzf_matches_tcz(cin, cout, depth, h, w):
-    """MVS_TCZ_KZF: kz-fused transposed convolution vs the shipped depth-fused kernel and vs fp64 (with skip add)."""
-    import torch.nn.functional as F
-    from mvsformer_b200 import engine
-
-    if not engine.tcz_supported(cin, cout, depth, 3, transposed=True):
-        pytest.skip("shape not covered by the tcz kernels")
-    g = S._gen(cin * 100 + cout + 1)
-    wp = engine.round_tf32(torch.randn(3, 3, 3, cin, cout, generator=g) * 0.1)
-    x = engine.round_tf32(torch.randn(2, depth, h, w, cin, generator=g))
-    shift = torch.randn(cout, generator=g)
-    skip = torch.randn(2, depth, 2 * h, 2 * w, cout, generator=g)
-    wz, nt = engine.pack_tcz_deconv_weights(wp)
-    wk, nt2 = engine.pack_tcz_kzf_deconv_weights(wp)
-    assert nt == nt2
-    ref = engine.deconv3d_tcz(x.to(DEV), wz.to(DEV), nt, cout, 3, shift.to(DEV), skip.to(DEV), True)
-    got = engine.deconv3d_tcz_kzf(x.to(DEV), wk.to(DEV), nt, cout, 3, shift.to(DEV), skip.to(DEV), True)
-    torch.cuda.synchronize()
-    want = F.conv_transpose3d(x.permute(0, 4, 1, 2, 3).double(), wp.permute(3, 4, 0, 1, 2).double(), stride=(1, 2, 2),
-                              padding=1, output_padding=(0, 1, 1))
-    want = (torch.relu(want + shift.double().view(1, -1, 1, 1, 1))).permute(0, 2, 3, 4, 1) + skip.double()
-    err_ref = float((ref.cpu().double() - want).abs().mean() / want.abs().mean())
-    err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
-    assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6
-    assert float((got - ref).abs().max()) < 1e-2
-
-
-@pytest.mark.parametrize("cin,cout,kd,depth,h,w", [(16, 16, 1, 4, 40, 128), (16, 8, 1, 3, 24, 256), (16, 16, 3, 4, 16, 128),
-                                                   (32, 32, 3, 4, 12, 128), (8, 16, 3, 8, 10, 128), (16, 16, 1, 1, 9, 120)])
-def test_tcr_khf_matches_tcr(cin, cout, kd, depth, h, w):
-    """MVS_TCZ_KZF: kh-fused row-tiled convolution (visibility-net layers with kd = 1, wide 3D layers) vs the shipped
-    row-tiled kernel and vs fp64."""
-    import torch.nn.functional as F
-    from mvsformer_b200 import engine
-
-    if not engine.tcr_supported(cin, cout, w):
-        pytest.skip("width not covered by the row-tiled kernel")
-    g = S._gen(cin * 100 + cout + kd)
-    wp = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g) * 0.1)
-    x = engine.round_tf32(torch.randn(2, depth, h, w, cin, generator=g))
-    shift = torch.randn(cout, generator=g)
-    wr, nt = engine.pack_tcr_weights(wp)
-    wk, nt2 = engine.pack_tcr_khf_weights(wp)
-    assert nt == nt2
-    ref = engine.conv3d_tcr(x.to(DEV), wr.to(DEV), nt, cout, kd, shift.to(DEV), None, True)
-    got = engine.conv3d_tcr_khf(x.to(DEV), wk.to(DEV), nt, cout, kd, shift.to(DEV), None, True)
-    torch.cuda.synchronize()
-    want = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), wp.permute(4, 3, 0, 1, 2).double(), padding=(kd // 2, 1, 1))
-    want = torch.relu(want + shift.double().view(1, -1, 1, 1, 1)).permute(0, 2, 3, 4, 1)
-    err_ref = float((ref.cpu().double() - want).abs().mean() / want.abs().mean())
-    err_got = float((got.cpu().double() - want).abs().mean() / want.abs().mean())
-    assert err_got < 2e-3 and err_got < 2 * err_ref + 1e-6
-    assert float((got - ref).abs().max()) < 1e-2
 
 
 def test_fusion_gpu_vs_reference_golden_and_oracle():
@@ -359,7 +194,7 @@ def test_epipole_fusion_gpu_vs_reference_golden(kind):
     assert (res["sim_depth"].cpu() == torch.from_numpy(g[kind + "_eval_sim_depth"])).float().mean() > 0.99
 
 
-# ---- round-2 channels-last cost-volume kernels (csrc/cost_volume_cl.cu) ------------------------------------------------
+# ---- channels-last cost-volume kernels (csrc/cost_volume_cl.cu) ------------------------------------------------
 def test_features_to_cl_is_an_exact_permutation():
     from mvsformer_b200 import engine
     ts = [torch.randn(2, 3, c, h, w, device=DEV) for c, h, w in ((64, 16, 24), (32, 32, 48), (16, 37, 50), (8, 5, 7))]
@@ -372,9 +207,9 @@ def test_features_to_cl_is_an_exact_permutation():
 @pytest.mark.parametrize("s", [0, 1, 2, 3])
 @pytest.mark.parametrize("wild", [False, True])
 @pytest.mark.parametrize("shape", [(128, 192, 2, 4), (64, 104, 1, 3)])
-def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
+def test_channels_last_cost_volume_matches_generic_kernels(s, wild, shape):
     """Same arithmetic, different summation order over the channels of a sample: volume / entropy / similarity of the
-    channels-last kernels vs the round-1 kernels (each separately pinned to the oracle in test_gpu_parity.py), incl.
+    channels-last kernels vs the generic NCHW kernels of csrc/cost_volume.cu (each separately pinned to the oracle in test_gpu_parity.py), incl.
     samples outside the staged box / the image (predicated global path) and partial tiles (width 104/8 = 13 px)."""
     from tests.helpers import rel_l1
     height, width, batch, views = shape
@@ -395,9 +230,9 @@ def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
         finally:
             config.set_cv_layout("cl")
     (v0, s0, e0, w0), (v1, s1, e1, w1) = res["nchw"], res["cl"]
-    assert rel_l1(e1, e0) < 2e-6, rel_l1(e1, e0)
-    assert rel_l1(w1, w0) < 2e-6
-    assert rel_l1(v1, v0) < 5e-6, rel_l1(v1, v0)
+    assert rel_l1(e1, e0) < 1e-5, rel_l1(e1, e0)
+    assert rel_l1(w1, w0) < 1e-5
+    assert rel_l1(v1, v0) < 2e-5, rel_l1(v1, v0)
     # the channels-last kernels take the argmax of the similarity inside the kernel: compare the chosen hypotheses
     from mvsformer_b200 import engine
     sd0 = engine.argmax_gather(s0, hyp.to(DEV))
@@ -408,10 +243,11 @@ def test_channels_last_cost_volume_matches_nchw_kernels(s, wild, shape):
 
 # ---- fused visibility net (csrc/vis_fused.cu) ----------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(4, 144, 192), (3, 37, 50), (2, 30, 14), (1, 31, 15), (5, 200, 333)])
-def test_fused_vis_net_matches_the_four_kernel_route(shape):
-    """Same TF32 operands and rounding points as the unfused tensor-core route (which tests/test_gpu_parity.py holds to the
-    oracle); only the order in which the three kernel rows' partial sums are added differs (fp32).  Incl. partial tiles and
-    maps smaller than a tile."""
+def test_fused_vis_net_matches_the_fp32_kernel(shape):
+    """The fused tcgen05 kernel (TF32 operands for the 16->16 and 16->8 layers, fp32 accumulation) vs the FP32 CUDA-core
+    kernel of csrc/vis_net.cu (which tests/test_gpu_parity.py holds to the oracle at 1e-5): the difference is the TF32
+    rounding of two layers' operands (2^-11 relative each) seen through the sigmoid.  Incl. partial tiles and maps smaller
+    than a tile."""
     from tests.helpers import rel_l1
     m, h, w = shape
     net = StageNet(dict(STAGE_ARGS), 8, 2).eval()
@@ -430,6 +266,6 @@ def test_fused_vis_net_matches_the_four_kernel_route(shape):
         config.set_conv_precision(old)
     torch.cuda.synchronize()
     assert got.shape == want.shape
-    # a 1e-7 difference in a partial sum can flip the TF32 rounding of an activation (2^-11 relative), hence the margins
-    assert rel_l1(got, want) < 2e-5, rel_l1(got, want)
-    assert float((got - want).abs().max()) < 2e-3
+    # (against the unfused TF32 route it replaced, same operands, the fused kernel agreed to 2e-5: profiles/r02_gpu_tests.log)
+    assert rel_l1(got, want) < 3e-3, rel_l1(got, want)
+    assert float((got - want).abs().max()) < 3e-2

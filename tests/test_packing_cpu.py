@@ -36,19 +36,34 @@ def test_pack_tc_weights_layout():
         assert abs(float(both - w[kz, kh, kw, ci, co])) <= abs(float(w[kz, kh, kw, ci, co])) * 2 ** -20   # hi + lo ~ fp32
 
 
-def test_pack_tcz_and_tcr_layouts():
+def test_pack_tma_weights_layout():
+    """[kd,3,3,Cin,Cout] -> [Cout tiles][kh][kw][Cin/4][kd][n_tile][4]: per (tap, channel quad) the B rows are [kz][n]
+    (operand of the kz-fused MMA of csrc/conv3d_tma.cu)."""
     kd, cin, cout = 3, 16, 8
     w = _w(kd, cin, cout, 1)
-    wz, nt = engine.pack_tcz_weights(w, stride2=False)
-    assert nt == 16 and wz.shape == (1, 3, 1, kd, 3, 4, 16, 4)
     wr = engine.round_tf32(w)
-    for (kz, kh, kw, ci, co) in [(0, 0, 0, 0, 0), (2, 1, 2, 13, 7), (1, 2, 0, 5, 3)]:
-        assert wz[0, kh, 0, kz, kw, ci // 4, co, ci % 4] == wr[kz, kh, kw, ci, co]
-    assert wz[0, :, :, :, :, :, 8:, :].abs().sum() == 0           # Cout padded to the N tile with zeros
-    wt, nt2 = engine.pack_tcr_weights(w)
-    assert nt2 == 16 and wt.shape == (1, kd, 3, 3, 4, 16, 4)
-    for (kz, kh, kw, ci, co) in [(2, 1, 2, 13, 7), (1, 2, 0, 5, 3)]:
-        assert wt[0, kz, kh, kw, ci // 4, co, ci % 4] == wr[kz, kh, kw, ci, co]
+    for mode in (engine.TMA_S1, engine.TMA_S2, engine.TMA_DECONV):
+        wt, nt = engine.pack_tma_weights(w, mode)
+        assert nt == engine.tma_n_tile(cin, cout, mode) and wt.shape == (1, 3, 3, cin // 4, kd, nt, 4)
+        for (kz, kh, kw, ci, co) in [(0, 0, 0, 0, 0), (2, 1, 2, 13, 7), (1, 2, 0, 5, 3)]:
+            assert wt[0, kh, kw, ci // 4, kz, co, ci % 4] == wr[kz, kh, kw, ci, co]
+        assert wt[..., 8:, :].abs().sum() == 0                      # Cout padded to the N tile with zeros
+    wt, nt = engine.pack_tma_weights(_w(3, 32, 64, 3))             # two Cout tiles of 32
+    assert nt == 32 and wt.shape == (2, 3, 3, 8, 3, 32, 4)
+    assert wt[1, 1, 2, 5, 0, 7, 3] == engine.round_tf32(_w(3, 32, 64, 3))[0, 1, 2, 23, 39]
+
+
+def test_pack_vis_fused_weights_layout():
+    """[Cout,16,3,3] -> [kw][4 quads][rows][4], rows = [kh][cout] zero-padded (operand of the kh-fused MMA of csrc/vis_fused.cu)."""
+    g = torch.Generator().manual_seed(5)
+    for cout, rows in ((16, 48), (8, 32)):
+        w = torch.randn(cout, 16, 3, 3, generator=g)
+        p = engine.pack_vis_fused_weights(w, rows)
+        wr = engine.round_tf32(w)
+        assert p.shape == (3, 4, rows, 4)
+        for (co, ci, kh, kw) in [(0, 0, 0, 0), (cout - 1, 15, 2, 1), (3, 6, 1, 2)]:
+            assert p[kw, ci // 4, kh * cout + co, ci % 4] == wr[co, ci, kh, kw]
+        assert p[:, :, 3 * cout:].abs().sum() == 0
 
 
 def test_pack_deconv_layouts():
@@ -57,22 +72,26 @@ def test_pack_deconv_layouts():
     wr = engine.round_tf32(w)
     taps = {0: [(1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2)], 1: [(0, 0), (0, 1), (0, 2)]}
     hi, lo, nt = engine.pack_tc_deconv_weights(w, x3=False)
-    wz, ntz = engine.pack_tcz_deconv_weights(w)
-    assert lo is None and nt == ntz == 16
+    assert lo is None and nt == 16
     for dy, lst in taps.items():
         for t, (kh, kw) in enumerate(lst):
             for (kz, ci, co) in [(0, 0, 0), (2, 29, 15)]:
                 assert hi[0, kz, dy, 0, t, ci // 4, co, ci % 4] == wr[kz, kh, kw, ci, co]
-                assert wz[0, dy, 0, kz, t, ci // 4, co, ci % 4] == wr[kz, kh, kw, ci, co]
     assert hi[0, :, 1, :, 3:].abs().sum() == 0                      # the three unused tap slots of dy = 1
 
 
-def test_tcz_shape_rules():
-    assert engine.tcz_supported(16, 16, 4, 3) and engine.tcz_supported(64, 64, 8, 3)
-    assert not engine.tcz_supported(64, 64, 2, 3)                   # weight ring would not fit shared memory
-    assert engine.tcz_supported(64, 32, 8, 3, transposed=True) and not engine.tcz_supported(8, 8, 4, 3, transposed=True)
-    assert engine.tcr_supported(16, 16, 768) and engine.tcr_supported(16, 8, 1536)
-    assert not engine.tcr_supported(16, 16, 192) and not engine.tcr_supported(64, 64, 768)
+def test_tma_shape_rules():
+    """Every CostRegNet3D layer with depth stride 1 of the cfg-2 cascade is covered; TMEM bounds the rest."""
+    for d in (4, 8):
+        for cin, cout in ((16, 16), (32, 32), (64, 64)):
+            assert engine.tma_supported(cin, cout, d, 3)
+        for cin, cout in ((8, 16), (16, 32), (32, 64)):
+            assert engine.tma_supported(cin, cout, d, 3, stride2=True)
+        for cin, cout in ((64, 32), (32, 16), (16, 8)):
+            assert engine.tma_supported(cin, cout, d, 3, transposed=True)
+    assert not engine.tma_supported(64, 32, 16, 3, transposed=True)        # 4 parity classes x 16 slices x 16 columns > 512
+    assert not engine.tma_supported(16, 16, 64, 3)                         # 64 slices x 16 columns > 512 TMEM columns
+    assert not engine.tma_supported(24, 16, 4, 3) and not engine.tma_supported(16, 16, 4, 2)
 
 
 def test_packed_sample_roundtrip():
@@ -105,240 +124,3 @@ def test_feature_cache_lru_and_pinning():
         c.reserve("f", pinned=("c", "d", "e"))
     with pytest.raises(ValueError):
         FeatureCache(1)
-
-
-def _emulate_tcz_kzf(x, w_packed_flat, nt, cin, cout, kd, depth, zc):
-    """Host emulation of the MMA issue loop of conv3d_tcz_kernel<.., KZF=true> (conv3d_tcz_kzf.cu), stride 1:
-    same group / slab order, same window, column, accumulate-flag and B-descriptor arithmetic, with the tensor-core
-    product written as a matrix product.  x [D,H,W,Cin] (numpy), returns y [D,H,W,Cout]."""
-    cs = engine.tc_channel_slice(cin)
-    ch_n, nch, pd = cs // 4, cin // cs, kd // 2
-    d_, h_, w_ = x.shape[:3]
-    ngroups = 3 * nch
-    plane = kd * nt * 16                      # bytes between the K chunks of a tap
-    btap = ch_n * plane                       # bytes per kw
-    bgroup = 3 * btap
-    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
-    y = np.zeros((d_, h_, w_, cout), np.float64)
-    ntiles = (cout + nt - 1) // nt
-    for ct in range(ntiles):
-        for z0 in range(0, d_, zc):
-            nz = min(zc, d_ - z0)
-            tmem = np.full((h_ * w_, zc * nt), np.nan)          # garbage until an accumulate=0 MMA writes it
-            started = 0
-            iz_lo, iz_hi = max(z0 - pd, 0), min(z0 + nz - 1 + pd, d_ - 1)
-            for g in range(ngroups):
-                kh, ch = g // nch, g % nch
-                group = w_packed_flat[(ct * ngroups + g) * (bgroup // 4):(ct * ngroups + g + 1) * (bgroup // 4)]
-                for iz in range(iz_lo, iz_hi + 1):
-                    kz_lo, kz_hi = max(0, iz + pd - (z0 + nz - 1)), min(kd - 1, iz + pd - z0)
-                    if kz_lo > kz_hi:
-                        continue
-                    zi_top = iz + pd - kz_lo - z0
-                    dwin = (nz - 1 - zi_top) * nt
-                    for kw in range(3):
-                        for kk in range(cs // 8):
-                            a = xp[iz, kh:kh + h_, kw:kw + w_, ch * cs + kk * 8: ch * cs + kk * 8 + 8].reshape(-1, 8)
-
-                            def b_rows(first_row, nrows):
-                                out = np.empty((nrows, 8))
-                                for r in range(nrows):
-                                    for k in range(8):
-                                        byte = kw * btap + (2 * kk + k // 4) * plane + (first_row + r) * 16 + (k % 4) * 4
-                                        out[r, k] = group[byte // 4]
-                                return out
-                            if g == 0 and kw == 0 and kk == 0:
-                                for kz in range(kz_lo, kz_hi + 1):
-                                    zi = iz + pd - kz - z0
-                                    col = (nz - 1 - zi) * nt
-                                    prod = a @ b_rows(kz * nt, nt).T
-                                    tmem[:, col:col + nt] = prod + (tmem[:, col:col + nt] if (started >> zi) & 1 else 0.0)
-                                    started |= 1 << zi
-                            else:
-                                n = (kz_hi - kz_lo + 1) * nt
-                                tmem[:, dwin:dwin + n] += a @ b_rows(kz_lo * nt, n).T
-            for zi in range(nz):
-                col = (nz - 1 - zi) * nt
-                ncout = min(nt, cout - ct * nt)
-                y[z0 + zi, :, :, ct * nt: ct * nt + ncout] = tmem[:, col:col + ncout].reshape(h_, w_, ncout)
-    return y
-
-
-def test_tcz_kzf_issue_loop_and_packing():
-    """The opt-in kz-fused convolution: packed-weight layout + window / column / accumulate logic of the kernel's
-    MMA issue loop, emulated on the host, reproduce conv3d for every depth chunking (no accumulator is read before
-    it is initialised: uninitialised TMEM is NaN here)."""
-    import torch.nn.functional as F
-    for cin, cout, depth in ((16, 16, 4), (64, 32, 4), (8, 8, 8)):
-        kd = 3
-        g = torch.Generator().manual_seed(cin + cout)
-        w = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g))
-        x = engine.round_tf32(torch.randn(depth, 5, 6, cin, generator=g))
-        wk, nt = engine.pack_tcz_kzf_weights(w, stride2=False)
-        cs = engine.tc_channel_slice(cin)
-        assert wk.shape == ((cout + nt - 1) // nt, 3, cin // cs, 3, cs // 4, kd, nt, 4)
-        want = F.conv3d(x.permute(3, 0, 1, 2).unsqueeze(0).double(), w.permute(4, 3, 0, 1, 2).double(), padding=1)[0]
-        want = want.permute(1, 2, 3, 0).numpy()
-        for zc in (1, 2, 4):
-            got = _emulate_tcz_kzf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, depth, zc)
-            assert np.isfinite(got).all(), (cin, cout, zc)
-            assert np.abs(got - want).max() < 1e-9, (cin, cout, zc)
-
-
-def _emulate_deconv_tcz_kzf(x, flat, nt, cin, cout, kd, zc):
-    """Host emulation of the MMA issue loop of deconv3d_tcz_kzf_kernel (conv3d_tcz_kzf.cu): groups (dy, channel
-    slice), slabs iz, taps -> parity class, accumulators [class][slice], per-slice initialisation in group 0,
-    fused N = 3 * NT windows elsewhere.  x [D,H,W,Cin] -> y [D,2H,2W,Cout] (stride (1,2,2), pad 1, output_padding (0,1,1))."""
-    cs = engine.tc_channel_slice(cin)
-    ch_n, nch, pd = cs // 4, cin // cs, kd // 2
-    d_, h_, w_ = x.shape[:3]
-    ngroups = 2 * nch
-    plane = kd * nt * 16
-    btap = ch_n * plane
-    bgroup = 6 * btap
-    xp = np.pad(x, ((0, 0), (0, 1), (0, 1), (0, 0)))          # zero row / column past the image (dy = 1, sh = 1)
-    y = np.zeros((d_, 2 * h_, 2 * w_, cout))
-    for ct in range((cout + nt - 1) // nt):
-        for z0 in range(0, d_, zc):
-            nz = min(zc, d_ - z0)
-            tmem = np.full((h_ * w_, nz * 4 * nt), np.nan)
-            started = 0
-            iz_lo, iz_hi = max(z0 - pd, 0), min(z0 + nz - 1 + pd, d_ - 1)
-            for g in range(ngroups):
-                dy, ch = g // nch, g % nch
-                group = flat[(ct * ngroups + g) * (bgroup // 4):(ct * ngroups + g + 1) * (bgroup // 4)]
-                for iz in range(iz_lo, iz_hi + 1):
-                    kz_lo, kz_hi = max(0, z0 - iz + pd), min(kd - 1, z0 + nz - 1 - iz + pd)
-                    if kz_lo > kz_hi:
-                        continue
-                    zi_lo = iz - pd + kz_lo - z0
-                    for t in range(6 if dy == 0 else 3):
-                        kh = 1 + t // 3 if dy == 0 else 0
-                        kw = t % 3
-                        cls = (0 if kh == 1 else 2) + (0 if kw == 1 else 1)
-                        sh = 1 if kw == 0 else 0
-                        dwin = (cls * nz + zi_lo) * nt
-                        starter = g == 0 and t in (0, 1, 3, 4)
-                        for kk in range(cs // 8):
-                            a = xp[iz, dy:dy + h_, sh:sh + w_, ch * cs + kk * 8: ch * cs + kk * 8 + 8].reshape(-1, 8)
-
-                            def b_rows(first_row, nrows):
-                                out = np.empty((nrows, 8))
-                                for r in range(nrows):
-                                    for k in range(8):
-                                        byte = t * btap + (2 * kk + k // 4) * plane + (first_row + r) * 16 + (k % 4) * 4
-                                        out[r, k] = group[byte // 4]
-                                return out
-                            if starter and kk == 0:
-                                for kz in range(kz_lo, kz_hi + 1):
-                                    slot = cls * nz + (iz - pd + kz - z0)
-                                    prod = a @ b_rows(kz * nt, nt).T
-                                    col = slot * nt
-                                    tmem[:, col:col + nt] = prod + (tmem[:, col:col + nt] if (started >> slot) & 1 else 0.0)
-                                    started |= 1 << slot
-                            else:
-                                n = (kz_hi - kz_lo + 1) * nt
-                                tmem[:, dwin:dwin + n] += a @ b_rows(kz_lo * nt, n).T
-            ncout = min(nt, cout - ct * nt)
-            for zi in range(nz):
-                for cls in range(4):
-                    col = (cls * nz + zi) * nt
-                    y[z0 + zi, (cls >> 1)::2, (cls & 1)::2, ct * nt: ct * nt + ncout] = \
-                        tmem[:, col:col + ncout].reshape(h_, w_, ncout)
-    return y
-
-
-def test_deconv_tcz_kzf_issue_loop_and_packing():
-    import torch.nn.functional as F
-    for cin, cout, depth in ((16, 8, 4), (32, 16, 4), (64, 32, 8)):
-        kd = 3
-        g = torch.Generator().manual_seed(cin * 7 + cout)
-        w = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g))            # packed [kd,3,3,Cin,Cout]
-        x = engine.round_tf32(torch.randn(depth, 4, 5, cin, generator=g))
-        wk, nt = engine.pack_tcz_kzf_deconv_weights(w)
-        cs = engine.tc_channel_slice(cin)
-        assert wk.shape == ((cout + nt - 1) // nt, 2, cin // cs, 6, cs // 4, kd, nt, 4)
-        want = F.conv_transpose3d(x.permute(3, 0, 1, 2).unsqueeze(0).double(), w.permute(3, 4, 0, 1, 2).double(),
-                                  stride=(1, 2, 2), padding=1, output_padding=(0, 1, 1))[0].permute(1, 2, 3, 0).numpy()
-        for zc in (1, 2, 4):
-            got = _emulate_deconv_tcz_kzf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, zc)
-            assert np.isfinite(got).all(), (cin, cout, zc)
-            assert np.abs(got - want).max() < 1e-9, (cin, cout, zc)
-
-
-def _emulate_tcr_khf(x, flat, nt, cin, cout, kd, rows, zc):
-    """Host emulation of the MMA issue loop of conv3d_tcr_khf_kernel (conv3d_tcz_kzf.cu) for one 128-column block:
-    CTAs of `rows` output rows x `zc` slices, iterations over input rows (iz, iy), accumulators [slice][row descending],
-    an MMA fused over kh whenever its whole window is initialised.  x [D,H,W,Cin] with W <= 128."""
-    ch_n, pd = cin // 4, kd // 2
-    d_, h_, w_ = x.shape[:3]
-    plane = 3 * nt * 16
-    btap = ch_n * plane
-    b_bytes = kd * 3 * btap
-    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (0, 0)))
-    y = np.zeros((d_, h_, w_, cout))
-    fused = unfused = 0
-    for ct in range((cout + nt - 1) // nt):
-        wts = flat[ct * (b_bytes // 4):(ct + 1) * (b_bytes // 4)]
-        for z0 in range(0, d_, zc):
-            nz = min(zc, d_ - z0)
-            for y0 in range(0, h_, rows):
-                nr = min(rows, h_ - y0)
-                tmem = np.full((w_, rows * zc * nt), np.nan)
-                started = 0
-                iz_lo, iz_hi = max(z0 - pd, 0), min(z0 + nz - 1 + pd, d_ - 1)
-                iy_lo, iy_hi = max(y0 - 1, 0), min(y0 + nr, h_ - 1)
-                for iz in range(iz_lo, iz_hi + 1):
-                    for iy in range(iy_lo, iy_hi + 1):
-                        kh_lo, kh_hi = max(0, iy + 1 - (y0 + nr - 1)), min(2, iy + 1 - y0)
-                        for kz in range(kd):
-                            oz = iz + pd - kz
-                            if oz < z0 or oz >= z0 + nz or kh_lo > kh_hi:
-                                continue
-                            nk = kh_hi - kh_lo + 1
-                            slot0 = (oz - z0) * rows + (nr - 1 - (iy + 1 - kh_lo - y0))
-                            wmask = ((1 << nk) - 1) << slot0
-                            for kw in range(3):
-                                for kk in range(cin // 8):
-                                    a = xp[iz, iy, kw:kw + w_, kk * 8:kk * 8 + 8]
-
-                                    def b_rows(first_row, nrows):
-                                        out = np.empty((nrows, 8))
-                                        for r in range(nrows):
-                                            for k in range(8):
-                                                byte = (kz * 3 + kw) * btap + (2 * kk + k // 4) * plane + (first_row + r) * 16 + (k % 4) * 4
-                                                out[r, k] = wts[byte // 4]
-                                        return out
-                                    if (started & wmask) == wmask:
-                                        tmem[:, slot0 * nt:(slot0 + nk) * nt] += a @ b_rows(kh_lo * nt, nk * nt).T
-                                        fused += 1
-                                    else:
-                                        for kh in range(kh_lo, kh_hi + 1):
-                                            slot = slot0 + kh - kh_lo
-                                            prod = a @ b_rows(kh * nt, nt).T
-                                            tmem[:, slot * nt:(slot + 1) * nt] = prod + (tmem[:, slot * nt:(slot + 1) * nt]
-                                                                                         if (started >> slot) & 1 else 0.0)
-                                            started |= 1 << slot
-                                            unfused += 1
-                ncout = min(nt, cout - ct * nt)
-                for zi in range(nz):
-                    for ri in range(nr):
-                        col = (zi * rows + (nr - 1 - ri)) * nt
-                        y[z0 + zi, y0 + ri, :, ct * nt: ct * nt + ncout] = tmem[:, col:col + ncout]
-    return y, fused, unfused
-
-
-def test_tcr_khf_issue_loop_and_packing():
-    import torch.nn.functional as F
-    for cin, cout, kd, depth, height, rows, zc in ((16, 16, 1, 3, 19, 8, 1), (16, 8, 1, 2, 8, 8, 1), (32, 32, 3, 4, 7, 2, 4),
-                                                   (8, 16, 3, 2, 5, 2, 2)):
-        g = torch.Generator().manual_seed(cin * 11 + cout + kd)
-        w = engine.round_tf32(torch.randn(kd, 3, 3, cin, cout, generator=g))
-        x = engine.round_tf32(torch.randn(depth, height, 9, cin, generator=g))
-        wk, nt = engine.pack_tcr_khf_weights(w)
-        assert wk.shape == ((cout + nt - 1) // nt, kd, 3, cin // 4, 3, nt, 4)
-        want = F.conv3d(x.permute(3, 0, 1, 2).unsqueeze(0).double(), w.permute(4, 3, 0, 1, 2).double(),
-                        padding=(kd // 2, 1, 1))[0].permute(1, 2, 3, 0).numpy()
-        got, fused, unfused = _emulate_tcr_khf(x.double().numpy(), wk.reshape(-1).double().numpy(), nt, cin, cout, kd, rows, zc)
-        assert np.isfinite(got).all() and np.abs(got - want).max() < 1e-9, (cin, cout, kd)
-        assert fused > unfused / 2                      # most MMAs take the fused form
