@@ -597,10 +597,12 @@ def run_engine(args, rank, world, local_rank):
         run_e2e_scan(max(3, args.warmup))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        streamer.host_wait_s, streamer.host_steps = 0.0, 0
         e0.record()
         run_e2e_scan(args.steps)
         e1.record()
         barrier()
+        host_wait_ms = 1e3 * streamer.host_wait_s / max(streamer.host_steps, 1)
         ms_t = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
             dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -671,6 +673,7 @@ def run_engine(args, rank, world, local_rank):
             "e2e": {"value": world * args.steps / (ms_scan * 1e-3), "unit": UNIT, "ms_per_step": ms_scan / args.steps,
                     "h2d_bytes_per_step": h2d_scan, "d2h_bytes_per_step": d2h,
                     "h2d_gbs_aggregate": world * h2d_scan / (ms_scan / args.steps * 1e-3) / 1e9,
+                    "host_blocked_on_results_ms_per_step": host_wait_ms,     # ~0 would mean the host paces the loop, not the GPU
                     "api": "mvsformer_b200.pipeline.StreamedCascade.run_scan: pinned host features of a scan in, host depth + "
                            "confidence out; consecutive reference views share 4 of their 5 views (DTU pairing), every view "
                            "crosses PCIe once, is re-laid out channels-last on the device once, and is addressed in place by "

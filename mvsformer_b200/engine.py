@@ -310,6 +310,16 @@ def depth_regression(p, depth_values):
     p, depth_values = _f32(p).contiguous(), _f32(depth_values).contiguous()
     require_cuda(p, depth_values)
     b, d, h, w = p.shape
+    # the reference broadcasts: [D] (conf_regression's arange), [B,D], [B,D,1,1] or a full [B,D,H,W] map (module.py:597-603)
+    if depth_values.dim() == 1:
+        depth_values = depth_values.unsqueeze(0).expand(b, -1).contiguous()
+    elif depth_values.dim() == 4 and tuple(depth_values.shape[2:]) == (1, 1):
+        depth_values = depth_values.reshape(depth_values.shape[0], -1)
+    if depth_values.dim() == 2 and depth_values.shape[0] == 1 and b > 1:
+        depth_values = depth_values.expand(b, -1).contiguous()
+    if tuple(depth_values.shape) not in ((b, d), (b, d, h, w)):
+        raise RuntimeError("depth_regression: depth_values %s do not broadcast against p %s"
+                           % (tuple(depth_values.shape), tuple(p.shape)))
     is_map = 1 if depth_values.dim() == 4 else 0
     out = torch.empty(b, h, w, device=p.device, dtype=torch.float32)
     check(_lib.load().mvs_depth_regression(ptr(p), ptr(depth_values), is_map, ptr(out), b, d, h, w, stream()),
@@ -352,6 +362,9 @@ def schedule_range(cur_depth, ndepth, depth_interval_pixel, h, w):
     cur_depth, itv = _f32(cur_depth).contiguous(), _f32(depth_interval_pixel).contiguous()
     require_cuda(cur_depth, itv)
     b = cur_depth.shape[0]
+    if tuple(cur_depth.shape) != (b, h // 2, w // 2):
+        raise RuntimeError("schedule_range: the previous-stage depth must be [B,%d,%d] (got %s)"
+                           % (h // 2, w // 2, tuple(cur_depth.shape)))
     out = torch.empty(b, ndepth, h, w, device=cur_depth.device, dtype=torch.float32)
     check(_lib.load().mvs_schedule_range(ptr(cur_depth), ptr(itv), ptr(out), b, ndepth, h, w, stream()), "mvs_schedule_range")
     return out

@@ -22,6 +22,8 @@ out once, when it is uploaded), and a sample's views are addressed in place thro
 """
 from collections import OrderedDict
 
+import time
+
 import torch
 
 
@@ -112,7 +114,8 @@ class StreamedCascade:
         self.net = net
         self.device = torch.device(device)
         self.tmp = tmp
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)      # host -> device (+ re-layout of a new view)
+        self.d2h_stream = torch.cuda.Stream(device=self.device)       # device -> host: the other copy engine, off the compute stream
         self.ring = ring
         self._out = None
         self._dev_ring = None            # [(device flat buffer, "consumed" event)] for PackedSample uploads
@@ -124,6 +127,10 @@ class StreamedCascade:
         self._staging = None             # {"stageK": [C, h, w]} landing buffers of an upload (re-laid out into the pool)
         self._compute_done = None        # event: the last enqueued cascade has read the pools
         self._slot_used = {}             # slot -> event of the last cascade that read it
+        self._small = None               # ring of device sets (cameras, depth range) of run_scan
+        self._small_i = 0
+        self.host_wait_s = 0.0           # time the host spent blocked on results (≈ 0 means the host, not the GPU, paces the loop)
+        self.host_steps = 0
 
     def _upload(self, sample):
         """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
@@ -186,15 +193,28 @@ class StreamedCascade:
                         engine.features_to_cl([self._staging[k] for k in keys[k0:k0 + 4]],
                                               outs=[self._pools[k][slot] for k in keys[k0:k0 + 4]])
                 slots.append(slot)
-            cams = {k: v.to(self.device, non_blocking=True) for k, v in sample.proj_matrices.items()}
-            dv = sample.depth_values.to(self.device, non_blocking=True)
+            cams, dv = self._small_set(sample)
+            for k, v in sample.proj_matrices.items():
+                cams[k].copy_(v, non_blocking=True)
+            dv.copy_(sample.depth_values, non_blocking=True)
             uploaded += sum(4 * v.numel() for v in sample.proj_matrices.values()) + 4 * sample.depth_values.numel()
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
-        main = torch.cuda.current_stream(self.device)
-        for t in list(cams.values()) + [dv]:
-            t.record_stream(main)
         return slots, cams, dv, ready, uploaded
+
+    def _small_set(self, sample):
+        """Device buffers for a sample's cameras and depth range: ``ring + 1`` persistent sets used in rotation (allocated
+        once from the compute stream's pool — no cross-stream allocator traffic in the loop).  The set handed to sample
+        i+1 was last read by cascade i-ring, whose result has been synchronised on before sample i's turn."""
+        shapes = {k: tuple(v.shape) for k, v in sample.proj_matrices.items()}
+        shapes["dv"] = tuple(sample.depth_values.shape)
+        if self._small is None or self._small[0] != shapes:
+            with torch.cuda.stream(torch.cuda.current_stream(self.device)):
+                sets = [({k: torch.empty(shapes[k], dtype=torch.float32, device=self.device) for k in sample.proj_matrices},
+                         torch.empty(shapes["dv"], dtype=torch.float32, device=self.device)) for _ in range(self.ring + 1)]
+            self._small = (shapes, sets)
+        self._small_i += 1
+        return self._small[1][self._small_i % (self.ring + 1)]
 
     def run_scan(self, samples, capacity=64, keep_cache=False):
         """Like ``run`` for ``ScanSample``s that share views: each view's features cross PCIe once
@@ -237,21 +257,39 @@ class StreamedCascade:
                 # staged only now: an upload that evicts a slot waits for the cascade enqueued above, which may read it
                 nxt = next(it, None)
                 staged = self._stage_scan(nxt) if nxt is not None else None  # overlaps with this view's compute
-                bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
-                hd, hc, done = bufs[i % len(bufs)]
-                hd.copy_(out["refined_depth"], non_blocking=True)
-                hc.copy_(out["photometric_confidence"], non_blocking=True)
-                done.record(main)
-                self.d2h_bytes = 4 * (hd.numel() + hc.numel())
-                pending.append((hd, hc, done))
+                pending.append(self._download(out, i, main))
+                del out
                 if len(pending) >= self.ring:
-                    od, oc, oe = pending.pop(0)
-                    oe.synchronize()
+                    od, oc, oe = pending.pop(0)[:3]
+                    self._wait(oe)
                     yield od, oc
                 i += 1
-        for od, oc, oe in pending:
-            oe.synchronize()
+        for od, oc, oe, _, _ in pending:
+            self._wait(oe)
             yield od, oc
+
+    def _wait(self, event):
+        t0 = time.perf_counter()
+        event.synchronize()
+        self.host_wait_s += time.perf_counter() - t0
+        self.host_steps += 1
+
+    def _download(self, out, i, main):
+        """Enqueue the device -> host copy of a finished cascade's result on the D2H stream (so it overlaps the next
+        cascade instead of sitting between two of them).  The device tensors ride along in the returned tuple: they must
+        stay allocated until the copy has finished, i.e. until ``done`` has been synchronised on."""
+        depth, conf = out["refined_depth"], out["photometric_confidence"]
+        bufs = self._ring_buffers(depth, conf)
+        hd, hc, done = bufs[i % len(bufs)]
+        computed = torch.cuda.Event()
+        computed.record(main)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(computed)
+            hd.copy_(depth, non_blocking=True)
+            hc.copy_(conf, non_blocking=True)
+            done.record(self.d2h_stream)
+        self.d2h_bytes = 4 * (hd.numel() + hc.numel())
+        return hd, hc, done, depth, conf
 
     def _ring_buffers(self, depth, conf):
         if self._out is None or self._out[0][0].shape != depth.shape:
@@ -286,18 +324,13 @@ class StreamedCascade:
                 if slot is not None:                                         # staging slot may be refilled after this
                     slot[1] = torch.cuda.Event()
                     slot[1].record(main)
-                bufs = self._ring_buffers(out["refined_depth"], out["photometric_confidence"])
-                hd, hc, done = bufs[i % len(bufs)]
-                hd.copy_(out["refined_depth"], non_blocking=True)
-                hc.copy_(out["photometric_confidence"], non_blocking=True)
-                done.record(main)
-                self.d2h_bytes = 4 * (hd.numel() + hc.numel())
-                pending.append((hd, hc, done))
+                pending.append(self._download(out, i, main))
+                del out
                 if len(pending) >= self.ring:                                # hand out the oldest result
-                    od, oc, oe = pending.pop(0)
-                    oe.synchronize()
+                    od, oc, oe = pending.pop(0)[:3]
+                    self._wait(oe)
                     yield od, oc
                 i += 1
-        for od, oc, oe in pending:
-            oe.synchronize()
+        for od, oc, oe, _, _ in pending:
+            self._wait(oe)
             yield od, oc

@@ -6,6 +6,7 @@ mkdir -p gpurun_out/check
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/check/pytest.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/check/smoke.log 2>&1
 timeout 400 python bench.py > gpurun_out/check/bench.json 2> gpurun_out/check/bench.err
+timeout 200 python bench.py --steps 20 --warmup 3 --no-train-step --no-eager --no-cpu-baseline --no-parity > gpurun_out/check/bench_20steps.json 2> gpurun_out/check/bench_20steps.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/check/bench_reference.json 2> gpurun_out/check/bench_reference.err
 KERN='mvs|tc::|k1cl|conv3d|vis_|corr_|cost_|tma3|prob_|regression|schedule|init_|confidence|relproj|argmax|nchw'
 timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active \

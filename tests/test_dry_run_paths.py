@@ -148,6 +148,16 @@ def test_other_module_entry_points_host_path(dry):
         assert cls(8, 8).eval()(x).shape == (1, 1, 8, 16, 24)
     p, dv = torch.zeros(1, 8, 4, 6), torch.zeros(1, 8)
     assert M.depth_regression(p, dv).shape == (1, 4, 6) and M.conf_regression(p, 2).shape == (1, 4, 6)
+    # the broadcast forms the reference accepts (models/module.py:597-603) are expanded, anything else is refused
+    p2 = torch.zeros(2, 8, 4, 6)
+    for form in (torch.zeros(8), torch.zeros(1, 8), torch.zeros(2, 8, 1, 1), torch.zeros(2, 8, 4, 6)):
+        assert M.depth_regression(p2, form).shape == (2, 4, 6)
+    for bad in (torch.zeros(2, 7), torch.zeros(3, 8), torch.zeros(2, 8, 4, 5)):
+        with pytest.raises(RuntimeError):
+            M.depth_regression(p2, bad)
+    assert M.schedule_range(torch.ones(1, 8, 12), 16, torch.ones(1), 16, 24).shape == (1, 16, 16, 24)
+    with pytest.raises(RuntimeError):
+        M.schedule_range(torch.ones(1, 16, 24), 16, torch.ones(1), 16, 24)          # same-size map: not [B,H/2,W/2]
     assert M.init_inverse_range(torch.ones(1, 192), 32, None, None, 4, 6).shape == (1, 32, 4, 6)
     eye = torch.eye(4).unsqueeze(0)
     warped, mask = Wp.homo_warping_3D_with_mask(torch.zeros(1, 8, 4, 6), eye, eye, dv)
