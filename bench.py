@@ -363,7 +363,8 @@ def cpu_threads():
 
 def bind_to_gpu_numa_node(index):
     """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs of the GPU's NUMA node, so that N ranks do
-    not all stream their uploads out of node 0 (round-1 e2e scaling: 0.41 at N = 8).  Returns the node or None."""
+    not all stream their uploads out of node 0 (round-1 e2e scaling: 0.41 at N = 8).  Returns the node, or a string saying
+    why nothing was bound (the gpurun boxes expose no NUMA topology to the container: sysfs reports node -1)."""
     try:
         bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
                              capture_output=True, text=True, timeout=10).stdout.strip().lower()
@@ -372,7 +373,7 @@ def bind_to_gpu_numa_node(index):
         with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            return "not bound: /sys/bus/pci/devices/%s/numa_node = %d (no NUMA topology exposed)" % (bus, node)
         with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
             cpus = set()
             for part in f.read().strip().split(","):
@@ -382,8 +383,8 @@ def bind_to_gpu_numa_node(index):
         if allowed:
             os.sched_setaffinity(0, allowed)
         return node
-    except Exception:
-        return None
+    except Exception as exc:
+        return "not bound: %s" % type(exc).__name__
 
 
 def measured_peaks():

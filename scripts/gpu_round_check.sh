@@ -15,5 +15,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.a
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"cost_volume_cl_kernel|nchw_to_cl|corr_aggregate" -s 27 -c 9 -o gpurun_out/check/k1 \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train-step --no-eager --no-parity > gpurun_out/check/ncu_full.log 2>&1
 python scripts/summarise_ncu.py gpurun_out/check/k1.ncu-rep gpurun_out/check/k1_full.csv > gpurun_out/check/summ.log 2>&1
+python scripts/traffic_from_launches.py gpurun_out/check/launches.csv gpurun_out/check/traffic.json >> gpurun_out/check/summ.log 2>&1
 rm -f gpurun_out/check/k1.ncu-rep
 cat gpurun_out/check/pytest.log gpurun_out/check/smoke.log; tail -c 400 gpurun_out/check/bench.json
