@@ -528,11 +528,18 @@ def run_engine(args, rank, world, local_rank):
     tmp = list(S.EVAL_TMP)
     lib = _lib.load()
 
-    def step_resident():
+    def step_single():
         return net(feats_d, cams_d, dv_d, tmp=tmp)
 
-    from mvsformer_b200.pipeline import PackedSample, StreamedCascade
-    streamer = StreamedCascade(net, device, tmp)
+    from mvsformer_b200.pipeline import CascadeLanes, PackedSample, StreamedCascade
+    # --lanes N: N reference views in flight per GPU, round-robin over N compute streams (the narrow kernels of one view run
+    # under the wide kernels of another); every view is still one full cascade, the step count is the number of views
+    lanes = CascadeLanes(net, device, args.lanes) if args.lanes > 1 else None
+
+    def step_resident():
+        return lanes.submit(feats_d, cams_d, dv_d, tmp=tmp)[0] if lanes is not None else step_single()
+
+    streamer = StreamedCascade(net, device, tmp, lanes=args.lanes)
     packed = PackedSample(feats_h, cams_h, dv_h)          # one pinned buffer -> one DMA per reference view
 
     def run_e2e(steps):
@@ -567,6 +574,8 @@ def run_engine(args, rank, world, local_rank):
         e0.record()
         for _ in range(steps):
             fn()
+        if lanes is not None:
+            lanes.join()                       # the timing stream waits for every lane
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -616,7 +625,7 @@ def run_engine(args, rank, world, local_rank):
         barrier()
         psteps = min(args.steps, 5)
         for _ in range(psteps):
-            step_resident()
+            step_single()                      # one view at a time: per-kernel times are not inflated by a concurrent view
         barrier()
         prof.uninstall(engine)
         kernels = prof.summary(psteps)
@@ -670,7 +679,7 @@ def run_engine(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if config.conv_precision() == "fp32" else "f32 (conv MMA operands %s, fp32 accumulate)" % config.conv_precision(),
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": dict(workload_config(world), views_in_flight_per_gpu=args.lanes),
             "e2e": {"value": world * args.steps / (ms_scan * 1e-3), "unit": UNIT, "ms_per_step": ms_scan / args.steps,
                     "h2d_bytes_per_step": h2d_scan, "d2h_bytes_per_step": d2h,
                     "h2d_gbs_aggregate": world * h2d_scan / (ms_scan / args.steps * 1e-3) / 1e9,
@@ -714,6 +723,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference", "eager"])
+    ap.add_argument("--lanes", type=int, default=1, help="reference views in flight per GPU (compute streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (reference modules on cuda:0)")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity check against the CPU oracle")

@@ -260,39 +260,41 @@ class CascadeMVS(nn.Module):
         self.depth_interals_ratio = args["depth_interals_ratio"]
         self.inverse_depth = args.get("inverse_depth", False)
         self.fusions = nn.ModuleList([StageNet(args, self.ndepths[i], i) for i in range(len(self.ndepths))])
-        self._side, self._cl_ready = None, None
+        self._side = {}                     # compute stream -> its side stream (calls on different streams do not share one)
 
     def _features_cl(self, features):
-        """Channels-last copies of all stages' features in ONE launch (eval, 'cnn' fusion, shapes the channels-last
-        kernels cover); None otherwise — every StageNet then decides for itself."""
+        """-> (channels-last copies of all stages' features, event the compute stream must wait for before stage 2) — eval,
+        'cnn' fusion, shapes the channels-last kernels cover; (None, None) otherwise: every StageNet then decides for
+        itself."""
         nst = len(self.ndepths)
         if self.training or nst > 4 or config.cv_layout() != "cl":
-            return None
+            return None, None
         feats = [features["stage%d" % (s + 1)] for s in range(nst)]
         groups = self.args["base_ch"]
         for s, f in enumerate(feats):
             if self.fusions[s].fusion_type != "cnn" or f.dim() != 5 or not f.is_cuda \
                     or not engine.cl_supported(f.shape[2], self.ndepths[s], groups):
-                return None
+                return None, None
         # stage 1 on the compute stream; stages 2-4 (HBM-bound copies) on a side stream, under the latency-bound kernels
         # of stage 1 — each stage waits for its own features only
         main = torch.cuda.current_stream(feats[0].device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=feats[0].device)
+        side = self._side.get(main.cuda_stream)
+        if side is None:
+            side = self._side[main.cuda_stream] = torch.cuda.Stream(device=feats[0].device)
         out = engine.features_to_cl(feats[:1])
+        done = None
         if nst > 1:
             # destinations are allocated on the compute stream (its allocator pool; no cross-stream frees), only the copies
             # run on the side stream; the compute stream waits for them before stage 2, i.e. before anything is released
             rest = [torch.empty(f.shape[:2] + (f.shape[3], f.shape[4], f.shape[2]), device=f.device, dtype=torch.float32)
                     for f in feats[1:]]
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
                 engine.features_to_cl(feats[1:], outs=rest)
                 done = torch.cuda.Event()
-                done.record(self._side)
+                done.record(side)
             out += rest
-            self._cl_ready = done
-        return out
+        return out, done
 
     def forward(self, features, proj_matrices, depth_values, tmp=2.0, full_hw=None, pools_cl=None, view_slots=None):
         """features {"stageK": [B,V,C,h,w]}, proj_matrices {"stageK": [B,V,2,4,4]}, depth_values [B,ND].
@@ -318,7 +320,7 @@ class CascadeMVS(nn.Module):
         use_conf = self.args["depth_type"] in ("ce", "mixup_ce")
         prob_maps = torch.zeros(b, full_hw[0], full_hw[1], dtype=torch.float32, device=device) if use_conf else None
         depth_interval = depth_values[:, 1] - depth_values[:, 0]
-        feats_cl = None if pools_cl is not None else self._features_cl(features)
+        feats_cl, cl_ready = (None, None) if pools_cl is not None else self._features_cl(features)
         for s in range(nst):
             feats = None if pools_cl is not None else features["stage%d" % (s + 1)]
             h, w = pools_cl["stage%d" % (s + 1)].shape[1:3] if pools_cl is not None else feats.shape[-2:]
@@ -335,9 +337,8 @@ class CascadeMVS(nn.Module):
                 outputs_stage = self.fusions[s](None, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
                                                 features_cl=pools_cl["stage%d" % (s + 1)], view_slots=view_slots)
             elif feats_cl is not None:
-                if s == 1 and self._cl_ready is not None:
-                    torch.cuda.current_stream(device).wait_event(self._cl_ready)      # stages 2-4 were re-laid out on the side stream
-                    self._cl_ready = None
+                if s == 1 and cl_ready is not None:
+                    torch.cuda.current_stream(device).wait_event(cl_ready)            # stages 2-4 were re-laid out on the side stream
                 outputs_stage = self.fusions[s](feats, proj_matrices["stage%d" % (s + 1)], depth_samples, tmp=tmp,
                                                 features_cl=feats_cl[s])
             else:

@@ -109,11 +109,54 @@ class PackedSample:
         return feats, cams, dv
 
 
+class CascadeLanes:
+    """Round-robin of reference views over ``lanes`` CUDA streams of one GPU.  A reference view's cascade is a strict chain
+    of 70 launches, a third of which (stage 1-2 layers, heads, projections) cannot fill 148 SMs; with two views in flight
+    the narrow kernels of one run under the wide kernels of the other.  Views are independent (no data is shared but the
+    read-only weights), so the results are those of sequential calls."""
+
+    def __init__(self, net, device, lanes=2):
+        self.net = net
+        self.device = torch.device(device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
+        self._n = 0
+
+    def next_stream(self):
+        """The lane of the next view; it is made to wait for everything enqueued on the caller's stream so far."""
+        lane = self.streams[self._n % len(self.streams)]
+        lane.wait_stream(torch.cuda.current_stream(self.device))
+        self._n += 1
+        return lane
+
+    def submit(self, *args, **kwargs):
+        """``net(*args, **kwargs)`` on the next lane; returns (outputs, lane).  The outputs are ordered on ``lane``: use them
+        there, wait for an event recorded on it, or call ``join()``."""
+        lane = self.next_stream()
+        with torch.cuda.stream(lane):
+            out = self.net(*args, **kwargs)
+        if self._n == 1:
+            # first call: the BN-folded / operand-packed weights were just built on this lane; the other lanes read them
+            torch.cuda.current_stream(self.device).wait_stream(lane)
+            torch.cuda.synchronize(self.device)
+        return out, lane
+
+    def join(self):
+        """The caller's stream waits for every lane."""
+        main = torch.cuda.current_stream(self.device)
+        for lane in self.streams:
+            main.wait_stream(lane)
+
+
 class StreamedCascade:
-    def __init__(self, net, device, tmp, ring=2):
+    def __init__(self, net, device, tmp, ring=None, lanes=1):
+        """``lanes`` > 1: consecutive reference views alternate between that many compute streams (CascadeLanes);
+        ``ring`` = results in flight before the oldest is handed out (default lanes + 1, so ``lanes`` cascades stay enqueued
+        while the host prepares the next)."""
         self.net = net
         self.device = torch.device(device)
         self.tmp = tmp
+        self.lanes = CascadeLanes(net, self.device, lanes) if lanes > 1 else None
+        ring = ring if ring is not None else (lanes + 1 if lanes > 1 else 2)
         self.copy_stream = torch.cuda.Stream(device=self.device)      # host -> device (+ re-layout of a new view)
         self.d2h_stream = torch.cuda.Stream(device=self.device)       # device -> host: the other copy engine, off the compute stream
         self.ring = ring
@@ -129,6 +172,7 @@ class StreamedCascade:
         self._slot_used = {}             # slot -> event of the last cascade that read it
         self._small = None               # ring of device sets (cameras, depth range) of run_scan
         self._small_i = 0
+        self._lanes_warm = False
         self.host_wait_s = 0.0           # time the host spent blocked on results (≈ 0 means the host, not the GPU, paces the loop)
         self.host_steps = 0
 
@@ -136,12 +180,12 @@ class StreamedCascade:
         """sample = PackedSample, or (features dict, proj_matrices dict, depth_values) of pinned host tensors."""
         main = torch.cuda.current_stream(self.device)
         if isinstance(sample, PackedSample):
-            # persistent device staging ring (no allocator traffic): slot i % 2 is overwritten only
-            # after the compute that read it (two uploads ago) has been enqueued and finished
+            # persistent device staging ring (no allocator traffic): a slot is overwritten only after the
+            # compute that read it (ring + 1 uploads ago) has been enqueued and finished
             n = sample.flat.numel()
             if self._dev_ring is None or self._dev_ring[0][0].numel() != n:
-                self._dev_ring = [[torch.empty(n, dtype=torch.float32, device=self.device), None] for _ in range(2)]
-            slot = self._dev_ring[self._up % 2]
+                self._dev_ring = [[torch.empty(n, dtype=torch.float32, device=self.device), None] for _ in range(self.ring + 1)]
+            slot = self._dev_ring[self._up % len(self._dev_ring)]
             self._up += 1
             with torch.cuda.stream(self.copy_stream):
                 if slot[1] is not None:
@@ -247,23 +291,30 @@ class StreamedCascade:
         with torch.no_grad():
             while staged is not None:
                 slots, c, d, ready, uploaded = staged
-                main.wait_event(ready)
+                lane = self.lanes.next_stream() if self.lanes is not None else main
+                lane.wait_event(ready)
                 self.h2d_bytes = uploaded
-                out = self.net(None, c, d, tmp=self.tmp, pools_cl=self._pools, view_slots=slots)
+                with torch.cuda.stream(lane):
+                    out = self.net(None, c, d, tmp=self.tmp, pools_cl=self._pools, view_slots=slots)
+                if self.lanes is not None and not self._lanes_warm:
+                    torch.cuda.synchronize(self.device)             # weights packed on the first lane are read by the others
+                    self._lanes_warm = True
                 self._compute_done = torch.cuda.Event()
-                self._compute_done.record(main)
+                self._compute_done.record(lane)
                 for sl in slots:
                     self._slot_used[sl] = self._compute_done
                 # staged only now: an upload that evicts a slot waits for the cascade enqueued above, which may read it
                 nxt = next(it, None)
                 staged = self._stage_scan(nxt) if nxt is not None else None  # overlaps with this view's compute
-                pending.append(self._download(out, i, main))
+                pending.append(self._download(out, i, lane))
                 del out
                 if len(pending) >= self.ring:
                     od, oc, oe = pending.pop(0)[:3]
                     self._wait(oe)
                     yield od, oc
                 i += 1
+        if self.lanes is not None:
+            self.lanes.join()
         for od, oc, oe, _, _ in pending:
             self._wait(oe)
             yield od, oc
@@ -274,7 +325,7 @@ class StreamedCascade:
         self.host_wait_s += time.perf_counter() - t0
         self.host_steps += 1
 
-    def _download(self, out, i, main):
+    def _download(self, out, i, lane):
         """Enqueue the device -> host copy of a finished cascade's result on the D2H stream (so it overlaps the next
         cascade instead of sitting between two of them).  The device tensors ride along in the returned tuple: they must
         stay allocated until the copy has finished, i.e. until ``done`` has been synchronised on."""
@@ -282,7 +333,7 @@ class StreamedCascade:
         bufs = self._ring_buffers(depth, conf)
         hd, hc, done = bufs[i % len(bufs)]
         computed = torch.cuda.Event()
-        computed.record(main)
+        computed.record(lane)
         with torch.cuda.stream(self.d2h_stream):
             self.d2h_stream.wait_event(computed)
             hd.copy_(depth, non_blocking=True)
@@ -319,18 +370,28 @@ class StreamedCascade:
                 f, c, d, ready, slot = staged
                 nxt = next(it, None)
                 staged = self._upload(nxt) if nxt is not None else None      # overlaps with this view's compute
-                main.wait_event(ready)
-                out = self.net(f, c, d, tmp=self.tmp)
+                lane = self.lanes.next_stream() if self.lanes is not None else main
+                lane.wait_event(ready)
+                with torch.cuda.stream(lane):
+                    out = self.net(f, c, d, tmp=self.tmp)
+                if self.lanes is not None and not self._lanes_warm:
+                    torch.cuda.synchronize(self.device)             # weights packed on the first lane are read by the others
+                    self._lanes_warm = True
                 if slot is not None:                                         # staging slot may be refilled after this
                     slot[1] = torch.cuda.Event()
-                    slot[1].record(main)
-                pending.append(self._download(out, i, main))
+                    slot[1].record(lane)
+                elif lane is not main:                                       # plain tensors from the copy stream's pool
+                    for t in list(f.values()) + list(c.values()) + [d]:
+                        t.record_stream(lane)
+                pending.append(self._download(out, i, lane))
                 del out
                 if len(pending) >= self.ring:                                # hand out the oldest result
                     od, oc, oe = pending.pop(0)[:3]
                     self._wait(oe)
                     yield od, oc
                 i += 1
+        if self.lanes is not None:
+            self.lanes.join()
         for od, oc, oe, _, _ in pending:
             self._wait(oe)
             yield od, oc

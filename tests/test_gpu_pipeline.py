@@ -30,13 +30,15 @@ def _direct(net, feats, cams, dv):
     return out["refined_depth"].cpu(), out["photometric_confidence"].cpu()
 
 
-def test_streamed_cascade_matches_direct_calls():
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_streamed_cascade_matches_direct_calls(lanes):
+    """lanes = 2: consecutive reference views alternate between two compute streams (CascadeLanes) — same bits."""
     net = _net()
     cams = {k: v.pin_memory() for k, v in S.make_cameras(1, V, H, W).items()}
     dv = S.make_depth_range(1).pin_memory()
     samples = [{k: v.pin_memory() for k, v in S.make_features(1, V, H, W, seed=100 + i).items()} for i in range(4)]
     want = [_direct(net, f, cams, dv) for f in samples]
-    streamer = StreamedCascade(net, DEV, list(S.EVAL_TMP))
+    streamer = StreamedCascade(net, DEV, list(S.EVAL_TMP), lanes=lanes)
     got = [(d.clone(), c.clone()) for d, c in streamer.run((f, cams, dv) for f in samples)]
     assert len(got) == len(want)
     for (gd, gc), (wd, wc) in zip(got, want):
@@ -48,7 +50,8 @@ def test_streamed_cascade_matches_direct_calls():
         assert torch.equal(gd, wd) and torch.equal(gc, wc)
 
 
-def test_run_scan_serves_shared_views_from_the_cache():
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_run_scan_serves_shared_views_from_the_cache(lanes):
     """A scan of 7 views, reference view i with source views i+1, i+2 (wrapping): every view crosses
     PCIe once with a large cache; with 4 slots (V + 1) views are evicted and re-uploaded; results are
     bit-identical to dense calls either way."""
@@ -73,7 +76,7 @@ def test_run_scan_serves_shared_views_from_the_cache():
         want.append(_direct(net, dense, cams, dv))
     for capacity, expect_loads in ((16, nviews), (4, None)):
         loads.clear()
-        streamer = StreamedCascade(net, DEV, list(S.EVAL_TMP))
+        streamer = StreamedCascade(net, DEV, list(S.EVAL_TMP), lanes=lanes)
         samples = [ScanSample(v, load, cams, dv) for v in ids]
         got = [(d.clone(), c.clone()) for d, c in streamer.run_scan(iter(samples), capacity=capacity)]
         assert len(got) == nviews
@@ -132,3 +135,21 @@ def test_yielded_results_survive_one_more_step():
         held.append((d, c))
         if i >= 1:                                                  # the previous pair, one next() later
             assert torch.equal(held[i - 1][0], want[i - 1][0]) and torch.equal(held[i - 1][1], want[i - 1][1])
+
+
+def test_cascade_lanes_match_sequential_calls():
+    """CascadeLanes.submit: six reference views round-robin over two streams, each result bit-identical to a plain call."""
+    from mvsformer_b200.pipeline import CascadeLanes
+    net = _net()
+    cams = {k: v.to(DEV) for k, v in S.make_cameras(1, V, H, W).items()}
+    dv = S.make_depth_range(1).to(DEV)
+    feats = [{k: v.to(DEV) for k, v in S.make_features(1, V, H, W, seed=300 + i).items()} for i in range(6)]
+    with torch.no_grad():
+        want = [net(f, cams, dv, tmp=list(S.EVAL_TMP))["refined_depth"].clone() for f in feats]
+        torch.cuda.synchronize()
+        lanes = CascadeLanes(net, DEV, 2)
+        outs = [lanes.submit(f, cams, dv, tmp=list(S.EVAL_TMP))[0] for f in feats]
+        lanes.join()
+        torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        assert torch.equal(o["refined_depth"], w)
