@@ -585,7 +585,12 @@ def run_engine(args, rank, world, local_rank):
 
     with torch.no_grad():
         for _ in range(args.warmup):
+            step_single()
+        ms_single, _ = timed(step_single, args.steps)           # one view at a time: the latency of a reference view
+        for _ in range(max(args.warmup, 2 * args.lanes)):       # every lane's allocator pool reaches its steady state
             step_resident()
+        if lanes is not None:
+            lanes.join()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -693,6 +698,9 @@ def run_engine(args, rank, world, local_rank):
                           "h2d_gbs_aggregate": world * h2d / (ms_e2e / args.steps * 1e-3) / 1e9,
                           "api": "mvsformer_b200.pipeline.StreamedCascade.run: every reference view uploads all five views "
                                  "(531 MB, PCIe-bound) — what a caller without scan structure gets"},
+            "single_view": {"ms_per_step": ms_single / args.steps, "value": world * args.steps / (ms_single * 1e-3), "unit": UNIT,
+                            "note": "one reference view in flight (--lanes 1): the latency of a view; `value` keeps "
+                                    "views_in_flight_per_gpu views in flight on as many CUDA streams"},
             "numa_node": numa, "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "roofline_conv": roof_conv,
             "cost_volume": cost_volume, "kernels": kernels}
     if world == 1 and not args.no_parity:
@@ -723,7 +731,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference", "eager"])
-    ap.add_argument("--lanes", type=int, default=1, help="reference views in flight per GPU (compute streams)")
+    ap.add_argument("--lanes", type=int, default=3, help="reference views in flight per GPU (compute streams); B200 A/B: "
+                    "1 -> 220.8, 2 -> 232, 3 -> 247.0 maps/s (profiles/r02i_lanes_ab.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (reference modules on cuda:0)")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity check against the CPU oracle")

@@ -22,50 +22,89 @@ struct ProbWeights {
     float bias;
 };
 
-template <int KS>
+// 1x1x1 `prob` conv + bias (CostRegNet3D / CostRegNet2D, models/module.py:582): one voxel per thread, two LDG.128.
 __global__ void __launch_bounds__(256)
-prob_conv_kernel(const float* __restrict__ x, float* __restrict__ pre, int D, int H, int W, int64_t total,
-                 const __grid_constant__ ProbWeights P) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+prob_conv1_kernel(const float* __restrict__ x, float* __restrict__ pre, int64_t total, const __grid_constant__ ProbWeights P) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int64_t out_idx = idx;
-    const int ox = (int)(idx % W); idx /= W;
-    const int oy = (int)(idx % H); idx /= H;
-    const int oz = (int)(idx % D);
-    const int64_t b = idx / D;
+    const float4* p = reinterpret_cast<const float4*>(x + idx * 8);
+    const float4 a = __ldg(p), c = __ldg(p + 1);
     float acc = P.bias;
-    if (KS == 1) {
-        const float4* p = reinterpret_cast<const float4*>(x + out_idx * 8);
-        const float4 a = __ldg(p), c = __ldg(p + 1);
-        acc = fmaf(a.x, P.w[0][0], acc); acc = fmaf(a.y, P.w[0][1], acc); acc = fmaf(a.z, P.w[0][2], acc); acc = fmaf(a.w, P.w[0][3], acc);
-        acc = fmaf(c.x, P.w[0][4], acc); acc = fmaf(c.y, P.w[0][5], acc); acc = fmaf(c.z, P.w[0][6], acc); acc = fmaf(c.w, P.w[0][7], acc);
-    } else {
-        // eight independent accumulators (one per input channel): a single 216-deep FMA chain made this kernel
-        // latency-bound (54 + 99 us at stages 1-2 for 85 MB, profiles/r02_launches_step.csv)
-        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    acc = fmaf(a.x, P.w[0][0], acc); acc = fmaf(a.y, P.w[0][1], acc); acc = fmaf(a.z, P.w[0][2], acc); acc = fmaf(a.w, P.w[0][3], acc);
+    acc = fmaf(c.x, P.w[0][4], acc); acc = fmaf(c.y, P.w[0][5], acc); acc = fmaf(c.z, P.w[0][6], acc); acc = fmaf(c.w, P.w[0][7], acc);
+    pre[idx] = acc;
+}
+
+// 3x3x3 `prob` conv (8 -> 1, CostRegNet.prob, models/module.py:491), marching form.  A one-voxel-per-thread kernel reads 54
+// LDG.128 per voxel and was L1-bound (54 + 99 us at stages 1-2 for 85 MB of input, profiles/r02_launches_step.csv).
+// Here a CTA owns a 32 x 8 pixel tile and marches over PZ output slices: each input slice tile (+1 halo, zero-filled
+// outside the volume = the conv's zero padding) is staged ONCE in shared memory, split into its two channel halves so that
+// a warp's LDS.128 is conflict-free, and feeds the three output slices it belongs to (partial sums a0/a1/a2 roll through
+// registers).  The next slice is prefetched into registers under the FMAs; one __syncthreads per slice.
+constexpr int PT_X = 32, PT_Y = 8, PH_X = PT_X + 2, PH_Y = PT_Y + 2, PZ = 8, PTILE = PH_X * PH_Y;
+
+__device__ __forceinline__ float dot8(const float4& a, const float4& c, const float (&w)[8], float acc) {
+    acc = fmaf(a.x, w[0], acc); acc = fmaf(a.y, w[1], acc); acc = fmaf(a.z, w[2], acc); acc = fmaf(a.w, w[3], acc);
+    acc = fmaf(c.x, w[4], acc); acc = fmaf(c.y, w[5], acc); acc = fmaf(c.z, w[6], acc); acc = fmaf(c.w, w[7], acc);
+    return acc;
+}
+
+__global__ void __launch_bounds__(256)
+prob_conv3_tiled_kernel(const float* __restrict__ x, float* __restrict__ pre, int D, int H, int W, int zchunks,
+                        const __grid_constant__ ProbWeights P) {
+    __shared__ float4 s[2][2][PTILE];                       // [buffer][channel half][row * PH_X + col]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int x0 = blockIdx.x * PT_X, y0 = blockIdx.y * PT_Y;
+    const int64_t b = blockIdx.z / zchunks;
+    const int z0 = (blockIdx.z % zchunks) * PZ, z1 = min(D, z0 + PZ);          // output slices [z0, z1)
+    const int ox = x0 + tx, oy = y0 + ty;
+    const bool live = ox < W && oy < H;
+
+    float4 regs[3];
+    auto fetch = [&](int iz) {
 #pragma unroll
-        for (int kz = 0; kz < 3; ++kz) {
-            const int iz = oz - 1 + kz;
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + 256 * k;                     // (voxel, half) pairs of the slice tile, 16-byte granules
+            const int v = e >> 1, row = v / PH_X, col = v - row * PH_X;
+            const int gy = y0 - 1 + row, gx = x0 - 1 + col;
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < 2 * PTILE && iz >= 0 && iz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                r = __ldg(reinterpret_cast<const float4*>(x + (((b * D + iz) * H + gy) * (int64_t)W + gx) * 8) + (e & 1));
+            regs[k] = r;
+        }
+    };
+    auto stash = [&](int buf) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = oy - 1 + ky;
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + 256 * k;
+            if (e < 2 * PTILE) s[buf][e & 1][e >> 1] = regs[k];
+        }
+    };
+
+    fetch(z0 - 1);
+    stash(0);
+    __syncthreads();
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;                      // partial sums of out[zi-1], out[zi], out[zi+1]
+    for (int zi = z0 - 1; zi <= z1; ++zi) {
+        const int buf = (zi - (z0 - 1)) & 1;
+        if (zi < z1) fetch(zi + 1);                          // in flight under the FMAs below
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = ox - 1 + kx;
-                    if (iz < 0 || iz >= D || iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-                    const float4* p = reinterpret_cast<const float4*>(x + (((b * D + iz) * H + iy) * (int64_t)W + ix) * 8);
-                    const float4 a = __ldg(p), c = __ldg(p + 1);
-                    const int t = (kz * 3 + ky) * 3 + kx;
-                    a8[0] = fmaf(a.x, P.w[t][0], a8[0]); a8[1] = fmaf(a.y, P.w[t][1], a8[1]);
-                    a8[2] = fmaf(a.z, P.w[t][2], a8[2]); a8[3] = fmaf(a.w, P.w[t][3], a8[3]);
-                    a8[4] = fmaf(c.x, P.w[t][4], a8[4]); a8[5] = fmaf(c.y, P.w[t][5], a8[5]);
-                    a8[6] = fmaf(c.z, P.w[t][6], a8[6]); a8[7] = fmaf(c.w, P.w[t][7], a8[7]);
-                }
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int v = (ty + ky) * PH_X + tx + kx;
+                const float4 a = s[buf][0][v], c = s[buf][1][v];
+                a2 = dot8(a, c, P.w[ky * 3 + kx], a2);               // kz = 0: this slice is the one below out[zi+1]
+                a1 = dot8(a, c, P.w[9 + ky * 3 + kx], a1);           // kz = 1
+                a0 = dot8(a, c, P.w[18 + ky * 3 + kx], a0);          // kz = 2
             }
         }
-        acc += ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+        const int oz = zi - 1;
+        if (live && oz >= z0 && oz < z1) pre[((b * D + oz) * H + oy) * (int64_t)W + ox] = a0 + P.bias;
+        a0 = a1; a1 = a2; a2 = 0.f;
+        if (zi < z1) stash(buf ^ 1);
+        __syncthreads();
     }
-    pre[out_idx] = acc;
 }
 
 // One thread per pixel.  D <= HEAD_DMAX; the column is re-read from L1/L2 for the second softmax
@@ -261,9 +300,13 @@ extern "C" int mvs_prob_conv_cl(const float* x, const float* w_host, const float
     P.bias = bias_host ? bias_host[0] : 0.0f;
     const int64_t total = (int64_t)B * D * H * W;
     if (ksize == 1)
-        prob_conv_kernel<1><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pre, D, H, W, total, P);
-    else
-        prob_conv_kernel<3><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pre, D, H, W, total, P);
+        prob_conv1_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pre, total, P);
+    else {
+        const int zchunks = cdiv(D, PZ);
+        MVS_REQUIRE((int64_t)B * zchunks <= 65535 && cdiv(H, PT_Y) <= 65535, "mvs_prob_conv_cl: volume too large for one launch");
+        dim3 grid(cdiv(W, PT_X), cdiv(H, PT_Y), B * zchunks);
+        prob_conv3_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, pre, D, H, W, zchunks, P);
+    }
     MVS_LAUNCH_OK("prob_conv_kernel");
     return MVS_OK;
 }

@@ -464,3 +464,20 @@ def test_baseline_cfg3_cfg4_properties(name, batch, views, height, width):
         one = net({k: v[:1].contiguous() for k, v in feats.items()}, {k: v[:1].contiguous() for k, v in cams.items()},
                   dv[:1].contiguous(), tmp=list(S.EVAL_TMP))
         assert rel_l1(one["refined_depth"], out["refined_depth"][:1]) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 13, 37), (1, 17, 9, 33), (1, 1, 3, 3), (1, 8, 8, 32), (1, 32, 72, 96), (3, 9, 16, 70)])
+@pytest.mark.parametrize("ksize", [1, 3])
+def test_prob_conv_entry_point(shape, ksize):
+    """mvs_prob_conv_cl vs fp64 F.conv3d: the 3x3x3 kernel marches a 32x8 pixel tile over 8-slice chunks (partial tiles,
+    volumes thinner than a chunk, chunk seams at z = 8, 16, ...); the 1x1x1 one adds the bias."""
+    b, d, h, w = shape
+    g = S._gen(b * 1000 + d * 100 + h + w + ksize)
+    x = torch.randn(b, d, h, w, 8, generator=g)
+    wt = torch.randn(ksize ** 3, 8, generator=g) * 0.3
+    bias = torch.randn(1, generator=g) if ksize == 1 else None
+    w5 = wt.reshape(ksize, ksize, ksize, 8).permute(3, 0, 1, 2).unsqueeze(0).double()
+    want = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), w5, bias.double() if bias is not None else None, padding=ksize // 2)[:, 0]
+    got = engine.prob_conv_cl(cu(x), np.ascontiguousarray(wt.numpy()), bias.numpy() if bias is not None else None, ksize).cpu()
+    assert got.shape == want.shape
+    assert rel_l1(got, want) < 2e-6 and max_abs(got, want.float()) < 2e-5
