@@ -201,7 +201,12 @@ class KernelProfiler:
             vox = (x.numel() // x.shape[-1]) if mode == 2 else (out.numel() // out.shape[-1])
             return numel_bytes(x, out, skip), 2 * kd * 9 * x.shape[-1] * cout * vox
 
+        def conv_tma_prob_cost(out, x, w_tma, kd, shift, skip, prob_w_host, prob_bias, relu=True):
+            vox = x.numel() // x.shape[-1]                                                # transposed 16 -> 8 + the 1x1x1 prob conv
+            return numel_bytes(x, out, skip), 2 * kd * 9 * 16 * 8 * vox + 2 * 8 * out.numel()
+
         self._wrap(engine, "conv3d_tma", "conv3d_tma", conv_tma_cost)                    # persistent TMA-fed kernels
+        self._wrap(engine, "conv3d_tma_prob", "conv3d_tma", conv_tma_prob_cost)
         self._wrap(engine, "conv3d_cl", "conv3d", conv_cost)
         self._wrap(engine, "deconv3d_cl", "deconv3d", deconv_cost)
         self._wrap(engine, "conv3d_tc", "conv3d_tc", conv_tc_cost)

@@ -319,6 +319,14 @@ int mvs_vis_fused(const float* entropy, const float* params, const float* w2, co
 int mvs_conv3d_tma(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D, int H,
                    int W, int Cin, int Cout, int n_tile, int kd, int mode, int relu, void* stream);
 
+/* The regulariser's last two layers in one kernel (CostRegNet3D eval, models/module.py:575,582,592-593): mode-2 transposed
+ * convolution 16 -> 8 (+ shift, ReLU, + skip) with the 1x1x1 `prob` convolution 8 -> 1 (+ bias) applied to its result in the
+ * epilogue; the 8-channel tensor never reaches HBM.  x [B,D,H,W,16], w packed as for mvs_conv3d_tma (mode 2, n_tile 16),
+ * skip [B,D,2H,2W,8] or NULL, prob_w_host [8] (HOST), pre [B,D,2H,2W].  Bit-identical to mvs_conv3d_tma followed by
+ * mvs_prob_conv_cl (ksize 1). */
+int mvs_conv3d_tma_prob(const float* x, const float* w, const float* shift, const float* skip, const float* prob_w_host,
+                        float prob_bias, float* pre, int B, int D, int H, int W, int Cin, int kd, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

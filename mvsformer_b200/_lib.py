@@ -10,7 +10,9 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmvs_b200.so")
+# MVS_LIB_PATH: load another build of the SAME library (A/B of kernel generations, scripts/ab_libs.sh); a build that lacks a
+# declared entry point still loads — calling the missing entry point raises
+LIB_PATH = os.environ.get("MVS_LIB_PATH") or os.path.join(_HERE, "lib", "libmvs_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mvs_b200.h")
 
 _lib = None
@@ -44,6 +46,7 @@ _SIGNATURES = {
     "mvs_conv3d_tc": (c_i, [c_f] * 6 + [c_i] * 11 + [c_f]),
     "mvs_deconv3d_tc": (c_i, [c_f] * 6 + [c_i] * 10 + [c_f]),
     "mvs_conv3d_tma": (c_i, [c_f] * 5 + [c_i] * 10 + [c_f]),
+    "mvs_conv3d_tma_prob": (c_i, [c_f] * 5 + [c_fl, c_f] + [c_i] * 7 + [c_f]),
     "mvs_ncdhw_to_cl_tf32": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "mvs_tc_probe": (c_i, [c_f, c_i, c_f, c_i] + [ctypes.c_uint] * 4 + [c_i, c_i, ctypes.c_uint, ctypes.c_uint, c_f, c_f]),
     "mvs_tc_probe_ts": (c_i, [c_f, c_i, c_f, c_i] + [ctypes.c_uint] * 4 + [c_i, c_i, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, c_f, c_f]),
@@ -109,6 +112,8 @@ def load():
             "(or __graft_entry__.build()). There is no fallback path." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
+        if not hasattr(lib, name) and os.environ.get("MVS_LIB_PATH"):
+            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -25,6 +25,10 @@ only the entropy map and the weight map touch HBM; ``0`` = the FP32 CUDA-core ke
 3x3x3 layers (CostRegNet3D) through the persistent, warp-specialised, TMA-fed tcgen05 kernels of csrc/conv3d_tma.cu
 (TF32 mode only).
 
+``prob_fused`` (``MVS_PROB_FUSED``, default 1) — eval, TF32 mode: CostRegNet3D's last transposed layer (16 -> 8) applies the
+1x1x1 ``prob`` conv in its epilogue (mvs_conv3d_tma_prob), so the regulariser's 8-channel output tensor never reaches HBM;
+bit-identical to the two-kernel route (``0``).
+
 ``train_conv`` (``MVS_TRAIN_CONV`` = ``fp32`` (default) | ``tf32x3`` | ``tf32``) — arithmetic of the training path's
 forward and data-gradient convolutions: the FP32 CUDA-core kernels, or the tcgen05 kernels of the inference path
 (``tf32x3`` keeps fp32-grade accuracy; the reference itself trains the regulariser under fp16 autocast).  Weight
@@ -38,6 +42,7 @@ _state = {"conv_precision": os.environ.get("MVS_CONV_PRECISION", "tf32x3"),
           "cv_layout": os.environ.get("MVS_CV_LAYOUT", "cl"),
           "vis_fused": os.environ.get("MVS_VIS_FUSED", "1") not in ("", "0"),
           "conv_tma": os.environ.get("MVS_CONV_TMA", "1") not in ("", "0"),
+          "prob_fused": os.environ.get("MVS_PROB_FUSED", "1") not in ("", "0"),
           "train_conv": os.environ.get("MVS_TRAIN_CONV", "fp32")}
 if _state["train_conv"] not in ("fp32", "tf32x3", "tf32"):
     raise RuntimeError("MVS_TRAIN_CONV must be fp32, tf32x3 or tf32")
@@ -81,6 +86,14 @@ def conv_tma():
 
 def set_conv_tma(flag):
     _state["conv_tma"] = bool(flag)
+
+
+def prob_fused():
+    return _state["prob_fused"]
+
+
+def set_prob_fused(flag):
+    _state["prob_fused"] = bool(flag)
 
 
 def train_conv():

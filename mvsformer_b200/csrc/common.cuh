@@ -54,6 +54,43 @@ __device__ __forceinline__ float round_to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// round_to_tf32(fmaxf(x, 0)) for every input, in three instructions: cvt.rna.tf32.f32 is not a machine instruction on
+// sm_100 — ptxas expands it to "unless |x| is inf / NaN: bits += 0x1000", then clears the low 13 bits (six instructions with
+// the test).  After the ReLU the value is in [0, +inf] (fmaxf drops a NaN), where the plain add + mask is the same function.
+__device__ __forceinline__ float relu_round_tf32(float x) {
+    return __uint_as_float((__float_as_uint(fmaxf(x, 0.0f)) + 0x1000u) & 0xffffe000u);
+}
+
+// Packed FP32 pairs (sm_100: FFMA2 / FMUL2).  A three-register FFMA occupies the FMA pipe for two issue cycles per warp on
+// Blackwell; the packed forms do two IEEE-rounded operations per lane in the same slot, so each component is bit-identical
+// to the scalar fmaf / multiply it replaces.  A pair lives in one aligned 64-bit register.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+    return d;
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 }  // namespace mvs
 
 #include "geometry.cuh"

@@ -42,6 +42,7 @@ struct Dims {
     int relu;
     int tiles_x, tiles_y, nitems;
     int nbuf;                // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
+    float pw[8], pbias;      // PROB: the regulariser's 1x1x1 `prob` conv (8 -> 1, + bias) applied in the epilogue
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -121,7 +122,11 @@ struct Smem {
 
 // x channels-last [B,D,H,W,CIN]; y [B,D,Ho,Wo,Cout]; w packed [Cout tiles][kh][kw][CIN/4][kd][NT][4] (TF32-rounded, BN folded)
 // NEPI = epilogue warps (8, or 4 where the stages leave no room for eight staging buffers)
-template <int MODE, int CIN, int NT, int STAGES, int KD, int NEPI>
+// PROB (Cout = 8, the regulariser's last layer): the 8-channel result never reaches HBM — the epilogue applies the 1x1x1
+// `prob` conv + bias (models/module.py:582,593) to it and writes prob_volume_pre [B,D,Ho,Wo] through `y`: 1/8 of the stores,
+// no second pass over the tensor.  Same arithmetic as the two-kernel route (TF32-rounded activations, the FMA chain of
+// prob_conv1_kernel in channel order), so the results are bit-identical.
+template <int MODE, int CIN, int NT, int STAGES, int KD, int NEPI, bool PROB = false>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restrict__ w, const float* __restrict__ shift,
                   const float* __restrict__ skip, float* __restrict__ y, Dims d) {
@@ -270,12 +275,14 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
         const int chunk = lane % cpr, rsub = lane / cpr;
         const bool cvalid = co0 + chunk * 4 < d.Cout;
         const float4 sh = (shift && cvalid) ? __ldg(reinterpret_cast<const float4*>(shift + co0) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // PROB (cpr = 2): the `prob` weights of this lane's four channels
+        const float4 pw = (PROB && chunk == 1) ? make_float4(d.pw[4], d.pw[5], d.pw[6], d.pw[7]) : make_float4(d.pw[0], d.pw[1], d.pw[2], d.pw[3]);
         int it = 0;
         for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
             const int buf = d.nbuf == 2 ? (it & 1) : 0, use = d.nbuf == 2 ? (it >> 1) : it;
             const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y, b = item / (d.tiles_x * d.tiles_y);
             // output element this lane writes in store instruction j of accumulator block cz (class, slice)
-            auto locate = [&](int cz, int j, size_t* o) -> bool {
+            auto locate = [&](int cz, int j, size_t* o, size_t* voxel) -> bool {
                 const int cls = cz / d.D, blk = cz - cls * d.D;
                 const int z = MODE == MODE_DECONV ? blk : d.D - 1 - blk;
                 const int row = j * rpi + rsub;                       // accumulator row within the quarter
@@ -286,7 +293,8 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                     live = ty_v < d.H && tx_v < d.W;
                     oy = 2 * ty_v + (cls >> 1); ox = 2 * tx_v + (cls & 1);
                 }
-                *o = ((((size_t)b * d.D + z) * d.Ho + oy) * d.Wo + ox) * d.Cout + co0 + chunk * 4;
+                *voxel = (((size_t)b * d.D + z) * d.Ho + oy) * d.Wo + ox;
+                *o = *voxel * d.Cout + co0 + chunk * 4;
                 return live && cvalid && j < cpr;
             };
             // The skip tensor does not depend on the MMAs: its loads run one accumulator block ahead (the first block's before
@@ -295,8 +303,8 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
             auto prefetch_skip = [&](int cz) {
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) {
-                    size_t o;
-                    skn[j] = (skip && locate(cz, j, &o)) ? __ldg(reinterpret_cast<const float4*>(skip + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    size_t o, vx;
+                    skn[j] = (skip && locate(cz, j, &o, &vx)) ? __ldg(reinterpret_cast<const float4*>(skip + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
             const int nblk = NCLS * d.D;
@@ -320,15 +328,26 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) {
-                    size_t o;
-                    if (!locate(cz, j, &o)) continue;
+                    size_t o, vox;
+                    const bool ok = locate(cz, j, &o, &vox);
+                    if (PROB ? j >= cpr : !ok) continue;              // PROB: warp-uniform (every lane takes part in the shuffle)
                     float4 r = *reinterpret_cast<const float4*>(stg + (j * rpi + rsub) * L::STG_PITCH + chunk * 4);
                     r.x += sh.x; r.y += sh.y; r.z += sh.z; r.w += sh.w;
                     if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
                     r.x += skc[j].x; r.y += skc[j].y; r.z += skc[j].z; r.w += skc[j].w;
                     // consumers read this tensor as a TF32 operand: round once here
                     r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
-                    *reinterpret_cast<float4*>(y + o) = r;
+                    if (PROB) {
+                        // the two lanes of a voxel (channels 0-3, 4-7) run ONE chain bias -> c0 .. c7: the even lane's partial
+                        // sum is handed to the odd lane, which finishes and stores
+                        float acc = d.pbias;
+                        acc = fmaf(r.x, pw.x, acc); acc = fmaf(r.y, pw.y, acc); acc = fmaf(r.z, pw.z, acc); acc = fmaf(r.w, pw.w, acc);
+                        float fin = __shfl_sync(0xffffffffu, acc, lane & ~1);
+                        fin = fmaf(r.x, pw.x, fin); fin = fmaf(r.y, pw.y, fin); fin = fmaf(r.z, pw.z, fin); fin = fmaf(r.w, pw.w, fin);
+                        if (ok && chunk == 1) y[vox] = fin;
+                    } else {
+                        *reinterpret_cast<float4*>(y + o) = r;
+                    }
                 }
             }
             tc_fence_before_sync();
@@ -386,17 +405,21 @@ static int sm_count() {
     return n;
 }
 
-template <int MODE, int CIN, int NT, int STAGES, int KD, int NEPI>
+template <int MODE, int CIN, int NT, int STAGES, int KD, int NEPI, bool PROB = false>
 static int launch_k(const float* x, const float* w, const float* shift, const float* skip, float* y, int B, int D, int H, int W,
-                    int Cout, int relu, cudaStream_t st) {
+                    int Cout, int relu, cudaStream_t st, const float* prob_w = nullptr, float prob_bias = 0.0f) {
     using L = Smem<MODE, CIN, NT, STAGES, NEPI>;
     const size_t smem = L::total(KD);
     MVS_REQUIRE(smem <= 227 * 1024, "mvs_conv3d_tma: needs %zu bytes of shared memory", smem);
     CUtensorMap map;
     int rc = make_act_map(&map, x, B * D, H, W, CIN, L::CH, L::PX, L::PY, MODE == MODE_S2 ? 2 : 1);
     if (rc) return rc;
-    Dims d;
+    Dims d = {};
     d.B = B; d.D = D; d.H = H; d.W = W; d.Cout = Cout; d.relu = relu;
+    if (PROB) {
+        for (int i = 0; i < 8; ++i) d.pw[i] = prob_w[i];
+        d.pbias = prob_bias;
+    }
     d.Ho = MODE == MODE_S2 ? (H + 1) / 2 : (MODE == MODE_DECONV ? 2 * H : H);
     d.Wo = MODE == MODE_S2 ? (W + 1) / 2 : (MODE == MODE_DECONV ? 2 * W : W);
     const int th = MODE == MODE_DECONV ? H : d.Ho, tw = MODE == MODE_DECONV ? W : d.Wo;      // the tiled plane
@@ -406,7 +429,7 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     MVS_REQUIRE(ncols <= 512, "mvs_conv3d_tma: %d accumulator columns exceed the tensor memory", ncols);
     d.nbuf = 2 * ncols <= 512 ? 2 : 1;
     const int ntiles = cdiv(Cout, NT);
-    auto kern = conv3d_tma_kernel<MODE, CIN, NT, STAGES, KD, NEPI>;
+    auto kern = conv3d_tma_kernel<MODE, CIN, NT, STAGES, KD, NEPI, PROB>;
     MVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int gx = sm_count() / ntiles;
     if (gx < 1) gx = 1;
@@ -456,4 +479,23 @@ extern "C" int mvs_conv3d_tma(const float* x, const float* w, const float* shift
     MVS_TMA_CASE(MODE_DECONV, 16, 16, 6, 8);
 #undef MVS_TMA_CASE
     MVS_UNSUPPORTED("mvs_conv3d_tma: no instantiation for mode %d, Cin=%d, n_tile=%d", mode, Cin, n_tile);
+}
+
+// The regulariser's last two layers in one kernel (CostRegNet3D, models/module.py:575,582,592-593): transposed conv 16 -> 8
+// (+ folded BN shift, ReLU, + skip) and the 1x1x1 `prob` conv 8 -> 1 (+ bias) applied to its result in the epilogue.
+// x [B,D,H,W,16] channels-last; w packed as for mvs_conv3d_tma mode 2 (n_tile 16); skip [B,D,2H,2W,8] or NULL;
+// prob_w_host [8] / prob_bias: host values; pre [B,D,2H,2W].  Bit-identical to mvs_conv3d_tma + mvs_prob_conv_cl.
+extern "C" int mvs_conv3d_tma_prob(const float* x, const float* w, const float* shift, const float* skip, const float* prob_w_host,
+                                   float prob_bias, float* pre, int B, int D, int H, int W, int Cin, int kd, int relu, void* stream) {
+    using namespace mvs::tc::tma3;
+    MVS_REQUIRE(x && w && pre && prob_w_host, "mvs_conv3d_tma_prob: null pointer");
+    MVS_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "mvs_conv3d_tma_prob: empty shape");
+    MVS_REQUIRE(kd == 1 || kd == 3, "mvs_conv3d_tma_prob: kernel depth must be 1 or 3 (got %d)", kd);
+    MVS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && (!skip || ((uintptr_t)skip & 15) == 0),
+                "mvs_conv3d_tma_prob: tensors must be 16-byte aligned");
+    if (Cin != 16) MVS_UNSUPPORTED("mvs_conv3d_tma_prob: only Cin = 16 (-> 8 -> 1) is built (got %d)", Cin);
+    if (4 * D * 16 > 512) MVS_UNSUPPORTED("mvs_conv3d_tma_prob: %d depth slices exceed the tensor memory", D);
+    cudaStream_t st = (cudaStream_t)stream;
+    return kd == 1 ? launch_k<MODE_DECONV, 16, 16, 6, 1, 8, true>(x, w, shift, skip, pre, B, D, H, W, 8, relu, st, prob_w_host, prob_bias)
+                   : launch_k<MODE_DECONV, 16, 16, 6, 3, 8, true>(x, w, shift, skip, pre, B, D, H, W, 8, relu, st, prob_w_host, prob_bias);
 }

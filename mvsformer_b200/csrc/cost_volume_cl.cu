@@ -350,19 +350,50 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
                 for (int cp = 0; cp < (SIM ? NCP : 1); ++cp) { a_c[cp] = 0.0f; wn[cp] = 0.0f; }
             }
 
-            // one chunk: four channels of the warped sample (w) against the reference (r); all indices static
+            // one chunk: four channels of the warped sample (w) against the reference (r); all indices static.  Where two
+            // neighbouring channels feed two DIFFERENT accumulators (one group per channel; the per-c' similarity sums) the
+            // pair is one packed FFMA2 — each half is the scalar fmaf it replaces, in the same order (common.cuh)
             auto accumulate = [&](int j, const float4& r4, const float4& w4) {
                 const float r[4] = {r4.x, r4.y, r4.z, r4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+                if (GROUPS && CPG == 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; i += 2) {
+                        const int g = GROUPS ? 4 * j + i : 0;
+                        const float2 o = unpack2(ffma2(pack2(r[i], r[i + 1]), pack2(w[i], w[i + 1]), pack2(ag[g], ag[GROUPS ? g + 1 : 0])));
+                        ag[g] = o.x; ag[GROUPS ? g + 1 : 0] = o.y;
+                    }
+                }
+                if (SIM && NCP >= 2) {
+#pragma unroll
+                    for (int i = 0; i < 4; i += 2) {
+                        const int c0 = SIM ? (4 * j + i) % NCP : 0, c1 = SIM ? (4 * j + i + 1) % NCP : 0;
+                        const f32x2 wp = pack2(w[i], w[i + 1]);
+                        const float2 a = unpack2(ffma2(pack2(r[i], r[i + 1]), wp, pack2(a_c[c0], a_c[c1])));
+                        const float2 n = unpack2(ffma2(wp, wp, pack2(wn[c0], wn[c1])));
+                        a_c[c0] = a.x; a_c[c1] = a.y; wn[c0] = n.x; wn[c1] = n.y;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int lc = 4 * j + i;                             // local channel of the item
-                    if (GROUPS) ag[GROUPS ? lc / CPG : 0] = fmaf(r[i], w[i], ag[GROUPS ? lc / CPG : 0]);
-                    if (SIM) {
+                    if (GROUPS && CPG > 1) ag[GROUPS ? lc / CPG : 0] = fmaf(r[i], w[i], ag[GROUPS ? lc / CPG : 0]);
+                    if (SIM && NCP < 2) {
                         a_c[SIM ? lc % NCP : 0] = fmaf(r[i], w[i], a_c[SIM ? lc % NCP : 0]);
                         wn[SIM ? lc % NCP : 0] = fmaf(w[i], w[i], wn[SIM ? lc % NCP : 0]);
                     }
                     if (!GROUPS && !SIM) sview = fmaf(r[i], w[i], sview);
                 }
+            };
+            // bilinear blend of four texel chunks, two channels per packed operation: ((t00*w00 + t01*w01) + t10*w10) + t11*w11
+            // with the roundings of the nested scalar fmaf chain
+            auto blend = [&](const float4& t00, const float4& t01, const float4& t10, const float4& t11, float w00, float w01, float w10,
+                             float w11) {
+                const f32x2 b00 = pack2(w00, w00), b01 = pack2(w01, w01), b10 = pack2(w10, w10), b11 = pack2(w11, w11);
+                const float2 lo = unpack2(ffma2(pack2(t11.x, t11.y), b11, ffma2(pack2(t10.x, t10.y), b10,
+                                          ffma2(pack2(t01.x, t01.y), b01, fmul2(pack2(t00.x, t00.y), b00)))));
+                const float2 hi = unpack2(ffma2(pack2(t11.z, t11.w), b11, ffma2(pack2(t10.z, t10.w), b10,
+                                          ffma2(pack2(t01.z, t01.w), b01, fmul2(pack2(t00.z, t00.w), b00)))));
+                return make_float4(lo.x, lo.y, hi.x, hi.y);
             };
 
             if (live && inbox) {
@@ -372,11 +403,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
                 for (int j = 0; j < NQ; ++j) {
                     const int q = j ^ xq;
                     const float4 t00 = t[q], t01 = t[NQ + q], t10 = t[BW * NQ + q], t11 = t[(BW + 1) * NQ + q];
-                    float4 w;
-                    w.x = fmaf(t11.x, w11, fmaf(t10.x, w10, fmaf(t01.x, w01, t00.x * w00)));
-                    w.y = fmaf(t11.y, w11, fmaf(t10.y, w10, fmaf(t01.y, w01, t00.y * w00)));
-                    w.z = fmaf(t11.z, w11, fmaf(t10.z, w10, fmaf(t01.z, w01, t00.z * w00)));
-                    w.w = fmaf(t11.w, w11, fmaf(t10.w, w10, fmaf(t01.w, w01, t00.w * w00)));
+                    const float4 w = blend(t00, t01, t10, t11, w00, w01, w10, w11);
                     const float4 r = REF_SMEM ? reinterpret_cast<const float4*>(s_ref)[pix * C4 + ch * NQ + q] : rreg[REF_SMEM ? 0 : j];
                     accumulate(j, r, w);
                 }
@@ -391,11 +418,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
                     const int q = j ^ xq;
                     const float4 t00 = __ldg(src + (int64_t)tp.o00 * C4 + q), t01 = __ldg(src + (int64_t)tp.o01 * C4 + q);
                     const float4 t10 = __ldg(src + (int64_t)tp.o10 * C4 + q), t11 = __ldg(src + (int64_t)tp.o11 * C4 + q);
-                    float4 w;
-                    w.x = fmaf(t11.x, tp.w11, fmaf(t10.x, tp.w10, fmaf(t01.x, tp.w01, t00.x * tp.w00)));
-                    w.y = fmaf(t11.y, tp.w11, fmaf(t10.y, tp.w10, fmaf(t01.y, tp.w01, t00.y * tp.w00)));
-                    w.z = fmaf(t11.z, tp.w11, fmaf(t10.z, tp.w10, fmaf(t01.z, tp.w01, t00.z * tp.w00)));
-                    w.w = fmaf(t11.w, tp.w11, fmaf(t10.w, tp.w10, fmaf(t01.w, tp.w01, t00.w * tp.w00)));
+                    const float4 w = blend(t00, t01, t10, t11, tp.w00, tp.w01, tp.w10, tp.w11);
                     const float4 r = REF_SMEM ? reinterpret_cast<const float4*>(s_ref)[pix * C4 + ch * NQ + q] : rreg[REF_SMEM ? 0 : j];
                     accumulate(j, r, w);
                 }
@@ -423,9 +446,13 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
                 for (int g = 0; g < GPI; g += 4) *reinterpret_cast<float4*>(out + g) = make_float4(o[g], o[g + 1], o[g + 2], o[g + 3]);
             }
             if (PASS_B) {
+                const f32x2 icp = pack2(inv_cpg, inv_cpg), wv2 = pack2(wv, wv);
 #pragma unroll
-                for (int g = 0; g < (PASS_B ? G : 1); ++g)
-                    acc[PASS_B ? jh : 0][g] = fmaf(ag[PASS_B ? g : 0] * inv_cpg, wv, acc[PASS_B ? jh : 0][g]);
+                for (int g = 0; g < (PASS_B ? G : 2); g += 2) {           // acc = fmaf(ag * inv_cpg, wv, acc), two groups per FFMA2
+                    const int j0 = PASS_B ? jh : 0, g0 = PASS_B ? g : 0, g1 = PASS_B ? g + 1 : 0;
+                    const float2 o = unpack2(ffma2(fmul2(pack2(ag[g0], ag[g1]), icp), wv2, pack2(acc[j0][g0], acc[j0][g1])));
+                    acc[j0][g0] = o.x; acc[j0][g1] = o.y;
+                }
             } else if (ch == NCH - 1) {
                 s_col[pix * SD + k] = sview * inv_cpg;                    // read back by this thread only
                 if (SIM) {

@@ -111,11 +111,10 @@ prob_conv3_tiled_kernel(const float* __restrict__ x, float* __restrict__ pre, in
 // instead of being held in registers (keeps the kernel generic in D).
 __global__ void __launch_bounds__(256)
 regression_head_kernel(const float* __restrict__ pre, const float* __restrict__ dv, float tmp, int mode,
-                       float* __restrict__ prob, float* __restrict__ depth, float* __restrict__ conf, int D, int64_t hw,
-                       int64_t total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t b = i / hw, pix = i % hw;
+                       float* __restrict__ prob, float* __restrict__ depth, float* __restrict__ conf, int D, int64_t hw) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // grid.y = batch item: no 64-bit division
+    if (pix >= hw) return;
+    const int64_t b = blockIdx.y, i = b * hw + pix;
     const float* col = pre + b * D * hw + pix;
     const float* dcol = dv + b * D * hw + pix;
     float mx = -FLT_MAX;
@@ -218,13 +217,11 @@ __device__ __forceinline__ Lerp lerp_axis(int o, int n_in, int n_out) {
 // inverse = 0: module.py:687-699.
 __global__ void __launch_bounds__(256)
 schedule_kernel(const float* __restrict__ depth, const float* __restrict__ hypo, int Dprev, float split_itv,
-                const float* __restrict__ interval, int inverse, float* __restrict__ out, int D, int H, int W,
-                int64_t total) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int x = (int)(i % W); i /= W;
-    const int y = (int)(i % H);
-    const int64_t b = i / H;
+                const float* __restrict__ interval, int inverse, float* __restrict__ out, int D, int H, int W) {
+    // 32 x 8 pixel blocks, grid.z = batch item: no 64-bit division to find (b, y, x)
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const int64_t b = blockIdx.z;
     const int h2 = H / 2, w2 = W / 2;
     const Lerp ly = lerp_axis(y, h2, H), lx = lerp_axis(x, w2, W);
     float lo[4], hi[4];
@@ -264,13 +261,10 @@ schedule_kernel(const float* __restrict__ depth, const float* __restrict__ hypo,
 }
 
 __global__ void confidence_accumulate_kernel(const float* __restrict__ conf, int h, int w, float* __restrict__ acc,
-                                             float* __restrict__ up, int H, int W, float scale, int64_t total) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t o = i;
-    const int x = (int)(i % W); i /= W;
-    const int y = (int)(i % H);
-    const int64_t b = i / H;
+                                             float* __restrict__ up, int H, int W, float scale) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const int64_t b = blockIdx.z, o = (b * H + y) * (int64_t)W + x;
     // F.interpolate(mode='nearest'): src = floor(dst * in/out) computed in fp32
     const int sy = min((int)floorf((float)y * ((float)h / (float)H)), h - 1);
     const int sx = min((int)floorf((float)x * ((float)w / (float)W)), w - 1);
@@ -318,9 +312,10 @@ extern "C" int mvs_regression_head(const float* pre, const float* depth_values, 
     if (rc) return rc;
     MVS_REQUIRE(confidence, "mvs_regression_head: null confidence output");
     MVS_REQUIRE(mode == 0 || mode == 1, "mvs_regression_head: mode must be 0 (eval) or 1 (train), got %d", mode);
-    const int64_t hw = (int64_t)H * W, total = hw * B;
-    regression_head_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(pre, depth_values, tmp, mode, prob_volume,
-                                                                              depth, confidence, D, hw, total);
+    const int64_t hw = (int64_t)H * W;
+    MVS_REQUIRE(B <= 65535, "mvs_regression_head: batch %d too large for one launch", B);
+    regression_head_kernel<<<dim3(cdiv(hw, 256), B), 256, 0, (cudaStream_t)stream>>>(pre, depth_values, tmp, mode, prob_volume,
+                                                                                    depth, confidence, D, hw);
     MVS_LAUNCH_OK("regression_head_kernel");
     return MVS_OK;
 }
@@ -374,9 +369,9 @@ extern "C" int mvs_schedule_inverse_range(const float* depth, const float* depth
     if (rc) return rc;
     MVS_REQUIRE(Dprev >= 3, "mvs_schedule_inverse_range: previous stage needs >= 3 hypotheses (got %d)", Dprev);
     MVS_REQUIRE(D >= 2 && H >= 2 && W >= 2, "mvs_schedule_inverse_range: D, H, W must be >= 2");
-    const int64_t total = (int64_t)B * H * W;
-    schedule_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(depth, depth_hypo, Dprev, split_itv, nullptr, 1, out,
-                                                                       D, H, W, total);
+    MVS_REQUIRE(B <= 65535 && cdiv(H, 8) <= 65535, "mvs_schedule_inverse_range: map too large for one launch");
+    schedule_kernel<<<dim3(cdiv(W, 32), cdiv(H, 8), B), 256, 0, (cudaStream_t)stream>>>(depth, depth_hypo, Dprev, split_itv, nullptr, 1,
+                                                                                       out, D, H, W);
     MVS_LAUNCH_OK("schedule_kernel");
     return MVS_OK;
 }
@@ -387,8 +382,8 @@ extern "C" int mvs_schedule_range(const float* depth, const float* interval, flo
     int rc = check_map_args("mvs_schedule_range", depth, interval, out, B, D, H, W);
     if (rc) return rc;
     MVS_REQUIRE(D >= 2 && H >= 2 && W >= 2, "mvs_schedule_range: D, H, W must be >= 2");
-    const int64_t total = (int64_t)B * H * W;
-    schedule_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(depth, nullptr, 0, 0.0f, interval, 0, out, D, H, W, total);
+    MVS_REQUIRE(B <= 65535 && cdiv(H, 8) <= 65535, "mvs_schedule_range: map too large for one launch");
+    schedule_kernel<<<dim3(cdiv(W, 32), cdiv(H, 8), B), 256, 0, (cudaStream_t)stream>>>(depth, nullptr, 0, 0.0f, interval, 0, out, D, H, W);
     MVS_LAUNCH_OK("schedule_kernel");
     return MVS_OK;
 }
@@ -398,8 +393,8 @@ extern "C" int mvs_confidence_accumulate(const float* conf, int h, int w, float*
     using namespace mvs;
     MVS_REQUIRE(conf && acc, "mvs_confidence_accumulate: null pointer");
     MVS_REQUIRE(B >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "mvs_confidence_accumulate: empty shape");
-    const int64_t total = (int64_t)B * H * W;
-    confidence_accumulate_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, nullptr, H, W, scale, total);
+    MVS_REQUIRE(B <= 65535 && cdiv(H, 8) <= 65535, "mvs_confidence_accumulate: map too large for one launch");
+    confidence_accumulate_kernel<<<dim3(cdiv(W, 32), cdiv(H, 8), B), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, nullptr, H, W, scale);
     MVS_LAUNCH_OK("confidence_accumulate_kernel");
     return MVS_OK;
 }
@@ -409,8 +404,8 @@ extern "C" int mvs_confidence_upsample_accumulate(const float* conf, int h, int 
     using namespace mvs;
     MVS_REQUIRE(conf && acc && up, "mvs_confidence_upsample_accumulate: null pointer");
     MVS_REQUIRE(B >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "mvs_confidence_upsample_accumulate: empty shape");
-    const int64_t total = (int64_t)B * H * W;
-    confidence_accumulate_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, up, H, W, scale, total);
+    MVS_REQUIRE(B <= 65535 && cdiv(H, 8) <= 65535, "mvs_confidence_upsample_accumulate: map too large for one launch");
+    confidence_accumulate_kernel<<<dim3(cdiv(W, 32), cdiv(H, 8), B), 256, 0, (cudaStream_t)stream>>>(conf, h, w, acc, up, H, W, scale);
     MVS_LAUNCH_OK("confidence_accumulate_kernel");
     return MVS_OK;
 }

@@ -38,6 +38,9 @@ constexpr int ABYTES = AY * AX * PIXB;           // 36 KB, a multiple of 1024
 constexpr int N2 = 48, N3 = 32;                  // MMA N: [3 kh][16] and [3 kh][8] padded to 32
 constexpr int W2BYTES = 3 * 4 * N2 * 16, W3BYTES = 3 * 4 * N3 * 16;      // packed [kw][quad][kh][n][4]
 constexpr int XBYTES = 2 * AY * 16 * PIXB;       // exchange buffers for T[1], T[2]: [2][32 rows][16 pixels][64 B]
+#ifndef VIS_EB
+#define VIS_EB 8
+#endif
 constexpr int NPROD = 7, NEPI = 8;               // producer / epilogue warps
 constexpr int THREADS = 32 * (1 + NPROD + NEPI);
 constexpr size_t SMEM = 3 * ABYTES + W2BYTES + W3BYTES + XBYTES + 256 + 1024;
@@ -171,42 +174,84 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
         }
     } else if (warp <= NPROD) {
         // ================================================= layer-1 producers (CUDA cores) ==============================
-        const int pt = (warp - 1) * 32 + lane;
-        int it = 0;
-        for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
-            const int b = it & 1;
+        // A lane computes TWO horizontally adjacent pixels of the 32 x 18 operand array at a time, one in each half of a
+        // packed FP32 pair: a·w + acc for both pixels is ONE FFMA2 with the weight broadcast (half the FMA-pipe slots of
+        // the scalar form; each half is the same IEEE fma, so the results are bit-identical), and the pair shares its
+        // 3 x 4 entropy footprint (12 loads instead of 18).  The 288 pairs of a tile are dealt to the 224 producer lanes
+        // starting at a warp that rotates with the tile, so the 64 left-over pairs do not always land on the same warps;
+        // the footprint of a lane's first pair of the NEXT tile is loaded as soon as this tile's has been consumed, and this
+        // tile's second pair before the wait for the operand buffer: no global-load latency sits between the wait and the FMAs.
+        constexpr int PAIRS_X = AX / 2, NPAIR = AY * PAIRS_X, PLANES = NPROD * 32, EB = VIS_EB;
+        static_assert(AX % 2 == 0 && NPAIR > PLANES && NPAIR <= 2 * PLANES, "pair schedule");
+        auto pair_of = [&](int it, int second) { return ((warp - 1 + it) % NPROD) * 32 + lane + second * PLANES; };
+        struct Org { int y0, x0; const float* ent; };                                     // A1 origin (= tile origin - 2), map base
+        auto origin = [&](int item) {
             const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y, m = item / (d.tiles_x * d.tiles_y);
-            const float* ent = entropy + (int64_t)m * d.H * d.W;
-            if (it >= 2) mbar_wait(&free1[b], ((it >> 1) - 1) & 1);
-            uint8_t* a1 = sA1 + b * ABYTES;
-            for (int pix = pt; pix < AY * AX; pix += NPROD * 32) {
-                const int y = ty * OUT_Y - 2 + pix / AX, x = tx * OUT_X - 2 + pix % AX;      // A1 origin = tile origin - 2
-                float r[16];
-                if (y >= 0 && y < d.H && x >= 0 && x < d.W) {
-                    float in[9];
+            return Org{ty * OUT_Y - 2, tx * OUT_X - 2, entropy + (int64_t)m * d.H * d.W};
+        };
+        // entropy footprint rows y-1..y+1, columns x-1..x+2 of the pair at (y, x), (y, x+1); zero outside the image
+        auto load12 = [&](const Org& o, int pr, float (&v)[12]) {
+            const int y = o.y0 + pr / PAIRS_X, x = o.x0 + 2 * (pr % PAIRS_X);
+            bool cok[4];
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int yy = y - 1 + t / 3, xx = x - 1 + t % 3;
-                        in[t] = (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) ? __ldg(ent + (int64_t)yy * d.W + xx) : 0.0f;
-                    }
+            for (int c = 0; c < 4; ++c) cok[c] = (unsigned)(x - 1 + c) < (unsigned)d.W;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float a = P.b1[e];
+            for (int r = 0; r < 3; ++r) {
+                const int yy = y - 1 + r;
+                const bool rok = (unsigned)yy < (unsigned)d.H;
+                const float* row = o.ent + (int64_t)yy * d.W + (x - 1);
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) a = fmaf(in[t], P.w1[e][t], a);
-                        r[e] = round_to_tf32(fmaxf(a, 0.0f));
-                    }
-                } else {
+                for (int c = 0; c < 4; ++c) v[r * 4 + c] = (rok && cok[c]) ? __ldg(row + c) : 0.0f;
+            }
+        };
+        auto compute_pair = [&](const Org& o, int pr, const float (&v)[12], uint8_t* a1) {
+            const int py = pr / PAIRS_X, px = 2 * (pr % PAIRS_X);
+            const int y = o.y0 + py, x = o.x0 + px;
+            const bool rowin = (unsigned)y < (unsigned)d.H;
+            const bool in0 = rowin && (unsigned)x < (unsigned)d.W, in1 = rowin && (unsigned)(x + 1) < (unsigned)d.W;
+            f32x2 in[9];                                                                  // tap t of (left pixel, right pixel)
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) r[e] = 0.0f;     // outside the image: layer 2's zero padding
+            for (int t = 0; t < 9; ++t) in[t] = pack2(v[(t / 3) * 4 + t % 3], v[(t / 3) * 4 + t % 3 + 1]);
+            const int pix = py * AX + px;
+#pragma unroll
+            for (int eh = 0; eh < 16; eh += EB) {                                         // EB channels at a time (registers)
+                float r0[EB], r1[EB];
+#pragma unroll
+                for (int e = 0; e < EB; ++e) {
+                    f32x2 a = pack2(P.b1[eh + e], P.b1[eh + e]);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) a = ffma2(in[t], pack2(P.w1[eh + e][t], P.w1[eh + e][t]), a);
+                    const float2 o = unpack2(a);
+                    r0[e] = in0 ? relu_round_tf32(o.x) : 0.0f;                 // outside the image: layer 2's zero padding
+                    r1[e] = in1 ? relu_round_tf32(o.y) : 0.0f;
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<float4*>(a1 + sw64_offset(pix, c)) = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                for (int c = 0; c < EB / 4; ++c) {
+                    *reinterpret_cast<float4*>(a1 + sw64_offset(pix, eh / 4 + c)) = make_float4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
+                    *reinterpret_cast<float4*>(a1 + sw64_offset(pix + 1, eh / 4 + c)) = make_float4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
+                }
             }
+        };
+        int it = 0;
+        float nxt[12];
+        Org cur = origin(blockIdx.x);                      // (unused when the CTA has no tile)
+        if ((int)blockIdx.x < d.nitems) load12(cur, pair_of(0, 0), nxt);
+        for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
+            const int b = it & 1;
+            const int p0 = pair_of(it, 0), p1 = pair_of(it, 1);
+            const bool more = item + (int)gridDim.x < d.nitems;
+            const Org nxo = origin(more ? item + (int)gridDim.x : item);
+            float sec[12];
+            if (p1 < NPAIR) load12(cur, p1, sec);
+            if (it >= 2) mbar_wait(&free1[b], ((it >> 1) - 1) & 1);
+            uint8_t* a1 = sA1 + b * ABYTES;
+            compute_pair(cur, p0, nxt, a1);
+            if (more) load12(nxo, pair_of(it + 1, 0), nxt);                               // lands under the next wait
+            if (p1 < NPAIR) compute_pair(cur, p1, sec, a1);
             fence_proxy_async_smem();                      // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&full1[b]);
+            cur = nxo;
         }
     } else {
         // ================================================= epilogue warps ==============================================
@@ -253,12 +298,14 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
                     for (int c = 0; c < 2; ++c) {
                         const float4 a1 = *reinterpret_cast<const float4*>(sX1 + sw64_offset((oy + 1) * 16 + ox, c));
                         const float4 a2 = *reinterpret_cast<const float4*>(sX2 + sw64_offset((oy + 2) * 16 + ox, c));
-                        const float e1[4] = {a1.x, a1.y, a1.z, a1.w}, e2[4] = {a2.x, a2.y, a2.z, a2.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float act = round_to_tf32(fmaxf((u0[tt][4 * c + i] + e1[i]) + e2[i] + P.shift3[4 * c + i], 0.f));
-                            z = fmaf(act, P.w4[4 * c + i], z);
-                        }
+                        const float2 lo = unpack2(fadd2(fadd2(fadd2(pack2(u0[tt][4 * c], u0[tt][4 * c + 1]), pack2(a1.x, a1.y)), pack2(a2.x, a2.y)),
+                                                        pack2(P.shift3[4 * c], P.shift3[4 * c + 1])));
+                        const float2 hi = unpack2(fadd2(fadd2(fadd2(pack2(u0[tt][4 * c + 2], u0[tt][4 * c + 3]), pack2(a1.z, a1.w)), pack2(a2.z, a2.w)),
+                                                        pack2(P.shift3[4 * c + 2], P.shift3[4 * c + 3])));
+                        z = fmaf(relu_round_tf32(lo.x), P.w4[4 * c], z);
+                        z = fmaf(relu_round_tf32(lo.y), P.w4[4 * c + 1], z);
+                        z = fmaf(relu_round_tf32(hi.x), P.w4[4 * c + 2], z);
+                        z = fmaf(relu_round_tf32(hi.y), P.w4[4 * c + 3], z);
                     }
                     weight[((int64_t)m * d.H + y) * d.W + x] = 1.0f / (1.0f + expf(-z));
                 }
@@ -302,11 +349,16 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
                 for (int c = 0; c < 4; ++c) {
                     const float4 a1 = *reinterpret_cast<const float4*>(sX1 + sw64_offset((y2 + 1) * 16 + x2, c));
                     const float4 a2 = *reinterpret_cast<const float4*>(sX2 + sw64_offset((y2 + 2) * 16 + x2, c));
+                    // ((T0 + T1) + T2) + shift, two channels per packed add
+                    const float2 lo = unpack2(fadd2(fadd2(fadd2(pack2(t0[tt][4 * c], t0[tt][4 * c + 1]), pack2(a1.x, a1.y)), pack2(a2.x, a2.y)),
+                                                    pack2(P.shift2[4 * c], P.shift2[4 * c + 1])));
+                    const float2 hi = unpack2(fadd2(fadd2(fadd2(pack2(t0[tt][4 * c + 2], t0[tt][4 * c + 3]), pack2(a1.z, a1.w)), pack2(a2.z, a2.w)),
+                                                    pack2(P.shift2[4 * c + 2], P.shift2[4 * c + 3])));
                     float4 v;
-                    v.x = inside ? round_to_tf32(fmaxf((t0[tt][4 * c] + a1.x) + a2.x + P.shift2[4 * c], 0.f)) : 0.f;
-                    v.y = inside ? round_to_tf32(fmaxf((t0[tt][4 * c + 1] + a1.y) + a2.y + P.shift2[4 * c + 1], 0.f)) : 0.f;
-                    v.z = inside ? round_to_tf32(fmaxf((t0[tt][4 * c + 2] + a1.z) + a2.z + P.shift2[4 * c + 2], 0.f)) : 0.f;
-                    v.w = inside ? round_to_tf32(fmaxf((t0[tt][4 * c + 3] + a1.w) + a2.w + P.shift2[4 * c + 3], 0.f)) : 0.f;
+                    v.x = inside ? relu_round_tf32(lo.x) : 0.f;
+                    v.y = inside ? relu_round_tf32(lo.y) : 0.f;
+                    v.z = inside ? relu_round_tf32(hi.x) : 0.f;
+                    v.w = inside ? relu_round_tf32(hi.y) : 0.f;
                     *reinterpret_cast<float4*>(sA2 + sw64_offset(y2 * AX + x2, c)) = v;
                 }
             }

@@ -532,6 +532,23 @@ def conv3d_tma(x, w_tma, n_tile, cout, kd, shift, skip, relu=True, mode=TMA_S1):
     return y
 
 
+def conv3d_tma_prob(x, w_tma, kd, shift, skip, prob_w_host, prob_bias, relu=True):
+    """Transposed conv 16 -> 8 (mode TMA_DECONV, + shift, ReLU, + skip) with the 1x1x1 ``prob`` conv 8 -> 1 in its epilogue
+    (mvs_conv3d_tma_prob): x [B,D,H,W,16] -> prob_volume_pre [B,D,2H,2W]; prob_w_host: float32 numpy [8]."""
+    require_cuda(x, w_tma, shift, skip)
+    b, d, h, w, cin = x.shape
+    if skip is not None and tuple(skip.shape) != (b, d, 2 * h, 2 * w, 8):
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s (skip connection)"
+                           % (tuple(skip.shape), (b, d, 2 * h, 2 * w, 8)))
+    if prob_w_host.size != 8:
+        raise RuntimeError("prob weights must hold 8 values, got %d" % prob_w_host.size)
+    pre = torch.empty(b, d, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
+    check(_lib.load().mvs_conv3d_tma_prob(ptr(x), ptr(w_tma), ptr(shift), ptr(skip), prob_w_host.ctypes.data_as(ctypes.c_void_p),
+                                          float(prob_bias), ptr(pre), b, d, h, w, cin, kd, 1 if relu else 0, stream()),
+          "mvs_conv3d_tma_prob")
+    return pre
+
+
 def tc_probe_ts(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, n, nk, a_kstep, b_kstep, a_shift_bytes=0):
     require_cuda(a_img, b_img)
     out = torch.empty(128, n, device=a_img.device, dtype=torch.float32)

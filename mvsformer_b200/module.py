@@ -304,7 +304,9 @@ class _RegNetBase(nn.Module):
     """Shared U-Net driver: 3 strided levels down, 3 transposed levels up with skip adds after
     the ReLU (models/module.py:495-505 / :584-594)."""
 
-    def _unet_cl(self, x):
+    def _unet_cl(self, x, with_prob=False):
+        """-> the U-Net's output [B,D,H,W,base]; ``with_prob``: -> prob_volume_pre [B,D,H,W] when the last transposed layer can
+        take the ``prob`` conv into its epilogue (``_prob_fusable``), else the output as before."""
         c0 = x
         c2 = self.conv2.forward_cl(self.conv1.forward_cl(c0))
         c4 = self.conv4.forward_cl(self.conv3.forward_cl(c2))
@@ -314,15 +316,42 @@ class _RegNetBase(nn.Module):
         if not isinstance(self.inner, nn.Identity):
             # 1x1x1 projection of the input skip when in_channels != base_channels (module.py:486-489, :502)
             c0 = autograd.thin_conv_module(c0, self.inner)
-        return self.conv11.forward_cl(y, skip=c0)
+        if with_prob and self._prob_fusable(y):
+            w_host, b_host = self._prob_weights()
+            wd, shift = self.conv11.packed()
+            wt, _ = self.conv11._fold.get_derived("tma_m2", lambda v: engine.pack_tma_weights(v[0], engine.TMA_DECONV))
+            return engine.conv3d_tma_prob(y, wt, wd.shape[0], shift, c0, w_host, float(b_host[0]) if b_host is not None else 0.0), True
+        y = self.conv11.forward_cl(y, skip=c0)
+        return (y, False) if with_prob else y
+
+    def _prob_fusable(self, y):
+        """Eval, TF32 mode, the persistent TMA kernels on, a 3x3x3 16 -> 8 transposed last layer (depth stride 1: the layer
+        _run_deconv sends to mvs_conv3d_tma) followed by a 1x1x1 ``prob`` conv 8 -> 1: CostRegNet3D as the shipped configs
+        build it (stages 3-4)."""
+        conv11, prob = self.conv11, self.prob
+        if self.training or not config.prob_fused() or config.conv_precision() != "tf32" or not config.conv_tma():
+            return False
+        if (not isinstance(conv11, (_SeqDeconv, Deconv3d)) or tuple(prob.kernel_size) != (1, 1, 1) or prob.in_channels != 8
+                or prob.out_channels != 1):
+            return False
+        conv = conv11[0] if isinstance(conv11, _SeqDeconv) else conv11.conv
+        if isinstance(conv11, Deconv3d) and (conv11.bn is None or not conv11.relu):
+            return False
+        kd = _triple(conv.kernel_size)[0]
+        return (conv.in_channels == 16 and conv.out_channels == 8 and _deconv_depth_stride(conv) == 1 and kd == 3
+                and engine.tma_supported(16, 8, y.shape[1], kd, transposed=True))
+
+    def _prob_weights(self):
+        conv = self.prob
+        if not hasattr(self, "_prob_cache"):
+            object.__setattr__(self, "_prob_cache", _ProbCache())
+        return self._prob_cache.get([conv.weight, conv.bias], lambda: _prob_host(conv))
 
     def _prob_cl(self, y):
         conv = self.prob
         if self.training:
             return autograd.thin_conv_module(y, conv).squeeze(-1)
-        if not hasattr(self, "_prob_cache"):
-            object.__setattr__(self, "_prob_cache", _ProbCache())
-        w_host, b_host = self._prob_cache.get([conv.weight, conv.bias], lambda: _prob_host(conv))
+        w_host, b_host = self._prob_weights()
         return engine.prob_conv_cl(y, w_host, b_host, conv.kernel_size[0])
 
     def forward_cl(self, x):
@@ -333,10 +362,10 @@ class _RegNetBase(nn.Module):
             # the reference fails at the first skip add with torch's size-mismatch RuntimeError
             raise RuntimeError("The size of tensor a must match the size of tensor b: cost volume [D=%d,H=%d,W=%d] "
                                "is not divisible by the U-Net's total stride 8" % (d, h, w))
-        y = self._unet_cl(x)
         if getattr(self, "last_layer", True):
-            return self._prob_cl(y)
-        return y
+            y, done = self._unet_cl(x, with_prob=True)
+            return y if done else self._prob_cl(y)
+        return self._unet_cl(x)
 
     def forward(self, x):
         if self.training:

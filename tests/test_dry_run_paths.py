@@ -84,10 +84,13 @@ def test_inference_host_path(dry, mode, layout, tma, fused):
         assert dry.calls.count("mvs_cost_volume_aggregate" + ("_tf32" if mode == "tf32" else "")) == 4
         assert dry.calls.count("mvs_argmax_gather") == 4
     if mode == "tf32" and tma:           # depth-unstrided layers on the persistent TMA kernels, the rest on the generic tcgen05 ones
-        assert dry.calls.count("mvs_conv3d_tma") == 24
+        # stages 3-4: the last transposed layer takes the 1x1x1 `prob` conv into its epilogue (config.prob_fused)
+        assert dry.calls.count("mvs_conv3d_tma") == 22 and dry.calls.count("mvs_conv3d_tma_prob") == 2
+        assert dry.calls.count("mvs_prob_conv_cl") == 2
         assert dry.calls.count("mvs_conv3d_tc") + dry.calls.count("mvs_deconv3d_tc") == 12
     else:
-        assert "mvs_conv3d_tma" not in called
+        assert "mvs_conv3d_tma" not in called and "mvs_conv3d_tma_prob" not in called
+        assert dry.calls.count("mvs_prob_conv_cl") == 4
     if mode == "tf32" and fused:
         assert dry.calls.count("mvs_vis_fused") == 4 and "mvs_vis_weight" not in called
     else:
@@ -96,6 +99,22 @@ def test_inference_host_path(dry, mode, layout, tma, fused):
         assert "mvs_conv3d_cl" in called and not any("_tc" in c or "_tma" in c for c in called)
     elif not (mode == "tf32" and tma):
         assert dry.calls.count("mvs_conv3d_tc") + dry.calls.count("mvs_deconv3d_tc") == 36
+
+
+def test_prob_fused_knob_off_keeps_the_two_kernel_route(dry):
+    feats, cams, dv = _cascade_inputs()
+    net = CascadeMVS(dict(CASCADE_ARGS)).eval()
+    old = config.conv_precision()
+    config.set_conv_precision("tf32")
+    config.set_prob_fused(False)
+    try:
+        with torch.no_grad():
+            net(feats, cams, dv, tmp=list(S.EVAL_TMP))
+    finally:
+        config.set_conv_precision(old)
+        config.set_prob_fused(True)
+    assert dry.calls.count("mvs_conv3d_tma") == 24 and "mvs_conv3d_tma_prob" not in dry.calls
+    assert dry.calls.count("mvs_prob_conv_cl") == 4
 
 
 @pytest.mark.parametrize("train_conv", ["fp32", "tf32x3", "tf32"])

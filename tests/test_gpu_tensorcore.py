@@ -278,3 +278,58 @@ def test_conv3d_tma_transposed(cin, cout, kd, D, H, W, batch):
     got = engine.conv3d_tma(x_cl, wt, nt, cout, kd, shift.to(DEV), skip_cl, True, engine.TMA_DECONV).permute(0, 4, 1, 2, 3).cpu()
     assert got.shape == want.shape
     assert rel_l1(got, want + skip.double()) < 5e-4
+
+
+@pytest.mark.parametrize("kd,D,H,W,batch,with_skip", [(3, 4, 8, 12, 2, True), (3, 8, 33, 50, 1, True), (3, 1, 9, 9, 1, False),
+                                                       (3, 4, 144, 192, 1, True), (1, 4, 20, 28, 1, True)])
+def test_conv3d_tma_prob_matches_two_kernel_route(kd, D, H, W, batch, with_skip):
+    """mvs_conv3d_tma_prob (transposed 16 -> 8 with the 1x1x1 `prob` conv in its epilogue, models/module.py:575,582) is
+    BIT-identical to mvs_conv3d_tma + mvs_prob_conv_cl, partial tiles included, and stays within TF32 rounding of fp64."""
+    import numpy as np
+    g = S._gen(900 + kd + D + H + W)
+    w = engine.round_tf32(torch.randn(16, 8, kd, 3, 3, generator=g) * (2.0 / (16 * kd * 9 / 4)) ** 0.5)
+    shift = 0.1 * torch.randn(8, generator=g)
+    x = engine.round_tf32(torch.randn(batch, 16, D, H, W, generator=g))
+    skip = torch.randn(batch, 8, D, 2 * H, 2 * W, generator=g) if with_skip else None
+    pw = torch.randn(8, generator=g)
+    pb = float(torch.randn(1, generator=g))
+    wt, nt = engine.pack_tma_weights(w.permute(2, 3, 4, 0, 1).contiguous().to(DEV), engine.TMA_DECONV)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    skip_cl = skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV) if with_skip else None
+    pw_host = np.ascontiguousarray(pw.numpy().astype(np.float32))
+    y = engine.conv3d_tma(x_cl, wt, nt, 8, kd, shift.to(DEV), skip_cl, True, engine.TMA_DECONV)
+    two = engine.prob_conv_cl(y, pw_host.reshape(1, 8), np.array([pb], dtype=np.float32), 1)
+    one = engine.conv3d_tma_prob(x_cl, wt, kd, shift.to(DEV), skip_cl, pw_host, pb, True)
+    assert one.shape == two.shape == (batch, D, 2 * H, 2 * W)
+    assert torch.equal(one, two)
+    ref = torch.relu(F.conv_transpose3d(x.double(), w.double(), stride=(1, 2, 2), padding=(kd // 2, 1, 1), output_padding=(0, 1, 1))
+                     + shift.double().view(1, -1, 1, 1, 1))
+    if with_skip:
+        ref = ref + skip.double()
+    want = (ref * pw.double().view(1, 8, 1, 1, 1)).sum(1) + pb
+    assert float((one.cpu().double() - want).abs().mean() / want.abs().mean()) < 2e-3
+
+
+def test_cost_reg_net_3d_prob_fused_is_bit_identical():
+    """CostRegNet3D eval in TF32 mode: config.prob_fused on / off give the same prob_volume_pre bit for bit."""
+    from mvsformer_b200 import config, module as M
+    net = M.CostRegNet3D(8, 8).eval()
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=16))
+    net = net.to(DEV)
+    x = torch.randn(1, 8, 4, 64, 96, generator=S._gen(17)).to(DEV)
+    old = config.conv_precision()
+    try:
+        config.set_conv_precision("tf32")
+        config.set_prob_fused(True)
+        before = engine._lib.load().mvs_launch_count()
+        fused = net(x)
+        n_fused = engine._lib.load().mvs_launch_count() - before
+        config.set_prob_fused(False)
+        before = engine._lib.load().mvs_launch_count()
+        plain = net(x)
+        n_plain = engine._lib.load().mvs_launch_count() - before
+    finally:
+        config.set_conv_precision(old)
+        config.set_prob_fused(True)
+    assert torch.equal(fused, plain)
+    assert n_fused == n_plain - 1                           # the separate `prob` kernel is gone
