@@ -42,6 +42,7 @@ struct Dims {
     int relu;
     int tiles_x, tiles_y, nitems;
     int nbuf;                // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
+    int epi_pipe;            // epilogue: TMEM reads issued one accumulator block ahead (MVS_TMA_EPI_PIPE, default 1)
     float pw[8], pbias;      // PROB: the regulariser's 1x1x1 `prob` conv (8 -> 1, + bias) applied in the epilogue
 };
 
@@ -281,56 +282,71 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
         for (int item = blockIdx.x; item < d.nitems; item += gridDim.x, ++it) {
             const int buf = d.nbuf == 2 ? (it & 1) : 0, use = d.nbuf == 2 ? (it >> 1) : it;
             const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y, b = item / (d.tiles_x * d.tiles_y);
-            // output element this lane writes in store instruction j of accumulator block cz (class, slice)
-            auto locate = [&](int cz, int j, size_t* o, size_t* voxel) -> bool {
-                const int cls = cz / d.D, blk = cz - cls * d.D;
-                const int z = MODE == MODE_DECONV ? blk : d.D - 1 - blk;
+            // Output voxel this lane writes in store instruction j of accumulator block cz (class, slice) = block origin
+            // (one 64-bit product per block) + the lane's pixel offset inside a slice (per item, 32-bit): the address math
+            // of the drain loop is two adds per store.
+            int pixoff[CPR];
+            unsigned livemask = 0;
+#pragma unroll
+            for (int j = 0; j < CPR; ++j) {
                 const int row = j * rpi + rsub;                       // accumulator row within the quarter
                 const int ty_v = ty * 16 + q * 4 + (row >> 3), tx_v = tx * 8 + (row & 7);
-                int oy = ty_v, ox = tx_v;
-                bool live = ty_v < d.Ho && tx_v < d.Wo;
-                if (MODE == MODE_DECONV) {                            // tile voxel = input voxel; class = output parity
-                    live = ty_v < d.H && tx_v < d.W;
-                    oy = 2 * ty_v + (cls >> 1); ox = 2 * tx_v + (cls & 1);
-                }
-                *voxel = (((size_t)b * d.D + z) * d.Ho + oy) * d.Wo + ox;
-                *o = *voxel * d.Cout + co0 + chunk * 4;
-                return live && cvalid && j < cpr;
+                // transposed: tile voxel = input voxel, the class adds the output parity
+                const bool live = MODE == MODE_DECONV ? (ty_v < d.H && tx_v < d.W) : (ty_v < d.Ho && tx_v < d.Wo);
+                pixoff[j] = MODE == MODE_DECONV ? 2 * ty_v * d.Wo + 2 * tx_v : ty_v * d.Wo + tx_v;
+                if (live && cvalid && j < cpr) livemask |= 1u << j;
+            }
+            const size_t plane = (size_t)d.Ho * d.Wo;
+            auto block_base = [&](int cz) -> size_t {
+                const int cls = cz / d.D, blk = cz - cls * d.D;
+                const int z = MODE == MODE_DECONV ? blk : d.D - 1 - blk;
+                return ((size_t)b * d.D + z) * plane + (MODE == MODE_DECONV ? (size_t)((cls >> 1) * d.Wo + (cls & 1)) : (size_t)0);
             };
             // The skip tensor does not depend on the MMAs: its loads run one accumulator block ahead (the first block's before
             // the wait on the accumulators), so their latency never sits between a TMEM drain and its stores.
             float4 skn[CPR];
+            size_t base_n = 0;
             auto prefetch_skip = [&](int cz) {
+                base_n = block_base(cz);
 #pragma unroll
-                for (int j = 0; j < CPR; ++j) {
-                    size_t o, vx;
-                    skn[j] = (skip && locate(cz, j, &o, &vx)) ? __ldg(reinterpret_cast<const float4*>(skip + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int j = 0; j < CPR; ++j)
+                    skn[j] = (skip && ((livemask >> j) & 1u)) ? __ldg(reinterpret_cast<const float4*>(skip + (base_n + pixoff[j]) * d.Cout + co0 + chunk * 4))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             const int nblk = NCLS * d.D;
             if (half < nblk) prefetch_skip(half);
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after_sync();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ncols;
+            uint32_t accr[NT];
+            auto load_block = [&](int cz) {
+#pragma unroll
+                for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16_async(tacc + (uint32_t)cz * NT + c0, accr + c0);
+            };
+            if (d.epi_pipe && half < nblk) load_block(half);
 #pragma unroll 1
             for (int cz = half; cz < nblk; cz += NEPI / 4) {
                 float4 skc[CPR];
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) skc[j] = skn[j];
+                const size_t base_c = base_n;
                 if (cz + NEPI / 4 < nblk) prefetch_skip(cz + NEPI / 4);
-                float acc[NT];
-#pragma unroll
-                for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tacc + (uint32_t)cz * NT + c0, acc + c0);
+                // The block's accumulator rows were requested one block ago (or before the loop): the TMEM read latency ran
+                // under the previous block's stores.  Once they are staged in shared memory the registers are free, and the
+                // next block's read is issued before this block's stores.
+                if (!d.epi_pipe) load_block(cz);
+                tmem_ld_wait();
                 __syncwarp();                                         // previous block's reads of the buffer are done
 #pragma unroll
                 for (int c4 = 0; c4 < CPR; ++c4)
-                    *reinterpret_cast<float4*>(stg + lane * L::STG_PITCH + c4 * 4) = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+                    *reinterpret_cast<uint4*>(stg + lane * L::STG_PITCH + c4 * 4) = make_uint4(accr[c4 * 4], accr[c4 * 4 + 1], accr[c4 * 4 + 2], accr[c4 * 4 + 3]);
                 __syncwarp();
+                if (d.epi_pipe && cz + NEPI / 4 < nblk) load_block(cz + NEPI / 4);
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) {
-                    size_t o, vox;
-                    const bool ok = locate(cz, j, &o, &vox);
+                    const bool ok = (livemask >> j) & 1u;
                     if (PROB ? j >= cpr : !ok) continue;              // PROB: warp-uniform (every lane takes part in the shuffle)
+                    const size_t vox = base_c + pixoff[j], o = vox * d.Cout + co0 + chunk * 4;
                     float4 r = *reinterpret_cast<const float4*>(stg + (j * rpi + rsub) * L::STG_PITCH + chunk * 4);
                     r.x += sh.x; r.y += sh.y; r.z += sh.z; r.w += sh.w;
                     if (d.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
@@ -416,6 +432,12 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     if (rc) return rc;
     Dims d = {};
     d.B = B; d.D = D; d.H = H; d.W = W; d.Cout = Cout; d.relu = relu;
+    static int epi_pipe = -1;
+    if (epi_pipe < 0) {
+        const char* e = getenv("MVS_TMA_EPI_PIPE");
+        epi_pipe = (e && e[0] == '0') ? 0 : 1;
+    }
+    d.epi_pipe = epi_pipe;
     if (PROB) {
         for (int i = 0; i < 8; ++i) d.pw[i] = prob_w[i];
         d.pbias = prob_bias;

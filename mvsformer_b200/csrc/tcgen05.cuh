@@ -68,6 +68,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait: the registers are valid only after tmem_ld_wait() — nothing may read them in between
+// (issue the load, do independent work, wait, then use; the pattern of CUTLASS' tmem_load + fence_view_async_tmem_load).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave").  Canonical layout in 16-byte
 // units: ((8, m), 2) : ((1, SBO), LBO) — a core matrix is 8 rows x 16 B stored contiguously

@@ -174,44 +174,46 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
         }
     } else if (warp <= NPROD) {
         // ================================================= layer-1 producers (CUDA cores) ==============================
-        // A lane computes TWO horizontally adjacent pixels of the 32 x 18 operand array at a time, one in each half of a
+        // A lane computes TWO vertically adjacent pixels of the 32 x 18 operand array at a time, one in each half of a
         // packed FP32 pair: a·w + acc for both pixels is ONE FFMA2 with the weight broadcast (half the FMA-pipe slots of
         // the scalar form; each half is the same IEEE fma, so the results are bit-identical), and the pair shares its
-        // 3 x 4 entropy footprint (12 loads instead of 18).  The 288 pairs of a tile are dealt to the 224 producer lanes
-        // starting at a warp that rotates with the tile, so the 64 left-over pairs do not always land on the same warps;
-        // the footprint of a lane's first pair of the NEXT tile is loaded as soon as this tile's has been consumed, and this
-        // tile's second pair before the wait for the operand buffer: no global-load latency sits between the wait and the FMAs.
-        constexpr int PAIRS_X = AX / 2, NPAIR = AY * PAIRS_X, PLANES = NPROD * 32, EB = VIS_EB;
-        static_assert(AX % 2 == 0 && NPAIR > PLANES && NPAIR <= 2 * PLANES, "pair schedule");
+        // 4 x 3 entropy footprint (12 loads instead of 18).  Consecutive lanes take consecutive pixels of a row, so their
+        // 64-byte operand rows fall on different banks (a horizontal pair per lane was measured 2-way conflicted: 128-byte
+        // lane stride).  The 288 pairs of a tile are dealt to the 224 producer lanes starting at a warp that rotates with
+        // the tile, so the 64 left-over pairs do not always land on the same warps; the footprint of a lane's first pair
+        // of the NEXT tile is loaded as soon as this tile's has been consumed, and this tile's second pair before the
+        // wait for the operand buffer: no global-load latency sits between the wait and the FMAs.
+        constexpr int NPAIR = (AY / 2) * AX, PLANES = NPROD * 32, EB = VIS_EB;
+        static_assert(AY % 2 == 0 && NPAIR > PLANES && NPAIR <= 2 * PLANES, "pair schedule");
         auto pair_of = [&](int it, int second) { return ((warp - 1 + it) % NPROD) * 32 + lane + second * PLANES; };
         struct Org { int y0, x0; const float* ent; };                                     // A1 origin (= tile origin - 2), map base
         auto origin = [&](int item) {
             const int tx = item % d.tiles_x, ty = (item / d.tiles_x) % d.tiles_y, m = item / (d.tiles_x * d.tiles_y);
             return Org{ty * OUT_Y - 2, tx * OUT_X - 2, entropy + (int64_t)m * d.H * d.W};
         };
-        // entropy footprint rows y-1..y+1, columns x-1..x+2 of the pair at (y, x), (y, x+1); zero outside the image
+        // entropy footprint rows y-1..y+2, columns x-1..x+1 of the pair at (y, x), (y+1, x); zero outside the image
         auto load12 = [&](const Org& o, int pr, float (&v)[12]) {
-            const int y = o.y0 + pr / PAIRS_X, x = o.x0 + 2 * (pr % PAIRS_X);
-            bool cok[4];
+            const int y = o.y0 + 2 * (pr / AX), x = o.x0 + pr % AX;
+            bool cok[3];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) cok[c] = (unsigned)(x - 1 + c) < (unsigned)d.W;
+            for (int c = 0; c < 3; ++c) cok[c] = (unsigned)(x - 1 + c) < (unsigned)d.W;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < 4; ++r) {
                 const int yy = y - 1 + r;
                 const bool rok = (unsigned)yy < (unsigned)d.H;
                 const float* row = o.ent + (int64_t)yy * d.W + (x - 1);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[r * 4 + c] = (rok && cok[c]) ? __ldg(row + c) : 0.0f;
+                for (int c = 0; c < 3; ++c) v[r * 3 + c] = (rok && cok[c]) ? __ldg(row + c) : 0.0f;
             }
         };
         auto compute_pair = [&](const Org& o, int pr, const float (&v)[12], uint8_t* a1) {
-            const int py = pr / PAIRS_X, px = 2 * (pr % PAIRS_X);
+            const int py = 2 * (pr / AX), px = pr % AX;
             const int y = o.y0 + py, x = o.x0 + px;
-            const bool rowin = (unsigned)y < (unsigned)d.H;
-            const bool in0 = rowin && (unsigned)x < (unsigned)d.W, in1 = rowin && (unsigned)(x + 1) < (unsigned)d.W;
-            f32x2 in[9];                                                                  // tap t of (left pixel, right pixel)
+            const bool colin = (unsigned)x < (unsigned)d.W;
+            const bool in0 = colin && (unsigned)y < (unsigned)d.H, in1 = colin && (unsigned)(y + 1) < (unsigned)d.H;
+            f32x2 in[9];                                                                  // tap t of (upper pixel, lower pixel)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) in[t] = pack2(v[(t / 3) * 4 + t % 3], v[(t / 3) * 4 + t % 3 + 1]);
+            for (int t = 0; t < 9; ++t) in[t] = pack2(v[(t / 3) * 3 + t % 3], v[(t / 3 + 1) * 3 + t % 3]);
             const int pix = py * AX + px;
 #pragma unroll
             for (int eh = 0; eh < 16; eh += EB) {                                         // EB channels at a time (registers)
@@ -221,14 +223,14 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
                     f32x2 a = pack2(P.b1[eh + e], P.b1[eh + e]);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) a = ffma2(in[t], pack2(P.w1[eh + e][t], P.w1[eh + e][t]), a);
-                    const float2 o = unpack2(a);
-                    r0[e] = in0 ? relu_round_tf32(o.x) : 0.0f;                 // outside the image: layer 2's zero padding
-                    r1[e] = in1 ? relu_round_tf32(o.y) : 0.0f;
+                    const float2 o2 = unpack2(a);
+                    r0[e] = in0 ? relu_round_tf32(o2.x) : 0.0f;                           // outside the image: layer 2's zero padding
+                    r1[e] = in1 ? relu_round_tf32(o2.y) : 0.0f;
                 }
 #pragma unroll
                 for (int c = 0; c < EB / 4; ++c) {
                     *reinterpret_cast<float4*>(a1 + sw64_offset(pix, eh / 4 + c)) = make_float4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
-                    *reinterpret_cast<float4*>(a1 + sw64_offset(pix + 1, eh / 4 + c)) = make_float4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
+                    *reinterpret_cast<float4*>(a1 + sw64_offset(pix + AX, eh / 4 + c)) = make_float4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
                 }
             }
         };

@@ -22,19 +22,23 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-if [ -f build/ab/libmvs_b200_base.so ]; then
-  run base "" MVS_LIB_PATH=build/ab/libmvs_b200_base.so MVS_PROB_FUSED=0
-  run base_lanes1 "--lanes 1" MVS_LIB_PATH=build/ab/libmvs_b200_base.so MVS_PROB_FUSED=0
+if ! grep -q " passed" $OUT/pytest.log || grep -q "failed" $OUT/pytest.log; then     # is the pipelined conv epilogue the cause?
+  MVS_TMA_EPI_PIPE=0 timeout 300 python -m pytest tests/test_gpu_tensorcore.py tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -8 > $OUT/pytest_nopipe.log
 fi
-run new_noprob "" MVS_PROB_FUSED=0
-run new "" MVS_PROB_FUSED=1
-run new_lanes1 "--lanes 1" MVS_PROB_FUSED=1
+for lib in base mid; do
+  if [ -f build/ab/libmvs_b200_$lib.so ]; then
+    run $lib "" MVS_LIB_PATH=build/ab/libmvs_b200_$lib.so MVS_PROB_FUSED=$([ $lib = base ] && echo 0 || echo 1)
+  fi
+done
+run new_nopipe "" MVS_TMA_EPI_PIPE=0
+run new "" MVS_TMA_EPI_PIPE=1
+run new_lanes1 "--lanes 1" MVS_TMA_EPI_PIPE=1
 KERN='mvs|tc::|k1cl|conv3d|vis_|corr_|cost_|tma3|prob_|regression|schedule|init_|confidence|relproj|argmax|nchw'
 timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,sm__inst_executed_pipe_fma.sum \
   --clock-control none -k regex:"$KERN" -c 900 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 1 --warmup 3 --lanes 1 --no-cpu-baseline --no-train-step --no-eager --no-parity > $OUT/ncu_bench.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"cost_volume_cl_kernel|vis_fused_kernel" -s 27 -c 9 -o $OUT/k1vis \
+[ -n "$AB_FULL" ] && timeout 400 ncu --set full --clock-control none --import-source on -k regex:"cost_volume_cl_kernel|vis_fused_kernel" -s 27 -c 9 -o $OUT/k1vis \
   python bench.py --steps 1 --warmup 3 --lanes 1 --no-cpu-baseline --no-train-step --no-eager --no-parity > $OUT/ncu_full.log 2>&1
-python scripts/summarise_ncu.py $OUT/k1vis.ncu-rep $OUT/k1vis_full.csv > $OUT/summ.log 2>&1
+[ -n "$AB_FULL" ] && python scripts/summarise_ncu.py $OUT/k1vis.ncu-rep $OUT/k1vis_full.csv > $OUT/summ.log 2>&1
 rm -f $OUT/k1vis.ncu-rep
-cat $OUT/pytest.log
+cat $OUT/pytest.log $OUT/pytest_nopipe.log 2>/dev/null
