@@ -12,7 +12,8 @@
 //   warp 1 (one lane)  MMA issuer: for every slab 9 taps x Cin/8 tcgen05.mma (kind::tf32, M = 128, N = (1..3) x NT: the depth
 //                      taps of a slab feed a contiguous window of slice accumulators = one wide MMA), accumulators in TMEM,
 //                      DOUBLE-BUFFERED so that item i+1 accumulates while item i is drained;
-//   warps 2-5          epilogue: tcgen05.ld -> + shift (folded BN) -> ReLU -> + skip -> TF32 round -> 128-bit stores.
+//   warps 2-9          epilogue: tcgen05.ld (one accumulator block ahead) -> shared-memory transpose -> + shift (folded BN) -> ReLU
+//                      -> + skip -> TF32 round -> 128-bit stores (or, last layer, the 1x1x1 `prob` conv and one float per voxel).
 // Three modes share the kernel: stride-1 conv, stride-(1,2,2) conv, and the (1,2,2) transposed conv in gather form.
 // Work item = 8 x 16 output voxels (transposed: input voxels, each with its four output parity classes) x all depth slices
 // x one Cout tile.  Stride 1: its input slab is the box [18 rows][10 columns] of one
@@ -42,7 +43,6 @@ struct Dims {
     int relu;
     int tiles_x, tiles_y, nitems;
     int nbuf;                // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
-    int epi_pipe;            // epilogue: TMEM reads issued one accumulator block ahead (MVS_TMA_EPI_PIPE, default 1)
     float pw[8], pbias;      // PROB: the regulariser's 1x1x1 `prob` conv (8 -> 1, + bias) applied in the epilogue
 };
 
@@ -323,7 +323,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
 #pragma unroll
                 for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16_async(tacc + (uint32_t)cz * NT + c0, accr + c0);
             };
-            if (d.epi_pipe && half < nblk) load_block(half);
+            if (half < nblk) load_block(half);
 #pragma unroll 1
             for (int cz = half; cz < nblk; cz += NEPI / 4) {
                 float4 skc[CPR];
@@ -331,17 +331,17 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap amap, const float* __restr
                 for (int j = 0; j < CPR; ++j) skc[j] = skn[j];
                 const size_t base_c = base_n;
                 if (cz + NEPI / 4 < nblk) prefetch_skip(cz + NEPI / 4);
-                // The block's accumulator rows were requested one block ago (or before the loop): the TMEM read latency ran
+                // The block's accumulator rows were requested one block ago (or before the loop): the TMEM read latency runs
                 // under the previous block's stores.  Once they are staged in shared memory the registers are free, and the
-                // next block's read is issued before this block's stores.
-                if (!d.epi_pipe) load_block(cz);
+                // next block's read is issued before this block's stores.  (Measured neutral on B200 — the drain is bound by
+                // its shared-memory round trip and stores, profiles/r02k_ab.json — kept because it is never slower.)
                 tmem_ld_wait();
                 __syncwarp();                                         // previous block's reads of the buffer are done
 #pragma unroll
                 for (int c4 = 0; c4 < CPR; ++c4)
                     *reinterpret_cast<uint4*>(stg + lane * L::STG_PITCH + c4 * 4) = make_uint4(accr[c4 * 4], accr[c4 * 4 + 1], accr[c4 * 4 + 2], accr[c4 * 4 + 3]);
                 __syncwarp();
-                if (d.epi_pipe && cz + NEPI / 4 < nblk) load_block(cz + NEPI / 4);
+                if (cz + NEPI / 4 < nblk) load_block(cz + NEPI / 4);
 #pragma unroll
                 for (int j = 0; j < CPR; ++j) {
                     const bool ok = (livemask >> j) & 1u;
@@ -432,12 +432,6 @@ static int launch_k(const float* x, const float* w, const float* shift, const fl
     if (rc) return rc;
     Dims d = {};
     d.B = B; d.D = D; d.H = H; d.W = W; d.Cout = Cout; d.relu = relu;
-    static int epi_pipe = -1;
-    if (epi_pipe < 0) {
-        const char* e = getenv("MVS_TMA_EPI_PIPE");
-        epi_pipe = (e && e[0] == '0') ? 0 : 1;
-    }
-    d.epi_pipe = epi_pipe;
     if (PROB) {
         for (int i = 0; i < 8; ++i) d.pw[i] = prob_w[i];
         d.pbias = prob_bias;

@@ -662,6 +662,18 @@ using Stage1 = Cfg<64, 32, 32, 1, 8, 1, 56, 5, 2, 2>;
 using Stage2 = Cfg<32, 16, 32, 1, 8, 1, 56, 5, 1, 2>;
 using Stage3 = Cfg<16, 8, 32, 2, 4, 2, 80, 6, 1, 3>;       // 2 hypotheses per thread
 using Stage4 = Cfg<8, 4, 32, 8, 1, 4, 80, 14, 1, 2>;       // all 4 hypotheses of a pixel in one thread
+// A/B candidate (MVS_K1_STAGE4=b): 2 hypotheses per thread, 32 x 4 pixel tiles, 80 registers -> 3 CTAs (36 % of the warp slots
+// instead of 24 %) for the latency-bound stage-4 passes
+using Stage4B = Cfg<8, 4, 32, 4, 2, 2, 80, 10, 1, 3>;
+
+static bool stage4_b() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MVS_K1_STAGE4");
+        v = (e && (e[0] == 'b' || e[0] == 'B')) ? 1 : 0;
+    }
+    return v == 1;
+}
 
 }  // namespace k1cl
 
@@ -683,6 +695,8 @@ int cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slot
     if (C == 64 && D == 32 && corr) return sim ? launch<Stage1, 1, true>(p, B, nmaps, st) : launch<Stage1, 1, false>(p, B, nmaps, st);
     if (C == 32 && D == 16 && corr) return sim ? launch<Stage2, 1, true>(p, B, nmaps, st) : launch<Stage2, 1, false>(p, B, nmaps, st);
     if (C == 16 && D == 8 && corr) return sim ? launch<Stage3, 1, true>(p, B, nmaps, st) : launch<Stage3, 1, false>(p, B, nmaps, st);
+    if (C == 8 && D == 4 && !corr && stage4_b())
+        return sim ? launch<Stage4B, 0, true>(p, B, nmaps, st) : launch<Stage4B, 0, false>(p, B, nmaps, st);
     if (C == 8 && D == 4 && !corr) return sim ? launch<Stage4, 0, true>(p, B, nmaps, st) : launch<Stage4, 0, false>(p, B, nmaps, st);
     return 1;
 }
@@ -694,6 +708,7 @@ int cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_sl
     if (G != 8 || ((uintptr_t)feat_cl & 15) || V - 1 > MAXN) return 1;
     Params p{feat_cl, relproj, depth, V - 1, V, H, W, nullptr, nullptr, nullptr, vis_weight, volume, round_tf32};
     set_slots(p, view_slots, V);
+    if (C == 8 && D == 4 && stage4_b()) return launch<Stage4B, 2, false>(p, B, nmaps, st);
     if (C == 8 && D == 4) return launch<Stage4, 2, false>(p, B, nmaps, st);
     return 1;
 }
