@@ -186,25 +186,6 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
         s_box[0] = s_box[1] = s_box[2] = s_box[3] = INT_MAX;
         s_cnt[0] = s_cnt[1] = 0;
     }
-    for (int i = tid; i < D * TP; i += 256) {                            // hypotheses of the tile, coalesced along x
-        const int k = i / TP, q = i - k * TP;
-        const int qx = blockIdx.x * TW + (q % TW), qy = blockIdx.y * CFG::TH + (q / TW);
-        s_dep[q * SD + k] = (qx < p.W && qy < p.H) ? __ldg(p.depth + ((int64_t)b * D + k) * hw + (int64_t)qy * p.W + qx) : 1.0f;
-    }
-    for (int i = tid; i < p.N * 12; i += 256) s_rel[i] = __ldg(p.relproj + (int64_t)b * p.N * 12 + i);
-    if (SIM)
-        for (int i = tid; i < TP * SD; i += 256) s_cos[i] = 0.0f;
-    if (REF_SMEM) {
-        float4* s_ref4 = reinterpret_cast<float4*>(s_ref);
-        for (int i = tid; i < TP * C4; i += 256) {
-            const int q = i / C4, cq = i - q * C4;
-            const int qx = blockIdx.x * TW + (q % TW), qy = blockIdx.y * CFG::TH + (q / TW);
-            s_ref4[i] = (qx < p.W && qy < p.H) ? __ldg(feat4 + ((int64_t)(p.use_slots ? p.slot[0] : b * p.V) * hw + (int64_t)qy * p.W + qx) * C4 + cq)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    __syncthreads();
-
     auto issue = [&](int it) {                                            // one thread; box of item `it` complete, its slot free
         const int slot = it & 1, ch = it % NCH, v = it / (NCH * NHB);
         const int bx0 = s_box[slot * 2] == INT_MAX ? 0 : s_box[slot * 2];
@@ -238,6 +219,43 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
 #pragma unroll
         for (int j = 0; j < (REF_SMEM ? 1 : C4); ++j) rreg[j] = live ? __ldg(ref4 + (j ^ xq)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // (the reference-feature loads above are in flight while the tile's tables are filled)
+    {   // hypotheses of the tile, coalesced along x; every load is issued before the first store (the loop used to expose one
+        // global-load latency per iteration: 7-15 % of the stall samples of the stage-3/4 kernels, profiles/r02m_k1_source_stalls.json)
+        constexpr int NLD = (D * TP + 255) / 256;
+        float hv[NLD];
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+            const int i = tid + u * 256, k = i / TP, q = i - k * TP;
+            const int qx = blockIdx.x * TW + (q % TW), qy = blockIdx.y * CFG::TH + (q / TW);
+            hv[u] = (i < D * TP && qx < p.W && qy < p.H) ? __ldg(p.depth + ((int64_t)b * D + k) * hw + (int64_t)qy * p.W + qx) : 1.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+            const int i = tid + u * 256, k = i / TP, q = i - k * TP;
+            if (i < D * TP) s_dep[q * SD + k] = hv[u];
+        }
+    }
+    for (int i = tid; i < p.N * 12; i += 256) s_rel[i] = __ldg(p.relproj + (int64_t)b * p.N * 12 + i);
+    if (SIM)
+        for (int i = tid; i < TP * SD; i += 256) s_cos[i] = 0.0f;
+    if (REF_SMEM) {
+        float4* s_ref4 = reinterpret_cast<float4*>(s_ref);
+        constexpr int NRF = (TP * C4 + 255) / 256;                        // loads first, stores after (as above)
+        float4 rv[REF_SMEM ? NRF : 1];
+#pragma unroll
+        for (int u = 0; u < (REF_SMEM ? NRF : 1); ++u) {
+            const int i = tid + u * 256, q = i / C4, cq = i - q * C4;
+            const int qx = blockIdx.x * TW + (q % TW), qy = blockIdx.y * CFG::TH + (q / TW);
+            rv[u] = (i < TP * C4 && qx < p.W && qy < p.H)
+                        ? __ldg(feat4 + ((int64_t)(p.use_slots ? p.slot[0] : b * p.V) * hw + (int64_t)qy * p.W + qx) * C4 + cq)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < (REF_SMEM ? NRF : 1); ++u)
+            if (tid + u * 256 < TP * C4) s_ref4[tid + u * 256] = rv[u];
+    }
+    __syncthreads();
     // 1 / max(||ref[:, c']||, 1e-12): F.normalize of the reference features (SIM), indexed by LOCAL c'
     float rinv[SIM ? NCP : 1];
     if (SIM) {
@@ -312,6 +330,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
 #pragma unroll
         for (int g = 0; g < (PASS_B ? G : 1); ++g) acc[j][g] = 0.0f;
     float wsum = 0.0f;
+    float wv_next = (PASS_B && live) ? __ldg(p.vis_weight + (int64_t)b * p.N * hw + pixoff) : 0.0f;     // view 0
     float a_c[SIM ? NCP : 1], wn[SIM ? NCP : 1];                          // SIM: per-c' dot products / squared norms
     float sview = 0.0f;
 
@@ -323,9 +342,9 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
             else item_pos(it + 2, n2x, n2y);
         }
         float wv = 0.0f;
-        if (PASS_B) {
-            wv = live ? __ldg(p.vis_weight + ((int64_t)b * p.N + v) * hw + pixoff) : 0.0f;
-            wsum += wv;
+        if (PASS_B) {                                                     // this item's weight was requested one item ago
+            wv = wv_next;
+            if (it + 1 < NI) wv_next = live ? __ldg(p.vis_weight + ((int64_t)b * p.N + (it + 1) / (NCH * NHB)) * hw + pixoff) : 0.0f;
         }
         mbar_wait(&full[slot], (it >> 1) & 1);
         if (have2) box_contrib(slot, n2x, n2y);                           // this slot's box counters were re-armed by issue(it)
@@ -464,6 +483,7 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
                 }
             }
         }
+        if (PASS_B) wsum += wv;
         __syncwarp();
         if (lane == 0 && have2 && atom_inc_acq_rel(&s_cnt[slot]) == 7) issue(it + 2);   // last warp out fetches item it+2
 
@@ -656,25 +676,13 @@ static int launch(const Params& p, int B, int nmaps, cudaStream_t st) {
 
 // Tilings (pixel tile, hypotheses per item, box) chosen from measured coverage of the bench workload's noisy depth maps
 // (scripts/box_coverage.py): >= 99.9 % of the samples of every view take the shared-memory path.  Hypotheses per thread
-// (KPT) from an A/B on the B200 (profiles/r02b_k1_tiling_ab.json): KPT = 1 costs +6 % at stage 3 and +25 % at stage 4.
+// (KPT) from an A/B on the B200 (profiles/r02b_k1_tiling_ab.json): KPT = 1 costs +6 % at stage 3 and +25 % at stage 4; stage 4
+// with KPT = 2 at 80 registers / 3 CTAs per SM is 5 % slower than KPT = 4 at 2 CTAs (profiles/r02l_k1_stage4_tiling_ab.json).
 //             C   D  TW TH HB KPT BW  BH NCH MINB
 using Stage1 = Cfg<64, 32, 32, 1, 8, 1, 56, 5, 2, 2>;
 using Stage2 = Cfg<32, 16, 32, 1, 8, 1, 56, 5, 1, 2>;
 using Stage3 = Cfg<16, 8, 32, 2, 4, 2, 80, 6, 1, 3>;       // 2 hypotheses per thread
 using Stage4 = Cfg<8, 4, 32, 8, 1, 4, 80, 14, 1, 2>;       // all 4 hypotheses of a pixel in one thread
-// A/B candidate (MVS_K1_STAGE4=b): 2 hypotheses per thread, 32 x 4 pixel tiles, 80 registers -> 3 CTAs (36 % of the warp slots
-// instead of 24 %) for the latency-bound stage-4 passes
-using Stage4B = Cfg<8, 4, 32, 4, 2, 2, 80, 10, 1, 3>;
-
-static bool stage4_b() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("MVS_K1_STAGE4");
-        v = (e && (e[0] == 'b' || e[0] == 'B')) ? 1 : 0;
-    }
-    return v == 1;
-}
-
 }  // namespace k1cl
 
 // Pass A over channels-last features; corr != nullptr also stores the per-view group correlation (C/G >= 2 only).
@@ -695,8 +703,6 @@ int cost_volume_cl_entropy(const float* feat_cl, int nmaps, const int* view_slot
     if (C == 64 && D == 32 && corr) return sim ? launch<Stage1, 1, true>(p, B, nmaps, st) : launch<Stage1, 1, false>(p, B, nmaps, st);
     if (C == 32 && D == 16 && corr) return sim ? launch<Stage2, 1, true>(p, B, nmaps, st) : launch<Stage2, 1, false>(p, B, nmaps, st);
     if (C == 16 && D == 8 && corr) return sim ? launch<Stage3, 1, true>(p, B, nmaps, st) : launch<Stage3, 1, false>(p, B, nmaps, st);
-    if (C == 8 && D == 4 && !corr && stage4_b())
-        return sim ? launch<Stage4B, 0, true>(p, B, nmaps, st) : launch<Stage4B, 0, false>(p, B, nmaps, st);
     if (C == 8 && D == 4 && !corr) return sim ? launch<Stage4, 0, true>(p, B, nmaps, st) : launch<Stage4, 0, false>(p, B, nmaps, st);
     return 1;
 }
@@ -708,7 +714,6 @@ int cost_volume_cl_aggregate(const float* feat_cl, int nmaps, const int* view_sl
     if (G != 8 || ((uintptr_t)feat_cl & 15) || V - 1 > MAXN) return 1;
     Params p{feat_cl, relproj, depth, V - 1, V, H, W, nullptr, nullptr, nullptr, vis_weight, volume, round_tf32};
     set_slots(p, view_slots, V);
-    if (C == 8 && D == 4 && stage4_b()) return launch<Stage4B, 2, false>(p, B, nmaps, st);
     if (C == 8 && D == 4) return launch<Stage4, 2, false>(p, B, nmaps, st);
     return 1;
 }
