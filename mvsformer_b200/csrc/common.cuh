@@ -91,6 +91,14 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
     return d;
 }
 
+// acc[0..3] += a * w.{x,y,z,w} as two packed FMAs (a broadcast): bit-identical to four fmaf(a, w.k, acc[k])
+__device__ __forceinline__ void fma4_bcast(float* acc, float a, const float4& w) {
+    const f32x2 aa = pack2(a, a);
+    const float2 lo = unpack2(ffma2(pack2(w.x, w.y), aa, pack2(acc[0], acc[1])));
+    const float2 hi = unpack2(ffma2(pack2(w.z, w.w), aa, pack2(acc[2], acc[3])));
+    acc[0] = lo.x; acc[1] = lo.y; acc[2] = hi.x; acc[3] = hi.y;
+}
+
 }  // namespace mvs
 
 #include "geometry.cuh"

@@ -12,7 +12,8 @@
 //   stride-1, in gather form: a thread owns the output pair (2j, 2j+1) of one output row, for
 //   which the contributing taps are fixed (kw=1 | kw=2 and kw=0), so no work is predicated off.
 //
-// These kernels are FP32-FMA bound (AI of a 3x3x3 16->16 layer = 432 flop/B); the tcgen05
+// These kernels are FP32-FMA bound (AI of a 3x3x3 16->16 layer = 432 flop/B) and use the packed FFMA2 form (a three-register
+// FFMA holds the FMA pipe for two issue cycles per warp on sm_100; fma.rn.f32x2 does two IEEE fmas in that slot); the tcgen05
 // implicit-GEMM path (conv3d_tc.cu) supersedes them for the heavy layers.
 #include "common.cuh"
 
@@ -89,10 +90,7 @@ conv3d_cl_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 #pragma unroll
                             for (int j = 0; j < VPT; ++j) {
                                 const float a = u == 0 ? v[j].x : (u == 1 ? v[j].y : (u == 2 ? v[j].z : v[j].w));
-                                acc[j][q * 4 + 0] = fmaf(a, ww.x, acc[j][q * 4 + 0]);
-                                acc[j][q * 4 + 1] = fmaf(a, ww.y, acc[j][q * 4 + 1]);
-                                acc[j][q * 4 + 2] = fmaf(a, ww.z, acc[j][q * 4 + 2]);
-                                acc[j][q * 4 + 3] = fmaf(a, ww.w, acc[j][q * 4 + 3]);
+                                fma4_bcast(&acc[j][q * 4], a, ww);          // two FFMA2 (packed FP32) instead of four FFMA
                             }
                         }
                     }
@@ -184,14 +182,9 @@ deconv3d_cl_kernel(const float* __restrict__ x, const float* __restrict__ w, con
                         const float4 k0 = reinterpret_cast<const float4*>(w0 + ro)[q];
                         const float4 k1 = reinterpret_cast<const float4*>(w1 + ro)[q];
                         const float4 k2 = reinterpret_cast<const float4*>(w2 + ro)[q];
-                        acc0[q * 4 + 0] = fmaf(a, k1.x, acc0[q * 4 + 0]);
-                        acc0[q * 4 + 1] = fmaf(a, k1.y, acc0[q * 4 + 1]);
-                        acc0[q * 4 + 2] = fmaf(a, k1.z, acc0[q * 4 + 2]);
-                        acc0[q * 4 + 3] = fmaf(a, k1.w, acc0[q * 4 + 3]);
-                        acc1[q * 4 + 0] = fmaf(a, k2.x, fmaf(bn, k0.x, acc1[q * 4 + 0]));
-                        acc1[q * 4 + 1] = fmaf(a, k2.y, fmaf(bn, k0.y, acc1[q * 4 + 1]));
-                        acc1[q * 4 + 2] = fmaf(a, k2.z, fmaf(bn, k0.z, acc1[q * 4 + 2]));
-                        acc1[q * 4 + 3] = fmaf(a, k2.w, fmaf(bn, k0.w, acc1[q * 4 + 3]));
+                        fma4_bcast(&acc0[q * 4], a, k1);                    // packed FP32: two FFMA2 per four channels
+                        fma4_bcast(&acc1[q * 4], bn, k0);                   // (same order as fmaf(a, k2, fmaf(bn, k0, acc1)))
+                        fma4_bcast(&acc1[q * 4], a, k2);
                     }
                 }
             }

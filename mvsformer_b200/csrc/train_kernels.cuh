@@ -399,10 +399,20 @@ __device__ __forceinline__ void conv_wgrad_thread(const float* __restrict__ smal
             float a[TS], c[TB];
             load_vec<TS>(ps + (int64_t)x * d.Cs, a);
             load_vec<TB>(pb + x * bstep, c);
+#if defined(__CUDA_ARCH__)
+            if (TB % 4 == 0) {                                   // packed FP32 (FFMA2): each half is the scalar fmaf below
 #pragma unroll
-            for (int i = 0; i < TS; ++i)
+                for (int i = 0; i < TS; ++i)
 #pragma unroll
-                for (int j = 0; j < TB; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+                    for (int j = 0; j < TB; j += 4) fma4_bcast(&acc[i][j], a[i], make_float4(c[j], c[j + 1], c[j + 2], c[j + 3]));
+            } else
+#endif
+            {
+#pragma unroll
+                for (int i = 0; i < TS; ++i)
+#pragma unroll
+                    for (int j = 0; j < TB; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+            }
         }
     }
     if (!any) return;
