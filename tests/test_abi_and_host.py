@@ -38,6 +38,15 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"kernel size" in lib.mvs_last_error_string()
     rc = lib.mvs_relative_projections(p, 1, 40, p, None)
     assert rc == -1 and b"source views" in lib.mvs_last_error_string()
+    # mvs_conv3d_tma_prob (last transposed layer + `prob` conv): null pointers, kernel depth, channel count, TMEM capacity
+    rc = lib.mvs_conv3d_tma_prob(p, p, None, None, None, 0.0, p, 1, 4, 8, 8, 16, 3, 1, None)
+    assert rc == -1 and b"null pointer" in lib.mvs_last_error_string()
+    rc = lib.mvs_conv3d_tma_prob(p, p, None, None, p, 0.0, p, 1, 4, 8, 8, 16, 2, 1, None)
+    assert rc == -1 and b"kernel depth" in lib.mvs_last_error_string()
+    rc = lib.mvs_conv3d_tma_prob(p, p, None, None, p, 0.0, p, 1, 4, 8, 8, 32, 3, 1, None)
+    assert rc < 0 and b"Cin = 16" in lib.mvs_last_error_string()
+    rc = lib.mvs_conv3d_tma_prob(p, p, None, None, p, 0.0, p, 1, 16, 8, 8, 16, 3, 1, None)
+    assert rc < 0 and b"tensor memory" in lib.mvs_last_error_string()
 
 
 def test_no_cpu_fallback():
