@@ -38,9 +38,6 @@ constexpr int ABYTES = AY * AX * PIXB;           // 36 KB, a multiple of 1024
 constexpr int N2 = 48, N3 = 32;                  // MMA N: [3 kh][16] and [3 kh][8] padded to 32
 constexpr int W2BYTES = 3 * 4 * N2 * 16, W3BYTES = 3 * 4 * N3 * 16;      // packed [kw][quad][kh][n][4]
 constexpr int XBYTES = 2 * AY * 16 * PIXB;       // exchange buffers for T[1], T[2]: [2][32 rows][16 pixels][64 B]
-#ifndef VIS_EB
-#define VIS_EB 8
-#endif
 constexpr int NPROD = 7, NEPI = 8;               // producer / epilogue warps
 constexpr int THREADS = 32 * (1 + NPROD + NEPI);
 constexpr size_t SMEM = 3 * ABYTES + W2BYTES + W3BYTES + XBYTES + 256 + 1024;
@@ -183,7 +180,7 @@ vis_fused_kernel(const float* __restrict__ entropy, const float* __restrict__ w2
         // the tile, so the 64 left-over pairs do not always land on the same warps; the footprint of a lane's first pair
         // of the NEXT tile is loaded as soon as this tile's has been consumed, and this tile's second pair before the
         // wait for the operand buffer: no global-load latency sits between the wait and the FMAs.
-        constexpr int NPAIR = (AY / 2) * AX, PLANES = NPROD * 32, EB = VIS_EB;
+        constexpr int NPAIR = (AY / 2) * AX, PLANES = NPROD * 32, EB = 8;     // EB: channels per register block
         static_assert(AY % 2 == 0 && NPAIR > PLANES && NPAIR <= 2 * PLANES, "pair schedule");
         auto pair_of = [&](int it, int second) { return ((warp - 1 + it) % NPROD) * 32 + lane + second * PLANES; };
         struct Org { int y0, x0; const float* ent; };                                     // A1 origin (= tile origin - 2), map base
