@@ -737,7 +737,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference", "eager"])
     ap.add_argument("--lanes", type=int, default=3, help="reference views in flight per GPU (compute streams); B200 A/B: "
-                    "1 -> 220.8, 2 -> 232, 3 -> 247.0 maps/s (profiles/r02i_lanes_ab.json)")
+                    "1 -> 220.8, 2 -> 232, 3 -> 247.0 maps/s (profiles/r02i_lanes_ab.json); final build 1 -> 238.6, "
+                    "3 -> 271-278 (profiles/r02k_ab.json, r02o_bench_20steps.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (reference modules on cuda:0)")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity check against the CPU oracle")
