@@ -418,11 +418,22 @@ cost_volume_cl_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
             if (live && inbox) {
                 const float4* t = tile4 + (ly * BW + lx) * NQ;
                 const float w00 = (1.0f - fx) * (1.0f - fy), w01 = fx * (1.0f - fy), w10 = (1.0f - fx) * fy, w11 = fx * fy;
+                // 64-byte texels (stage 3): an LDS.128 phase is the 4 + 4 hypothesis lanes of two pixels; a lane's bank group is
+                // 4 * (texel x parity) + chunk, and the chunk rotation only separates the lanes of ONE pixel — on noisy depth maps
+                // the two pixels' texel parities are random and 38 % of the load wavefronts were conflict replays
+                // (l1tex__data_bank_conflicts..._op_ld 19.4 M of 50.8 M, profiles/r02m_k1_source_stalls.json).  The two x taps of
+                // a row are neighbouring texels = opposite parities, so each lane takes FIRST the tap whose parity equals its
+                // pixel's position in the phase: every load instruction is then conflict-free whatever is sampled.
+                constexpr bool XSWAP = NQ == 4 && HB == 4;
+                static_assert(!XSWAP || (BW * NQ) % 8 == 0, "tile rows keep the bank phase");
+                const bool swp = XSWAP && (((lx ^ (lane >> 2)) & 1) != 0);
+                const int oa = swp ? NQ : 0, ob = swp ? 0 : NQ;            // first / second x tap, in 16-byte units
+                const float wa0 = swp ? w01 : w00, wb0 = swp ? w00 : w01, wa1 = swp ? w11 : w10, wb1 = swp ? w10 : w11;
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
                     const int q = j ^ xq;
-                    const float4 t00 = t[q], t01 = t[NQ + q], t10 = t[BW * NQ + q], t11 = t[(BW + 1) * NQ + q];
-                    const float4 w = blend(t00, t01, t10, t11, w00, w01, w10, w11);
+                    const float4 t00 = t[oa + q], t01 = t[ob + q], t10 = t[BW * NQ + oa + q], t11 = t[BW * NQ + ob + q];
+                    const float4 w = blend(t00, t01, t10, t11, wa0, wb0, wa1, wb1);
                     const float4 r = REF_SMEM ? reinterpret_cast<const float4*>(s_ref)[pix * C4 + ch * NQ + q] : rreg[REF_SMEM ? 0 : j];
                     accumulate(j, r, w);
                 }
