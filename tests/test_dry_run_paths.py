@@ -240,3 +240,33 @@ def test_bench_kernel_profiler_cost_functions(dry, monkeypatch, layout):
     else:
         assert {"cv_entropy(passA)", "cv_aggregate(passB)"} <= set(summ)
     assert "conv3d_tma" in summ and "vis_net(fused)" in summ
+
+
+def test_prob_fusion_is_limited_to_the_layers_the_fused_kernel_implements():
+    """module._RegNetBase._prob_fusable: only CostRegNet3D's 3x3x3 16 -> 8 transposed last layer + 1x1x1 prob conv, in eval,
+    TF32 mode, with the persistent TMA kernels and the knob on."""
+    from mvsformer_b200 import module as M
+    y = torch.zeros(1, 4, 16, 16, 16)
+    net3d, net, net2d = M.CostRegNet3D(8, 8).eval(), M.CostRegNet(8, 8).eval(), M.CostRegNet2D(8, 8).eval()
+    old = config.conv_precision()
+    try:
+        config.set_conv_precision("tf32")
+        assert net3d._prob_fusable(y)
+        assert not net._prob_fusable(y)                    # 3x3x3 prob conv, depth-strided transposed layer
+        assert not net2d._prob_fusable(y)                  # (1,3,3) transposed layer: not the kernel _run_deconv would pick
+        assert not net3d.train()._prob_fusable(y)
+        net3d.eval()
+        assert not net3d._prob_fusable(torch.zeros(1, 16, 16, 16, 16))     # 4 classes x 16 slices x 16 columns > tensor memory
+        config.set_prob_fused(False)
+        assert not net3d._prob_fusable(y)
+        config.set_prob_fused(True)
+        config.set_conv_tma(False)
+        assert not net3d._prob_fusable(y)
+        config.set_conv_tma(True)
+        for mode in ("tf32x3", "fp32"):
+            config.set_conv_precision(mode)
+            assert not net3d._prob_fusable(y)
+    finally:
+        config.set_conv_precision(old)
+        config.set_prob_fused(True)
+        config.set_conv_tma(True)
